@@ -1,0 +1,847 @@
+// K2 companions — everything in the generator that is not a tensor-core GEMM: the 19->256 head, the fused
+// LayerNorm/GroupNorm + LeakyReLU passes (bf16 NHWC activations, fp32 statistics) with their backward, the final
+// 64->1 convolution + ReLU, weight (re)packing, and CUDA-core (SIMT) reference versions of the implicit GEMMs.
+// Reference: Generator.forward (expertsim/models/proton/generator.py:13-52).
+#include "common.cuh"
+
+namespace es {
+
+// row r of a generator batch -> (group, pass, half-batch row j)
+struct RowMap { int g, pass, j; };
+__device__ __forceinline__ RowMap map_row(const es_group* grp, int E, int r, int two_pass) {
+  RowMap m{-1, 0, 0};
+  m.g = find_group(grp, E, r);
+  if (m.g < 0) return m;
+  const es_group G = grp[m.g];
+  const int local = r - G.row_start;
+  if (two_pass) {
+    m.pass = local >= G.pass_rows ? 1 : 0;
+    m.j = G.row_start / 2 + local - m.pass * G.pass_rows;
+  } else {
+    m.j = r;
+  }
+  return m;
+}
+
+// ----------------------------------------------------------------------------------------------- fc1 (19 -> 256)
+constexpr int kF1 = 256, kIn = 19, kNz = 10, kNc = 9;
+
+__global__ void __launch_bounds__(256)
+gen_fc1_fwd_kernel(const float* __restrict__ z1, const float* __restrict__ z2, const float* __restrict__ cond,
+                   const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, long sw, long sv, const es_group* __restrict__ grp, int E,
+                   int total_rows, int two_pass, float* __restrict__ x0, float* __restrict__ lin,
+                   __nv_bfloat16* __restrict__ h) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= total_rows) return;
+  const RowMap m = map_row(grp, E, r, two_pass);
+  if (m.g < 0) return;
+  const int slot = grp[m.g].slot;
+  const float* zz = m.pass ? z2 : z1;
+  float xin = 0.f;
+  if (lane < kNz) xin = zz[(size_t)m.j * kNz + lane];
+  else if (lane < kIn) xin = cond[(size_t)m.j * kNc + lane - kNz];
+  if (lane < kIn) x0[(size_t)r * kIn + lane] = xin;
+  const float* W = w + slot * sw;
+  float v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int o = lane + 32 * q;
+    float acc = b[slot * sv + o];
+    for (int k = 0; k < kIn; ++k) acc = fmaf(W[o * kIn + k], __shfl_sync(0xffffffffu, xin, k), acc);
+    v[q] = acc;
+    s += acc;
+    lin[(size_t)r * kF1 + o] = acc;
+  }
+  const float mean = warp_sum(s) * (1.f / kF1);
+  float ss = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) ss += (v[q] - mean) * (v[q] - mean);
+  const float rstd = rsqrtf(warp_sum(ss) * (1.f / kF1) + kNormEps);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int o = lane + 32 * q;
+    const float y = (v[q] - mean) * rstd * gamma[slot * sv + o] + beta[slot * sv + o];
+    h[(size_t)r * kF1 + o] = f2bf(lrelu(y));
+  }
+}
+
+// one CTA = (group, chunk): rows of the group strided by chunks; gradients staged in shared memory
+__global__ void __launch_bounds__(256)
+gen_fc1_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ x0, const float* __restrict__ lin,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, long sw, long sv,
+                   const es_group* __restrict__ grp, int chunks, float* __restrict__ dw, float* __restrict__ db,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float s_dw[kF1 * kIn];
+  __shared__ float s_v[3][kF1];
+  const int g = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+  const es_group G = grp[g];
+  if (G.rows == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kF1 * kIn; i += 256) s_dw[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * kF1; i += 256) (&s_v[0][0])[i] = 0.f;
+  __syncthreads();
+  const int slot = G.slot;
+  for (int i = ch * 8 + warp; i < G.rows; i += chunks * 8) {
+    const int r = G.row_start + i;
+    float v[8], xh[8], dyn[8];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { v[q] = lin[(size_t)r * kF1 + lane + 32 * q]; s += v[q]; }
+    const float mean = warp_sum(s) * (1.f / kF1);
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ss += (v[q] - mean) * (v[q] - mean);
+    const float rstd = rsqrtf(warp_sum(ss) * (1.f / kF1) + kNormEps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int o = lane + 32 * q;
+      xh[q] = (v[q] - mean) * rstd;
+      const float ga = gamma[slot * sv + o];
+      const float y = xh[q] * ga + beta[slot * sv + o];
+      const float d = dh[(size_t)r * kF1 + o] * (y > 0.f ? 1.f : kLReLU);
+      atomicAdd(&s_v[1][o], d * xh[q]);   // dgamma
+      atomicAdd(&s_v[2][o], d);           // dbeta
+      dyn[q] = d * ga;
+      s1 += dyn[q];
+      s2 += dyn[q] * xh[q];
+    }
+    s1 = warp_sum(s1) * (1.f / kF1);
+    s2 = warp_sum(s2) * (1.f / kF1);
+    const float xin = lane < kIn ? x0[(size_t)r * kIn + lane] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int o = lane + 32 * q;
+      const float dl = rstd * (dyn[q] - s1 - xh[q] * s2);
+      atomicAdd(&s_v[0][o], dl);          // dbias
+      for (int k = 0; k < kIn; ++k) atomicAdd(&s_dw[o * kIn + k], dl * __shfl_sync(0xffffffffu, xin, k));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kF1 * kIn; i += 256) atomicAdd(&dw[slot * sw + i], s_dw[i]);
+  for (int i = threadIdx.x; i < kF1; i += 256) {
+    atomicAdd(&db[slot * sv + i], s_v[0][i]);
+    atomicAdd(&dgamma[slot * sv + i], s_v[1][i]);
+    atomicAdd(&dbeta[slot * sv + i], s_v[2][i]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- big LayerNorm
+// one CTA per row, three sweeps (mean, centred second moment, normalise); sweeps 2-3 hit L2.
+__global__ void __launch_bounds__(512)
+ln_lrelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    long slot_stride, int F, const es_group* __restrict__ grp, int n_groups,
+                    __nv_bfloat16* __restrict__ y, float* __restrict__ stats) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int g = find_group(grp, n_groups, r);
+  if (g < 0) return;
+  const int slot = grp[g].slot;
+  const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * F);
+  const int n4 = F / 8;
+  float f[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    unpack8(__ldg(x4 + i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += f[k];
+  }
+  const float mean = block_sum(s, red) / (float)F;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    unpack8(__ldg(x4 + i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ss += (f[k] - mean) * (f[k] - mean);
+  }
+  const float rstd = rsqrtf(block_sum(ss, red) / (float)F + kNormEps);
+  if (threadIdx.x == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma + slot * slot_stride);
+  const float4* b4 = reinterpret_cast<const float4*>(beta + slot * slot_stride);
+  uint4* y4 = reinterpret_cast<uint4*>(y + (size_t)r * F);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    unpack8(__ldg(x4 + i), f);
+    const float4 ga = __ldg(g4 + 2 * i), gb = __ldg(g4 + 2 * i + 1), ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
+    const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = lrelu((f[k] - mean) * rstd * gg[k] + be[k]);
+    y4[i] = pack8(f);
+  }
+}
+
+// nearest-upsample fan-in tables: source index s receives upsampled indices [lo[s], hi[s])
+__device__ __forceinline__ void build_fanin(int Ns, int Nu, int* lo, int* hi) {
+  const float sc = (float)Ns / (float)Nu;
+  for (int s = 0; s < Ns; ++s) { lo[s] = Nu; hi[s] = 0; }
+  for (int u = 0; u < Nu; ++u) {
+    int s = (int)floorf((float)u * sc);
+    s = s < Ns - 1 ? s : Ns - 1;
+    if (u < lo[s]) lo[s] = u;
+    if (u + 1 > hi[s]) hi[s] = u + 1;
+  }
+}
+
+// gradient arriving at source pixel (sy,sx), channels [c8, c8+8): sum over its upsample fan-out
+__device__ __forceinline__ void load_da8(const __nv_bfloat16* __restrict__ dy_row, int Wu, int C, int c8, const int* ylo,
+                                         const int* yhi, const int* xlo, const int* xhi, int sy, int sx, float* out) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[k] = 0.f;
+  float f[8];
+  for (int uy = ylo[sy]; uy < yhi[sy]; ++uy)
+    for (int ux = xlo[sx]; ux < xhi[sx]; ++ux) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy_row + ((size_t)uy * Wu + ux) * C + c8)), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[k] += f[k];
+    }
+}
+
+__global__ void __launch_bounds__(512)
+ln_lrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int Hu, int Wu, int C,
+                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, long slot_stride, const es_group* __restrict__ grp, int n_groups,
+                    __nv_bfloat16* __restrict__ dx) {
+  __shared__ float red[32];
+  __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
+  const int r = blockIdx.x;
+  const int g = find_group(grp, n_groups, r);
+  if (g < 0) return;
+  const int slot = grp[g].slot;
+  if (threadIdx.x == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+  __syncthreads();
+  const int F = Hs * Ws * C, n4 = F / 8, c4 = C / 8;
+  const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+  const __nv_bfloat16* dyr = dy_up + (size_t)r * Hu * Wu * C;
+  const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * F);
+  const float* ga = gamma + slot * slot_stride;
+  const float* be = beta + slot * slot_stride;
+  float s1 = 0.f, s2 = 0.f;
+  float xv[8], da[8];
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int pix = i / c4, c8 = (i % c4) * 8;
+    load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+    unpack8(__ldg(x4 + i), xv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (xv[k] - mean) * rstd;
+      const float gk = ga[(size_t)i * 8 + k];
+      const float yv = xh * gk + be[(size_t)i * 8 + k];
+      const float d = da[k] * (yv > 0.f ? 1.f : kLReLU) * gk;
+      s1 += d;
+      s2 += d * xh;
+    }
+  }
+  s1 = block_sum(s1, red) / (float)F;
+  s2 = block_sum(s2, red) / (float)F;
+  uint4* dx4 = reinterpret_cast<uint4*>(dx + (size_t)r * F);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int pix = i / c4, c8 = (i % c4) * 8;
+    load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+    unpack8(__ldg(x4 + i), xv);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (xv[k] - mean) * rstd;
+      const float gk = ga[(size_t)i * 8 + k];
+      const float yv = xh * gk + be[(size_t)i * 8 + k];
+      const float d = da[k] * (yv > 0.f ? 1.f : kLReLU) * gk;
+      o[k] = rstd * (d - s1 - xh * s2);
+    }
+    dx4[i] = pack8(o);
+  }
+}
+
+// column reductions for the big LayerNorm: each thread owns 8 consecutive features and walks the rows of one group
+__global__ void __launch_bounds__(128)
+ln_affine_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int Hu, int Wu, int C,
+                     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dx,
+                     const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     long slot_stride, const es_group* __restrict__ grp, const int* __restrict__ row_map,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+  __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
+  const es_group G = grp[blockIdx.y];
+  if (G.rows == 0) return;
+  if (threadIdx.x == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+  __syncthreads();
+  const int F = Hs * Ws * C, n4 = F / 8, c4 = C / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int pix = i / c4, c8 = (i % c4) * 8;
+  const float* ga = gamma + G.slot * slot_stride + (size_t)i * 8;
+  const float* be = beta + G.slot * slot_stride + (size_t)i * 8;
+  float gk[8], bk[8], ag[8], ab[8], al[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { gk[k] = ga[k]; bk[k] = be[k]; ag[k] = ab[k] = al[k] = 0.f; }
+  float xv[8], da[8], dv[8];
+  for (int rr = 0; rr < G.rows; ++rr) {
+    const int r = G.row_start + rr;
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    load_da8(dy_up + (size_t)r * Hu * Wu * C, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)r * F) + i), xv);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (size_t)r * F) + i), dv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (xv[k] - mean) * rstd;
+      const float yv = xh * gk[k] + bk[k];
+      const float d = da[k] * (yv > 0.f ? 1.f : kLReLU);
+      ag[k] += d * xh;
+      ab[k] += d;
+      al[k] += dv[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int f = i * 8 + k;
+    const size_t o = G.slot * slot_stride + (row_map ? row_map[f] : f);
+    dgamma[o] += ag[k];
+    dbeta[o] += ab[k];
+    dbias[o] += al[k];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- GroupNorm (NHWC bf16)
+// One CTA (256 threads) per sample.  Thread t always owns channel octet (t % (C/8)), so per-channel partial sums stay in
+// registers; group statistics are combined through shared memory.
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int Hu,
+                int Wu, const float* __restrict__ gamma, const float* __restrict__ beta, long slot_stride, int C,
+                int groups, const es_group* __restrict__ grp, int n_groups, __nv_bfloat16* __restrict__ out,
+                float* __restrict__ stats, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                float* __restrict__ dbias) {
+  __shared__ float s_a[256], s_b[256];     // per-channel accumulators
+  __shared__ float s_g1[64], s_g2[64];     // per-group results
+  __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
+  const int r = blockIdx.x;
+  const int g = find_group(grp, n_groups, r);
+  if (g < 0) return;
+  const int slot = grp[g].slot;
+  const int P = Hs * Ws, c4 = C / 8, cpg = C / groups;
+  const int tid = threadIdx.x;
+  const int cu = tid % c4, c8 = cu * 8, pstep = 256 / c4, p0 = tid / c4;
+  const float cnt = (float)(cpg * P);
+  if (BWD && tid == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+  s_a[tid] = 0.f; s_b[tid] = 0.f;
+  __syncthreads();
+  const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * P * C);
+  float gk[8], bk[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { gk[k] = gamma[slot * slot_stride + c8 + k]; bk[k] = beta[slot * slot_stride + c8 + k]; }
+  float f[8];
+  if (!BWD) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pix = p0; pix < P; pix += pstep) {
+      unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_a[c8 + k], acc[k]);
+    __syncthreads();
+    if (tid < groups) {
+      float s = 0.f;
+      for (int k = 0; k < cpg; ++k) s += s_a[tid * cpg + k];
+      s_g1[tid] = s / cnt;
+    }
+    __syncthreads();
+    float mu[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mu[k] = s_g1[(c8 + k) / cpg]; acc[k] = 0.f; }
+    for (int pix = p0; pix < P; pix += pstep) {
+      unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += (f[k] - mu[k]) * (f[k] - mu[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_b[c8 + k], acc[k]);
+    __syncthreads();
+    if (tid < groups) {
+      float s = 0.f;
+      for (int k = 0; k < cpg; ++k) s += s_b[tid * cpg + k];
+      const float rstd = rsqrtf(s / cnt + kNormEps);
+      s_g2[tid] = rstd;
+      stats[((size_t)r * groups + tid) * 2] = s_g1[tid];
+      stats[((size_t)r * groups + tid) * 2 + 1] = rstd;
+    }
+    __syncthreads();
+    float rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rs[k] = s_g2[(c8 + k) / cpg];
+    uint4* y4 = reinterpret_cast<uint4*>(out + (size_t)r * P * C);
+    for (int pix = p0; pix < P; pix += pstep) {
+      unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = lrelu((f[k] - mu[k]) * rs[k] * gk[k] + bk[k]);
+      y4[(size_t)pix * c4 + cu] = pack8(f);
+    }
+  } else {
+    float mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int gi = (c8 + k) / cpg;
+      mu[k] = stats[((size_t)r * groups + gi) * 2];
+      rs[k] = stats[((size_t)r * groups + gi) * 2 + 1];
+    }
+    const __nv_bfloat16* dyr = dy_up + (size_t)r * Hu * Wu * C;
+    float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float da[8];
+    for (int pix = p0; pix < P; pix += pstep) {
+      load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+      unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (f[k] - mu[k]) * rs[k];
+        const float yv = xh * gk[k] + bk[k];
+        const float d = da[k] * (yv > 0.f ? 1.f : kLReLU);
+        ag[k] += d * xh;
+        ab[k] += d;
+        a1[k] += d * gk[k];
+        a2[k] += d * gk[k] * xh;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&s_a[c8 + k], a1[k]); atomicAdd(&s_b[c8 + k], a2[k]); }
+    // per-channel affine gradients: combine the threads that share a channel octet through shuffles is not possible
+    // (they sit in different warps), so go straight to global atomics, one per channel per thread
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&dgamma[slot * slot_stride + c8 + k], ag[k]);
+      atomicAdd(&dbeta[slot * slot_stride + c8 + k], ab[k]);
+    }
+    __syncthreads();
+    if (tid < groups) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int k = 0; k < cpg; ++k) { s1 += s_a[tid * cpg + k]; s2 += s_b[tid * cpg + k]; }
+      s_g1[tid] = s1 / cnt;
+      s_g2[tid] = s2 / cnt;
+    }
+    __syncthreads();
+    float m1[8], m2[8], al[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { m1[k] = s_g1[(c8 + k) / cpg]; m2[k] = s_g2[(c8 + k) / cpg]; }
+    uint4* dx4 = reinterpret_cast<uint4*>(out + (size_t)r * P * C);
+    for (int pix = p0; pix < P; pix += pstep) {
+      load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+      unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (f[k] - mu[k]) * rs[k];
+        const float yv = xh * gk[k] + bk[k];
+        const float d = da[k] * (yv > 0.f ? 1.f : kLReLU) * gk[k];
+        o[k] = rs[k] * (d - m1[k] - xh * m2[k]);
+        al[k] += o[k];
+      }
+      dx4[(size_t)pix * c4 + cu] = pack8(o);
+    }
+    if (dbias) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&dbias[slot * slot_stride + c8 + k], al[k]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- output conv (C -> 1)
+__global__ void __launch_bounds__(256)
+gen_out_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, long sw,
+                   int Hs, int Ws, int C, int KH, int KW, int pad, const es_group* __restrict__ grp, int E,
+                   int two_pass, float* __restrict__ img1, float* __restrict__ img2) {
+  extern __shared__ float s_w[];  // [KH*KW][C]
+  const int r = blockIdx.x;
+  const RowMap m = map_row(grp, E, r, two_pass);
+  if (m.g < 0) return;
+  const int slot = grp[m.g].slot;
+  for (int i = threadIdx.x; i < KH * KW * C; i += blockDim.x) {
+    const int tap = i / C, c = i % C;   // reference layout [1][C][KH][KW]
+    s_w[i] = w[slot * sw + (size_t)c * KH * KW + tap];
+  }
+  __syncthreads();
+  const float bias = b[slot];
+  const int Ho = Hs + 2 * pad - KH + 1, Wo = Ws + 2 * pad - KW + 1;
+  float* dst = (m.pass ? img2 : img1) + (size_t)m.j * Ho * Wo;
+  const __nv_bfloat16* xr = x + (size_t)r * Hs * Ws * C;
+  float f[8];
+  for (int p = threadIdx.x; p < Ho * Wo; p += blockDim.x) {
+    const int oy = p / Wo, ox = p % Wo;
+    float acc = bias;
+    for (int ky = 0; ky < KH; ++ky) {
+      const int sy = oy + ky - pad;
+      if (sy < 0 || sy >= Hs) continue;
+      for (int kx = 0; kx < KW; ++kx) {
+        const int sx = ox + kx - pad;
+        if (sx < 0 || sx >= Ws) continue;
+        const uint4* px = reinterpret_cast<const uint4*>(xr + ((size_t)sy * Ws + sx) * C);
+        const float* wt = s_w + (ky * KW + kx) * C;
+        for (int c8 = 0; c8 < C / 8; ++c8) {
+          unpack8(__ldg(px + c8), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc = fmaf(f[k], wt[c8 * 8 + k], acc);
+        }
+      }
+    }
+    dst[p] = fmaxf(acc, 0.f);
+  }
+}
+
+// dx[sy,sx,c] = sum_{ky,kx} dimg_masked[sy-ky+pad, sx-kx+pad] * w[c,ky,kx];  dw[c,ky,kx] += sum dimg_masked * x;  db += sum dimg_masked
+__global__ void __launch_bounds__(256)
+gen_out_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, long sw, int Hs, int Ws, int C,
+                   int KH, int KW, int pad, const float* __restrict__ img1, const float* __restrict__ img2,
+                   const float* __restrict__ dimg1, const float* __restrict__ dimg2, const es_group* __restrict__ grp,
+                   int E, int two_pass, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float sm[];
+  const int Ho = Hs + 2 * pad - KH + 1, Wo = Ws + 2 * pad - KW + 1;
+  float* s_w = sm;                       // [KH*KW][C]
+  float* s_dw = s_w + KH * KW * C;       // [KH*KW][C]
+  float* s_d = s_dw + KH * KW * C;       // [Ho*Wo] masked dimg
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const RowMap m = map_row(grp, E, r, two_pass);
+  if (m.g < 0) return;
+  const int slot = grp[m.g].slot;
+  for (int i = threadIdx.x; i < KH * KW * C; i += blockDim.x) {
+    const int tap = i / C, c = i % C;
+    s_w[i] = w[slot * sw + (size_t)c * KH * KW + tap];
+    s_dw[i] = 0.f;
+  }
+  const float* im = (m.pass ? img2 : img1) + (size_t)m.j * Ho * Wo;
+  const float* di = (m.pass ? dimg2 : dimg1) + (size_t)m.j * Ho * Wo;
+  float dsum = 0.f;
+  for (int p = threadIdx.x; p < Ho * Wo; p += blockDim.x) {
+    const float d = im[p] > 0.f ? di[p] : 0.f;   // ReLU backward
+    s_d[p] = d;
+    dsum += d;
+  }
+  dsum = block_sum(dsum, red);   // contains the __syncthreads that publishes s_w / s_d
+  if (threadIdx.x == 0) atomicAdd(&db[slot], dsum);
+  const int c4 = C / 8;
+  const __nv_bfloat16* xr = x + (size_t)r * Hs * Ws * C;
+  __nv_bfloat16* dxr = dx + (size_t)r * Hs * Ws * C;
+  // thread owns channel octet cu (fixed) and walks pixels, so the weight-gradient partials stay in registers
+  const int cu = threadIdx.x % c4, pstep = blockDim.x / c4;
+  float accw[4][8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) accw[t][k] = 0.f;
+  float f[8];
+  for (int pix = threadIdx.x / c4; pix < Hs * Ws; pix += pstep) {
+    const int sy = pix / Ws, sx = pix % Ws;
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xr + (size_t)pix * C) + cu), f);
+    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int ky = 0; ky < KH; ++ky) {
+      const int oy = sy - ky + pad;
+      if (oy < 0 || oy >= Ho) continue;
+      for (int kx = 0; kx < KW; ++kx) {
+        const int ox = sx - kx + pad;
+        if (ox < 0 || ox >= Wo) continue;
+        const float d = s_d[oy * Wo + ox];
+        const int tap = ky * KW + kx;
+        const float* wt = s_w + tap * C + cu * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          o[k] = fmaf(d, wt[k], o[k]);
+          if (tap < 4) accw[tap][k] = fmaf(d, f[k], accw[tap][k]);
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(dxr + (size_t)pix * C)[cu] = pack8(o);
+  }
+  for (int tap = 0; tap < KH * KW && tap < 4; ++tap)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_dw[tap * C + cu * 8 + k], accw[tap][k]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < KH * KW * C; i += blockDim.x) {
+    const int tap = i / C, c = i % C;
+    atomicAdd(&dw[slot * sw + (size_t)c * KH * KW + tap], s_dw[i]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- packing
+__global__ void pack_conv_kernel(const float* __restrict__ w, long slot_stride, int N, int C, int KH, int KW,
+                                 __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const int slot = blockIdx.y;
+  const long total = (long)N * C * KH * KW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    // i indexes the forward packed layout [N][KH][KW][C]
+    const int c = i % C;
+    const int kx = (i / C) % KW, ky = (i / ((long)C * KW)) % KH, n = i / ((long)C * KW * KH);
+    const float v = w[slot * slot_stride + (((long)n * C + c) * KH + ky) * KW + kx];
+    if (wf) wf[slot * total + i] = f2bf(v);
+    // data-gradient weights: [C][KH][KW][N] with the window flipped
+    if (wd) wd[slot * total + (((long)c * KH + (KH - 1 - ky)) * KW + (KW - 1 - kx)) * N + n] = f2bf(v);
+  }
+}
+
+__global__ void pack_dense_kernel(const float* __restrict__ w, long slot_stride, int N, int K,
+                                  const int* __restrict__ row_map, __nv_bfloat16* __restrict__ wp) {
+  const int slot = blockIdx.y;
+  const long total = (long)N * K;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int n = i / K, k = i % K;
+    const int nr = row_map ? row_map[n] : n;
+    wp[slot * total + i] = f2bf(w[slot * slot_stride + (long)nr * K + k]);
+  }
+}
+
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, int N, int C, int KH, int KW,
+                                         float* __restrict__ dw, long slot_stride) {
+  const int slot = blockIdx.y;
+  const long total = (long)N * C * KH * KW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    // i indexes the reference layout [N][C][KH][KW]
+    const int kx = i % KW, ky = (i / KW) % KH, c = (i / ((long)KW * KH)) % C, n = i / ((long)KW * KH * C);
+    dw[slot * slot_stride + i] = dwp[slot * total + (((long)n * KH + ky) * KW + kx) * C + c];
+  }
+}
+
+__global__ void permute_features_kernel(const float* __restrict__ in, long in_stride, const int* __restrict__ row_map,
+                                        int F, float* __restrict__ out, long out_stride, int inverse) {
+  const int slot = blockIdx.y;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
+    if (inverse) out[slot * out_stride + row_map[f]] = in[slot * in_stride + f];   // packed -> reference
+    else out[slot * out_stride + f] = in[slot * in_stride + row_map[f]];           // reference -> packed
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- SIMT checkers
+__global__ void igemm_fwd_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, es_conv_geom g,
+                                      const es_group* __restrict__ grp, int n_groups, long total) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = i % g.N;
+  const long pixi = i / g.N;
+  const int P = g.Ho * g.Wo;
+  const int row = pixi / P, pix = pixi % P, oy = pix / g.Wo, ox = pix % g.Wo;
+  const int gi = find_group(grp, n_groups, row);
+  if (gi < 0) return;
+  const int slot = grp[gi].slot;
+  const long KK = (long)g.KH * g.KW * g.C;
+  const float sy_sc = (float)g.Hs / (float)g.Hu, sx_sc = (float)g.Ws / (float)g.Wu;
+  float acc = bias ? bias[slot * g.N + n] : 0.f;
+  for (int ky = 0; ky < g.KH; ++ky)
+    for (int kx = 0; kx < g.KW; ++kx) {
+      const int uy = oy + ky - g.pad, ux = ox + kx - g.pad;
+      if (uy < 0 || uy >= g.Hu || ux < 0 || ux >= g.Wu) continue;
+      const int sy = min((int)floorf(uy * sy_sc), g.Hs - 1), sx = min((int)floorf(ux * sx_sc), g.Ws - 1);
+      const __nv_bfloat16* xp = x + (((long)row * g.Hs + sy) * g.Ws + sx) * g.C;
+      const __nv_bfloat16* wp = w + slot * g.N * KK + n * KK + (long)(ky * g.KW + kx) * g.C;
+      for (int c = 0; c < g.C; ++c) acc = fmaf(bf2f(xp[c]), bf2f(wp[c]), acc);
+    }
+  y[i] = f2bf(acc);
+}
+
+__global__ void igemm_wgrad_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                        float* __restrict__ dw, es_conv_geom g, const es_group* __restrict__ grp,
+                                        int n_groups) {
+  const long KK = (long)g.KH * g.KW * g.C;
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)g.N * KK) return;
+  const es_group G = grp[blockIdx.y];
+  if (G.rows == 0) return;
+  const int n = i / KK;
+  const int kk = i % KK, c = kk % g.C, tap = kk / g.C, ky = tap / g.KW, kx = tap % g.KW;
+  const float sy_sc = (float)g.Hs / (float)g.Hu, sx_sc = (float)g.Ws / (float)g.Wu;
+  float acc = 0.f;
+  for (int rr = 0; rr < G.rows; ++rr) {
+    const long row = G.row_start + rr;
+    for (int oy = 0; oy < g.Ho; ++oy) {
+      const int uy = oy + ky - g.pad;
+      if (uy < 0 || uy >= g.Hu) continue;
+      const int sy = min((int)floorf(uy * sy_sc), g.Hs - 1);
+      for (int ox = 0; ox < g.Wo; ++ox) {
+        const int ux = ox + kx - g.pad;
+        if (ux < 0 || ux >= g.Wu) continue;
+        const int sx = min((int)floorf(ux * sx_sc), g.Ws - 1);
+        acc = fmaf(bf2f(dy[((row * g.Ho + oy) * g.Wo + ox) * g.N + n]), bf2f(x[((row * g.Hs + sy) * g.Ws + sx) * g.C + c]), acc);
+      }
+    }
+  }
+  dw[G.slot * g.N * KK + i] += acc;
+}
+
+}  // namespace es
+
+using namespace es;
+
+extern "C" int es_gen_fc1_fwd(const float* z1, const float* z2, const float* cond, const float* w, const float* b,
+                              const float* gamma, const float* beta, long slot_stride_w, long slot_stride_v,
+                              const es_group* grp_gen, int E, int total_rows, int two_pass, float* x0, float* lin,
+                              void* h, void* stream) {
+  ES_REQUIRE(z1 && cond && w && b && gamma && beta && grp_gen && x0 && lin && h, "null pointer");
+  ES_REQUIRE(!two_pass || z2, "two-pass batch needs z2");
+  ES_REQUIRE(E >= 1 && E <= kMaxGroups && total_rows > 0, "bad sizes");
+  gen_fc1_fwd_kernel<<<ceil_div(total_rows, 8), 256, 0, as_stream(stream)>>>(
+      z1, z2, cond, w, b, gamma, beta, slot_stride_w, slot_stride_v, grp_gen, E, total_rows, two_pass, x0, lin,
+      (__nv_bfloat16*)h);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_gen_fc1_bwd(const float* dh, const float* x0, const float* lin, const float* gamma,
+                              const float* beta, long slot_stride_w, long slot_stride_v, const es_group* grp_gen,
+                              int E, int total_rows, float* dw, float* db, float* dgamma, float* dbeta, void* stream) {
+  ES_REQUIRE(dh && x0 && lin && gamma && beta && grp_gen && dw && db && dgamma && dbeta, "null pointer");
+  ES_REQUIRE(E >= 1 && E <= kMaxGroups && total_rows > 0, "bad sizes");
+  const int chunks = max(1, min(32, ceil_div(total_rows, 8 * 4 * E)));
+  gen_fc1_bwd_kernel<<<E * chunks, 256, 0, as_stream(stream)>>>(dh, x0, lin, gamma, beta, slot_stride_w,
+                                                                slot_stride_v, grp_gen, chunks, dw, db, dgamma, dbeta);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_ln_lrelu_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int F,
+                               const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream) {
+  ES_REQUIRE(x && gamma && beta && grp && y && stats, "null pointer");
+  ES_REQUIRE(F > 0 && F % 8 == 0 && total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups, "bad sizes");
+  ln_lrelu_fwd_kernel<<<total_rows, 512, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, gamma, beta, slot_stride, F,
+                                                                 grp, n_groups, (__nv_bfloat16*)y, stats);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_ln_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, int C, const void* x,
+                               const float* stats, const float* gamma, const float* beta, long slot_stride,
+                               const es_group* grp, int n_groups, int total_rows, void* dx, void* stream) {
+  ES_REQUIRE(dy_up && x && stats && gamma && beta && grp && dx, "null pointer");
+  ES_REQUIRE(C % 8 == 0 && Hs <= 64 && Ws <= 64 && Hu <= 64 && Wu <= 64 && Hu >= Hs && Wu >= Ws, "bad geometry");
+  ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups, "bad sizes");
+  ln_lrelu_bwd_kernel<<<total_rows, 512, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C,
+                                                                 (const __nv_bfloat16*)x, stats, gamma, beta,
+                                                                 slot_stride, grp, n_groups, (__nv_bfloat16*)dx);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_ln_affine_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, int C, const void* x,
+                                const void* dx, const float* stats, const float* gamma, const float* beta,
+                                long slot_stride, const es_group* grp, int n_groups, int total_rows,
+                                const int32_t* row_map, float* dgamma, float* dbeta, float* dbias_lin, void* stream) {
+  ES_REQUIRE(dy_up && x && dx && stats && gamma && beta && grp && dgamma && dbeta && dbias_lin, "null pointer");
+  ES_REQUIRE(C % 8 == 0 && Hs <= 64 && Ws <= 64 && Hu <= 64 && Wu <= 64, "bad geometry");
+  ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups, "bad sizes");
+  const int n4 = Hs * Ws * C / 8;
+  ln_affine_bwd_kernel<<<dim3(ceil_div(n4, 128), n_groups), 128, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dx, stats, gamma,
+      beta, slot_stride, grp, row_map, dgamma, dbeta, dbias_lin);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_gn_lrelu_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C,
+                               int groups, const es_group* grp, int n_groups, int total_rows, void* y, float* stats,
+                               void* stream) {
+  ES_REQUIRE(x && gamma && beta && grp && y && stats, "null pointer");
+  ES_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && groups <= 64 && C % groups == 0, "bad channels/groups");
+  ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups && P > 0, "bad sizes");
+  gn_lrelu_kernel<false><<<total_rows, 256, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)x, nullptr, P, 1, P, 1, gamma, beta, slot_stride, C, groups, grp, n_groups,
+      (__nv_bfloat16*)y, stats, nullptr, nullptr, nullptr);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_gn_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, const void* x, const float* stats,
+                               const float* gamma, const float* beta, long slot_stride, int C, int groups,
+                               const es_group* grp, int n_groups, int total_rows, void* dx, float* dgamma,
+                               float* dbeta, float* dbias_conv, void* stream) {
+  ES_REQUIRE(dy_up && x && stats && gamma && beta && grp && dx && dgamma && dbeta, "null pointer");
+  ES_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && groups <= 64 && C % groups == 0, "bad channels/groups");
+  ES_REQUIRE(Hs <= 64 && Ws <= 64 && Hu <= 64 && Wu <= 64 && Hu >= Hs && Wu >= Ws, "bad geometry");
+  ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups, "bad sizes");
+  gn_lrelu_kernel<true><<<total_rows, 256, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, gamma, beta, slot_stride, C, groups, grp,
+      n_groups, (__nv_bfloat16*)dx, const_cast<float*>(stats), dgamma, dbeta, dbias_conv);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_gen_out_fwd(const void* x, const float* w, const float* b, long slot_stride_w, int Hs, int Ws, int C,
+                              int KH, int KW, int pad, const es_group* grp_gen, int E, int total_rows, int two_pass,
+                              float* img1, float* img2, void* stream) {
+  ES_REQUIRE(x && w && b && grp_gen && img1 && (img2 || !two_pass), "null pointer");
+  ES_REQUIRE(C % 8 == 0 && KH * KW * C <= 8192 && total_rows > 0 && E >= 1 && E <= kMaxGroups, "bad sizes");
+  gen_out_fwd_kernel<<<total_rows, 256, KH * KW * C * sizeof(float), as_stream(stream)>>>(
+      (const __nv_bfloat16*)x, w, b, slot_stride_w, Hs, Ws, C, KH, KW, pad, grp_gen, E, two_pass, img1, img2);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_gen_out_bwd(const void* x, const float* w, long slot_stride_w, int Hs, int Ws, int C, int KH, int KW,
+                              int pad, const float* img1, const float* img2, const float* dimg1, const float* dimg2,
+                              const es_group* grp_gen, int E, int total_rows, int two_pass, void* dx, float* dw,
+                              float* db, void* stream) {
+  ES_REQUIRE(x && w && img1 && dimg1 && grp_gen && dx && dw && db, "null pointer");
+  ES_REQUIRE(!two_pass || (img2 && dimg2), "two-pass batch needs img2/dimg2");
+  ES_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && KH * KW <= 4 && total_rows > 0 && E >= 1 && E <= kMaxGroups, "bad sizes");
+  const int Ho = Hs + 2 * pad - KH + 1, Wo = Ws + 2 * pad - KW + 1;
+  const size_t smem = (2 * KH * KW * C + Ho * Wo) * sizeof(float);
+  gen_out_bwd_kernel<<<total_rows, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)x, w, slot_stride_w, Hs, Ws, C,
+                                                                   KH, KW, pad, img1, img2, dimg1, dimg2, grp_gen, E,
+                                                                   two_pass, (__nv_bfloat16*)dx, dw, db);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_pack_conv_weight(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW,
+                                   void* w_fwd, void* w_dgrad, void* stream) {
+  ES_REQUIRE(w && (w_fwd || w_dgrad) && slots >= 1 && N > 0 && C > 0 && KH > 0 && KW > 0, "bad arguments");
+  const long total = (long)N * C * KH * KW;
+  pack_conv_kernel<<<dim3((unsigned)min(ceil_div_l(total, 256), 2048L), slots), 256, 0, as_stream(stream)>>>(
+      w, slot_stride, N, C, KH, KW, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_pack_dense_weight(const float* w, long slot_stride, int slots, int N, int K, const int32_t* row_map,
+                                    void* w_packed, void* stream) {
+  ES_REQUIRE(w && w_packed && slots >= 1 && N > 0 && K > 0, "bad arguments");
+  const long total = (long)N * K;
+  pack_dense_kernel<<<dim3((unsigned)min(ceil_div_l(total, 256), 4096L), slots), 256, 0, as_stream(stream)>>>(
+      w, slot_stride, N, K, row_map, (__nv_bfloat16*)w_packed);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_unpack_conv_wgrad(const float* dw_packed, int slots, int N, int C, int KH, int KW, float* dw_ref,
+                                    long slot_stride, void* stream) {
+  ES_REQUIRE(dw_packed && dw_ref && slots >= 1, "bad arguments");
+  const long total = (long)N * C * KH * KW;
+  unpack_conv_wgrad_kernel<<<dim3((unsigned)min(ceil_div_l(total, 256), 2048L), slots), 256, 0, as_stream(stream)>>>(
+      dw_packed, N, C, KH, KW, dw_ref, slot_stride);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_permute_features(const float* in, long in_stride, const int32_t* row_map, int slots, int F, float* out,
+                                   long out_stride, int inverse, void* stream) {
+  ES_REQUIRE(in && row_map && out && slots >= 1 && F > 0, "bad arguments");
+  permute_features_kernel<<<dim3(min(ceil_div(F, 256), 1024), slots), 256, 0, as_stream(stream)>>>(
+      in, in_stride, row_map, F, out, out_stride, inverse);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_igemm_fwd_simt(const void* x, const void* w, const float* bias, void* y, const es_conv_geom* g,
+                                 const es_group* grp, int n_groups, int total_rows, void* stream) {
+  ES_REQUIRE(x && w && y && g && grp && total_rows > 0, "bad arguments");
+  const long total = (long)total_rows * g->Ho * g->Wo * g->N;
+  igemm_fwd_simt_kernel<<<(unsigned)ceil_div_l(total, 256), 256, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)y, *g, grp, n_groups, total);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_igemm_wgrad_simt(const void* x, const void* dy, float* dw, const es_conv_geom* g,
+                                   const es_group* grp, int n_groups, int total_rows, void* stream) {
+  ES_REQUIRE(x && dy && dw && g && grp && total_rows > 0, "bad arguments");
+  const long total = (long)g->N * g->KH * g->KW * g->C;
+  igemm_wgrad_simt_kernel<<<dim3((unsigned)ceil_div_l(total, 256), n_groups), 256, 0, as_stream(stream)>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw, *g, grp, n_groups);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}

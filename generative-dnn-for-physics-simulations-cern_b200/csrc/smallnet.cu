@@ -1,0 +1,831 @@
+// K3 — building blocks of the discriminator and the auxiliary coordinate regressor, forward and backward
+// (fp32, NCHW, grouped by expert through the es_group table).  Reference: Discriminator.forward
+// (expertsim/models/proton/discriminator.py:121-155), AuxReg / FeatureExtractor / ResidualBlock
+// (expertsim/models/proton/aux_reg.py:11-131) and the hook-based spectral norm of torch.
+//
+// The convolutions are direct CUDA-core kernels: a CTA stages S input samples and one 8-channel weight tile in shared
+// memory; each thread produces 8 output channels of one pixel (1 LDS for x, 2 broadcast LDS.128 for w per 8 FMAs).
+#include "common.cuh"
+
+namespace es {
+
+constexpr int kCoT = 8;
+
+// (group, chunk) scheduler for kernels whose CTA handles `per` consecutive rows of ONE group
+__device__ __forceinline__ bool chunk_of(const es_group* grp, int n_groups, int per, int cta, int& g, int& row0, int& nrows) {
+  for (int i = 0; i < n_groups; ++i) {
+    const int ch = ceil_div(grp[i].rows, per);
+    if (cta < ch) {
+      g = i;
+      row0 = grp[i].row_start + cta * per;
+      nrows = min(per, grp[i].rows - cta * per);
+      return true;
+    }
+    cta -= ch;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------------ conv forward
+__global__ void __launch_bounds__(256)
+conv2d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, long sw, long sb,
+                  es_conv2d g, const es_group* __restrict__ grp, int n_groups, int S, float* __restrict__ y) {
+  extern __shared__ float sm[];
+  int gi, row0, ns;
+  if (!chunk_of(grp, n_groups, S, blockIdx.x, gi, row0, ns)) return;
+  const int slot = grp[gi].slot, co0 = blockIdx.y * kCoT;
+  const int in_sz = g.Ci * g.Hi * g.Wi, taps = g.Ci * g.KH * g.KW, HWo = g.Ho * g.Wo;
+  float* s_x = sm;                 // [S][Ci][Hi][Wi]
+  float* s_w = sm + ((S * in_sz + 3) & ~3);     // [taps][8], 16-byte aligned
+  for (int i = threadIdx.x; i < ns * in_sz; i += blockDim.x) s_x[i] = x[(size_t)row0 * in_sz + i];
+  for (int i = threadIdx.x; i < taps * kCoT; i += blockDim.x) {
+    const int t = i / kCoT, c = i % kCoT;
+    s_w[i] = w[slot * sw + (size_t)(co0 + c) * taps + t];
+  }
+  __syncthreads();
+  float bias[kCoT];
+#pragma unroll
+  for (int c = 0; c < kCoT; ++c) bias[c] = b ? b[slot * sb + co0 + c] : 0.f;
+  for (int idx = threadIdx.x; idx < ns * HWo; idx += blockDim.x) {
+    const int s = idx / HWo, p = idx % HWo, oy = p / g.Wo, ox = p % g.Wo;
+    float acc[kCoT];
+#pragma unroll
+    for (int c = 0; c < kCoT; ++c) acc[c] = bias[c];
+    const float* xs = s_x + s * in_sz;
+    for (int ci = 0; ci < g.Ci; ++ci)
+      for (int ky = 0; ky < g.KH; ++ky) {
+        const int iy = oy * g.stride + ky - g.pad;
+        if (iy < 0 || iy >= g.Hi) continue;
+        for (int kx = 0; kx < g.KW; ++kx) {
+          const int ix = ox * g.stride + kx - g.pad;
+          if (ix < 0 || ix >= g.Wi) continue;
+          const float xv = xs[(ci * g.Hi + iy) * g.Wi + ix];
+          const float4* wv = reinterpret_cast<const float4*>(s_w + ((ci * g.KH + ky) * g.KW + kx) * kCoT);
+          const float4 w0 = wv[0], w1 = wv[1];
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        }
+      }
+    float* yo = y + ((size_t)(row0 + s) * g.Co + co0) * HWo + p;
+#pragma unroll
+    for (int c = 0; c < kCoT; ++c) yo[(size_t)c * HWo] = acc[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conv data gradient
+template <int CIT>
+__global__ void __launch_bounds__(256)
+conv2d_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, long sw, es_conv2d g,
+                       const es_group* __restrict__ grp, int n_groups, int S, float* __restrict__ dx, int accumulate) {
+  extern __shared__ float sm[];
+  int gi, row0, ns;
+  if (!chunk_of(grp, n_groups, S, blockIdx.x, gi, row0, ns)) return;
+  const int slot = grp[gi].slot, ci0 = blockIdx.y * CIT;
+  const int out_sz = g.Co * g.Ho * g.Wo, ktaps = g.KH * g.KW, HWi = g.Hi * g.Wi;
+  float* s_dy = sm;                    // [S][Co][Ho][Wo]
+  float* s_w = sm + S * out_sz;        // [Co][KH][KW][CIT]
+  for (int i = threadIdx.x; i < ns * out_sz; i += blockDim.x) s_dy[i] = dy[(size_t)row0 * out_sz + i];
+  for (int i = threadIdx.x; i < g.Co * ktaps * CIT; i += blockDim.x) {
+    const int c = i % CIT, t = (i / CIT) % ktaps, co = i / (CIT * ktaps);
+    s_w[i] = w[slot * sw + ((size_t)co * g.Ci + ci0 + c) * ktaps + t];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < ns * HWi; idx += blockDim.x) {
+    const int s = idx / HWi, p = idx % HWi, iy = p / g.Wi, ix = p % g.Wi;
+    float acc[CIT];
+#pragma unroll
+    for (int c = 0; c < CIT; ++c) acc[c] = 0.f;
+    const float* ds = s_dy + s * out_sz;
+    for (int ky = 0; ky < g.KH; ++ky) {
+      const int ty = iy + g.pad - ky;
+      if (ty < 0 || ty % g.stride != 0) continue;
+      const int oy = ty / g.stride;
+      if (oy >= g.Ho) continue;
+      for (int kx = 0; kx < g.KW; ++kx) {
+        const int tx = ix + g.pad - kx;
+        if (tx < 0 || tx % g.stride != 0) continue;
+        const int ox = tx / g.stride;
+        if (ox >= g.Wo) continue;
+        for (int co = 0; co < g.Co; ++co) {
+          const float d = ds[(co * g.Ho + oy) * g.Wo + ox];
+          const float* wv = s_w + ((co * g.KH + ky) * g.KW + kx) * CIT;
+#pragma unroll
+          for (int c = 0; c < CIT; ++c) acc[c] = fmaf(d, wv[c], acc[c]);
+        }
+      }
+    }
+    float* o = dx + ((size_t)(row0 + s) * g.Ci + ci0) * HWi + p;
+#pragma unroll
+    for (int c = 0; c < CIT; ++c) {
+      if (accumulate) o[(size_t)c * HWi] += acc[c];
+      else o[(size_t)c * HWi] = acc[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conv weight gradient
+// CTA = (group, chunk of `per` samples, 8-channel tile).  Threads own (ci,ky,kx) entries (up to 8 each) and keep
+// 8 accumulators per entry in registers; samples are staged one at a time in shared memory.
+constexpr int kMaxEnt = 7;
+__global__ void __launch_bounds__(256)
+conv2d_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, es_conv2d g,
+                         const es_group* __restrict__ grp, int n_groups, int per, float* __restrict__ dw,
+                         float* __restrict__ db, long sw, long sb) {
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  int gi, row0, ns;
+  if (!chunk_of(grp, n_groups, per, blockIdx.x, gi, row0, ns)) return;
+  const int slot = grp[gi].slot, co0 = blockIdx.y * kCoT;
+  const int in_sz = g.Ci * g.Hi * g.Wi, HWo = g.Ho * g.Wo, taps = g.Ci * g.KH * g.KW;
+  float* s_x = sm;              // [Ci][Hi][Wi]
+  float* s_d = sm + ((in_sz + 3) & ~3);      // [HWo][8], 16-byte aligned
+  float acc[kMaxEnt][kCoT];
+#pragma unroll
+  for (int j = 0; j < kMaxEnt; ++j)
+#pragma unroll
+    for (int c = 0; c < kCoT; ++c) acc[j][c] = 0.f;
+  float bsum = 0.f;
+  for (int s = 0; s < ns; ++s) {
+    __syncthreads();
+    const size_t row = row0 + s;
+    for (int i = threadIdx.x; i < in_sz; i += blockDim.x) s_x[i] = x[row * in_sz + i];
+    for (int i = threadIdx.x; i < HWo * kCoT; i += blockDim.x) {
+      const int c = i / HWo, p = i % HWo;   // coalesced global read, transposed smem write
+      s_d[p * kCoT + c] = dy[(row * g.Co + co0 + c) * HWo + p];
+    }
+    __syncthreads();
+    if (threadIdx.x < kCoT) {
+      float t = 0.f;
+      for (int p = 0; p < HWo; ++p) t += s_d[p * kCoT + threadIdx.x];
+      bsum += t;
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxEnt; ++j) {
+      const int e = threadIdx.x + j * 256;
+      if (e >= taps) break;
+      const int kx = e % g.KW, ky = (e / g.KW) % g.KH, ci = e / (g.KW * g.KH);
+      const float* xs = s_x + ci * g.Hi * g.Wi;
+      for (int oy = 0; oy < g.Ho; ++oy) {
+        const int iy = oy * g.stride + ky - g.pad;
+        if (iy < 0 || iy >= g.Hi) continue;
+        for (int ox = 0; ox < g.Wo; ++ox) {
+          const int ix = ox * g.stride + kx - g.pad;
+          if (ix < 0 || ix >= g.Wi) continue;
+          const float xv = xs[iy * g.Wi + ix];
+          const float4* dv = reinterpret_cast<const float4*>(s_d + (oy * g.Wo + ox) * kCoT);
+          const float4 d0 = dv[0], d1 = dv[1];
+          acc[j][0] = fmaf(xv, d0.x, acc[j][0]); acc[j][1] = fmaf(xv, d0.y, acc[j][1]);
+          acc[j][2] = fmaf(xv, d0.z, acc[j][2]); acc[j][3] = fmaf(xv, d0.w, acc[j][3]);
+          acc[j][4] = fmaf(xv, d1.x, acc[j][4]); acc[j][5] = fmaf(xv, d1.y, acc[j][5]);
+          acc[j][6] = fmaf(xv, d1.z, acc[j][6]); acc[j][7] = fmaf(xv, d1.w, acc[j][7]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxEnt; ++j) {
+    const int e = threadIdx.x + j * 256;
+    if (e >= taps) break;
+#pragma unroll
+    for (int c = 0; c < kCoT; ++c) atomicAdd(&dw[slot * sw + (size_t)(co0 + c) * taps + e], acc[j][c]);
+  }
+  if (db && threadIdx.x < kCoT) atomicAdd(&db[slot * sb + co0 + threadIdx.x], bsum);
+  (void)red;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm (NCHW fp32)
+__global__ void __launch_bounds__(128)
+groupnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     long ss, int C, int HW, int groups, int act, const es_group* __restrict__ grp, int n_groups,
+                     float* __restrict__ y, float* __restrict__ stats) {
+  __shared__ float red[32];
+  const int r = blockIdx.x / groups, gq = blockIdx.x % groups;
+  const int gi = find_group(grp, n_groups, r);
+  if (gi < 0) return;
+  const int slot = grp[gi].slot, cpg = C / groups, n = cpg * HW;
+  const float* xs = x + ((size_t)r * C + gq * cpg) * HW;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += xs[i];
+  const float mean = block_sum(s, red) / n;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float d = xs[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q, red) / n + kNormEps);
+  if (threadIdx.x == 0) { stats[(size_t)blockIdx.x * 2] = mean; stats[(size_t)blockIdx.x * 2 + 1] = rstd; }
+  float* ys = y + ((size_t)r * C + gq * cpg) * HW;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = gq * cpg + i / HW;
+    ys[i] = act_fwd((xs[i] - mean) * rstd * gamma[slot * ss + c] + beta[slot * ss + c], act);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+groupnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, long ss, int C, int HW, int groups,
+                     int act, const es_group* __restrict__ grp, int n_groups, float* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[32];
+  const int r = blockIdx.x / groups, gq = blockIdx.x % groups;
+  const int gi = find_group(grp, n_groups, r);
+  if (gi < 0) return;
+  const int slot = grp[gi].slot, cpg = C / groups, n = cpg * HW;
+  const float mean = stats[(size_t)blockIdx.x * 2], rstd = stats[(size_t)blockIdx.x * 2 + 1];
+  const size_t off = ((size_t)r * C + gq * cpg) * HW;
+  float s1 = 0.f, s2 = 0.f;
+  for (int cc = 0; cc < cpg; ++cc) {
+    const int c = gq * cpg + cc;
+    const float ga = gamma[slot * ss + c], be = beta[slot * ss + c];
+    float a = 0.f, b = 0.f;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const float xh = (x[off + cc * HW + i] - mean) * rstd;
+      const float d = dy[off + cc * HW + i] * act_grad(xh * ga + be, act);
+      a += d * xh;
+      b += d;
+    }
+    a = block_sum(a, red);
+    b = block_sum(b, red);
+    if (threadIdx.x == 0) { atomicAdd(&dgamma[slot * ss + c], a); atomicAdd(&dbeta[slot * ss + c], b); }
+    s1 += b * ga;   // every thread holds the block totals
+    s2 += a * ga;
+  }
+  s1 /= n;
+  s2 /= n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = gq * cpg + i / HW;
+    const float ga = gamma[slot * ss + c], be = beta[slot * ss + c];
+    const float xh = (x[off + i] - mean) * rstd;
+    const float d = dy[off + i] * act_grad(xh * ga + be, act) * ga;
+    dx[off + i] = rstd * (d - s1 - xh * s2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm (rows)
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long ss,
+                     int F, int act, const es_group* __restrict__ grp, int n_groups, int total_rows, float* __restrict__ y,
+                     float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= total_rows) return;
+  const int gi = find_group(grp, n_groups, r);
+  if (gi < 0) return;
+  const int slot = grp[gi].slot;
+  const float* xs = x + (size_t)r * F;
+  float s = 0.f;
+  for (int i = lane; i < F; i += 32) s += xs[i];
+  const float mean = warp_sum(s) / F;
+  float q = 0.f;
+  for (int i = lane; i < F; i += 32) { const float d = xs[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / F + kNormEps);
+  if (lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+  for (int i = lane; i < F; i += 32)
+    y[(size_t)r * F + i] = act_fwd((xs[i] - mean) * rstd * gamma[slot * ss + i] + beta[slot * ss + i], act);
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, long ss, int F, int act,
+                     const es_group* __restrict__ grp, int n_groups, int total_rows, float* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= total_rows) return;
+  const int gi = find_group(grp, n_groups, r);
+  if (gi < 0) return;
+  const int slot = grp[gi].slot;
+  const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < F; i += 32) {
+    const float ga = gamma[slot * ss + i];
+    const float xh = (x[(size_t)r * F + i] - mean) * rstd;
+    const float d = dy[(size_t)r * F + i] * act_grad(xh * ga + beta[slot * ss + i], act);
+    if (dgamma) { atomicAdd(&dgamma[slot * ss + i], d * xh); atomicAdd(&dbeta[slot * ss + i], d); }
+    s1 += d * ga;
+    s2 += d * ga * xh;
+  }
+  s1 = warp_sum(s1) / F;
+  s2 = warp_sum(s2) / F;
+  for (int i = lane; i < F; i += 32) {
+    const float ga = gamma[slot * ss + i];
+    const float xh = (x[(size_t)r * F + i] - mean) * rstd;
+    const float d = dy[(size_t)r * F + i] * act_grad(xh * ga + beta[slot * ss + i], act) * ga;
+    dx[(size_t)r * F + i] = rstd * (d - s1 - xh * s2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ max pooling
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, int C, int Hi, int Wi, int kh, int kw, int sh, int sw_,
+                                   int Ho, int Wo, long total, float* __restrict__ y, uint8_t* __restrict__ idx) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ox = i % Wo, oy = (i / Wo) % Ho;
+  const long rc = i / ((long)Wo * Ho);
+  const float* xs = x + rc * Hi * Wi;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) {
+      const float v = xs[(oy * sh + ky) * Wi + ox * sw_ + kx];
+      if (v > best) { best = v; bi = ky * kw + kx; }
+    }
+  y[i] = best;
+  idx[i] = (uint8_t)bi;
+}
+
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, int Hi, int Wi, int kh,
+                                   int kw, int sh, int sw_, int Ho, int Wo, long total, float* __restrict__ dx) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ix = i % Wi, iy = (i / Wi) % Hi;
+  const long rc = i / ((long)Wi * Hi);
+  float acc = 0.f;
+  for (int ky = 0; ky < kh; ++ky) {
+    const int ty = iy - ky;
+    if (ty < 0 || ty % sh != 0) continue;
+    const int oy = ty / sh;
+    if (oy >= Ho) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int tx = ix - kx;
+      if (tx < 0 || tx % sw_ != 0) continue;
+      const int ox = tx / sw_;
+      if (ox >= Wo) continue;
+      const long o = (rc * Ho + oy) * Wo + ox;
+      if (idx[o] == ky * kw + kx) acc += dy[o];
+    }
+  }
+  dx[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ small SGEMMs (linear)
+// C[m,n] = sum_k A(m,k) B(k,n) over one 64x64 tile; element access through functors (bounds -> 0).
+template <class FA, class FB, class FC>
+__device__ __forceinline__ void sgemm_tile(int M, int N, int K, int m0, int n0, FA fa, FB fb, FC fc) {
+  __shared__ float sA[16][65], sB[16][65];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int kk = i % 16, mm = i / 16;
+      sA[kk][mm] = (m0 + mm < M && k0 + kk < K) ? fa(m0 + mm, k0 + kk) : 0.f;
+      sB[kk][mm] = (n0 + mm < N && k0 + kk < K) ? fb(k0 + kk, n0 + mm) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (m0 + ty * 4 + i < M && n0 + tx * 4 + j < N) fc(m0 + ty * 4 + i, n0 + tx * 4 + j, acc[i][j]);
+}
+
+__global__ void __launch_bounds__(256)
+linear_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b, long sw,
+                  long sb, int I, int O, const es_group* __restrict__ grp, int n_groups, float* __restrict__ y) {
+  int gi, row0, ns;
+  if (!chunk_of(grp, n_groups, 64, blockIdx.x, gi, row0, ns)) return;
+  const int slot = grp[gi].slot;
+  const float* W = w + slot * sw;
+  sgemm_tile(ns, O, I, 0, blockIdx.y * 64,
+             [&](int m, int k) { return x[(size_t)(row0 + m) * ldx + k]; },
+             [&](int k, int n) { return W[(size_t)n * I + k]; },
+             [&](int m, int n, float v) { y[(size_t)(row0 + m) * O + n] = v + (b ? b[slot * sb + n] : 0.f); });
+}
+
+__global__ void __launch_bounds__(256)
+linear_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, long sw, int I, int O,
+                       const es_group* __restrict__ grp, int n_groups, float* __restrict__ dx, int lddx) {
+  int gi, row0, ns;
+  if (!chunk_of(grp, n_groups, 64, blockIdx.x, gi, row0, ns)) return;
+  const float* W = w + grp[gi].slot * sw;
+  sgemm_tile(ns, I, O, 0, blockIdx.y * 64,
+             [&](int m, int k) { return dy[(size_t)(row0 + m) * O + k]; },
+             [&](int k, int n) { return W[(size_t)k * I + n]; },
+             [&](int m, int n, float v) { dx[(size_t)(row0 + m) * lddx + n] = v; });
+}
+
+// dW[o,i] += sum_r dy[r,o] x[r,i] over a chunk of 256 rows of one group; grid = (chunks, O tiles, I tiles)
+__global__ void __launch_bounds__(256)
+linear_bwd_weight_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int I, int O,
+                         const es_group* __restrict__ grp, int n_groups, float* __restrict__ dw, float* __restrict__ db,
+                         long sw, long sb) {
+  int gi, row0, ns;
+  if (!chunk_of(grp, n_groups, 256, blockIdx.x, gi, row0, ns)) return;
+  const int slot = grp[gi].slot;
+  float* DW = dw + slot * sw;
+  sgemm_tile(O, I, ns, blockIdx.y * 64, blockIdx.z * 64,
+             [&](int m, int k) { return dy[(size_t)(row0 + k) * O + m]; },
+             [&](int k, int n) { return x[(size_t)(row0 + k) * ldx + n]; },
+             [&](int m, int n, float v) { atomicAdd(&DW[(size_t)m * I + n], v); });
+  if (db && blockIdx.z == 0) {
+    const int o = blockIdx.y * 64 + threadIdx.x;
+    if (threadIdx.x < 64 && o < O) {
+      float s = 0.f;
+      for (int k = 0; k < ns; ++k) s += dy[(size_t)(row0 + k) * O + o];
+      atomicAdd(&db[slot * sb + o], s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ spectral norm
+__global__ void __launch_bounds__(256)
+spectral_norm_fwd_kernel(const float* __restrict__ w_orig, float* __restrict__ u, float* __restrict__ v, long sw, long su,
+                         long sv, int O, int I, int do_iter, const es_group* __restrict__ grp, float* __restrict__ w_sn,
+                         long ssn, float* __restrict__ sigma_out, float* __restrict__ u_used, float* __restrict__ v_used) {
+  extern __shared__ float sm[];   // v[I], u[O], wv[O]
+  __shared__ float red[32];
+  const int slot = blockIdx.x;
+  if (grp && grp[slot].rows == 0) return;
+  const float* W = w_orig + slot * sw;
+  float* U = u + slot * su;
+  float* V = v + slot * sv;
+  float* s_v = sm;
+  float* s_u = sm + I;
+  float* s_wv = s_u + O;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = threadIdx.x; o < O; o += blockDim.x) s_u[o] = U[o];
+  for (int i = threadIdx.x; i < I; i += blockDim.x) s_v[i] = V[i];
+  __syncthreads();
+  if (do_iter) {
+    // v = normalize(W^T u)
+    float nrm = 0.f;
+    for (int i = threadIdx.x; i < I; i += blockDim.x) {
+      float a = 0.f;
+      for (int o = 0; o < O; ++o) a = fmaf(W[(size_t)o * I + i], s_u[o], a);
+      s_v[i] = a;
+      nrm += a * a;
+    }
+    nrm = sqrtf(block_sum(nrm, red));
+    const float inv = 1.f / fmaxf(nrm, 1e-12f);
+    for (int i = threadIdx.x; i < I; i += blockDim.x) { s_v[i] *= inv; V[i] = s_v[i]; }
+    __syncthreads();
+  }
+  // wv = W v (one warp per row)
+  for (int o = warp; o < O; o += 8) {
+    float a = 0.f;
+    for (int i = lane; i < I; i += 32) a = fmaf(W[(size_t)o * I + i], s_v[i], a);
+    a = warp_sum(a);
+    if (lane == 0) s_wv[o] = a;
+  }
+  __syncthreads();
+  if (do_iter) {
+    float nrm = 0.f;
+    for (int o = threadIdx.x; o < O; o += blockDim.x) nrm += s_wv[o] * s_wv[o];
+    nrm = sqrtf(block_sum(nrm, red));
+    const float inv = 1.f / fmaxf(nrm, 1e-12f);
+    for (int o = threadIdx.x; o < O; o += blockDim.x) { s_u[o] = s_wv[o] * inv; U[o] = s_u[o]; }
+    __syncthreads();
+  }
+  float sg = 0.f;
+  for (int o = threadIdx.x; o < O; o += blockDim.x) sg += s_u[o] * s_wv[o];
+  sg = block_sum(sg, red);
+  if (threadIdx.x == 0) sigma_out[slot] = sg;
+  const float inv = 1.f / sg;
+  float* WS = w_sn + slot * ssn;
+  for (int i = threadIdx.x; i < O * I; i += blockDim.x) WS[i] = W[i] * inv;
+  if (u_used) for (int o = threadIdx.x; o < O; o += blockDim.x) u_used[(size_t)slot * O + o] = s_u[o];
+  if (v_used) for (int i = threadIdx.x; i < I; i += blockDim.x) v_used[(size_t)slot * I + i] = s_v[i];
+}
+
+__global__ void __launch_bounds__(256)
+spectral_norm_bwd_kernel(const float* __restrict__ dw_sn, const float* __restrict__ w_sn, const float* __restrict__ u_used,
+                         const float* __restrict__ v_used, const float* __restrict__ sigma, long ssn, int O, int I,
+                         float* __restrict__ dw_orig, long sw) {
+  __shared__ float red[32];
+  const int slot = blockIdx.x;
+  const float* D = dw_sn + slot * ssn;
+  const float* WS = w_sn + slot * ssn;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < O * I; i += blockDim.x) dot += D[i] * WS[i];
+  dot = block_sum(dot, red);
+  const float inv = 1.f / sigma[slot];
+  for (int i = threadIdx.x; i < O * I; i += blockDim.x) {
+    const int o = i / I, k = i % I;
+    dw_orig[slot * sw + i] += (D[i] - dot * u_used[(size_t)slot * O + o] * v_used[(size_t)slot * I + k]) * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+__global__ void add_relu_kernel(const float* a, const float* b, long n, float* y) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaxf(a[i] + b[i], 0.f);
+}
+__global__ void relu_bwd_kernel(const float* dy, const float* y, long n, float* dx) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+__global__ void gap_fwd_kernel(const float* x, int HW, long rc, float* y) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= rc) return;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += x[i * HW + p];
+  y[i] = s / HW;
+}
+__global__ void gap_bwd_kernel(const float* dy, int HW, long total, float* dx) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < total) dx[i] = dy[i / HW] / HW;
+}
+__global__ void dropout_kernel(const float* x, const float* m, float scale, long n, float* y) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] * m[i] * scale;
+}
+__global__ void axpy_kernel(float a, const float* x, long n, float* y) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n) y[i] += a * x[i];
+}
+__global__ void copy_cols_kernel(const float* src, int lds, int cols, long total, float* dst, int ldd, int col0) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long r = i / cols;
+  const int c = i % cols;
+  dst[r * ldd + col0 + c] = src[r * lds + c];
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+__global__ void adam_bump_kernel(int32_t* step_count, const es_group* grp, int slots) {
+  const int s = threadIdx.x;
+  if (s < slots && (!grp || grp[s].rows > 0)) step_count[s] += 1;
+}
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
+            long slot_stride, float lr, float b1, float b2, float eps, const int32_t* __restrict__ step_count,
+            const es_group* __restrict__ grp) {
+  const int slot = blockIdx.y;
+  if (grp && grp[slot].rows == 0) return;
+  const int t = step_count[slot];
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const float bc2s = (float)sqrt(1.0 - pow((double)b2, (double)t));
+  const float step = (float)((double)lr / bc1);
+  const long base = slot * slot_stride;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float gg = g[base + i];
+    const float mm = m[base + i] + (gg - m[base + i]) * (1.f - b1);
+    const float vv = v[base + i] * b2 + gg * gg * (1.f - b2);
+    m[base + i] = mm;
+    v[base + i] = vv;
+    p[base + i] -= step * mm / (sqrtf(vv) / bc2s + eps);
+  }
+}
+
+static inline unsigned blocks_for(long n) { return (unsigned)ceil_div_l(n, 256); }
+
+}  // namespace es
+
+using namespace es;
+
+static bool conv_ok(const es_conv2d* g) {
+  return g && g->Ci > 0 && g->Co > 0 && g->stride > 0 && g->Ho == (g->Hi + 2 * g->pad - g->KH) / g->stride + 1 &&
+         g->Wo == (g->Wi + 2 * g->pad - g->KW) / g->stride + 1;
+}
+static int pick_samples(int per_sample_floats, int pixels, int extra_floats) {
+  int S = ceil_div(256, pixels);
+  const int budget = (200 * 1024 - extra_floats * 4) / 4;
+  if (S * per_sample_floats > budget) S = budget / per_sample_floats;
+  return S < 1 ? 1 : S;
+}
+
+extern "C" int es_conv2d_fwd(const float* x, const float* w, const float* b, long slot_stride_w, long slot_stride_b,
+                             const es_conv2d* g, const es_group* grp, int n_groups, int total_rows, float* y,
+                             void* stream) {
+  ES_REQUIRE(x && w && grp && y, "null pointer");
+  ES_REQUIRE(conv_ok(g) && g->Co % kCoT == 0, "bad conv geometry (Co must be a multiple of 8)");
+  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad sizes");
+  const int in_sz = g->Ci * g->Hi * g->Wi, wt = g->Ci * g->KH * g->KW * kCoT;
+  const int S = pick_samples(in_sz, g->Ho * g->Wo, wt);
+  const size_t smem = ((size_t)S * in_sz + wt + 4) * sizeof(float);
+  ES_REQUIRE(smem <= 220 * 1024, "input sample does not fit in shared memory");
+  ES_CUDA(cudaFuncSetAttribute(conv2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  conv2d_fwd_kernel<<<dim3(ceil_div(total_rows, S) + n_groups, g->Co / kCoT), 256, smem, as_stream(stream)>>>(
+      x, w, b, slot_stride_w, slot_stride_b, *g, grp, n_groups, S, y);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_conv2d_bwd_data(const float* dy, const float* w, long slot_stride_w, const es_conv2d* g,
+                                  const es_group* grp, int n_groups, int total_rows, float* dx, int accumulate,
+                                  void* stream) {
+  ES_REQUIRE(dy && w && grp && dx, "null pointer");
+  ES_REQUIRE(conv_ok(g) && (g->Ci == 1 || g->Ci % 8 == 0), "bad conv geometry (Ci must be 1 or a multiple of 8)");
+  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad sizes");
+  const int cit = g->Ci == 1 ? 1 : 8;
+  const int out_sz = g->Co * g->Ho * g->Wo, wt = g->Co * g->KH * g->KW * cit;
+  const int S = pick_samples(out_sz, g->Hi * g->Wi, wt);
+  const size_t smem = ((size_t)S * out_sz + wt) * sizeof(float);
+  ES_REQUIRE(smem <= 220 * 1024, "gradient sample does not fit in shared memory");
+  const dim3 grid(ceil_div(total_rows, S) + n_groups, g->Ci / cit);
+  if (cit == 1) {
+    ES_CUDA(cudaFuncSetAttribute(conv2d_bwd_data_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    conv2d_bwd_data_kernel<1><<<grid, 256, smem, as_stream(stream)>>>(dy, w, slot_stride_w, *g, grp, n_groups, S, dx, accumulate);
+  } else {
+    ES_CUDA(cudaFuncSetAttribute(conv2d_bwd_data_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    conv2d_bwd_data_kernel<8><<<grid, 256, smem, as_stream(stream)>>>(dy, w, slot_stride_w, *g, grp, n_groups, S, dx, accumulate);
+  }
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_conv2d_bwd_weight(const float* x, const float* dy, const es_conv2d* g, const es_group* grp,
+                                    int n_groups, int total_rows, float* dw, float* db, long slot_stride_w,
+                                    long slot_stride_b, void* stream) {
+  ES_REQUIRE(x && dy && grp && dw, "null pointer");
+  ES_REQUIRE(conv_ok(g) && g->Co % kCoT == 0, "bad conv geometry");
+  ES_REQUIRE(g->Ci * g->KH * g->KW <= kMaxEnt * 256, "too many taps per output channel");
+  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad sizes");
+  const size_t smem = ((size_t)g->Ci * g->Hi * g->Wi + (size_t)g->Ho * g->Wo * kCoT + 4) * sizeof(float);
+  ES_REQUIRE(smem <= 220 * 1024, "sample does not fit in shared memory");
+  int per = ceil_div(total_rows * (g->Co / kCoT), 4 * 148);
+  if (per < 1) per = 1;
+  ES_CUDA(cudaFuncSetAttribute(conv2d_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  conv2d_bwd_weight_kernel<<<dim3(ceil_div(total_rows, per) + n_groups, g->Co / kCoT), 256, smem, as_stream(stream)>>>(
+      x, dy, *g, grp, n_groups, per, dw, db, slot_stride_w, slot_stride_b);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_groupnorm_fwd(const float* x, const float* gamma, const float* beta, long slot_stride, int C, int HW,
+                                int groups, int act, const es_group* grp, int n_groups, int total_rows, float* y,
+                                float* stats, void* stream) {
+  ES_REQUIRE(x && gamma && beta && grp && y && stats, "null pointer");
+  ES_REQUIRE(C > 0 && groups > 0 && C % groups == 0 && HW > 0 && total_rows > 0 && n_groups <= kMaxGroups, "bad sizes");
+  groupnorm_fwd_kernel<<<total_rows * groups, 128, 0, as_stream(stream)>>>(x, gamma, beta, slot_stride, C, HW, groups, act,
+                                                                          grp, n_groups, y, stats);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_groupnorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma,
+                                const float* beta, long slot_stride, int C, int HW, int groups, int act,
+                                const es_group* grp, int n_groups, int total_rows, float* dx, float* dgamma,
+                                float* dbeta, void* stream) {
+  ES_REQUIRE(dy && x && stats && gamma && beta && grp && dx && dgamma && dbeta, "null pointer");
+  ES_REQUIRE(C > 0 && groups > 0 && C % groups == 0 && HW > 0 && total_rows > 0 && n_groups <= kMaxGroups, "bad sizes");
+  groupnorm_bwd_kernel<<<total_rows * groups, 128, 0, as_stream(stream)>>>(dy, x, stats, gamma, beta, slot_stride, C, HW,
+                                                                          groups, act, grp, n_groups, dx, dgamma, dbeta);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_layernorm_fwd(const float* x, const float* gamma, const float* beta, long slot_stride, int F, int act,
+                                const es_group* grp, int n_groups, int total_rows, float* y, float* stats,
+                                void* stream) {
+  ES_REQUIRE(x && gamma && beta && grp && y && stats && F > 0 && total_rows > 0 && n_groups <= kMaxGroups, "bad arguments");
+  layernorm_fwd_kernel<<<ceil_div(total_rows, 8), 256, 0, as_stream(stream)>>>(x, gamma, beta, slot_stride, F, act, grp,
+                                                                              n_groups, total_rows, y, stats);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma,
+                                const float* beta, long slot_stride, int F, int act, const es_group* grp, int n_groups,
+                                int total_rows, float* dx, float* dgamma, float* dbeta, void* stream) {
+  ES_REQUIRE(dy && x && stats && gamma && beta && grp && dx && F > 0 && total_rows > 0 && n_groups <= kMaxGroups, "bad arguments");
+  ES_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "dgamma and dbeta go together");
+  layernorm_bwd_kernel<<<ceil_div(total_rows, 8), 256, 0, as_stream(stream)>>>(dy, x, stats, gamma, beta, slot_stride, F,
+                                                                              act, grp, n_groups, total_rows, dx, dgamma,
+                                                                              dbeta);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_maxpool_fwd(const float* x, int C, int Hi, int Wi, int kh, int kw, int sh, int sw, int total_rows,
+                              float* y, uint8_t* idx, void* stream) {
+  ES_REQUIRE(x && y && idx && C > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && total_rows > 0, "bad arguments");
+  const int Ho = (Hi - kh) / sh + 1, Wo = (Wi - kw) / sw + 1;
+  const long total = (long)total_rows * C * Ho * Wo;
+  maxpool_fwd_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(x, C, Hi, Wi, kh, kw, sh, sw, Ho, Wo, total, y, idx);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_maxpool_bwd(const float* dy, const uint8_t* idx, int C, int Hi, int Wi, int kh, int kw, int sh, int sw,
+                              int total_rows, float* dx, void* stream) {
+  ES_REQUIRE(dy && dx && idx && C > 0 && total_rows > 0, "bad arguments");
+  const int Ho = (Hi - kh) / sh + 1, Wo = (Wi - kw) / sw + 1;
+  const long total = (long)total_rows * C * Hi * Wi;
+  maxpool_bwd_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(dy, idx, Hi, Wi, kh, kw, sh, sw, Ho, Wo, total, dx);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_linear_fwd(const float* x, int ldx, const float* w, const float* b, long slot_stride_w,
+                             long slot_stride_b, int I, int O, const es_group* grp, int n_groups, int total_rows, float* y,
+                             void* stream) {
+  ES_REQUIRE(x && w && grp && y && I > 0 && O > 0 && ldx >= I && total_rows > 0 && n_groups <= kMaxGroups, "bad arguments");
+  linear_fwd_kernel<<<dim3(ceil_div(total_rows, 64) + n_groups, ceil_div(O, 64)), 256, 0, as_stream(stream)>>>(
+      x, ldx, w, b, slot_stride_w, slot_stride_b, I, O, grp, n_groups, y);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_linear_bwd_data(const float* dy, const float* w, long slot_stride_w, int I, int O, const es_group* grp,
+                                  int n_groups, int total_rows, float* dx, int lddx, void* stream) {
+  ES_REQUIRE(dy && w && grp && dx && I > 0 && O > 0 && lddx >= I && total_rows > 0 && n_groups <= kMaxGroups, "bad arguments");
+  linear_bwd_data_kernel<<<dim3(ceil_div(total_rows, 64) + n_groups, ceil_div(I, 64)), 256, 0, as_stream(stream)>>>(
+      dy, w, slot_stride_w, I, O, grp, n_groups, dx, lddx);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_linear_bwd_weight(const float* x, int ldx, const float* dy, int I, int O, const es_group* grp,
+                                    int n_groups, int total_rows, float* dw, float* db, long slot_stride_w,
+                                    long slot_stride_b, void* stream) {
+  ES_REQUIRE(x && dy && grp && dw && I > 0 && O > 0 && total_rows > 0 && n_groups <= kMaxGroups, "bad arguments");
+  linear_bwd_weight_kernel<<<dim3(ceil_div(total_rows, 256) + n_groups, ceil_div(O, 64), ceil_div(I, 64)), 256, 0,
+                             as_stream(stream)>>>(x, ldx, dy, I, O, grp, n_groups, dw, db, slot_stride_w, slot_stride_b);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_spectral_norm_fwd(const float* w_orig, float* u, float* v, long slot_stride_w, long slot_stride_u,
+                                    long slot_stride_v, int slots, int O, int I, int do_power_iter, const es_group* grp,
+                                    float* w_sn, long slot_stride_sn, float* sigma_out, float* u_used, float* v_used,
+                                    void* stream) {
+  ES_REQUIRE(w_orig && u && v && w_sn && sigma_out && slots >= 1 && O > 0 && I > 0, "bad arguments");
+  const size_t smem = ((size_t)I + 2 * O) * sizeof(float);
+  ES_REQUIRE(smem <= 48 * 1024, "spectral norm vectors do not fit in shared memory");
+  spectral_norm_fwd_kernel<<<slots, 256, smem, as_stream(stream)>>>(w_orig, u, v, slot_stride_w, slot_stride_u,
+                                                                   slot_stride_v, O, I, do_power_iter, grp, w_sn,
+                                                                   slot_stride_sn, sigma_out, u_used, v_used);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_spectral_norm_bwd(const float* dw_sn, const float* w_sn, const float* u_used, const float* v_used,
+                                    const float* sigma, long slot_stride_sn, int slots, int O, int I, float* dw_orig,
+                                    long slot_stride_w, void* stream) {
+  ES_REQUIRE(dw_sn && w_sn && u_used && v_used && sigma && dw_orig && slots >= 1, "bad arguments");
+  spectral_norm_bwd_kernel<<<slots, 256, 0, as_stream(stream)>>>(dw_sn, w_sn, u_used, v_used, sigma, slot_stride_sn, O, I,
+                                                                dw_orig, slot_stride_w);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_add_relu_fwd(const float* a, const float* b, long n, float* y, void* stream) {
+  ES_REQUIRE(a && b && y && n > 0, "bad arguments");
+  add_relu_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(a, b, n, y);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+extern "C" int es_relu_bwd(const float* dy, const float* y, long n, float* dx, void* stream) {
+  ES_REQUIRE(dy && y && dx && n > 0, "bad arguments");
+  relu_bwd_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(dy, y, n, dx);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+extern "C" int es_gap_fwd(const float* x, int C, int HW, int total_rows, float* y, void* stream) {
+  ES_REQUIRE(x && y && C > 0 && HW > 0 && total_rows > 0, "bad arguments");
+  gap_fwd_kernel<<<blocks_for((long)total_rows * C), 256, 0, as_stream(stream)>>>(x, HW, (long)total_rows * C, y);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+extern "C" int es_gap_bwd(const float* dy, int C, int HW, int total_rows, float* dx, void* stream) {
+  ES_REQUIRE(dy && dx && C > 0 && HW > 0 && total_rows > 0, "bad arguments");
+  const long total = (long)total_rows * C * HW;
+  gap_bwd_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(dy, HW, total, dx);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+extern "C" int es_dropout(const float* x, const float* keep_mask, float p, long n, float* y, void* stream) {
+  ES_REQUIRE(x && keep_mask && y && n > 0 && p >= 0.f && p < 1.f, "bad arguments");
+  dropout_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(x, keep_mask, 1.f / (1.f - p), n, y);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+extern "C" int es_axpy(float alpha, const float* x, long n, float* y, void* stream) {
+  ES_REQUIRE(x && y && n > 0, "bad arguments");
+  axpy_kernel<<<blocks_for(n), 256, 0, as_stream(stream)>>>(alpha, x, n, y);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+extern "C" int es_copy_cols(const float* src, int lds, int cols, int rows, float* dst, int ldd, int col0, void* stream) {
+  ES_REQUIRE(src && dst && cols > 0 && rows > 0 && lds >= cols && ldd >= col0 + cols, "bad arguments");
+  const long total = (long)rows * cols;
+  copy_cols_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(src, lds, cols, total, dst, ldd, col0);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_adam_step(float* p, const float* g, float* m, float* v, long n, long slot_stride, int slots, float lr,
+                            float beta1, float beta2, float eps, int32_t* step_count, const es_group* grp, void* stream) {
+  ES_REQUIRE(p && g && m && v && step_count && n > 0 && slots >= 1 && slots <= 1024, "bad arguments");
+  adam_bump_kernel<<<1, 1024, 0, as_stream(stream)>>>(step_count, grp, slots);
+  ES_LAUNCH_CHECK();
+  const unsigned bx = (unsigned)min(ceil_div_l(n, 256 * 4), 148L * 8);
+  adam_kernel<<<dim3(bx < 1 ? 1 : bx, slots), 256, 0, as_stream(stream)>>>(p, g, m, v, n, slot_stride, lr, beta1, beta2, eps,
+                                                                         step_count, grp);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}

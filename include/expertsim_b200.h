@@ -1,0 +1,302 @@
+/*
+ * expertsim_b200.h — C-ABI of the B200-native ExpertSim hot path (libexpertsim_b200.so).
+ *
+ * The reference (patrick-bedkowski/Generative-DNN-for-Physics-Simulations-CERN) has no native code and no FFI:
+ * every "kernel" is an ATen/cuDNN/cuBLAS call issued from eager PyTorch.  Each entry point
+ * below therefore cites the reference Python call site (file:line under /root/reference) whose arithmetic it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.  Every function returns 0 on success or a negative
+ *    es_status; es_last_error() returns a thread-local message for the last failure.
+ *  - All buffers are CALLER-OWNED DEVICE pointers.  Work is enqueued asynchronously on `stream`
+ *    (a cudaStream_t passed as void*); no hidden synchronisation, no allocation, no global mutable state.
+ *  - "rows" are samples in EXPERT-SORTED order (the stable token->expert permutation produced by
+ *    es_router_partition).  A group table `grp` is a device array of es_group; group g uses weight slot
+ *    grp[g].slot, i.e. parameter pointer + slot * slot_stride.  Groups with rows == 0 do no work, so the
+ *    reference's "B_e <= 1 -> skip expert" rule (models/moe.py:126-135) needs no host sync.
+ *  - fp32 tensors are NCHW as in the reference; bf16 generator activations are NHWC (channels-last).
+ */
+#ifndef EXPERTSIM_B200_H
+#define EXPERTSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ES_OK = 0,
+  ES_ERR_INVALID = -1,     /* bad argument (shape, null pointer, unsupported size) */
+  ES_ERR_CUDA = -2,        /* CUDA runtime error at launch */
+  ES_ERR_UNSUPPORTED = -3
+} es_status;
+
+/* One contiguous run of rows that shares one set of expert weights. */
+typedef struct {
+  int32_t row_start;   /* first row (sample) of the group in the sorted batch */
+  int32_t rows;        /* number of rows; 0 = inactive (skipped expert) */
+  int32_t slot;        /* expert index = weight slot */
+  int32_t pass_rows;   /* rows per generator pass (rows == passes * pass_rows) */
+} es_group;
+
+const char* es_last_error(void);
+int es_version(void);
+/* returns 1 when the loaded library contains sm_100a code and a CUDA device of CC 10.x is present */
+int es_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  router gating + sort-free stable token->expert permutation
+ *     replaces RouterNetwork.forward (expertsim/models/routers/router.py:21-26, F.gumbel_softmax) and the
+ *     routing block of MoEWrapper.train_step (expertsim/models/moe.py:76-77,97-103,123-126).
+ * ---------------------------------------------------------------------------------------------- */
+/* cond[B,9], router params (fc_layers.{0,2,4,6}), gumbel[B,E] (injected -log(Exp(1)) noise), tau ->
+ * logits[B,E], gates[B,E] (softmax((logits+gumbel)/tau)), idx[B] (int64 argmax, first max wins),
+ * hidden activations h1[B,128], h2[B,64], h3[B,32] (kept for es_router_bwd),
+ * blk_hist[ceil(B/256), E] per-block expert histogram (input of es_router_partition). */
+int es_router_fwd(const float* cond, int B, int E,
+                  const float* w0, const float* b0, const float* w2, const float* b2,
+                  const float* w4, const float* b4, const float* w6, const float* b6,
+                  const float* gumbel, float tau,
+                  float* logits, float* gates, int64_t* idx,
+                  float* h1, float* h2, float* h3, int32_t* blk_hist, void* stream);
+
+/* Stable partition: counts[E], offsets[E+1], perm[B] (perm[j] = original index of the j-th sorted sample;
+ * ascending inside an expert, exactly (idx==e).nonzero() of moe.py:123), plus the group tables used by every
+ * grouped kernel:  grp_half[E]  rows = counts[e] (0 if counts[e] < min_rows)   row_start = offsets[e]
+ *                  grp_gen[E]   the generator's two-pass batch: row_start = 2*offsets[e], rows = 2*counts[e]
+ * min_rows = 2 in training (skip rule), 1 at inference.  scratch: int32[ceil(B/256)*E + E]. */
+int es_router_partition(const int64_t* idx, int B, int E, int min_rows, const int32_t* blk_hist,
+                        int32_t* counts, int32_t* offsets, int32_t* perm,
+                        es_group* grp_half, es_group* grp_gen, int32_t* scratch, void* stream);
+
+/* out[j, :] = in[perm[j], :] for j < B  (row gather, fp32, `width` floats per row) — cond[mask], real[mask]...
+ * (moe.py:143,150,165-168) done once for all experts. */
+int es_gather_rows(const float* in, const int32_t* perm, int B, int width, float* out, void* stream);
+/* out[perm[j], :] = in[j, :]  (scatter back to original order; moe.py:197-198) */
+int es_scatter_rows(const float* in, const int32_t* perm, int B, int width, float* out, void* stream);
+
+/* Router loss (moe.py:407-435 with train/utils.py:398-419,623-642) and its backward through the gumbel
+ * softmax and the MLP, accumulated into the router's gradient buffers (dw*, db* must be zeroed by the caller).
+ *   alb  = alb_strength * mean_e exp(1/(sum_b gates[b,e] + 1e-6)), weighted by alb_weight (decreasing_weight)
+ *   ent  = +util_strength * sum_e pbar_e log(pbar_e + 1e-9),  pbar = mean_b gates
+ * gate_sums[E] (sum_b gates[b,e]) must have been produced by es_router_gate_sums (all-reduced across ranks
+ * by the caller under data parallelism).  B_global = global batch for the mean in pbar.
+ * extra_dgates (nullable) [B,E] is added to dL/dgates (the expert-distribution term).
+ * losses_out[2] = {alb (unweighted by alb_weight), entropy term}. */
+int es_router_gate_sums(const float* gates, int B, int E, float* gate_sums, void* stream);
+int es_router_bwd(const float* cond, int B, int E, int B_global,
+                  const float* w2, const float* w4, const float* w6,
+                  const float* gates, const float* h1, const float* h2, const float* h3,
+                  const float* gate_sums, float tau,
+                  float alb_strength, float alb_weight, float util_strength, const float* extra_dgates,
+                  float* dw0, float* db0, float* dw2, float* db2, float* dw4, float* db4, float* dw6, float* db6,
+                  float* losses_out, void* stream);
+/* expert-distribution loss (train/utils.py:372-395 as used at moe.py:264-268): gates are the straight-through
+ * one-hot gates, m[B] the per-sample photon sums.  loss_out[1] += ed_strength*0.1*sum_{b,b'}[idx_b==idx_b']|m_b-m_b'|/B;
+ * dgates[B,E] = d loss / d gates_soft. */
+int es_router_ed_loss(const int64_t* idx, const float* m, int B, int E, float ed_strength,
+                      float* dgates, float* loss_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  fused loss tails (warp-shuffle reductions, vectorised loads)
+ * ---------------------------------------------------------------------------------------------- */
+/* Discriminator hinge loss (moe.py:518-523): per active group e
+ *   loss[e] = (mean relu(1-real) + mean relu(1+fake)) * counts_global[e]/B_global ; d_real/d_fake = dloss/dscore.
+ * counts_global[E] float (global B_e; equals the local count on one GPU). */
+int es_hinge_d(const float* real_score, const float* fake_score, const es_group* grp, int E,
+               const float* counts_global, int B_global,
+               float* d_real, float* d_fake, float* loss, void* stream);
+
+/* Generator loss tails, phase 1 (per-sample terms + per-expert partial sums):
+ *   photon sums s[r] = sum_hw(exp(img)-1)                          (moe.py:611-616)
+ *   SDI div[r] = mean|lat1-lat2| / (mean|z1-z2| + 1e-5)            (moe.py:576-580)
+ *   sums[e][0..7] += {sum std, sum 1/(div+1e-5), sum s, sum s^2, sum|s-I|, sum logcosh-coord terms, sum score1, rows}
+ * img[R,HW] fp32, lat[R,64], z[R,10], std[R], intensity[R], coords/pos[R,2], score1[R]. */
+int es_gen_loss_reduce(const float* img, int HW, const float* lat1, const float* lat2,
+                       const float* z1, const float* z2, const float* stdv, const float* intensity,
+                       const float* coords, const float* pos, const float* score1,
+                       const es_group* grp, int E, int total_rows, float* s_out, float* div_out, double* sums, void* stream);
+/* phase 2: per-expert losses and every gradient that enters the backward pass (moe.py:544-563):
+ *   losses[e][0..5] = {gen_loss (total, scaled by B_e/B), div_loss, intensity_loss, aux_loss, std(s), mean(s)}
+ *   d_score1[R], d_lat1/d_lat2[R,64], d_coords[R,2], and d_img[R,HW] += in_strength*sign(s-I)/B_e * exp(img) * w_e
+ * sums[E][8] are the (all-reduced) partial sums of phase 1. */
+int es_gen_loss_grads(const float* img, int HW, const float* lat1, const float* lat2,
+                      const float* z1, const float* z2, const float* stdv, const float* intensity,
+                      const float* coords, const float* pos, const float* s, const float* divv,
+                      const es_group* grp, int E, int total_rows, const double* sums, int B_global,
+                      float di_strength, float in_strength, float aux_strength,
+                      float* d_score1, float* d_lat1, float* d_lat2, float* d_coords, float* d_img,
+                      float* losses, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  generator: grouped (per-expert) bf16 tcgen05 GEMM / implicit GEMM
+ *     replaces Generator.forward (expertsim/models/proton/generator.py:46-52) and its autograd backward.
+ * ---------------------------------------------------------------------------------------------- */
+/* Geometry of one implicit-GEMM convolution over NHWC bf16 activations.  The source map [Hs,Ws,C] is virtually
+ * nearest-upsampled to [Hu,Wu] (src = floor(dst*Hs/Hu), torch 'nearest'), zero padded by `pad`, and convolved
+ * with a KHxKW window, stride 1, giving [Ho,Wo,N].  A dense layer is Hs=Ws=Hu=Wu=Ho=Wo=KH=KW=1, pad=0. */
+typedef struct {
+  int32_t Hs, Ws, C;
+  int32_t Hu, Wu;
+  int32_t Ho, Wo;
+  int32_t KH, KW, pad;
+  int32_t N;            /* output channels */
+} es_conv_geom;
+
+/* y[row, oy, ox, n] = sum_{ky,kx,c} x_up[row, oy+ky-pad, ox+kx-pad, c] * w[slot][n][ky][kx][c] (+ bias[slot][n])
+ * x: bf16 [rows,Hs,Ws,C]; w: bf16 packed [slots][N][KH*KW*C]; bias fp32 [slots][N] or NULL; y: bf16 [rows,Ho,Wo,N].
+ * Used for the forward convs, for their data gradients (with transposed/flipped packed weights) and for fc2. */
+int es_igemm_fwd(const void* x, const void* w, const float* bias, void* y, const es_conv_geom* g,
+                 const es_group* grp, int n_groups, int total_rows, void* stream);
+/* dw[slot][n][ky][kx][c] += sum_{row,oy,ox} dy[row,oy,ox,n] * x_up[row,oy+ky-pad,ox+kx-pad,c]   (fp32, packed layout,
+ * split-K with fp32 atomics; dw must be zeroed by the caller). */
+int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es_conv_geom* g,
+                   const es_group* grp, int n_groups, int total_rows, void* stream);
+/* dense data gradient with the weight read in its forward layout: dx[row, k] += sum_n dy[row, n] * w[slot][n][k]
+ * (fc2: N=92160, K=256; split over n with fp32 atomics; dx fp32 [rows,K] zeroed by the caller). */
+int es_dense_dgrad(const void* dy, const void* w, float* dx, int N, int K,
+                   const es_group* grp, int n_groups, int total_rows, void* stream);
+/* dense weight gradient: dw[slot][row_map[n]][k] = sum_row dy[row,n] * x[row,k]  (fp32, direct store; row_map (nullable)
+ * un-permutes the channels-last feature order back to the reference's NCHW flattening). */
+int es_dense_wgrad(const void* dy, const void* x, float* dw, int N, int K, const int32_t* row_map,
+                   const es_group* grp, int n_groups, int total_rows, void* stream);
+/* Test-only SIMT (CUDA-core, fp32 accumulate) versions of the two implicit GEMMs; same arguments.  They exist so the
+ * tcgen05 path can be cross-checked on the device at sizes the CPU oracle cannot reach.  Never called by the product. */
+int es_igemm_fwd_simt(const void* x, const void* w, const float* bias, void* y, const es_conv_geom* g,
+                      const es_group* grp, int n_groups, int total_rows, void* stream);
+int es_igemm_wgrad_simt(const void* x, const void* dy, float* dw, const es_conv_geom* g,
+                        const es_group* grp, int n_groups, int total_rows, void* stream);
+
+/* generator head: x0 = [z | cond] (19) -> Linear(19,256) + LayerNorm(256) + LeakyReLU(0.1) (proton/generator.py:13-17).
+ * In the two-pass training batch, row r of group e takes z from z1 (first pass_rows rows) or z2 and cond from the
+ * half-batch row offsets.  lin[rows,256] fp32 (pre-norm, kept for backward), h[rows,256] bf16. */
+int es_gen_fc1_fwd(const float* z1, const float* z2, const float* cond, const float* w, const float* b,
+                   const float* gamma, const float* beta, long slot_stride_w, long slot_stride_v,
+                   const es_group* grp_gen, int E, int total_rows, int two_pass, float* x0, float* lin, void* h, void* stream);
+int es_gen_fc1_bwd(const float* dh, const float* x0, const float* lin, const float* gamma, const float* beta,
+                   long slot_stride_w, long slot_stride_v, const es_group* grp_gen, int E, int total_rows,
+                   float* dw, float* db, float* dgamma, float* dbeta, void* stream);
+
+/* LayerNorm over all F features of a row + LeakyReLU (fc2.1: F=92160; proton/generator.py:18-22), bf16 in/out,
+ * fp32 statistics.  stats[row][2] = {mean, rstd}. */
+int es_ln_lrelu_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int F,
+                    const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream);
+/* GroupNorm(groups) + LeakyReLU over NHWC bf16 [rows,P,C] (proton/generator.py:28-29,34-35,39-40). stats[row][groups][2]. */
+int es_gn_lrelu_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C, int groups,
+                    const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream);
+/* Backward of norm+LeakyReLU.  `dy_up` is the gradient w.r.t. the (virtually upsampled) consumer input
+ * [rows,Hu,Wu,C]; it is summed over the pixels that map to each source pixel [Hs,Ws] (nearest-upsample backward).
+ * dx (bf16, gradient w.r.t. the pre-norm tensor), dgamma/dbeta/dbias_conv (fp32, atomically accumulated). */
+int es_gn_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, const void* x, const float* stats,
+                    const float* gamma, const float* beta, long slot_stride, int C, int groups,
+                    const es_group* grp, int n_groups, int total_rows,
+                    void* dx, float* dgamma, float* dbeta, float* dbias_conv, void* stream);
+int es_ln_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, int C, const void* x, const float* stats,
+                    const float* gamma, const float* beta, long slot_stride,
+                    const es_group* grp, int n_groups, int total_rows, void* dx, void* stream);
+/* column reductions of the big LayerNorm: dgamma[slot][f] += sum_row dyn*xhat, dbeta += sum_row dyn, dbias_lin += sum_row dx;
+ * results are written at row_map[f] (reference NCHW feature order) when row_map is given */
+int es_ln_affine_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, int C, const void* x, const void* dx,
+                     const float* stats, const float* gamma, const float* beta, long slot_stride,
+                     const es_group* grp, int n_groups, int total_rows, const int32_t* row_map,
+                     float* dgamma, float* dbeta, float* dbias_lin, void* stream);
+
+/* last generator layer: Conv2d(64->1, k2, pad 1) + ReLU (proton/generator.py:42-43) on CUDA cores.
+ * x bf16 [rows,Hs,Ws,64] -> img fp32; in the two-pass batch the image row goes to img1 or img2 [half rows, Ho*Wo]. */
+int es_gen_out_fwd(const void* x, const float* w, const float* b, long slot_stride_w, int Hs, int Ws, int C, int KH, int KW, int pad,
+                   const es_group* grp_gen, int E, int total_rows, int two_pass, float* img1, float* img2, void* stream);
+int es_gen_out_bwd(const void* x, const float* w, long slot_stride_w, int Hs, int Ws, int C, int KH, int KW, int pad,
+                   const float* img1, const float* img2, const float* dimg1, const float* dimg2,
+                   const es_group* grp_gen, int E, int total_rows, int two_pass,
+                   void* dx, float* dw, float* db, void* stream);
+
+/* weight packing: fp32 reference layout -> bf16 kernel layout, all slots in one launch.
+ *   conv  [N,C,KH,KW] -> fwd  [N][KH][KW][C]      and (transposed, flipped) dgrad [C][KH][KW][N]
+ *   dense [N,K] with output-row permutation row_map (packed row n <- reference row row_map[n]) */
+int es_pack_conv_weight(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW,
+                        void* w_fwd, void* w_dgrad, void* stream);
+int es_pack_dense_weight(const float* w, long slot_stride, int slots, int N, int K, const int32_t* row_map,
+                         void* w_packed, void* stream);
+/* dw_ref[slot][n][c][ky][kx] = dw_packed[slot][n][ky][kx][c] */
+int es_unpack_conv_wgrad(const float* dw_packed, int slots, int N, int C, int KH, int KW, float* dw_ref, long slot_stride, void* stream);
+/* out[slot][row_map[f]] = in[slot][f]  (permute per-feature vectors between channels-last and NCHW feature order) */
+int es_permute_features(const float* in, long in_stride, const int32_t* row_map, int slots, int F, float* out, long out_stride,
+                        int inverse, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  discriminator and auxiliary regressor building blocks (fp32, NCHW, grouped by expert)
+ *     replace Discriminator.forward (proton/discriminator.py:148-155), AuxReg.forward (proton/aux_reg.py:33-40,
+ *     84-96,123-131) and their autograd backward.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t Ci, Hi, Wi, Co, Ho, Wo, KH, KW, stride, pad;
+} es_conv2d;
+
+int es_conv2d_fwd(const float* x, const float* w, const float* b, long slot_stride_w, long slot_stride_b,
+                  const es_conv2d* g, const es_group* grp, int n_groups, int total_rows, float* y, void* stream);
+int es_conv2d_bwd_data(const float* dy, const float* w, long slot_stride_w, const es_conv2d* g,
+                       const es_group* grp, int n_groups, int total_rows, float* dx, int accumulate, void* stream);
+int es_conv2d_bwd_weight(const float* x, const float* dy, const es_conv2d* g, const es_group* grp, int n_groups,
+                         int total_rows, float* dw, float* db, long slot_stride_w, long slot_stride_b, void* stream);
+
+/* act: 0 none, 1 ReLU, 2 LeakyReLU(0.1).  GroupNorm over [C/groups, H*W] per sample; stats[row][groups][2]. */
+int es_groupnorm_fwd(const float* x, const float* gamma, const float* beta, long slot_stride, int C, int HW, int groups, int act,
+                     const es_group* grp, int n_groups, int total_rows, float* y, float* stats, void* stream);
+int es_groupnorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma, const float* beta, long slot_stride,
+                     int C, int HW, int groups, int act, const es_group* grp, int n_groups, int total_rows,
+                     float* dx, float* dgamma, float* dbeta, void* stream);
+/* LayerNorm over the last dimension F (<=1024) + activation; stats[row][2]. */
+int es_layernorm_fwd(const float* x, const float* gamma, const float* beta, long slot_stride, int F, int act,
+                     const es_group* grp, int n_groups, int total_rows, float* y, float* stats, void* stream);
+int es_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma, const float* beta, long slot_stride,
+                     int F, int act, const es_group* grp, int n_groups, int total_rows,
+                     float* dx, float* dgamma, float* dbeta, void* stream);
+/* MaxPool2d(kernel (kh,kw), stride (sh,sw)), floor mode; idx (uint8) = winning tap for backward. */
+int es_maxpool_fwd(const float* x, int C, int Hi, int Wi, int kh, int kw, int sh, int sw, int total_rows,
+                   float* y, uint8_t* idx, void* stream);
+int es_maxpool_bwd(const float* dy, const uint8_t* idx, int C, int Hi, int Wi, int kh, int kw, int sh, int sw, int total_rows,
+                   float* dx, void* stream);
+/* y[row, 0:O] = x[row, 0:I] . W[slot][O,I]^T + b   /  dx = dy . W  /  dW += dy^T x, db += sum dy */
+int es_linear_fwd(const float* x, int ldx, const float* w, const float* b, long slot_stride_w, long slot_stride_b, int I, int O,
+                  const es_group* grp, int n_groups, int total_rows, float* y, void* stream);
+int es_linear_bwd_data(const float* dy, const float* w, long slot_stride_w, int I, int O,
+                       const es_group* grp, int n_groups, int total_rows, float* dx, int lddx, void* stream);
+int es_linear_bwd_weight(const float* x, int ldx, const float* dy, int I, int O, const es_group* grp, int n_groups, int total_rows,
+                         float* dw, float* db, long slot_stride_w, long slot_stride_b, void* stream);
+/* Spectral norm (hook-based torch.nn.utils.spectral_norm, torch/nn/utils/spectral_norm.py:62-113): per slot, one power
+ * iteration in place on u[O], v[I] (if do_power_iter), sigma = u.(W v), w_sn = w_orig / sigma.  sigma_out[slot]. */
+int es_spectral_norm_fwd(const float* w_orig, float* u, float* v, long slot_stride_w, long slot_stride_u, long slot_stride_v,
+                         int slots, int O, int I, int do_power_iter, const es_group* grp, float* w_sn, long slot_stride_sn,
+                         float* sigma_out, float* u_used, float* v_used, void* stream);
+/* dw_orig += (dw_sn - <dw_sn, w_sn> u v^T) / sigma */
+int es_spectral_norm_bwd(const float* dw_sn, const float* w_sn, const float* u_used, const float* v_used, const float* sigma,
+                         long slot_stride_sn, int slots, int O, int I, float* dw_orig, long slot_stride_w, void* stream);
+/* elementwise helpers: y = a + b then ReLU (residual join), its backward mask, mean over HW, dropout with a given keep-mask */
+int es_add_relu_fwd(const float* a, const float* b, long n, float* y, void* stream);
+int es_relu_bwd(const float* dy, const float* y, long n, float* dx, void* stream);
+int es_gap_fwd(const float* x, int C, int HW, int total_rows, float* y, void* stream);
+int es_gap_bwd(const float* dy, int C, int HW, int total_rows, float* dx, void* stream);
+int es_dropout(const float* x, const float* keep_mask, float p, long n, float* y, void* stream);
+int es_axpy(float alpha, const float* x, long n, float* y, void* stream);   /* y += alpha * x */
+int es_copy_cols(const float* src, int lds, int cols, int rows, float* dst, int ldd, int col0, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fused multi-tensor Adam (torch.optim.Adam defaults; expertsim/train/training_setup.py:20-40, stepped at
+ * moe.py:439,526,565-566).  One launch updates every parameter of every expert: the parameters of slot s occupy
+ * p + s*slot_stride .. + n.  step_count[slot] (device, int32) is advanced only for slots whose grp[s].rows > 0
+ * (an expert skipped by the B_e<=1 rule keeps its Adam step).  grp may be NULL (always step).
+ * ---------------------------------------------------------------------------------------------- */
+int es_adam_step(float* p, const float* g, float* m, float* v, long n, long slot_stride, int slots,
+                 float lr, float beta1, float beta2, float eps, int32_t* step_count, const es_group* grp, void* stream);
+
+/* batch inference tail: out[i] = expm1(img[i]) (train/utils.py:201) optionally scattered back to original sample order
+ * and widened to float64 as the reference's numpy result. */
+int es_expm1_scatter(const float* img, const int32_t* perm, int rows, int HW, double* out_f64, float* out_f32, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXPERTSIM_B200_H */

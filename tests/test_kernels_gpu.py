@@ -1,0 +1,700 @@
+"""Per-kernel parity tests: every C-ABI entry point against the CPU oracle / plain fp32 torch on the same inputs.
+
+Tolerances: integer outputs (expert index, counts, permutation) are compared bit-exactly; fp32 kernels to 1e-4..1e-5
+relative L2; bf16 tensor-core kernels to 1e-2 relative L2 (bf16 has 8 mantissa bits; inputs are pre-rounded to bf16 so
+only accumulation order and the output rounding differ)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle.expertsim_oracle as orc
+from gpu_util import DEV, L, bf16_round, check, cuda, groups, log
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def G(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ----------------------------------------------------------------------------------------------------------- K1
+def run_router(B, E, seed, tau=1.2, min_rows=2):
+    sd = orc.make_weights("proton", "router", seed, n_experts=E)
+    g = G(seed)
+    cond = torch.randn(B, 9, generator=g)
+    gumbel = -torch.empty(B, E).exponential_(generator=g).log()
+    d = {k: cuda(v) for k, v in sd.items()}
+    nblk = (B + 255) // 256
+    out = dict(logits=torch.empty(B, E, device=DEV), gates=torch.empty(B, E, device=DEV),
+               idx=torch.empty(B, dtype=torch.int64, device=DEV), h1=torch.empty(B, 128, device=DEV),
+               h2=torch.empty(B, 64, device=DEV), h3=torch.empty(B, 32, device=DEV),
+               hist=torch.empty(nblk, E, dtype=torch.int32, device=DEV))
+    L.call("es_router_fwd", cuda(cond), B, E, d["fc_layers.0.weight"], d["fc_layers.0.bias"], d["fc_layers.2.weight"],
+           d["fc_layers.2.bias"], d["fc_layers.4.weight"], d["fc_layers.4.bias"], d["fc_layers.6.weight"],
+           d["fc_layers.6.bias"], cuda(gumbel), tau, out["logits"], out["gates"], out["idx"], out["h1"], out["h2"],
+           out["h3"], out["hist"])
+    counts = torch.empty(E, dtype=torch.int32, device=DEV)
+    offsets = torch.empty(E + 1, dtype=torch.int32, device=DEV)
+    perm = torch.full((B,), -1, dtype=torch.int32, device=DEV)
+    gh = torch.empty(E, 4, dtype=torch.int32, device=DEV)
+    gg = torch.empty(E, 4, dtype=torch.int32, device=DEV)
+    scratch = torch.empty(nblk * E + E, dtype=torch.int32, device=DEV)
+    L.call("es_router_partition", out["idx"], B, E, min_rows, out["hist"], counts, offsets, perm, gh, gg, scratch)
+    torch.cuda.synchronize()
+    return sd, cond, gumbel, out, counts, offsets, perm, gh, gg
+
+
+@pytest.mark.parametrize("B,E", [(1, 1), (37, 3), (256, 3), (257, 8), (1000, 8), (5000, 5), (20000, 16)])
+def test_router_fwd_partition(B, E):
+    sd, cond, gumbel, out, counts, offsets, perm, gh, gg = run_router(B, E, seed=B + E)
+    gates, logits = orc.router_forward(sd, cond, gumbel, 1.2)
+    idx, cnt, masks = orc.route(gates, E)
+    check(f"router logits B={B} E={E}", out["logits"], logits, 1e-5)
+    check(f"router gates  B={B} E={E}", out["gates"], gates, 1e-5)
+    assert out["idx"].cpu().tolist() == idx.tolist(), "expert assignment must be bit-exact"
+    assert counts.cpu().tolist() == cnt.tolist()
+    assert perm.cpu().tolist() == torch.cat(masks).tolist(), "stable token->expert permutation must be bit-exact"
+    off = [0]
+    for c in cnt.tolist():
+        off.append(off[-1] + c)
+    assert offsets.cpu().tolist() == off
+    for e in range(E):
+        act = cnt[e].item() if cnt[e].item() >= 2 else 0
+        assert gh[e].cpu().tolist() == [off[e], act, e, act]
+        assert gg[e].cpu().tolist() == [2 * off[e], 2 * act, e, act]
+
+
+def test_gather_scatter_rows():
+    B, W = 333, 1680
+    g = G(1)
+    x = torch.randn(B, W, generator=g)
+    perm = torch.randperm(B, generator=g).to(torch.int32)
+    out = torch.empty(B, W, device=DEV)
+    L.call("es_gather_rows", cuda(x), cuda(perm), B, W, out)
+    assert torch.equal(out.cpu(), x[perm.long()])
+    back = torch.empty(B, W, device=DEV)
+    L.call("es_scatter_rows", out, cuda(perm), B, W, back)
+    assert torch.equal(back.cpu(), x)
+    x9 = torch.randn(B, 9, generator=g)
+    o9 = torch.empty(B, 9, device=DEV)
+    L.call("es_gather_rows", cuda(x9), cuda(perm), B, 9, o9)
+    assert torch.equal(o9.cpu(), x9[perm.long()])
+
+
+@pytest.mark.parametrize("B,E,util", [(64, 3, 0.0), (500, 8, 0.1)])
+def test_router_bwd(B, E, util):
+    sd, cond, gumbel, out, *_ = run_router(B, E, seed=11 + B)
+    tau, alb_s, alb_w = 1.2, 1e-5 if util == 0 else 1e-2, 0.2
+    live = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    gates, _ = orc.router_forward(live, cond, gumbel, tau)
+    alb = orc.adaptive_load_balancing_loss(gates.sum(0), alb_s)
+    ent = -1 * orc.utilization_entropy(gates, util) if util else torch.tensor(0.0)
+    extra = torch.randn(B, E, generator=G(5)) * 1e-3
+    loss = alb_w * alb + ent + (gates * extra).sum()
+    loss.backward()
+    names = ["fc_layers.0", "fc_layers.2", "fc_layers.4", "fc_layers.6"]
+    d = {k: cuda(v) for k, v in sd.items()}
+    gr = {k: torch.zeros_like(v) for k, v in d.items()}
+    sums = torch.empty(E, device=DEV)
+    L.call("es_router_gate_sums", out["gates"], B, E, sums)
+    losses = torch.zeros(2, device=DEV)
+    L.call("es_router_bwd", cuda(cond), B, E, B, d["fc_layers.2.weight"], d["fc_layers.4.weight"], d["fc_layers.6.weight"],
+           out["gates"], out["h1"], out["h2"], out["h3"], sums, tau, alb_s, alb_w, util, cuda(extra),
+           *[gr[f"{n}.{p}"] for n in names for p in ("weight", "bias")], losses)
+    check("router gate sums", sums, gates.detach().sum(0), 1e-5)
+    for n in names:
+        for p in ("weight", "bias"):
+            check(f"router grad {n}.{p} B={B}", gr[f"{n}.{p}"], live[f"{n}.{p}"].grad, 2e-4)
+    assert abs(losses[0].item() - float(alb)) <= 1e-4 * abs(float(alb))
+    assert abs(losses[1].item() - float(ent)) <= 1e-4 * max(abs(float(ent)), 1e-6)
+
+
+def test_router_ed_loss():
+    B, E = 200, 4
+    g = G(3)
+    idx = torch.randint(0, E, (B,), generator=g)
+    m = torch.rand(B, 1, generator=g) * 50
+    gates_soft = torch.rand(B, E, generator=g).softmax(1).requires_grad_(True)
+    gates = F.one_hot(idx, E).float() + (gates_soft - gates_soft.detach())
+    ref = orc.expert_distribution_loss(gates, m) * 0.01
+    ref.backward()
+    dg = torch.empty(B, E, device=DEV)
+    lo = torch.zeros(1, device=DEV)
+    L.call("es_router_ed_loss", cuda(idx), cuda(m.flatten()), B, E, 0.01, dg, lo)
+    check("expert-distribution loss grad", dg, gates_soft.grad, 1e-4)
+    assert abs(lo.item() - float(ref)) <= 1e-4 * abs(float(ref))
+
+
+# ----------------------------------------------------------------------------------------------------------- K4
+def test_hinge_d():
+    counts = [5, 0, 9, 1]
+    grp, R = groups(counts, min_rows=2)
+    g = G(2)
+    real = torch.randn(R, generator=g) * 2
+    fake = torch.randn(R, generator=g) * 2
+    Bg = 40
+    rr, ff = real.clone().requires_grad_(True), fake.clone().requires_grad_(True)
+    exp_loss, off = [], 0
+    for c in counts:
+        if c >= 2:
+            l = (F.relu(1 - rr[off:off + c]).mean() + F.relu(1 + ff[off:off + c]).mean()) * (c / Bg)
+            l.backward()
+            exp_loss.append(float(l))
+        else:
+            exp_loss.append(0.0)
+        off += c
+    dr, df = torch.zeros(R, device=DEV), torch.zeros(R, device=DEV)
+    loss = torch.zeros(len(counts), device=DEV)
+    L.call("es_hinge_d", cuda(real), cuda(fake), grp, len(counts), None, Bg, dr, df, loss)
+    check("hinge D loss", loss, torch.tensor(exp_loss), 1e-5)
+    check("hinge d_real", dr, rr.grad, 1e-6)
+    check("hinge d_fake", df, ff.grad, 1e-6)
+
+
+@pytest.mark.parametrize("arch", ["proton", "neutron"])
+def test_gen_loss_tails(arch):
+    H, W = orc.IMAGE_SHAPE[arch]
+    HW = H * W
+    counts = [6, 1, 11]
+    grp, R = groups(counts, min_rows=2)
+    g = G(7)
+    img = (torch.rand(R, 1, H, W, generator=g) < 0.05).float() * torch.rand(R, 1, H, W, generator=g) * 5
+    lat1, lat2 = torch.randn(R, 64, generator=g), torch.randn(R, 64, generator=g)
+    z1, z2 = torch.randn(R, 10, generator=g), torch.randn(R, 10, generator=g)
+    std, inten = torch.rand(R, 1, generator=g), torch.rand(R, 1, generator=g) * 100
+    coords, pos = torch.randn(R, 2, generator=g) * 10, torch.rand(R, 2, generator=g) * 30
+    score = torch.randn(R, 1, generator=g)
+    Bg, di, ins, aux = 32, 0.1, 1e-3, 1e-3
+    leaves = [t.clone().requires_grad_(True) for t in (img, lat1, lat2, coords, score)]
+    li, l1, l2, lc, ls = leaves
+    exp, off = [], 0
+    for c in counts:
+        if c >= 2:
+            s = slice(off, off + c)
+            gl = -ls[s].mean()
+            dv = orc.sdi_gan_regularization(l1[s], l2[s], z1[s], z2[s], std[s], di)
+            il, sums, sstd, smean = orc.intensity_regularization(li[s], inten[s], ins)
+            al = orc.regressor_loss(pos[s], lc[s]) * aux
+            tot = (gl + dv + il + al) * (c / Bg)
+            tot.backward()
+            exp.append([float(tot), float(dv), float(il), float(al), float(sstd), float(smean)])
+        else:
+            exp.append([0.0] * 6)
+        off += c
+    d_img = torch.zeros(R, HW, device=DEV)
+    s_out, div_out = torch.zeros(R, device=DEV), torch.zeros(R, device=DEV)
+    sums = torch.zeros(len(counts), 8, dtype=torch.float64, device=DEV)
+    c_ = lambda t: cuda(t.reshape(R, -1))
+    args = (c_(img), HW, c_(lat1), c_(lat2), c_(z1), c_(z2), c_(std), c_(inten), c_(coords), c_(pos))
+    L.call("es_gen_loss_reduce", *args, c_(score), grp, len(counts), R, s_out, div_out, sums)
+    d_s, d_l1, d_l2 = torch.zeros(R, device=DEV), torch.zeros(R, 64, device=DEV), torch.zeros(R, 64, device=DEV)
+    d_c = torch.zeros(R, 2, device=DEV)
+    losses = torch.zeros(len(counts), 6, device=DEV)
+    L.call("es_gen_loss_grads", *args, s_out, div_out, grp, len(counts), R, sums, Bg, di, ins, aux, d_s, d_l1, d_l2, d_c, d_img, losses)
+    check(f"{arch} gen losses", losses, torch.tensor(exp), 2e-5)
+    check(f"{arch} d_score", d_s, ls.grad.flatten(), 1e-6)
+    check(f"{arch} d_lat1", d_l1, l1.grad, 2e-5)
+    check(f"{arch} d_lat2", d_l2, l2.grad, 2e-5)
+    check(f"{arch} d_coords", d_c, lc.grad, 2e-5)
+    check(f"{arch} d_img (intensity)", d_img, li.grad.reshape(R, HW), 2e-5)
+
+
+# ----------------------------------------------------------------------------------------------------------- K2
+def conv_geom(Hs, Ws, C, Hu, Wu, KH, KW, pad, N):
+    return L.ESConvGeom(Hs, Ws, C, Hu, Wu, Hu + 2 * pad - KH + 1, Wu + 2 * pad - KW + 1, KH, KW, pad, N)
+
+
+GEOMS = {
+    "conv1_fwd": (18, 10, 512, 36, 20, 4, 4, 1, 256),
+    "conv2_fwd": (35, 19, 256, 56, 30, 4, 4, 1, 128),
+    "conv3_fwd": (55, 29, 128, 55, 29, 3, 3, 1, 64),
+    "conv3_dgrad": (55, 29, 64, 55, 29, 3, 3, 1, 128),
+    "conv2_dgrad": (55, 29, 128, 55, 29, 4, 4, 2, 256),
+    "conv1_dgrad": (35, 19, 256, 35, 19, 4, 4, 2, 512),
+    "neutron_conv1": (13, 13, 128, 26, 26, 3, 3, 0, 256),
+    "dense_small": (1, 1, 256, 1, 1, 1, 1, 0, 1024),
+}
+
+
+def ref_conv(x, w, bias, geo, counts, slots):
+    """fp32 reference of the grouped implicit GEMM on bf16-rounded operands; x [R,Hs,Ws,C], w [S,N,KH,KW,C]."""
+    Hs, Ws, C, Hu, Wu, KH, KW, pad, N = geo
+    out, off = [], 0
+    for c, s in zip(counts, slots):
+        if c == 0:
+            continue
+        xi = x[off:off + c].permute(0, 3, 1, 2)
+        if (Hu, Wu) != (Hs, Ws):
+            xi = F.interpolate(xi, size=(Hu, Wu), mode="nearest")
+        y = F.conv2d(xi, w[s].permute(0, 3, 1, 2), bias[s] if bias is not None else None, padding=pad)
+        out.append(y.permute(0, 2, 3, 1))
+        off += c
+    return torch.cat(out)
+
+
+@pytest.mark.parametrize("name", list(GEOMS))
+@pytest.mark.parametrize("impl", ["es_igemm_fwd", "es_igemm_fwd_simt"])
+def test_igemm_fwd(name, impl):
+    geo = GEOMS[name]
+    Hs, Ws, C, Hu, Wu, KH, KW, pad, N = geo
+    counts, slots = [3, 2], [1, 0]
+    if name == "dense_small":
+        counts, slots = [130, 77], [1, 0]
+    grp, R = groups(counts, slots)
+    g = G(sum(map(ord, name)))
+    x = bf16_round(torch.randn(R, Hs, Ws, C, generator=g))
+    w = bf16_round(torch.randn(2, N, KH, KW, C, generator=g) / math.sqrt(KH * KW * C))
+    bias = torch.randn(2, N, generator=g) * 0.1
+    want = ref_conv(x, w, bias, geo, counts, slots)
+    y = torch.zeros(R, want.shape[1], want.shape[2], N, dtype=BF, device=DEV)
+    L.call(impl, cuda(x, BF), cuda(w, BF), cuda(bias), y, conv_geom(*geo), grp, len(counts), R)
+    torch.cuda.synchronize()
+    check(f"{impl} {name}", y.float(), want, 6e-3, 3e-2)
+
+
+def test_igemm_fwd_fc2_fullsize():
+    """fc2: [rows,256] x [92160,256]^T with a ragged two-expert batch and an inactive group in between."""
+    counts, slots = [150, 0, 45], [0, 1, 2]
+    grp, R = groups(counts, slots)
+    g = G(42)
+    N, K = 92160, 256
+    x = bf16_round(torch.randn(R, K, generator=g))
+    w = bf16_round(torch.randn(3, N, K, generator=g) / 16)
+    bias = torch.randn(3, N, generator=g) * 0.1
+    y = torch.zeros(R, N, dtype=BF, device=DEV)
+    L.call("es_igemm_fwd", cuda(x, BF), cuda(w, BF), cuda(bias), y, conv_geom(1, 1, K, 1, 1, 1, 1, 0, N), grp, 3, R)
+    want = torch.cat([x[:150] @ w[0].T + bias[0], x[150:] @ w[2].T + bias[2]])
+    check("es_igemm_fwd fc2 92160x256", y.float(), want, 6e-3, 3e-2)
+
+
+@pytest.mark.parametrize("name", ["conv1_fwd", "conv2_fwd", "conv3_fwd", "neutron_conv1"])
+@pytest.mark.parametrize("impl", ["es_igemm_wgrad", "es_igemm_wgrad_simt"])
+def test_igemm_wgrad(name, impl):
+    geo = GEOMS[name]
+    Hs, Ws, C, Hu, Wu, KH, KW, pad, N = geo
+    counts, slots = [2, 3], [1, 0]
+    grp, R = groups(counts, slots)
+    g = G(7 + sum(map(ord, name)))
+    Ho, Wo = Hu + 2 * pad - KH + 1, Wu + 2 * pad - KW + 1
+    x = bf16_round(torch.randn(R, Hs, Ws, C, generator=g))
+    dy = bf16_round(torch.randn(R, Ho, Wo, N, generator=g))
+    w = torch.zeros(2, N, KH, KW, C, requires_grad=True)
+    out = ref_conv(x, w, None, geo, counts, slots)
+    out.backward(dy)
+    dw = torch.zeros(2, N, KH, KW, C, device=DEV)
+    L.call(impl, cuda(x, BF), cuda(dy, BF), dw, conv_geom(*geo), grp, len(counts), R)
+    torch.cuda.synchronize()
+    check(f"{impl} {name}", dw, w.grad, 2e-3, 1e-2)
+
+
+def test_dense_dgrad_wgrad():
+    counts, slots = [140, 0, 60], [2, 1, 0]
+    grp, R = groups(counts, slots)
+    g = G(9)
+    N, K = 92160, 256
+    dy = bf16_round(torch.randn(R, N, generator=g) * 0.1)
+    w = bf16_round(torch.randn(3, N, K, generator=g) / 16)
+    x = bf16_round(torch.randn(R, K, generator=g))
+    dx = torch.zeros(R, K, device=DEV)
+    L.call("es_dense_dgrad", cuda(dy, BF), cuda(w, BF), dx, N, K, grp, 3, R)
+    want = torch.cat([dy[:140] @ w[2], dy[140:] @ w[0]])
+    check("es_dense_dgrad fc2", dx, want, 3e-3, 1e-2)
+    row_map = torch.randperm(N, generator=g).to(torch.int32)
+    dw = torch.zeros(3, N, K, device=DEV)
+    L.call("es_dense_wgrad", cuda(dy, BF), cuda(x, BF), dw, N, K, cuda(row_map), grp, 3, R)
+    want_w = torch.zeros(3, N, K)
+    want_w[2][row_map.long()] = dy[:140].T @ x[:140]
+    want_w[0][row_map.long()] = dy[140:].T @ x[140:]
+    check("es_dense_wgrad fc2 (slot 2)", dw[2], want_w[2], 3e-3, 1e-2)
+    check("es_dense_wgrad fc2 (slot 0)", dw[0], want_w[0], 3e-3, 1e-2)
+    assert float(dw[1].abs().max()) == 0.0
+
+
+def test_pack_unpack():
+    g = G(4)
+    S, N, C, KH, KW = 2, 16, 64, 3, 2
+    w = torch.randn(S, N, C, KH, KW, generator=g)
+    wf = torch.zeros(S, N, KH, KW, C, dtype=BF, device=DEV)
+    wd = torch.zeros(S, C, KH, KW, N, dtype=BF, device=DEV)
+    L.call("es_pack_conv_weight", cuda(w), N * C * KH * KW, S, N, C, KH, KW, wf, wd)
+    assert torch.equal(wf.float().cpu(), bf16_round(w.permute(0, 1, 3, 4, 2)))
+    assert torch.equal(wd.float().cpu(), bf16_round(w.flip(3, 4).permute(0, 2, 3, 4, 1)))
+    dwp = torch.randn(S, N, KH, KW, C, generator=g)
+    dwr = torch.zeros(S, N, C, KH, KW, device=DEV)
+    L.call("es_unpack_conv_wgrad", cuda(dwp), S, N, C, KH, KW, dwr, N * C * KH * KW)
+    assert torch.equal(dwr.cpu(), dwp.permute(0, 1, 4, 2, 3))
+    Nd, K = 40, 24
+    wd2 = torch.randn(S, Nd, K, generator=g)
+    rm = torch.randperm(Nd, generator=g).to(torch.int32)
+    wp = torch.zeros(S, Nd, K, dtype=BF, device=DEV)
+    L.call("es_pack_dense_weight", cuda(wd2), Nd * K, S, Nd, K, cuda(rm), wp)
+    assert torch.equal(wp.float().cpu(), bf16_round(wd2[:, rm.long()]))
+    v = torch.randn(S, Nd, generator=g)
+    o = torch.zeros(S, Nd, device=DEV)
+    L.call("es_permute_features", cuda(v), Nd, cuda(rm), S, Nd, o, Nd, 0)
+    assert torch.equal(o.cpu(), v[:, rm.long()])
+    o2 = torch.zeros(S, Nd, device=DEV)
+    L.call("es_permute_features", o, Nd, cuda(rm), S, Nd, o2, Nd, 1)
+    assert torch.equal(o2.cpu(), v)
+
+
+def test_gen_fc1_fwd_bwd():
+    counts = [5, 0, 7]
+    E = 3
+    gh, B = groups(counts)
+    gg, _ = groups(counts, two_pass=True)
+    R = 2 * B
+    g = G(12)
+    z1, z2, cond = torch.randn(B, 10, generator=g), torch.randn(B, 10, generator=g), torch.randn(B, 9, generator=g)
+    W = torch.randn(E, 256, 19, generator=g) / 4
+    b, ga, be = torch.randn(E, 256, generator=g) * .1, 1 + .1 * torch.randn(E, 256, generator=g), .1 * torch.randn(E, 256, generator=g)
+    x0 = torch.zeros(R, 19, device=DEV)
+    lin = torch.zeros(R, 256, device=DEV)
+    h = torch.zeros(R, 256, dtype=BF, device=DEV)
+    L.call("es_gen_fc1_fwd", cuda(z1), cuda(z2), cuda(cond), cuda(W), cuda(b), cuda(ga), cuda(be), 256 * 19, 256, gg, E, R, 1, x0, lin, h)
+    leaves = [t.clone().requires_grad_(True) for t in (W, b, ga, be)]
+    lW, lb, lg, lbe = leaves
+    rows, off = [], 0
+    dh = torch.randn(R, 256, generator=g)
+    want_h = torch.zeros(R, 256)
+    for e, c in enumerate(counts):
+        for p, z in enumerate((z1, z2)):
+            xin = torch.cat((z[off:off + c], cond[off:off + c]), 1)
+            y = orc.lrelu(F.layer_norm(F.linear(xin, lW[e], lb[e]), (256,), lg[e], lbe[e], 1e-5))
+            r0 = 2 * off + p * c
+            want_h[r0:r0 + c] = y.detach()
+            (y * dh[r0:r0 + c]).sum().backward()
+        off += c
+    check("gen fc1 fwd", h.float(), want_h, 4e-3)
+    grads = [torch.zeros_like(cuda(t)) for t in (W, b, ga, be)]
+    L.call("es_gen_fc1_bwd", cuda(dh), x0, lin, cuda(ga), cuda(be), 256 * 19, 256, gg, E, R, *grads)
+    for nme, gt, lf in zip(("dW", "db", "dgamma", "dbeta"), grads, leaves):
+        check(f"gen fc1 bwd {nme}", gt, lf.grad, 1e-4)
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("P,C,groups_n,Hs,Ws,Hu,Wu", [(665, 256, 32, 35, 19, 56, 30), (1595, 128, 32, 55, 29, 55, 29), (1595, 64, 32, 55, 29, 55, 29)])
+def test_gn_lrelu_fwd_bwd(P, C, groups_n, Hs, Ws, Hu, Wu):
+    counts, slots = [2, 0, 3], [0, 1, 2]
+    grp, R = groups(counts, slots)
+    g = G(C)
+    x = bf16_round(torch.randn(R, C, Hs, Ws, generator=g) * 2 + 0.5)
+    ga, be = 1 + .2 * torch.randn(3, C, generator=g), .2 * torch.randn(3, C, generator=g)
+    y = torch.zeros(R, P, C, dtype=BF, device=DEV)
+    stats = torch.zeros(R, groups_n, 2, device=DEV)
+    L.call("es_gn_lrelu_fwd", cuda(nhwc(x), BF), cuda(ga), cuda(be), C, P, C, groups_n, grp, 3, R, y, stats)
+    lx = x.clone().requires_grad_(True)
+    lg, lb = ga.clone().requires_grad_(True), be.clone().requires_grad_(True)
+    dy_up = bf16_round(torch.randn(R, C, Hu, Wu, generator=g))
+    outs, off = [], 0
+    for c, s in zip(counts, slots):
+        if c:
+            o = orc.lrelu(F.group_norm(lx[off:off + c], groups_n, lg[s], lb[s], 1e-5))
+            outs.append(o)
+            up = F.interpolate(o, size=(Hu, Wu), mode="nearest") if (Hu, Wu) != (Hs, Ws) else o
+            (up * dy_up[off:off + c]).sum().backward()
+        off += c
+    check(f"gn_lrelu fwd C={C}", y.float().reshape(R, Hs, Ws, C), nhwc(torch.cat(outs).detach()), 5e-3)
+    dx = torch.zeros(R, P, C, dtype=BF, device=DEV)
+    dga, dbe, dbias = torch.zeros(3, C, device=DEV), torch.zeros(3, C, device=DEV), torch.zeros(3, C, device=DEV)
+    L.call("es_gn_lrelu_bwd", cuda(nhwc(dy_up), BF), Hs, Ws, Hu, Wu, cuda(nhwc(x), BF), stats, cuda(ga), cuda(be), C, C, groups_n,
+           grp, 3, R, dx, dga, dbe, dbias)
+    check(f"gn_lrelu bwd dx C={C}", dx.float().reshape(R, Hs, Ws, C), nhwc(lx.grad), 8e-3)
+    check(f"gn_lrelu bwd dgamma C={C}", dga, lg.grad, 2e-3)
+    check(f"gn_lrelu bwd dbeta C={C}", dbe, lb.grad, 2e-3)
+    want_db = torch.zeros(3, C)
+    off = 0
+    for c, s in zip(counts, slots):
+        want_db[s] = lx.grad[off:off + c].sum((0, 2, 3))
+        off += c
+    check(f"gn_lrelu bwd dbias C={C}", dbias, want_db, 2e-2)
+
+
+def test_ln_lrelu_fwd_bwd():
+    Hs, Ws, C, Hu, Wu = 18, 10, 512, 36, 20
+    F_ = Hs * Ws * C
+    counts, slots = [3, 2], [1, 0]
+    grp, R = groups(counts, slots)
+    g = G(21)
+    x = bf16_round(torch.randn(R, Hs, Ws, C, generator=g) * 1.5 + 0.3)  # packed (NHWC) feature order
+    ga, be = 1 + .2 * torch.randn(2, F_, generator=g), .2 * torch.randn(2, F_, generator=g)
+    y = torch.zeros(R, F_, dtype=BF, device=DEV)
+    stats = torch.zeros(R, 2, device=DEV)
+    L.call("es_ln_lrelu_fwd", cuda(x, BF), cuda(ga), cuda(be), F_, F_, grp, 2, R, y, stats)
+    lx = x.clone().requires_grad_(True)
+    lg, lb = ga.clone().requires_grad_(True), be.clone().requires_grad_(True)
+    dy_up = bf16_round(torch.randn(R, Hu, Wu, C, generator=g))
+    outs, off = [], 0
+    for c, s in zip(counts, slots):
+        o = orc.lrelu(F.layer_norm(lx[off:off + c].reshape(c, F_), (F_,), lg[s], lb[s], 1e-5))
+        outs.append(o)
+        up = F.interpolate(o.reshape(c, Hs, Ws, C).permute(0, 3, 1, 2), size=(Hu, Wu), mode="nearest")
+        (up * dy_up[off:off + c].permute(0, 3, 1, 2)).sum().backward()
+        off += c
+    check("ln_lrelu fwd", y.float(), torch.cat(outs).detach(), 5e-3)
+    dx = torch.zeros(R, F_, dtype=BF, device=DEV)
+    L.call("es_ln_lrelu_bwd", cuda(dy_up, BF), Hs, Ws, Hu, Wu, C, cuda(x, BF), stats, cuda(ga), cuda(be), F_, grp, 2, R, dx)
+    check("ln_lrelu bwd dx", dx.float(), lx.grad.reshape(R, F_), 8e-3)
+    rm = torch.randperm(F_, generator=g).to(torch.int32)
+    dga, dbe, dbl = torch.zeros(2, F_, device=DEV), torch.zeros(2, F_, device=DEV), torch.zeros(2, F_, device=DEV)
+    L.call("es_ln_affine_bwd", cuda(dy_up, BF), Hs, Ws, Hu, Wu, C, cuda(x, BF), dx, stats, cuda(ga), cuda(be), F_, grp, 2, R,
+           cuda(rm), dga, dbe, dbl)
+    inv = torch.empty(F_, dtype=torch.long)
+    inv[rm.long()] = torch.arange(F_)
+    check("ln affine dgamma", dga[:, rm.long()], lg.grad, 3e-3)
+    check("ln affine dbeta", dbe[:, rm.long()], lb.grad, 3e-3)
+    want = torch.stack([lx.grad[3:].reshape(2, F_).sum(0), lx.grad[:3].reshape(3, F_).sum(0)])
+    check("ln affine dbias", dbl[:, rm.long()], want, 2e-2)
+
+
+def test_gen_out_fwd_bwd():
+    counts = [3, 0, 2]
+    E = 3
+    gg, B = groups(counts, two_pass=True)
+    R = 2 * B
+    Hs, Ws, C = 55, 29, 64
+    g = G(31)
+    x = bf16_round(torch.randn(R, C, Hs, Ws, generator=g))
+    w = torch.randn(E, 1, C, 2, 2, generator=g) / 16
+    b = torch.randn(E, generator=g) * .1
+    img1, img2 = torch.zeros(B, 56 * 30, device=DEV), torch.zeros(B, 56 * 30, device=DEV)
+    L.call("es_gen_out_fwd", cuda(nhwc(x), BF), cuda(w), cuda(b), C * 4, Hs, Ws, C, 2, 2, 1, gg, E, R, 1, img1, img2)
+    lx, lw, lb = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    d1, d2 = torch.randn(B, 1, 56, 30, generator=g), torch.randn(B, 1, 56, 30, generator=g)
+    w1, w2 = torch.zeros(B, 1, 56, 30), torch.zeros(B, 1, 56, 30)
+    off = 0
+    for e, c in enumerate(counts):
+        for p, (dst, dd) in enumerate(((w1, d1), (w2, d2))):
+            r0 = 2 * off + p * c
+            o = F.relu(F.conv2d(lx[r0:r0 + c], lw[e], lb[e:e + 1], padding=1))
+            dst[off:off + c] = o.detach()
+            (o * dd[off:off + c]).sum().backward()
+        off += c
+    check("gen out conv fwd img1", img1, w1.reshape(B, -1), 1e-4)
+    check("gen out conv fwd img2", img2, w2.reshape(B, -1), 1e-4)
+    dx = torch.zeros(R, Hs * Ws, C, dtype=BF, device=DEV)
+    dw, db = torch.zeros(E, 1, C, 2, 2, device=DEV), torch.zeros(E, device=DEV)
+    L.call("es_gen_out_bwd", cuda(nhwc(x), BF), cuda(w), C * 4, Hs, Ws, C, 2, 2, 1, img1, img2, cuda(d1.reshape(B, -1)),
+           cuda(d2.reshape(B, -1)), gg, E, R, 1, dx, dw, db)
+    check("gen out conv bwd dx", dx.float().reshape(R, Hs, Ws, C), nhwc(lx.grad), 5e-3)
+    check("gen out conv bwd dw", dw, lw.grad, 1e-4)
+    check("gen out conv bwd db", db, lb.grad, 1e-4)
+
+
+# ----------------------------------------------------------------------------------------------------------- K3
+CONVS = {  # Ci,Hi,Wi,Co,KH,KW,stride,pad
+    "D.conv1": (1, 56, 30, 32, 3, 3, 1, 0), "D.conv2": (32, 27, 14, 16, 3, 3, 1, 0),
+    "A.conv1": (1, 56, 30, 32, 5, 5, 2, 1), "A.res1.conv1": (32, 26, 13, 32, 5, 5, 2, 2),
+    "A.res1.conv2": (32, 13, 7, 32, 5, 5, 1, 2), "A.res1.down": (32, 26, 13, 32, 1, 1, 2, 0),
+    "A.res2.conv1": (32, 12, 6, 64, 5, 5, 2, 2), "A.res2.conv2": (64, 6, 3, 64, 5, 5, 1, 2),
+    "nA.conv4": (128, 3, 17, 256, 3, 3, 1, 0),
+}
+
+
+@pytest.mark.parametrize("name", list(CONVS))
+def test_conv2d_fwd_bwd(name):
+    Ci, Hi, Wi, Co, KH, KW, st, pad = CONVS[name]
+    Ho, Wo = (Hi + 2 * pad - KH) // st + 1, (Wi + 2 * pad - KW) // st + 1
+    geo = L.ESConv2d(Ci, Hi, Wi, Co, Ho, Wo, KH, KW, st, pad)
+    counts, slots = [7, 0, 12], [2, 1, 0]
+    grp, R = groups(counts, slots)
+    g = G(len(name))
+    x = torch.randn(R, Ci, Hi, Wi, generator=g)
+    w = torch.randn(3, Co, Ci, KH, KW, generator=g) / math.sqrt(Ci * KH * KW)
+    b = torch.randn(3, Co, generator=g) * .1
+    dy = torch.randn(R, Co, Ho, Wo, generator=g)
+    lx, lw, lb = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    outs, off = [], 0
+    for c, s in zip(counts, slots):
+        if c:
+            o = F.conv2d(lx[off:off + c], lw[s], lb[s], stride=st, padding=pad)
+            outs.append(o)
+            (o * dy[off:off + c]).sum().backward()
+        off += c
+    y = torch.zeros(R, Co, Ho, Wo, device=DEV)
+    L.call("es_conv2d_fwd", cuda(x), cuda(w), cuda(b), Co * Ci * KH * KW, Co, geo, grp, 3, R, y)
+    check(f"conv2d fwd {name}", y, torch.cat(outs).detach(), 1e-5)
+    dx = torch.ones(R, Ci, Hi, Wi, device=DEV)
+    L.call("es_conv2d_bwd_data", cuda(dy), cuda(w), Co * Ci * KH * KW, geo, grp, 3, R, dx, 0)
+    check(f"conv2d bwd data {name}", dx, lx.grad, 1e-5)
+    L.call("es_conv2d_bwd_data", cuda(dy), cuda(w), Co * Ci * KH * KW, geo, grp, 3, R, dx, 1)
+    check(f"conv2d bwd data (accumulate) {name}", dx, 2 * lx.grad, 1e-5)
+    dw, db = torch.zeros(3, Co, Ci, KH, KW, device=DEV), torch.zeros(3, Co, device=DEV)
+    L.call("es_conv2d_bwd_weight", cuda(x), cuda(dy), geo, grp, 3, R, dw, db, Co * Ci * KH * KW, Co)
+    check(f"conv2d bwd weight {name}", dw, lw.grad, 2e-5)
+    check(f"conv2d bwd bias {name}", db, lb.grad, 2e-5)
+
+
+@pytest.mark.parametrize("C,H,W,groups_n,act", [(32, 54, 28, 8, 2), (16, 25, 12, 8, 2), (32, 27, 14, 8, 1), (64, 6, 3, 32, 0)])
+def test_groupnorm_fwd_bwd(C, H, W, groups_n, act):
+    counts, slots = [4, 5], [1, 0]
+    grp, R = groups(counts, slots)
+    g = G(C + H)
+    x = torch.randn(R, C, H, W, generator=g) * 2 + .5
+    ga, be = 1 + .2 * torch.randn(2, C, generator=g), .2 * torch.randn(2, C, generator=g)
+    dy = torch.randn(R, C, H, W, generator=g)
+    lx, lg, lb = x.clone().requires_grad_(True), ga.clone().requires_grad_(True), be.clone().requires_grad_(True)
+    f = {0: lambda t: t, 1: F.relu, 2: orc.lrelu}[act]
+    outs, off = [], 0
+    for c, s in zip(counts, slots):
+        o = f(F.group_norm(lx[off:off + c], groups_n, lg[s], lb[s], 1e-5))
+        outs.append(o)
+        (o * dy[off:off + c]).sum().backward()
+        off += c
+    y, stats = torch.zeros(R, C, H, W, device=DEV), torch.zeros(R, groups_n, 2, device=DEV)
+    L.call("es_groupnorm_fwd", cuda(x), cuda(ga), cuda(be), C, C, H * W, groups_n, act, grp, 2, R, y, stats)
+    check(f"groupnorm fwd C={C} act={act}", y, torch.cat(outs).detach(), 1e-5)
+    dx, dga, dbe = torch.zeros_like(y), torch.zeros(2, C, device=DEV), torch.zeros(2, C, device=DEV)
+    L.call("es_groupnorm_bwd", cuda(dy), cuda(x), stats, cuda(ga), cuda(be), C, C, H * W, groups_n, act, grp, 2, R, dx, dga, dbe)
+    check(f"groupnorm bwd dx C={C}", dx, lx.grad, 5e-5)
+    check(f"groupnorm bwd dgamma C={C}", dga, lg.grad, 5e-5)
+    check(f"groupnorm bwd dbeta C={C}", dbe, lb.grad, 5e-5)
+
+
+@pytest.mark.parametrize("F_,act", [(128, 2), (64, 2)])
+def test_layernorm_fwd_bwd(F_, act):
+    counts, slots = [9, 0, 20], [2, 1, 0]
+    grp, R = groups(counts, slots)
+    g = G(F_)
+    x = torch.randn(R, F_, generator=g) * 2 + .3
+    ga, be = 1 + .2 * torch.randn(3, F_, generator=g), .2 * torch.randn(3, F_, generator=g)
+    dy = torch.randn(R, F_, generator=g)
+    lx, lg, lb = x.clone().requires_grad_(True), ga.clone().requires_grad_(True), be.clone().requires_grad_(True)
+    outs, off = [], 0
+    for c, s in zip(counts, slots):
+        if c:
+            o = orc.lrelu(F.layer_norm(lx[off:off + c], (F_,), lg[s], lb[s], 1e-5))
+            outs.append(o)
+            (o * dy[off:off + c]).sum().backward()
+        off += c
+    y, stats = torch.zeros(R, F_, device=DEV), torch.zeros(R, 2, device=DEV)
+    L.call("es_layernorm_fwd", cuda(x), cuda(ga), cuda(be), F_, F_, act, grp, 3, R, y, stats)
+    check(f"layernorm fwd F={F_}", y, torch.cat(outs).detach(), 1e-5)
+    dx, dga, dbe = torch.zeros_like(y), torch.zeros(3, F_, device=DEV), torch.zeros(3, F_, device=DEV)
+    L.call("es_layernorm_bwd", cuda(dy), cuda(x), stats, cuda(ga), cuda(be), F_, F_, act, grp, 3, R, dx, dga, dbe)
+    check(f"layernorm bwd dx F={F_}", dx, lx.grad, 5e-5)
+    check(f"layernorm bwd dgamma F={F_}", dga, lg.grad, 5e-5)
+    check(f"layernorm bwd dbeta F={F_}", dbe, lb.grad, 5e-5)
+
+
+@pytest.mark.parametrize("C,H,W,k,s", [(32, 54, 28, (2, 2), (2, 2)), (16, 25, 12, (2, 1), (2, 1)), (32, 27, 14, (2, 2), (1, 1)), (64, 6, 3, (2, 2), (1, 1))])
+def test_maxpool(C, H, W, k, s):
+    R = 5
+    g = G(H)
+    x = torch.randn(R, C, H, W, generator=g).requires_grad_(True)
+    o = F.max_pool2d(x, k, s)
+    dy = torch.randn(o.shape, generator=g)
+    (o * dy).sum().backward()
+    y = torch.zeros(o.shape, device=DEV)
+    idx = torch.zeros(o.shape, dtype=torch.uint8, device=DEV)
+    L.call("es_maxpool_fwd", cuda(x.detach()), C, H, W, k[0], k[1], s[0], s[1], R, y, idx)
+    assert torch.equal(y.cpu(), o.detach())
+    dx = torch.zeros(R, C, H, W, device=DEV)
+    L.call("es_maxpool_bwd", cuda(dy), idx, C, H, W, k[0], k[1], s[0], s[1], R, dx)
+    check(f"maxpool bwd {H}x{W}", dx, x.grad, 1e-6)
+
+
+@pytest.mark.parametrize("I,O", [(2313, 128), (128, 64), (64, 1), (64, 2)])
+def test_linear(I, O):
+    counts, slots = [70, 0, 33], [0, 1, 2]
+    grp, R = groups(counts, slots)
+    g = G(I)
+    x = torch.randn(R, I, generator=g)
+    w, b = torch.randn(3, O, I, generator=g) / math.sqrt(I), torch.randn(3, O, generator=g) * .1
+    dy = torch.randn(R, O, generator=g)
+    lx, lw, lb = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    outs, off = [], 0
+    for c, s in zip(counts, slots):
+        if c:
+            o = F.linear(lx[off:off + c], lw[s], lb[s])
+            outs.append(o)
+            (o * dy[off:off + c]).sum().backward()
+        off += c
+    y = torch.zeros(R, O, device=DEV)
+    L.call("es_linear_fwd", cuda(x), I, cuda(w), cuda(b), O * I, O, I, O, grp, 3, R, y)
+    check(f"linear fwd {I}->{O}", y, torch.cat(outs).detach(), 1e-5)
+    dx = torch.zeros(R, I, device=DEV)
+    L.call("es_linear_bwd_data", cuda(dy), cuda(w), O * I, I, O, grp, 3, R, dx, I)
+    check(f"linear bwd data {I}->{O}", dx, lx.grad, 1e-5)
+    dw, db = torch.zeros(3, O, I, device=DEV), torch.zeros(3, O, device=DEV)
+    L.call("es_linear_bwd_weight", cuda(x), I, cuda(dy), I, O, grp, 3, R, dw, db, O * I, O)
+    check(f"linear bwd weight {I}->{O}", dw, lw.grad, 2e-5)
+    check(f"linear bwd bias {I}->{O}", db, lb.grad, 2e-5)
+
+
+@pytest.mark.parametrize("O,I", [(32, 9), (16, 288), (128, 2313), (64, 128), (1, 64)])
+def test_spectral_norm(O, I):
+    S = 3
+    g = G(O * I)
+    w = torch.randn(S, O, I, generator=g) / math.sqrt(I)
+    u = F.normalize(torch.randn(S, O, generator=g), dim=1)
+    v = F.normalize(torch.randn(S, I, generator=g), dim=1)
+    grp, _ = groups([4, 0, 5])  # slot 1 inactive: its u, v must not advance
+    du, dv = cuda(u.clone()), cuda(v.clone())
+    wsn = torch.zeros(S, O, I, device=DEV)
+    sig, uu, vu = torch.zeros(S, device=DEV), torch.zeros(S, O, device=DEV), torch.zeros(S, I, device=DEV)
+    L.call("es_spectral_norm_fwd", cuda(w), du, dv, O * I, O, I, S, O, I, 1, grp, wsn, O * I, sig, uu, vu)
+    dwsn = torch.randn(S, O, I, generator=g)
+    dwo = torch.zeros(S, O, I, device=DEV)
+    L.call("es_spectral_norm_bwd", cuda(dwsn), wsn, uu, vu, sig, O * I, S, O, I, dwo, O * I)
+    for s in (0, 2):
+        sd = {"l.weight_orig": w[s].clone().requires_grad_(True), "l.weight_u": u[s].clone(), "l.weight_v": v[s].clone()}
+        ws = orc.spectral_norm_weight(sd, "l", True)
+        (ws * dwsn[s]).sum().backward()
+        check(f"spectral norm W/sigma {O}x{I} slot {s}", wsn[s], ws.detach(), 2e-5)
+        check(f"spectral norm u {O}x{I}", du[s], sd["l.weight_u"], 2e-5)
+        check(f"spectral norm v {O}x{I}", dv[s], sd["l.weight_v"], 2e-5)
+        check(f"spectral norm bwd {O}x{I}", dwo[s], sd["l.weight_orig"].grad, 1e-4)
+    assert torch.equal(du[1].cpu(), u[1]) and torch.equal(dv[1].cpu(), v[1])
+
+
+def test_elementwise_and_adam():
+    g = G(77)
+    n = 10007
+    a, b = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    y = torch.zeros(n, device=DEV)
+    L.call("es_add_relu_fwd", cuda(a), cuda(b), n, y)
+    assert torch.equal(y.cpu(), F.relu(a + b))
+    dx = torch.zeros(n, device=DEV)
+    L.call("es_relu_bwd", cuda(b), y, n, dx)
+    assert torch.equal(dx.cpu(), torch.where(F.relu(a + b) > 0, b, torch.zeros(())))
+    x = torch.randn(6, 64, 5, 2, generator=g)
+    o = torch.zeros(6, 64, device=DEV)
+    L.call("es_gap_fwd", cuda(x), 64, 10, 6, o)
+    check("gap fwd", o, x.mean((2, 3)), 1e-6)
+    # Adam: 3 slots, slot 1 inactive, two steps
+    S, N = 3, 5000
+    p = torch.randn(S, N, generator=g)
+    st = [orc.AdamState({"p": p[s].clone()}, 1e-3) for s in range(S)]
+    pp = [{"p": p[s].clone()} for s in range(S)]
+    dp, dm, dv = cuda(p.clone()), torch.zeros(S, N, device=DEV), torch.zeros(S, N, device=DEV)
+    steps = torch.zeros(S, dtype=torch.int32, device=DEV)
+    grp, _ = groups([3, 0, 2])
+    for it in range(2):
+        gr = torch.randn(S, N, generator=g)
+        L.call("es_adam_step", dp, cuda(gr), dm, dv, N, N, S, 1e-3, 0.9, 0.999, 1e-8, steps, grp)
+        for s in (0, 2):
+            st[s].apply(pp[s], {"p": gr[s]})
+    assert steps.cpu().tolist() == [2, 0, 2]
+    for s in (0, 2):
+        check(f"adam slot {s}", dp[s], pp[s]["p"], 1e-6)
+    assert torch.equal(dp[1].cpu(), p[1])
+
+
+def test_expm1_scatter():
+    g = G(5)
+    R, HW = 9, 1680
+    img = torch.rand(R, HW, generator=g) * 3
+    perm = torch.randperm(R, generator=g).to(torch.int32)
+    o64 = torch.zeros(R, HW, dtype=torch.float64, device=DEV)
+    L.call("es_expm1_scatter", cuda(img), cuda(perm), R, HW, o64, None)
+    want = torch.zeros(R, HW, dtype=torch.float64)
+    want[perm.long()] = torch.expm1(img).double()
+    check("expm1 + scatter (f64)", o64, want, 1e-6)
