@@ -259,7 +259,7 @@ ln_affine_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, in
                      const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dx,
                      const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                      long slot_stride, const es_group* __restrict__ grp, const int* __restrict__ row_map,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+                     long out_stride, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
   __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
   const es_group G = grp[blockIdx.y];
   if (G.rows == 0) return;
@@ -294,7 +294,7 @@ ln_affine_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, in
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int f = i * 8 + k;
-    const size_t o = G.slot * slot_stride + (row_map ? row_map[f] : f);
+    const size_t o = G.slot * out_stride + (row_map ? row_map[f] : f);
     dgamma[o] += ag[k];
     dbeta[o] += ab[k];
     dbias[o] += al[k];
@@ -446,7 +446,7 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 
 // ----------------------------------------------------------------------------------------------- output conv (C -> 1)
 __global__ void __launch_bounds__(256)
-gen_out_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, long sw,
+gen_out_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, long sw, long sb,
                    int Hs, int Ws, int C, int KH, int KW, int pad, const es_group* __restrict__ grp, int E,
                    int two_pass, float* __restrict__ img1, float* __restrict__ img2) {
   extern __shared__ float s_w[];  // [KH*KW][C]
@@ -459,7 +459,7 @@ gen_out_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     s_w[i] = w[slot * sw + (size_t)c * KH * KW + tap];
   }
   __syncthreads();
-  const float bias = b[slot];
+  const float bias = b[slot * sb];
   const int Ho = Hs + 2 * pad - KH + 1, Wo = Ws + 2 * pad - KW + 1;
   float* dst = (m.pass ? img2 : img1) + (size_t)m.j * Ho * Wo;
   const __nv_bfloat16* xr = x + (size_t)r * Hs * Ws * C;
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(256)
 gen_out_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, long sw, int Hs, int Ws, int C,
                    int KH, int KW, int pad, const float* __restrict__ img1, const float* __restrict__ img2,
                    const float* __restrict__ dimg1, const float* __restrict__ dimg2, const es_group* __restrict__ grp,
-                   int E, int two_pass, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db) {
+                   int E, int two_pass, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long sb) {
   extern __shared__ float sm[];
   const int Ho = Hs + 2 * pad - KH + 1, Wo = Ws + 2 * pad - KW + 1;
   float* s_w = sm;                       // [KH*KW][C]
@@ -516,7 +516,7 @@ gen_out_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     dsum += d;
   }
   dsum = block_sum(dsum, red);   // contains the __syncthreads that publishes s_w / s_d
-  if (threadIdx.x == 0) atomicAdd(&db[slot], dsum);
+  if (threadIdx.x == 0) atomicAdd(&db[slot * sb], dsum);
   const int c4 = C / 8;
   const __nv_bfloat16* xr = x + (size_t)r * Hs * Ws * C;
   __nv_bfloat16* dxr = dx + (size_t)r * Hs * Ws * C;
@@ -720,14 +720,14 @@ extern "C" int es_ln_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu
 extern "C" int es_ln_affine_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, int C, const void* x,
                                 const void* dx, const float* stats, const float* gamma, const float* beta,
                                 long slot_stride, const es_group* grp, int n_groups, int total_rows,
-                                const int32_t* row_map, float* dgamma, float* dbeta, float* dbias_lin, void* stream) {
+                                const int32_t* row_map, long out_slot_stride, float* dgamma, float* dbeta, float* dbias_lin, void* stream) {
   ES_REQUIRE(dy_up && x && dx && stats && gamma && beta && grp && dgamma && dbeta && dbias_lin, "null pointer");
   ES_REQUIRE(C % 8 == 0 && Hs <= 64 && Ws <= 64 && Hu <= 64 && Wu <= 64, "bad geometry");
   ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups, "bad sizes");
   const int n4 = Hs * Ws * C / 8;
   ln_affine_bwd_kernel<<<dim3(ceil_div(n4, 128), n_groups), 128, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dx, stats, gamma,
-      beta, slot_stride, grp, row_map, dgamma, dbeta, dbias_lin);
+      beta, slot_stride, grp, row_map, out_slot_stride, dgamma, dbeta, dbias_lin);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
@@ -760,18 +760,18 @@ extern "C" int es_gn_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu
   return ES_OK;
 }
 
-extern "C" int es_gen_out_fwd(const void* x, const float* w, const float* b, long slot_stride_w, int Hs, int Ws, int C,
+extern "C" int es_gen_out_fwd(const void* x, const float* w, const float* b, long slot_stride_w, long slot_stride_b, int Hs, int Ws, int C,
                               int KH, int KW, int pad, const es_group* grp_gen, int E, int total_rows, int two_pass,
                               float* img1, float* img2, void* stream) {
   ES_REQUIRE(x && w && b && grp_gen && img1 && (img2 || !two_pass), "null pointer");
   ES_REQUIRE(C % 8 == 0 && KH * KW * C <= 8192 && total_rows > 0 && E >= 1 && E <= kMaxGroups, "bad sizes");
   gen_out_fwd_kernel<<<total_rows, 256, KH * KW * C * sizeof(float), as_stream(stream)>>>(
-      (const __nv_bfloat16*)x, w, b, slot_stride_w, Hs, Ws, C, KH, KW, pad, grp_gen, E, two_pass, img1, img2);
+      (const __nv_bfloat16*)x, w, b, slot_stride_w, slot_stride_b, Hs, Ws, C, KH, KW, pad, grp_gen, E, two_pass, img1, img2);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
 
-extern "C" int es_gen_out_bwd(const void* x, const float* w, long slot_stride_w, int Hs, int Ws, int C, int KH, int KW,
+extern "C" int es_gen_out_bwd(const void* x, const float* w, long slot_stride_w, long slot_stride_b, int Hs, int Ws, int C, int KH, int KW,
                               int pad, const float* img1, const float* img2, const float* dimg1, const float* dimg2,
                               const es_group* grp_gen, int E, int total_rows, int two_pass, void* dx, float* dw,
                               float* db, void* stream) {
@@ -782,7 +782,7 @@ extern "C" int es_gen_out_bwd(const void* x, const float* w, long slot_stride_w,
   const size_t smem = (2 * KH * KW * C + Ho * Wo) * sizeof(float);
   gen_out_bwd_kernel<<<total_rows, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)x, w, slot_stride_w, Hs, Ws, C,
                                                                    KH, KW, pad, img1, img2, dimg1, dimg2, grp_gen, E,
-                                                                   two_pass, (__nv_bfloat16*)dx, dw, db);
+                                                                   two_pass, (__nv_bfloat16*)dx, dw, db, slot_stride_b);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }

@@ -245,7 +245,7 @@ groupnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     }
     a = block_sum(a, red);
     b = block_sum(b, red);
-    if (threadIdx.x == 0) { atomicAdd(&dgamma[slot * ss + c], a); atomicAdd(&dbeta[slot * ss + c], b); }
+    if (threadIdx.x == 0 && dgamma) { atomicAdd(&dgamma[slot * ss + c], a); atomicAdd(&dbeta[slot * ss + c], b); }
     s1 += b * ga;   // every thread holds the block totals
     s2 += a * ga;
   }
@@ -670,7 +670,8 @@ extern "C" int es_groupnorm_bwd(const float* dy, const float* x, const float* st
                                 const float* beta, long slot_stride, int C, int HW, int groups, int act,
                                 const es_group* grp, int n_groups, int total_rows, float* dx, float* dgamma,
                                 float* dbeta, void* stream) {
-  ES_REQUIRE(dy && x && stats && gamma && beta && grp && dx && dgamma && dbeta, "null pointer");
+  ES_REQUIRE(dy && x && stats && gamma && beta && grp && dx, "null pointer");
+  ES_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "dgamma and dbeta go together");
   ES_REQUIRE(C > 0 && groups > 0 && C % groups == 0 && HW > 0 && total_rows > 0 && n_groups <= kMaxGroups, "bad sizes");
   groupnorm_bwd_kernel<<<total_rows * groups, 128, 0, as_stream(stream)>>>(dy, x, stats, gamma, beta, slot_stride, C, HW,
                                                                           groups, act, grp, n_groups, dx, dgamma, dbeta);

@@ -96,7 +96,11 @@ def _round4(n):
 
 
 class Holder(nn.Module):
-    """Anonymous container so dotted reference names ('fc1.0.weight') map onto real sub-modules."""
+    """Anonymous container so dotted reference names ('fc1.0.weight') map onto real sub-modules; integer indexing
+    works as on the reference's nn.Sequential blocks (``gen.fc2[0].weight``)."""
+
+    def __getitem__(self, i):
+        return self._modules[str(i)]
 
 
 def register_by_spec(module: nn.Module, spec: Spec):
@@ -162,6 +166,8 @@ class Arena:
         self.steps = z(n_slots, dt=torch.int32)
         self.Bf = z(n_slots, self.nb)
         self.modules: List[nn.Module] = []
+        self.version = 0      # bumped whenever parameters change (optimizer step, load_state_dict)
+        self.engine = None    # compute engine bound to this arena (created by the owner)
 
     # ---- raw addresses for the C-ABI (slot 0; slot e = + e * stride floats)
     def addr(self, name):

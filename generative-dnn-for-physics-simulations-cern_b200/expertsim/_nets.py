@@ -1,0 +1,439 @@
+"""Host-side sequencing of the grouped sm_100a kernels for the three expert networks (generator, discriminator,
+auxiliary regressor): explicit forward and hand-written backward, all experts in one launch per layer.
+
+Nothing here computes on the host: every numeric step is a call into libexpertsim_b200.so (see include/expertsim_b200.h);
+torch only allocates device buffers.  Shapes follow the reference modules:
+  generator      expertsim/models/proton/generator.py:13-52      (reference repo)
+  discriminator  expertsim/models/proton/discriminator.py:121-155, expertsim/models/neutron/discriminator.py:11-48
+  aux regressor  expertsim/models/proton/aux_reg.py:11-131
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from ._arena import Arena
+
+BF = torch.bfloat16
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def empty(*shape, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=_dev())
+
+
+def zeros(*shape, dtype=torch.float32):
+    return torch.zeros(shape, dtype=dtype, device=_dev())
+
+
+def conv_geom(Hs, Ws, C, Hu, Wu, KH, KW, pad, N):
+    return L.ESConvGeom(Hs, Ws, C, Hu, Wu, Hu + 2 * pad - KH + 1, Wu + 2 * pad - KW + 1, KH, KW, pad, N)
+
+
+def conv2d(Ci, Hi, Wi, Co, KH, KW, stride, pad):
+    return L.ESConv2d(Ci, Hi, Wi, Co, (Hi + 2 * pad - KH) // stride + 1, (Wi + 2 * pad - KW) // stride + 1, KH, KW, stride, pad)
+
+
+# =====================================================================================================================
+# generator (proton): bf16 NHWC activations, tcgen05 implicit GEMMs
+# =====================================================================================================================
+class GenEngineProton:
+    H, W = 56, 30
+    F2 = 92160                                   # 512 * 18 * 10
+    # (name, fwd geometry (Hs,Ws,C,Hu,Wu,KH,KW,pad,N), norm name, groups)
+    CONVS = (("conv_layers.1", (18, 10, 512, 36, 20, 4, 4, 1, 256), "conv_layers.2", 32),
+             ("conv_layers.5", (35, 19, 256, 56, 30, 4, 4, 1, 128), "conv_layers.6", 32),
+             ("conv_layers.8", (55, 29, 128, 55, 29, 3, 3, 1, 64), "conv_layers.9", 32))
+
+    def __init__(self, arena: Arena):
+        self.a = arena
+        E, dev = arena.E, arena.device
+        # packed feature f' = (y*10+x)*512 + c  <-  reference feature f = c*180 + y*10 + x   (NCHW view(-1,512,18,10))
+        fp = torch.arange(self.F2, device=dev)
+        self.row_map = ((fp % 512) * 180 + fp // 512).to(torch.int32).contiguous()
+        self.w_fc2 = torch.empty(E, self.F2, 256, dtype=BF, device=dev)
+        self.b_fc2 = torch.empty(E, self.F2, device=dev)
+        self.g_fc2 = torch.empty(E, self.F2, device=dev)
+        self.z_fc2 = torch.empty(E, self.F2, device=dev)
+        self.w_fwd, self.w_dg, self.dw_p = {}, {}, {}
+        for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
+            self.w_fwd[name] = torch.empty(E, N, KH, KW, C, dtype=BF, device=dev)
+            self.w_dg[name] = torch.empty(E, C, KH, KW, N, dtype=BF, device=dev)
+            self.dw_p[name] = torch.empty(E, N, KH, KW, C, device=dev)
+
+    def repack(self):
+        """fp32 master weights (reference layout) -> bf16 kernel layouts; called after every optimizer step."""
+        a, E = self.a, self.a.E
+        L.call("es_pack_dense_weight", a.addr("fc2.0.weight"), a.n, E, self.F2, 256, self.row_map, self.w_fc2)
+        for src, dst in (("fc2.0.bias", self.b_fc2), ("fc2.1.weight", self.g_fc2), ("fc2.1.bias", self.z_fc2)):
+            L.call("es_permute_features", a.addr(src), a.n, self.row_map, E, self.F2, dst, self.F2, 0)
+        for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
+            L.call("es_pack_conv_weight", a.addr(name + ".weight"), a.n, E, N, C, KH, KW, self.w_fwd[name], self.w_dg[name])
+
+    def forward(self, z1, z2, cond, grp, R, two_pass, keep=True, training=True, drop=None):
+        """z1,z2 [B,10], cond [B,9] in expert-sorted order; grp = generator group table; R = total rows.
+        Returns (img1 [B,HW], img2 or None, saved).  The proton generator has no train/eval difference (LayerNorm /
+        GroupNorm only, no dropout), so ``training`` and ``drop`` are accepted for interface symmetry and unused."""
+        a, E = self.a, self.a.E
+        B = R // 2 if two_pass else R
+        s = {"R": R, "two_pass": two_pass, "grp": grp}
+        s["x0"], s["lin1"], s["h1"] = empty(R, 19), empty(R, 256), empty(R, 256, dtype=BF)
+        L.call("es_gen_fc1_fwd", z1, z2, cond, a.addr("fc1.0.weight"), a.addr("fc1.0.bias"), a.addr("fc1.1.weight"),
+               a.addr("fc1.1.bias"), a.n, a.n, grp, E, R, int(two_pass), s["x0"], s["lin1"], s["h1"])
+        s["y2"] = empty(R, self.F2, dtype=BF)
+        L.call("es_igemm_fwd", s["h1"], self.w_fc2, self.b_fc2, s["y2"], conv_geom(1, 1, 256, 1, 1, 1, 1, 0, self.F2), grp, E, R)
+        act, s["st2"] = empty(R, self.F2, dtype=BF), empty(R, 2)
+        L.call("es_ln_lrelu_fwd", s["y2"], self.g_fc2, self.z_fc2, self.F2, self.F2, grp, E, R, act, s["st2"])
+        s["a2"] = act
+        for i, (name, geo, norm, groups) in enumerate(self.CONVS):
+            Hs, Ws, C, Hu, Wu, KH, KW, pad, N = geo
+            g = conv_geom(*geo)
+            P = g.Ho * g.Wo
+            y = empty(R, P, N, dtype=BF)
+            L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), y, g, grp, E, R)
+            nxt, st = empty(R, P, N, dtype=BF), empty(R, groups, 2)
+            L.call("es_gn_lrelu_fwd", y, a.addr(norm + ".weight"), a.addr(norm + ".bias"), a.n, P, N, groups, grp, E, R, nxt, st)
+            s[f"y{i + 3}"], s[f"st{i + 3}"], s[f"a{i + 3}"] = y, st, nxt
+            act = nxt
+        img1 = zeros(B, self.H * self.W)
+        img2 = zeros(B, self.H * self.W) if two_pass else None
+        L.call("es_gen_out_fwd", act, a.addr("conv_layers.11.weight"), a.addr("conv_layers.11.bias"), a.n, a.n, 55, 29, 64, 2, 2, 1,
+               grp, E, R, int(two_pass), img1, img2)
+        s["img1"], s["img2"] = img1, img2
+        return img1, img2, (s if keep else None)
+
+    def backward(self, s, dimg1, dimg2):
+        """Accumulates every generator parameter gradient into the arena's G tensor (reference layouts)."""
+        a, E, R, grp = self.a, self.a.E, s["R"], s["grp"]
+        for t in self.dw_p.values():
+            t.zero_()
+        da = empty(R, 55 * 29, 64, dtype=BF)
+        L.call("es_gen_out_bwd", s["a5"], a.addr("conv_layers.11.weight"), a.n, a.n, 55, 29, 64, 2, 2, 1, s["img1"], s["img2"],
+               dimg1, dimg2, grp, E, R, int(s["two_pass"]), da, a.gaddr("conv_layers.11.weight"), a.gaddr("conv_layers.11.bias"))
+        up = (55, 29)   # spatial size of `da` (gradient w.r.t. the input the next-later layer consumed)
+        for i in (2, 1, 0):
+            name, geo, norm, groups = self.CONVS[i]
+            Hs, Ws, C, Hu, Wu, KH, KW, pad, N = geo
+            g = conv_geom(*geo)
+            P = g.Ho * g.Wo
+            # norm + LeakyReLU backward; `da` lives on the (possibly upsampled) grid `up`, the layer output on (Ho,Wo)
+            dy = empty(R, P, N, dtype=BF)
+            L.call("es_gn_lrelu_bwd", da, g.Ho, g.Wo, up[0], up[1], s[f"y{i + 3}"], s[f"st{i + 3}"], a.addr(norm + ".weight"),
+                   a.addr(norm + ".bias"), a.n, N, groups, grp, E, R, dy, a.gaddr(norm + ".weight"), a.gaddr(norm + ".bias"),
+                   a.gaddr(name + ".bias"))
+            # weight gradient (packed fp32, unpacked below) and data gradient on the upsampled input grid
+            L.call("es_igemm_wgrad", s[f"a{i + 2}"], dy, self.dw_p[name], g, grp, E, R)
+            da = empty(R, Hu * Wu, C, dtype=BF)
+            L.call("es_igemm_fwd", dy, self.w_dg[name], None, da, conv_geom(g.Ho, g.Wo, N, g.Ho, g.Wo, KH, KW, KH - 1 - pad, C), grp, E, R)
+            up = (Hu, Wu)
+        dy2 = empty(R, self.F2, dtype=BF)
+        L.call("es_ln_lrelu_bwd", da, 18, 10, 36, 20, 512, s["y2"], s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R, dy2)
+        L.call("es_ln_affine_bwd", da, 18, 10, 36, 20, 512, s["y2"], dy2, s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R,
+               self.row_map, a.n, a.gaddr("fc2.1.weight"), a.gaddr("fc2.1.bias"), a.gaddr("fc2.0.bias"))
+        L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), self.F2, 256, self.row_map, grp, E, R)
+        dh1 = zeros(R, 256)
+        L.call("es_dense_dgrad", dy2, self.w_fc2, dh1, self.F2, 256, grp, E, R)
+        L.call("es_gen_fc1_bwd", dh1, s["x0"], s["lin1"], a.addr("fc1.1.weight"), a.addr("fc1.1.bias"), a.n, a.n, grp, E, R,
+               a.gaddr("fc1.0.weight"), a.gaddr("fc1.0.bias"), a.gaddr("fc1.1.weight"), a.gaddr("fc1.1.bias"))
+        for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
+            L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
+
+
+# =====================================================================================================================
+# discriminator (proton / neutron): fp32 NCHW
+# =====================================================================================================================
+class DiscEngine:
+    SN = ("conv_layers.0", "conv_layers.4", "fc1.0", "fc2.0", "fc3")
+
+    def __init__(self, arena: Arena, arch: str):
+        self.a, self.arch = arena, arch
+        self.H, self.W = (56, 30) if arch == "proton" else (44, 44)
+        self.c0 = conv2d(1, self.H, self.W, 32, 3, 3, 1, 0)
+        self.H1, self.W1 = self.c0.Ho // 2, self.c0.Wo // 2
+        self.c4 = conv2d(32, self.H1, self.W1, 16, 3, 3, 1, 0)
+        self.pool2 = (2, 1) if arch == "proton" else (2, 2)
+        self.H2, self.W2 = self.c4.Ho // self.pool2[0], self.c4.Wo // self.pool2[1]
+        self.flat = 16 * self.H2 * self.W2
+        self.dims = {"conv_layers.0": (32, 9), "conv_layers.4": (16, 288), "fc1.0": (128, self.flat + 9), "fc2.0": (64, 128),
+                     "fc3": (1, 64)}
+
+    def spectral(self, grp, training: bool):
+        """One spectral-norm evaluation of all five layers (a forward pre-hook firing in the reference): returns the
+        normalised weights and what backward needs.  In training mode u, v advance in place (one power iteration)."""
+        a, E = self.a, self.a.E
+        out = {}
+        for name in self.SN:
+            O, I = self.dims[name]
+            wsn, sig = empty(E, O * I), empty(E)
+            uu, vu = empty(E, O), empty(E, I)
+            L.call("es_spectral_norm_fwd", a.addr(name + ".weight_orig"), a.baddr(name + ".weight_u"), a.baddr(name + ".weight_v"),
+                   a.n, a.nb, a.nb, E, O, I, int(training), grp if training else None, wsn, O * I, sig, uu, vu)
+            out[name] = (wsn, sig, uu, vu)
+        return out
+
+    def forward(self, img, cond, grp, R, sn):
+        """img [R, H*W], cond [R, 9] (sorted order) -> score [R,1], latent [R,64], saved tensors."""
+        a, E, n = self.a, self.a.E, self.a.n
+        s = {"img": img, "R": R, "grp": grp}
+        y1 = empty(R, 32, self.c0.Ho, self.c0.Wo)
+        L.call("es_conv2d_fwd", img, sn["conv_layers.0"][0], a.addr("conv_layers.0.bias"), 32 * 9, n, self.c0, grp, E, R, y1)
+        a1, s["st1"] = empty(*y1.shape), empty(R, 8, 2)
+        L.call("es_groupnorm_fwd", y1, a.addr("conv_layers.1.weight"), a.addr("conv_layers.1.bias"), n, 32, self.c0.Ho * self.c0.Wo,
+               8, ACT_LRELU, grp, E, R, a1, s["st1"])
+        p1, s["i1"] = empty(R, 32, self.H1, self.W1), empty(R, 32, self.H1, self.W1, dtype=torch.uint8)
+        L.call("es_maxpool_fwd", a1, 32, self.c0.Ho, self.c0.Wo, 2, 2, 2, 2, R, p1, s["i1"])
+        y2 = empty(R, 16, self.c4.Ho, self.c4.Wo)
+        L.call("es_conv2d_fwd", p1, sn["conv_layers.4"][0], a.addr("conv_layers.4.bias"), 16 * 288, n, self.c4, grp, E, R, y2)
+        a2, s["st2"] = empty(*y2.shape), empty(R, 8, 2)
+        L.call("es_groupnorm_fwd", y2, a.addr("conv_layers.5.weight"), a.addr("conv_layers.5.bias"), n, 16, self.c4.Ho * self.c4.Wo,
+               8, ACT_LRELU, grp, E, R, a2, s["st2"])
+        kh, kw = self.pool2
+        p2, s["i2"] = empty(R, self.flat), empty(R, self.flat, dtype=torch.uint8)
+        L.call("es_maxpool_fwd", a2, 16, self.c4.Ho, self.c4.Wo, kh, kw, kh, kw, R, p2, s["i2"])
+        fcin = empty(R, self.flat + 9)
+        L.call("es_copy_cols", p2, self.flat, self.flat, R, fcin, self.flat + 9, 0)
+        L.call("es_copy_cols", cond, 9, 9, R, fcin, self.flat + 9, self.flat)
+        l1 = empty(R, 128)
+        L.call("es_linear_fwd", fcin, self.flat + 9, sn["fc1.0"][0], a.addr("fc1.0.bias"), 128 * (self.flat + 9), n, self.flat + 9, 128, grp, E, R, l1)
+        f1, s["s1"] = empty(R, 128), empty(R, 2)
+        L.call("es_layernorm_fwd", l1, a.addr("fc1.1.weight"), a.addr("fc1.1.bias"), n, 128, ACT_LRELU, grp, E, R, f1, s["s1"])
+        l2 = empty(R, 64)
+        L.call("es_linear_fwd", f1, 128, sn["fc2.0"][0], a.addr("fc2.0.bias"), 64 * 128, n, 128, 64, grp, E, R, l2)
+        lat, s["s2"] = empty(R, 64), empty(R, 2)
+        L.call("es_layernorm_fwd", l2, a.addr("fc2.1.weight"), a.addr("fc2.1.bias"), n, 64, ACT_LRELU, grp, E, R, lat, s["s2"])
+        score = zeros(R, 1)
+        L.call("es_linear_fwd", lat, 64, sn["fc3"][0], a.addr("fc3.bias"), 64, n, 64, 1, grp, E, R, score)
+        s.update(y1=y1, p1=p1, y2=y2, fcin=fcin, l1=l1, f1=f1, l2=l2, lat=lat)
+        return score, lat, s
+
+    def backward(self, s, sn, d_score, d_latent, want_w: bool, d_img=None, accumulate=False):
+        """want_w: accumulate parameter gradients into the arena (discriminator step).  d_img: output buffer for the
+        image gradient (generator step).  d_latent may be None."""
+        a, E, n, R, grp = self.a, self.a.E, self.a.n, s["R"], s["grp"]
+        dsn = {k: zeros(E, self.dims[k][0] * self.dims[k][1]) for k in self.SN} if want_w else None
+
+        def lin_w(x, ldx, dy, name):
+            if want_w:
+                O, I = self.dims[name]
+                L.call("es_linear_bwd_weight", x, ldx, dy, I, O, grp, E, R, dsn[name], a.gaddr(name + ".bias"), O * I, n)
+
+        d_lat = zeros(R, 64)
+        L.call("es_linear_bwd_data", d_score, sn["fc3"][0], 64, 64, 1, grp, E, R, d_lat, 64)
+        lin_w(s["lat"], 64, d_score, "fc3")
+        if d_latent is not None:
+            L.call("es_axpy", 1.0, d_latent, R * 64, d_lat)
+        dl2 = zeros(R, 64)
+        L.call("es_layernorm_bwd", d_lat, s["l2"], s["s2"], a.addr("fc2.1.weight"), a.addr("fc2.1.bias"), n, 64, ACT_LRELU, grp, E, R, dl2,
+               a.gaddr("fc2.1.weight") if want_w else None, a.gaddr("fc2.1.bias") if want_w else None)
+        df1 = zeros(R, 128)
+        L.call("es_linear_bwd_data", dl2, sn["fc2.0"][0], 64 * 128, 128, 64, grp, E, R, df1, 128)
+        lin_w(s["f1"], 128, dl2, "fc2.0")
+        dl1 = zeros(R, 128)
+        L.call("es_layernorm_bwd", df1, s["l1"], s["s1"], a.addr("fc1.1.weight"), a.addr("fc1.1.bias"), n, 128, ACT_LRELU, grp, E, R, dl1,
+               a.gaddr("fc1.1.weight") if want_w else None, a.gaddr("fc1.1.bias") if want_w else None)
+        I1 = self.flat + 9
+        dfc = zeros(R, I1)
+        L.call("es_linear_bwd_data", dl1, sn["fc1.0"][0], 128 * I1, I1, 128, grp, E, R, dfc, I1)
+        lin_w(s["fcin"], I1, dl1, "fc1.0")
+        dp2 = empty(R, self.flat)
+        L.call("es_copy_cols", dfc, I1, self.flat, R, dp2, self.flat, 0)
+        kh, kw = self.pool2
+        da2 = empty(R, 16, self.c4.Ho, self.c4.Wo)
+        L.call("es_maxpool_bwd", dp2, s["i2"], 16, self.c4.Ho, self.c4.Wo, kh, kw, kh, kw, R, da2)
+        dy2 = zeros(*da2.shape)
+        L.call("es_groupnorm_bwd", da2, s["y2"], s["st2"], a.addr("conv_layers.5.weight"), a.addr("conv_layers.5.bias"), n, 16,
+               self.c4.Ho * self.c4.Wo, 8, ACT_LRELU, grp, E, R, dy2,
+               a.gaddr("conv_layers.5.weight") if want_w else None, a.gaddr("conv_layers.5.bias") if want_w else None)
+        if want_w:
+            L.call("es_conv2d_bwd_weight", s["p1"], dy2, self.c4, grp, E, R, dsn["conv_layers.4"], a.gaddr("conv_layers.4.bias"), 16 * 288, n)
+        dp1 = zeros(R, 32, self.H1, self.W1)
+        L.call("es_conv2d_bwd_data", dy2, sn["conv_layers.4"][0], 16 * 288, self.c4, grp, E, R, dp1, 0)
+        da1 = empty(R, 32, self.c0.Ho, self.c0.Wo)
+        L.call("es_maxpool_bwd", dp1, s["i1"], 32, self.c0.Ho, self.c0.Wo, 2, 2, 2, 2, R, da1)
+        dy1 = zeros(*da1.shape)
+        L.call("es_groupnorm_bwd", da1, s["y1"], s["st1"], a.addr("conv_layers.1.weight"), a.addr("conv_layers.1.bias"), n, 32,
+               self.c0.Ho * self.c0.Wo, 8, ACT_LRELU, grp, E, R, dy1,
+               a.gaddr("conv_layers.1.weight") if want_w else None, a.gaddr("conv_layers.1.bias") if want_w else None)
+        if want_w:
+            L.call("es_conv2d_bwd_weight", s["img"], dy1, self.c0, grp, E, R, dsn["conv_layers.0"], a.gaddr("conv_layers.0.bias"), 32 * 9, n)
+        if d_img is not None:
+            L.call("es_conv2d_bwd_data", dy1, sn["conv_layers.0"][0], 32 * 9, self.c0, grp, E, R, d_img, int(accumulate))
+        if want_w:
+            for name in self.SN:
+                O, I = self.dims[name]
+                wsn, sig, uu, vu = sn[name]
+                L.call("es_spectral_norm_bwd", dsn[name], wsn, uu, vu, sig, O * I, E, O, I, a.gaddr(name + ".weight_orig"), n)
+
+
+# =====================================================================================================================
+# auxiliary regressor (proton): fp32 NCHW, residual feature extractor + MLP head
+# =====================================================================================================================
+class AuxEngineProton:
+    FE = "feature_extractor"
+
+    def __init__(self, arena: Arena):
+        self.a = arena
+        self.c1 = conv2d(1, 56, 30, 32, 5, 5, 2, 1)                     # -> [32,27,14]
+        # after MaxPool(k2,s1): [32,26,13]
+        self.blocks = []
+        H, W, Ci = 26, 13, 32
+        for blk, Co in (("res1", 32), ("res2", 64)):
+            ca = conv2d(Ci, H, W, Co, 5, 5, 2, 2)
+            cb = conv2d(Co, ca.Ho, ca.Wo, Co, 5, 5, 1, 2)
+            cd = conv2d(Ci, H, W, Co, 1, 1, 2, 0)
+            self.blocks.append((blk, ca, cb, cd, Co))
+            H, W, Ci = ca.Ho - 1, ca.Wo - 1, Co                         # MaxPool(k2,s1)
+        self.Hf, self.Wf = H, W                                         # [64,5,2]
+
+    # -- small wrappers ------------------------------------------------------------------------------------------
+    def _conv(self, x, name, g, grp, R):
+        a = self.a
+        y = empty(R, g.Co, g.Ho, g.Wo)
+        L.call("es_conv2d_fwd", x, a.addr(name + ".weight"), a.addr(name + ".bias"), a.n, a.n, g, grp, a.E, R, y)
+        return y
+
+    def _gn(self, x, name, C, HW, groups, act, grp, R):
+        a = self.a
+        y, st = empty(*x.shape), empty(R, groups, 2)
+        L.call("es_groupnorm_fwd", x, a.addr(name + ".weight"), a.addr(name + ".bias"), a.n, C, HW, groups, act, grp, a.E, R, y, st)
+        return y, st
+
+    def _pool(self, x, C, H, W, R):
+        y, idx = empty(R, C, H - 1, W - 1), empty(R, C, H - 1, W - 1, dtype=torch.uint8)
+        L.call("es_maxpool_fwd", x, C, H, W, 2, 2, 1, 1, R, y, idx)
+        return y, idx
+
+    def _conv_bwd(self, x, dy, name, g, grp, R, dx, accumulate, want_dx=True):
+        a = self.a
+        L.call("es_conv2d_bwd_weight", x, dy, g, grp, a.E, R, a.gaddr(name + ".weight"), a.gaddr(name + ".bias"), a.n, a.n)
+        if want_dx:
+            L.call("es_conv2d_bwd_data", dy, a.addr(name + ".weight"), a.n, g, grp, a.E, R, dx, int(accumulate))
+
+    def _gn_bwd(self, dy, x, st, name, C, HW, groups, act, grp, R):
+        a = self.a
+        dx = zeros(*x.shape)
+        L.call("es_groupnorm_bwd", dy, x, st, a.addr(name + ".weight"), a.addr(name + ".bias"), a.n, C, HW, groups, act, grp, a.E, R,
+               dx, a.gaddr(name + ".weight"), a.gaddr(name + ".bias"))
+        return dx
+
+    # -- forward / backward -----------------------------------------------------------------------------------------
+    def forward(self, img, grp, R, training, masks=None):
+        """img [R, 1680] -> coords [R,2].  masks = (keep128 [R,128], keep64 [R,64]) in training mode."""
+        a, E, fe = self.a, self.a.E, self.FE
+        s = {"img": img, "R": R, "grp": grp, "training": training, "masks": masks}
+        c = self._conv(img, f"{fe}.conv1.0", self.c1, grp, R)
+        n1, st = self._gn(c, f"{fe}.conv1.1", 32, 27 * 14, 8, ACT_RELU, grp, R)
+        x, idx = self._pool(n1, 32, 27, 14, R)
+        s.update(c1=c, st1=st, i1=idx)
+        for blk, ca, cb, cd, Co in self.blocks:
+            p = f"{fe}.{blk}"
+            HW = ca.Ho * ca.Wo
+            ya = self._conv(x, f"{p}.conv1.0", ca, grp, R)
+            na, sta = self._gn(ya, f"{p}.conv1.1", Co, HW, 32, ACT_RELU, grp, R)
+            yb = self._conv(na, f"{p}.conv2.0", cb, grp, R)
+            nb, stb = self._gn(yb, f"{p}.conv2.1", Co, HW, 32, ACT_NONE, grp, R)
+            yd = self._conv(x, f"{p}.downsample.0", cd, grp, R)
+            nd, std_ = self._gn(yd, f"{p}.downsample.1", Co, HW, 32, ACT_NONE, grp, R)
+            r = empty(R, Co, ca.Ho, ca.Wo)
+            L.call("es_add_relu_fwd", nb, nd, r.numel(), r)
+            xo, idx = self._pool(r, Co, ca.Ho, ca.Wo, R)
+            s[blk] = dict(x=x, ya=ya, sta=sta, na=na, yb=yb, stb=stb, yd=yd, std=std_, r=r, idx=idx)
+            x = xo
+        feat = empty(R, 64)
+        L.call("es_gap_fwd", x, 64, self.Hf * self.Wf, R, feat)
+        n = a.n
+        m1 = empty(R, 128)
+        L.call("es_linear_fwd", feat, 64, a.addr("regressor.0.weight"), a.addr("regressor.0.bias"), n, n, 64, 128, grp, E, R, m1)
+        h1, s["s1"] = empty(R, 128), empty(R, 2)
+        L.call("es_layernorm_fwd", m1, a.addr("regressor.1.weight"), a.addr("regressor.1.bias"), n, 128, ACT_LRELU, grp, E, R, h1, s["s1"])
+        h1d = h1
+        if training:
+            h1d = empty(R, 128)
+            L.call("es_dropout", h1, masks[0], 0.3, R * 128, h1d)
+        m2 = empty(R, 64)
+        L.call("es_linear_fwd", h1d, 128, a.addr("regressor.4.weight"), a.addr("regressor.4.bias"), n, n, 128, 64, grp, E, R, m2)
+        h2, s["s2"] = empty(R, 64), empty(R, 2)
+        L.call("es_layernorm_fwd", m2, a.addr("regressor.5.weight"), a.addr("regressor.5.bias"), n, 64, ACT_LRELU, grp, E, R, h2, s["s2"])
+        h2d = h2
+        if training:
+            h2d = empty(R, 64)
+            L.call("es_dropout", h2, masks[1], 0.3, R * 64, h2d)
+        coords = zeros(R, 2)
+        L.call("es_linear_fwd", h2d, 64, a.addr("regressor.8.weight"), a.addr("regressor.8.bias"), n, n, 64, 2, grp, E, R, coords)
+        s.update(feat=feat, m1=m1, h1d=h1d, m2=m2, h2d=h2d)
+        return coords, s
+
+    def backward(self, s, d_coords, d_img, accumulate=True):
+        """Parameter gradients -> arena G; image gradient accumulated into d_img [R,1680]."""
+        a, E, n, R, grp, fe = self.a, self.a.E, self.a.n, s["R"], s["grp"], self.FE
+        masks, training = s["masks"], s["training"]
+
+        def lin_bwd(x, ldx, dy, name, I, O, need_dx=True):
+            L.call("es_linear_bwd_weight", x, ldx, dy, I, O, grp, E, R, a.gaddr(name + ".weight"), a.gaddr(name + ".bias"), n, n)
+            if not need_dx:
+                return None
+            dx = zeros(R, I)
+            L.call("es_linear_bwd_data", dy, a.addr(name + ".weight"), n, I, O, grp, E, R, dx, I)
+            return dx
+
+        d = lin_bwd(s["h2d"], 64, d_coords, "regressor.8", 64, 2)
+        if training:
+            L.call("es_dropout", d, masks[1], 0.3, R * 64, d)
+        dm2 = zeros(R, 64)
+        L.call("es_layernorm_bwd", d, s["m2"], s["s2"], a.addr("regressor.5.weight"), a.addr("regressor.5.bias"), n, 64, ACT_LRELU, grp, E, R,
+               dm2, a.gaddr("regressor.5.weight"), a.gaddr("regressor.5.bias"))
+        d = lin_bwd(s["h1d"], 128, dm2, "regressor.4", 128, 64)
+        if training:
+            L.call("es_dropout", d, masks[0], 0.3, R * 128, d)
+        dm1 = zeros(R, 128)
+        L.call("es_layernorm_bwd", d, s["m1"], s["s1"], a.addr("regressor.1.weight"), a.addr("regressor.1.bias"), n, 128, ACT_LRELU, grp, E, R,
+               dm1, a.gaddr("regressor.1.weight"), a.gaddr("regressor.1.bias"))
+        dfeat = lin_bwd(s["feat"], 64, dm1, "regressor.0", 64, 128)
+        dx = empty(R, 64, self.Hf, self.Wf)
+        L.call("es_gap_bwd", dfeat, 64, self.Hf * self.Wf, R, dx)
+        for blk, ca, cb, cd, Co in reversed(self.blocks):
+            p, b = f"{fe}.{blk}", s[blk]
+            HW = ca.Ho * ca.Wo
+            dr = empty(R, Co, ca.Ho, ca.Wo)
+            L.call("es_maxpool_bwd", dx, b["idx"], Co, ca.Ho, ca.Wo, 2, 2, 1, 1, R, dr)
+            dsum = empty(*dr.shape)
+            L.call("es_relu_bwd", dr, b["r"], dr.numel(), dsum)
+            dyb = self._gn_bwd(dsum, b["yb"], b["stb"], f"{p}.conv2.1", Co, HW, 32, ACT_NONE, grp, R)
+            dna = zeros(R, Co, ca.Ho, ca.Wo)
+            self._conv_bwd(b["na"], dyb, f"{p}.conv2.0", cb, grp, R, dna, False)
+            dya = self._gn_bwd(dna, b["ya"], b["sta"], f"{p}.conv1.1", Co, HW, 32, ACT_RELU, grp, R)
+            dxin = zeros(*b["x"].shape)
+            self._conv_bwd(b["x"], dya, f"{p}.conv1.0", ca, grp, R, dxin, False)
+            dyd = self._gn_bwd(dsum, b["yd"], b["std"], f"{p}.downsample.1", Co, HW, 32, ACT_NONE, grp, R)
+            self._conv_bwd(b["x"], dyd, f"{p}.downsample.0", cd, grp, R, dxin, True)
+            dx = dxin
+        dn1 = empty(R, 32, 27, 14)
+        L.call("es_maxpool_bwd", dx, s["i1"], 32, 27, 14, 2, 2, 1, 1, R, dn1)
+        dc1 = self._gn_bwd(dn1, s["c1"], s["st1"], f"{fe}.conv1.1", 32, 27 * 14, 8, ACT_RELU, grp, R)
+        self._conv_bwd(s["img"], dc1, f"{fe}.conv1.0", self.c1, grp, R, d_img, accumulate)
+
+
+# =====================================================================================================================
+def engine_for(arena: Arena, arch: str, kind: str):
+    """The compute engine bound to ``arena`` (created on first use).  Generator engines keep bf16 kernel-layout
+    copies of the weights and are re-packed whenever ``arena.version`` moved (optimizer step, load_state_dict)."""
+    if arena.device.type != "cuda":
+        raise RuntimeError("expertsim (B200) computes on CUDA only; there is no CPU fallback")
+    if arena.engine is None:
+        if kind == "discriminator":
+            arena.engine = DiscEngine(arena, arch)
+        elif (arch, kind) == ("proton", "generator"):
+            arena.engine = GenEngineProton(arena)
+        elif (arch, kind) == ("proton", "aux_reg"):
+            arena.engine = AuxEngineProton(arena)
+        else:
+            raise NotImplementedError(f"no sm_100a engine for {arch}.{kind} yet")
+    eng = arena.engine
+    if hasattr(eng, "repack") and getattr(eng, "packed_version", -1) != arena.version:
+        eng.repack()
+        eng.packed_version = arena.version
+    return eng

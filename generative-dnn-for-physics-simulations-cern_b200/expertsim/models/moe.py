@@ -1,0 +1,387 @@
+"""MoE wrapper: the training step and batch inference of the Mixture-of-Experts conditional GAN.
+
+Drop-in for ``MoEWrapper`` (expertsim/models/moe.py:14-699 of the reference): same constructor, same
+``train_step`` / ``evaluate`` signatures, same metric keys, ``.generators/.discriminators/.aux_regs`` module lists and
+``.router``.  The arithmetic is NOT PyTorch: every numeric step is a grouped sm_100a kernel called through the C-ABI
+(include/expertsim_b200.h).  Where the reference loops ``for i in range(n_experts)`` over eager modules with two
+device->host syncs per expert (moe.py:121,522,562), this step is sync-free: the router kernel emits a stable
+token->expert permutation and device-side group tables, every layer runs ONCE for all experts (ragged groups), and
+the only thing that depends on the routing outcome lives on the device.
+
+Phase order inside a step (experts are independent, so the reference's per-expert D-step/G-step sequence can be
+regrouped across experts without changing any result; SURVEY.md §7 "serial semantics"):
+    route -> G(z1),G(z2) [one two-pass launch per layer] -> D(real),D(fake1) -> hinge -> D backward -> Adam(D)
+          -> D'(fake1),D'(fake2) with the UPDATED D -> aux(fake1) -> loss tails -> D'/aux backward to the images
+          -> G backward -> Adam(G), Adam(aux) -> router loss backward -> Adam(router)
+Spectral-norm power iterations advance once per D forward (4x per step), exactly like the reference's hook.
+
+Data parallelism (new; the reference is single-device): ``enable_data_parallel()`` makes every loss normaliser a
+GLOBAL-batch quantity (per-expert partial sums are all-reduced before the gradient kernels run) and sum-all-reduces
+the gradient arenas over NCCL before each fused Adam, which reproduces the single-GPU global-batch step.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .._arena import Arena
+from .._nets import engine_for
+
+IMAGE_SHAPE = {"proton": (56, 30), "neutron": (44, 44)}
+
+
+def _f(v, default=0.0):
+    return default if v is None else float(v)
+
+
+class MoEWrapper(nn.Module):
+    def __init__(self, generator, discriminator, aux_reg, router, n_experts, cfg, image_shape):
+        super().__init__()
+        self.cfg = cfg
+        self.n_experts = int(n_experts)
+        self.noise_dim = cfg.model.noise_dim
+        self.image_shape = tuple(image_shape)
+        self.arch = generator.ARCH
+        if self.image_shape != IMAGE_SHAPE[self.arch]:
+            raise ValueError(f"{self.arch} generator produces {IMAGE_SHAPE[self.arch]} images, config says {self.image_shape}")
+        # identical initial weights in every expert, as the reference's deepcopy (moe.py:29-31)
+        self.generators = nn.ModuleList([copy.deepcopy(generator) for _ in range(self.n_experts)])
+        self.discriminators = nn.ModuleList([copy.deepcopy(discriminator) for _ in range(self.n_experts)])
+        self.aux_regs = nn.ModuleList([copy.deepcopy(aux_reg) for _ in range(self.n_experts)])
+        self.router = router
+        self.g_steps = [0] * self.n_experts   # never advanced by the reference either (moe.py:37-38)
+        self.d_steps = [0] * self.n_experts
+        self._dp = None
+        self._arenas: Dict[str, Arena] = {}
+        self._bind()
+        ids = {id(p) for g in self.generators for p in g.parameters()}
+        assert len(ids) == sum(1 for g in self.generators for _ in g.parameters()), "experts must not share parameters"
+
+    # ------------------------------------------------------------------------------------------------ storage
+    def _bind(self):
+        """(Re)build the shared arenas: expert e of each network kind becomes slot e of one flat [E, n] tensor."""
+        dev = next(self.router.parameters()).device
+        self._arenas = {}
+        for key, mods in (("g", self.generators), ("d", self.discriminators), ("a", self.aux_regs), ("r", [self.router])):
+            arena = Arena(mods[0]._spec, len(mods), dev)
+            for e, m in enumerate(mods):
+                arena.adopt(m, e)
+            self._arenas[key] = arena
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        # .to()/.cuda()/.float() re-create the parameter storages: re-adopt them so experts stay slots of one arena
+        if self._arenas and not all(a.owns(a.modules[0]) for a in self._arenas.values()):
+            self._bind()
+        return self
+
+    def mark_weights_changed(self):
+        """Call after writing to parameters outside load_state_dict / the fused optimizers (bf16 copies are re-packed)."""
+        for a in self._arenas.values():
+            a.version += 1
+
+    def arena(self, key: str) -> Arena:
+        return self._arenas[key]
+
+    def _engines(self):
+        a = self._arenas
+        for arena in a.values():
+            if not arena.owns(arena.modules[0]):
+                self._bind()
+                a = self._arenas
+                break
+        return (engine_for(a["g"], self.arch, "generator"), engine_for(a["d"], self.arch, "discriminator"),
+                engine_for(a["a"], self.arch, "aux_reg"))
+
+    # ------------------------------------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, process_group=None):
+        """Shard the batch over the ranks of ``process_group`` (default: the world).  Each rank calls train_step with
+        ITS rows; gradients and loss normalisers are reduced so the update equals the single-device global-batch one."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dp = (dist, process_group, dist.get_world_size(process_group))
+        # identical replicas: broadcast rank 0's parameters and buffers
+        for arena in self._arenas.values():
+            dist.broadcast(arena.P, 0, group=process_group)
+            dist.broadcast(arena.Bf, 0, group=process_group)
+            arena.version += 1
+        return self
+
+    @property
+    def world_size(self):
+        return self._dp[2] if self._dp else 1
+
+    def _allreduce(self, t):
+        if self._dp:
+            dist, pg, _ = self._dp
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg)
+        return t
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _route(self, cond, gumbel, tau, min_rows):
+        """Router forward + stable partition.  Returns the router activations and the device-side tables."""
+        E, B, dev = self.n_experts, cond.shape[0], cond.device
+        r = self.router.raw_forward(cond, gumbel, tau)
+        nblk = (B + 255) // 256
+        r["counts"] = torch.empty(E, dtype=torch.int32, device=dev)
+        r["offsets"] = torch.empty(E + 1, dtype=torch.int32, device=dev)
+        r["perm"] = torch.empty(B, dtype=torch.int32, device=dev)
+        r["grp_half"] = torch.empty(E, 4, dtype=torch.int32, device=dev)
+        r["grp_gen"] = torch.empty(E, 4, dtype=torch.int32, device=dev)
+        scratch = torch.empty(nblk * E + E, dtype=torch.int32, device=dev)
+        L.call("es_router_partition", r["idx"], B, E, min_rows, r["hist"], r["counts"], r["offsets"], r["perm"],
+               r["grp_half"], r["grp_gen"], scratch)
+        return r
+
+    @staticmethod
+    def _gather(x, perm, width):
+        B = perm.shape[0]
+        out = torch.empty(B, width, device=x.device)
+        L.call("es_gather_rows", x, perm, B, width, out)
+        return out
+
+    @staticmethod
+    def _adam(arena: Arena, lr, grp):
+        L.call("es_adam_step", arena.P, arena.G, arena.M, arena.V, arena.n, arena.n, arena.E, float(lr), 0.9, 0.999, 1e-8,
+               arena.steps, grp)
+        arena.version += 1
+
+    @staticmethod
+    def _lr(opt, default):
+        if opt is None:
+            return default
+        if isinstance(opt, (list, tuple)):
+            opt = opt[0]
+        return float(opt.param_groups[0]["lr"])
+
+    def _tau(self, epoch):
+        rc = self.cfg.model.router
+        return max(float(rc.tau_min), float(rc.tau_start) * (float(rc.tau_decay) ** epoch))  # moe.py:62-74
+
+    # ------------------------------------------------------------------------------------------------ train step
+    def train_step(self, epoch, cond, real_images, true_positions, std, intensity, aux_reg_optimizers=None,
+                   generator_optimizers=None, discriminator_optimizers=None, router_optimizer=None, ema_helper=None,
+                   device=None, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """One optimisation step on a batch (reference moe.py:52-504).  ``noise`` (optional) injects every random draw,
+        indexed by ORIGINAL sample: 'gumbel' [B,E], 'z1','z2' [B,noise_dim] and, per network, dropout keep-masks — the
+        parity harness uses it; by default the draws come from torch's CUDA generator.  Learning rates are read from the
+        optimizers (``param_groups[0]['lr']``); the update itself is the fused multi-tensor Adam over the arenas.
+        Returns the reference's metric dict; values are 0-dim DEVICE tensors (no host sync inside the step)."""
+        gen, disc, aux = self._engines()
+        cfgm = self.cfg.model
+        rc = cfgm.router
+        E, B = self.n_experts, cond.shape[0]
+        H, W = self.image_shape
+        HW = H * W
+        dev = cond.device
+        world = self.world_size
+        Bg = B * world
+        a_g, a_d, a_a, a_r = (self._arenas[k] for k in "gdar")
+        f32 = lambda t, w: t.to(dev, torch.float32).reshape(B, w).contiguous()
+        cond = f32(cond, 9)
+        noise = noise or {}
+        gumbel = noise["gumbel"].to(dev).float().contiguous() if "gumbel" in noise else \
+            -torch.empty(B, E, device=dev).exponential_().log()
+        tau = self._tau(epoch)
+
+        # ---- K1: gating + stable partition (moe.py:76-77,97-103,123-126); the skip rule B_e<=1 is min_rows=2
+        r = self._route(cond, gumbel, tau, 2 if world == 1 else 1)
+        perm, gh, gg = r["perm"], r["grp_half"], r["grp_gen"]
+        counts_g = r["counts"].to(torch.float32)
+        if world > 1:   # skip rule and every mean use the GLOBAL per-expert count
+            self._allreduce(counts_g)
+            dead = (counts_g < 2).to(torch.int32)
+            gh[:, 1] *= 1 - dead
+            gh[:, 3] *= 1 - dead
+            gg[:, 1] *= 1 - dead
+            gg[:, 3] *= 1 - dead
+
+        # ---- expert-sorted views of the batch (cond[mask], real[mask], ...; moe.py:143,150,165-168)
+        cond_s = self._gather(cond, perm, 9)
+        real_s = self._gather(f32(real_images, HW), perm, HW)
+        pos_s = self._gather(f32(true_positions, 2), perm, 2)
+        std_s = self._gather(f32(std, 1), perm, 1)
+        int_s = self._gather(f32(intensity, 1), perm, 1)
+        if "z1" in noise:
+            z1 = self._gather(f32(noise["z1"], 10), perm, 10)
+            z2 = self._gather(f32(noise["z2"], 10), perm, 10)
+        else:   # i.i.d. rows: drawing directly in sorted order is the same distribution as randn(B_e, 10) per expert
+            z1, z2 = torch.randn(B, 10, device=dev), torch.randn(B, 10, device=dev)
+        drop = self._dropout_masks(noise, perm, B, dev)
+
+        # ---- G(z1) and G(z2): one two-pass batch of 2B rows (moe.py:143-145,535-538)
+        img1, img2, sg = gen.forward(z1, z2, cond_s, gg, 2 * B, True, training=self.training, drop=drop.get("g"))
+
+        # ---- discriminator step (moe.py:506-527)
+        sn_a = disc.spectral(gh, self.training)
+        s_real, _, sv_real = disc.forward(real_s, cond_s, gh, B, sn_a)
+        sn_b = disc.spectral(gh, self.training)
+        s_fake, _, sv_fake = disc.forward(img1, cond_s, gh, B, sn_b)
+        d_real, d_fake = torch.zeros(B, device=dev), torch.zeros(B, device=dev)
+        loss_d = torch.zeros(E, device=dev)
+        L.call("es_hinge_d", s_real, s_fake, gh, E, counts_g, Bg, d_real, d_fake, loss_d)
+        a_d.G.zero_()
+        disc.backward(sv_real, sn_a, d_real, None, want_w=True)
+        disc.backward(sv_fake, sn_b, d_fake, None, want_w=True)
+        self._allreduce(a_d.G)
+        self._adam(a_d, self._lr(discriminator_optimizers, cfgm.discriminator.lr_d), gh)
+        del sv_real, sv_fake
+
+        # ---- generator step (moe.py:529-571): D carries its UPDATED weights
+        sn_c = disc.spectral(gh, self.training)
+        score1, lat1, sv1 = disc.forward(img1, cond_s, gh, B, sn_c)
+        sn_d = disc.spectral(gh, self.training)
+        _, lat2, sv2 = disc.forward(img2, cond_s, gh, B, sn_d)
+        coords, sv_a = aux.forward(img1, gh, B, self.training, drop.get("a"))
+        sums = torch.zeros(E, 8, dtype=torch.float64, device=dev)
+        s_out, div_out = torch.zeros(B, device=dev), torch.zeros(B, device=dev)
+        L.call("es_gen_loss_reduce", img1, HW, lat1, lat2, z1, z2, std_s, int_s, coords, pos_s, score1, gh, E, B,
+               s_out, div_out, sums)
+        self._allreduce(sums)
+        d_score1, d_coords = torch.zeros(B, device=dev), torch.zeros(B, 2, device=dev)
+        d_lat1, d_lat2 = torch.zeros(B, 64, device=dev), torch.zeros(B, 64, device=dev)
+        d_img1, d_img2 = torch.zeros(B, HW, device=dev), torch.zeros(B, HW, device=dev)
+        losses = torch.zeros(E, 6, device=dev)
+        gcfg, stren_a = cfgm.generator, float(cfgm.aux_reg.strength)
+        L.call("es_gen_loss_grads", img1, HW, lat1, lat2, z1, z2, std_s, int_s, coords, pos_s, s_out, div_out, gh, E, B,
+               sums, Bg, float(gcfg.di_strength), float(gcfg.in_strength), stren_a, d_score1, d_lat1, d_lat2, d_coords,
+               d_img1, losses)
+        disc.backward(sv1, sn_c, d_score1, d_lat1, want_w=False, d_img=d_img1, accumulate=True)
+        disc.backward(sv2, sn_d, torch.zeros(B, device=dev), d_lat2, want_w=False, d_img=d_img2, accumulate=False)
+        a_a.G.zero_()
+        aux.backward(sv_a, d_coords, d_img1, accumulate=True)
+        a_g.G.zero_()
+        gen.backward(sg, d_img1, d_img2)
+        del sg, sv1, sv2, sv_a
+        self._allreduce(a_g.G)
+        self._allreduce(a_a.G)
+        self._adam(a_g, self._lr(generator_optimizers, gcfg.lr_g), gh)
+        self._adam(a_a, self._lr(aux_reg_optimizers, cfgm.aux_reg.lr_a), gh)
+
+        # ---- router loss (moe.py:213-449) and metrics
+        zero = torch.zeros((), device=dev)
+        gen_losses, mean_int = losses[:, 0], losses[:, 5]
+        if world > 1:
+            self._allreduce(loss_d)
+        if E > 1:
+            gan = gen_losses.mean() * float(rc.gan_strength)
+            gate_sums = torch.empty(E, device=dev)
+            L.call("es_router_gate_sums", r["gates"], B, E, gate_sums)
+            self._allreduce(gate_sums)
+            extra, ed = None, zero
+            if _f(rc.ed_strength) != 0:
+                if world > 1:
+                    raise NotImplementedError("ed_strength couples all sample pairs of the global batch; not sharded")
+                m = torch.zeros(B, 1, device=dev)
+                L.call("es_scatter_rows", s_out, perm, B, 1, m)       # moe.py:197-198
+                extra, edl = torch.zeros(B, E, device=dev), torch.zeros(1, device=dev)
+                L.call("es_router_ed_loss", r["idx"], m, B, E, float(rc.ed_strength), extra, edl)
+                ed = edl[0]
+            ds = _f(rc.diff_strength)
+            if ds != 0:   # -sum_{i<j} |mean_i - mean_j| * diff_strength^2 on detached scalars (moe.py:395-405)
+                diff = -(mean_int[:, None] - mean_int[None, :]).abs().triu(1).sum() * (ds * ds)
+            else:
+                diff = zero
+            alpha = min(max(epoch / float(rc.alpha), 0.0), 1.0)
+            dec_w = float(rc.min_weight) + (1.0 - float(rc.min_weight)) * alpha            # moe.py:412-422
+            lr_out = torch.zeros(2, device=dev)
+            a_r.G.zero_()
+            w = lambda n: a_r.addr(f"fc_layers.{n}.weight")
+            gw = [a_r.gaddr(f"fc_layers.{n}.{p}") for n in (0, 2, 4, 6) for p in ("weight", "bias")]
+            L.call("es_router_bwd", cond, B, E, Bg, w(2), w(4), w(6), r["gates"], r["h1"], r["h2"], r["h3"], gate_sums, tau,
+                   _f(rc.alb_strength), dec_w, _f(rc.util_strength), extra, *gw, lr_out)
+            alb, ent = lr_out[0], lr_out[1]
+            stop = rc.stop_router_training_epoch
+            if stop is None or epoch < stop:
+                router_loss = ed + gan + diff + ent + dec_w * alb
+                self._allreduce(a_r.G)
+                self._adam(a_r, self._lr(router_optimizer, rc.lr_r), None)
+            else:
+                router_loss = zero
+        else:
+            gan = router_loss = ed = diff = ent = alb = zero
+
+        m = {"gen_loss": gen_losses.mean(), "disc_loss": loss_d.mean(), "div_loss": losses[:, 1].sum() / E,
+             "intensity_loss": losses[:, 2].sum() / E, "aux_reg_loss": losses[:, 3].sum() / E, "router_loss": router_loss,
+             "expert_distribution_loss": ed, "differentiation_loss": diff, "expert_entropy_loss": ent,
+             "adaptive_load_balancing_loss": alb, "gan_loss": gan}
+        for i in range(E):
+            m.update({f"gen_loss_{i}": losses[i, 0], f"disc_loss_{i}": loss_d[i], f"div_loss_experts_{i}": losses[i, 1],
+                      f"intensity_loss_experts_{i}": losses[i, 2], f"aux_reg_loss_experts_{i}": losses[i, 3],
+                      f"std_intensities_experts_{i}": losses[i, 4], f"mean_intensities_experts_{i}": losses[i, 5],
+                      f"n_choosen_experts_mean_epoch_{i}": counts_g[i]})
+        self._last = {"idx": r["idx"], "counts": r["counts"], "perm": perm, "img1": img1, "img2": img2, "gates": r["gates"],
+                      "logits": r["logits"]}
+        return m
+
+    def _dropout_masks(self, noise, perm, B, dev):
+        """keep-masks of every nn.Dropout on the path, in expert-sorted order.  Proton: the aux-regressor head
+        (proton/aux_reg.py:25,29; p=0.3)."""
+        if not self.training:
+            return {}
+        if self.arch == "proton":
+            if "drop.a.regressor.3" in noise:
+                g = lambda k, w: self._gather(noise[k].to(dev).float().reshape(B, w).contiguous(), perm, w)
+                return {"a": (g("drop.a.regressor.3", 128), g("drop.a.regressor.7", 64))}
+            return {"a": ((torch.rand(B, 128, device=dev) >= 0.3).float(), (torch.rand(B, 64, device=dev) >= 0.3).float())}
+        raise NotImplementedError("neutron training path")
+
+    # ------------------------------------------------------------------------------------------------ inference
+    @torch.no_grad()
+    def generate(self, cond, noise=None, gumbel=None, out_dtype=torch.float32, to_host=False, chunk=16384,
+                 return_routing=False):
+        """Batch inference (reference moe.py:650-653 routing + train/utils.py:179-205 generation): router with Gumbel
+        noise at tau=1 -> arg-max expert -> every expert's generator in eval mode on its samples -> expm1, returned in
+        the ORIGINAL sample order as [N,H,W] (float32, or float64 like the reference's numpy result)."""
+        gen, _, _ = self._engines()
+        E, N = self.n_experts, cond.shape[0]
+        H, W = self.image_shape
+        dev = next(self.router.parameters()).device
+        outs, idxs = [], []
+        for s in range(0, N, chunk):
+            c = cond[s:s + chunk].to(dev, torch.float32, non_blocking=True).contiguous()
+            B = c.shape[0]
+            gmb = gumbel[s:s + chunk].to(dev).float().contiguous() if gumbel is not None else \
+                -torch.empty(B, E, device=dev).exponential_().log()
+            r = self._route(c, gmb, 1.0, 1)
+            z = noise[s:s + chunk].to(dev).float().contiguous() if noise is not None else torch.randn(B, 10, device=dev)
+            cs = self._gather(c, r["perm"], 9)
+            zs = self._gather(z, r["perm"], 10)
+            img, _, _ = gen.forward(zs, None, cs, r["grp_half"], B, False, keep=False, training=False)
+            o64 = torch.empty(B, H, W, dtype=torch.float64, device=dev) if out_dtype == torch.float64 else None
+            o32 = torch.empty(B, H, W, device=dev) if o64 is None else None
+            L.call("es_expm1_scatter", img, r["perm"], B, H * W, o64, o32)
+            o = o64 if o64 is not None else o32
+            outs.append(o.cpu() if to_host else o)
+            idxs.append(r["idx"])
+        out = outs[0] if len(outs) == 1 else torch.cat(outs)
+        return (out, torch.cat(idxs)) if return_routing else out
+
+    @torch.no_grad()
+    def evaluate(self, epoch, y_test, x_test, true_positions, std, intensity, cfg, device):
+        """Wasserstein metric of the reference (moe.py:644-692): 5 channel sums of real vs generated showers, overall and
+        per routed expert, repeated min(epoch//5+1, 5) times."""
+        from ..train.utils import calculate_joint_ws_across_experts, sum_channels_parallel
+        x_np = np.asarray(x_test.cpu() if isinstance(x_test, torch.Tensor) else x_test)
+        ch_org = np.array(list(sum_channels_parallel(np.expm1(x_np).reshape(-1, *self.image_shape))))
+        soft_gates, _ = self.router(y_test)
+        predicted = soft_gates.argmax(1).cpu().numpy()
+        idx_e = [np.where(predicted == i)[0] for i in range(self.n_experts)]
+        ch_org_e = [ch_org[ix] if len(ix) else np.zeros((0, 5)) for ix in idx_e]
+        y_e = [y_test[torch.as_tensor(ix, device=y_test.device)] for ix in idx_e]
+        ws_mean, ws_std, ws_mean_exp, ws_std_exp = calculate_joint_ws_across_experts(
+            min(epoch // 5 + 1, 5), [x_np[ix] for ix in idx_e], y_e, self.generators, ch_org, ch_org_e, self.noise_dim,
+            device, n_experts=self.n_experts, shape_images=self.image_shape)
+        log = {"ws_mean": ws_mean, "ws_std": ws_std, "epoch": epoch}
+        for i in range(self.n_experts):
+            log[f"ws_mean_{i}"], log[f"ws_std_{i}"] = ws_mean_exp[i], ws_std_exp[i]
+        return log
+
+    def get_expert_assignment_counts(self, expert_assignments: torch.Tensor) -> torch.Tensor:
+        return torch.bincount(expert_assignments, minlength=self.n_experts).float() / expert_assignments.size(0)

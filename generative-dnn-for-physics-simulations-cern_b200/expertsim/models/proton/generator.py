@@ -1,0 +1,30 @@
+"""Proton ZDC generator (56x30).  Drop-in for expertsim/models/proton/generator.py:5-52 of the reference: same
+constructor, same state_dict keys/shapes; forward runs the grouped bf16 tcgen05 kernels (eval semantics, no autograd)."""
+import torch
+
+from ..._nets import engine_for
+from .._base import ArenaModule, one_group
+
+
+class Generator(ArenaModule):
+    ARCH, KIND = "proton", "generator"
+    IMAGE_SHAPE = (56, 30)
+
+    def __init__(self, noise_dim, cond_dim, di_strength, in_strength, **kwargs):
+        super().__init__()
+        self.name = "Generator-v5-bigkernel-res56x30"
+        self.di_strength = di_strength
+        self.in_strength = in_strength
+        if (noise_dim, cond_dim) != (10, 9):
+            raise ValueError("the sm_100a generator head is specialised for noise_dim=10, cond_dim=9")
+        self._init_params(dict(noise_dim=noise_dim, cond_dim=cond_dim, di_strength=di_strength, in_strength=in_strength),
+                          noise_dim=noise_dim, cond_dim=cond_dim)
+
+    @torch.no_grad()
+    def forward(self, noise, cond):
+        arena = self._home()
+        eng = engine_for(arena, self.ARCH, self.KIND)
+        R = noise.shape[0]
+        grp = one_group(R, self._slot, noise.device)
+        img, _, _ = eng.forward(noise.float().contiguous(), None, cond.float().contiguous(), grp, R, False, keep=False)
+        return img.view(R, 1, *self.IMAGE_SHAPE)

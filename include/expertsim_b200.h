@@ -201,14 +201,14 @@ int es_ln_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, int C, co
  * results are written at row_map[f] (reference NCHW feature order) when row_map is given */
 int es_ln_affine_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, int C, const void* x, const void* dx,
                      const float* stats, const float* gamma, const float* beta, long slot_stride,
-                     const es_group* grp, int n_groups, int total_rows, const int32_t* row_map,
+                     const es_group* grp, int n_groups, int total_rows, const int32_t* row_map, long out_slot_stride,
                      float* dgamma, float* dbeta, float* dbias_lin, void* stream);
 
 /* last generator layer: Conv2d(64->1, k2, pad 1) + ReLU (proton/generator.py:42-43) on CUDA cores.
  * x bf16 [rows,Hs,Ws,64] -> img fp32; in the two-pass batch the image row goes to img1 or img2 [half rows, Ho*Wo]. */
-int es_gen_out_fwd(const void* x, const float* w, const float* b, long slot_stride_w, int Hs, int Ws, int C, int KH, int KW, int pad,
+int es_gen_out_fwd(const void* x, const float* w, const float* b, long slot_stride_w, long slot_stride_b, int Hs, int Ws, int C, int KH, int KW, int pad,
                    const es_group* grp_gen, int E, int total_rows, int two_pass, float* img1, float* img2, void* stream);
-int es_gen_out_bwd(const void* x, const float* w, long slot_stride_w, int Hs, int Ws, int C, int KH, int KW, int pad,
+int es_gen_out_bwd(const void* x, const float* w, long slot_stride_w, long slot_stride_b, int Hs, int Ws, int C, int KH, int KW, int pad,
                    const float* img1, const float* img2, const float* dimg1, const float* dimg2,
                    const es_group* grp_gen, int E, int total_rows, int two_pass,
                    void* dx, float* dw, float* db, void* stream);

@@ -445,7 +445,7 @@ def test_ln_lrelu_fwd_bwd():
     rm = torch.randperm(F_, generator=g).to(torch.int32)
     dga, dbe, dbl = torch.zeros(2, F_, device=DEV), torch.zeros(2, F_, device=DEV), torch.zeros(2, F_, device=DEV)
     L.call("es_ln_affine_bwd", cuda(dy_up, BF), Hs, Ws, Hu, Wu, C, cuda(x, BF), dx, stats, cuda(ga), cuda(be), F_, grp, 2, R,
-           cuda(rm), dga, dbe, dbl)
+           cuda(rm), F_, dga, dbe, dbl)
     inv = torch.empty(F_, dtype=torch.long)
     inv[rm.long()] = torch.arange(F_)
     check("ln affine dgamma", dga[:, rm.long()], lg.grad, 3e-3)
@@ -465,7 +465,7 @@ def test_gen_out_fwd_bwd():
     w = torch.randn(E, 1, C, 2, 2, generator=g) / 16
     b = torch.randn(E, generator=g) * .1
     img1, img2 = torch.zeros(B, 56 * 30, device=DEV), torch.zeros(B, 56 * 30, device=DEV)
-    L.call("es_gen_out_fwd", cuda(nhwc(x), BF), cuda(w), cuda(b), C * 4, Hs, Ws, C, 2, 2, 1, gg, E, R, 1, img1, img2)
+    L.call("es_gen_out_fwd", cuda(nhwc(x), BF), cuda(w), cuda(b), C * 4, 1, Hs, Ws, C, 2, 2, 1, gg, E, R, 1, img1, img2)
     lx, lw, lb = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     d1, d2 = torch.randn(B, 1, 56, 30, generator=g), torch.randn(B, 1, 56, 30, generator=g)
     w1, w2 = torch.zeros(B, 1, 56, 30), torch.zeros(B, 1, 56, 30)
@@ -481,7 +481,7 @@ def test_gen_out_fwd_bwd():
     check("gen out conv fwd img2", img2, w2.reshape(B, -1), 1e-4)
     dx = torch.zeros(R, Hs * Ws, C, dtype=BF, device=DEV)
     dw, db = torch.zeros(E, 1, C, 2, 2, device=DEV), torch.zeros(E, device=DEV)
-    L.call("es_gen_out_bwd", cuda(nhwc(x), BF), cuda(w), C * 4, Hs, Ws, C, 2, 2, 1, img1, img2, cuda(d1.reshape(B, -1)),
+    L.call("es_gen_out_bwd", cuda(nhwc(x), BF), cuda(w), C * 4, 1, Hs, Ws, C, 2, 2, 1, img1, img2, cuda(d1.reshape(B, -1)),
            cuda(d2.reshape(B, -1)), gg, E, R, 1, dx, dw, db)
     check("gen out conv bwd dx", dx.float().reshape(R, Hs, Ws, C), nhwc(lx.grad), 5e-3)
     check("gen out conv bwd dw", dw, lw.grad, 1e-4)
