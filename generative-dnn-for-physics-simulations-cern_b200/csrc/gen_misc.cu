@@ -609,7 +609,7 @@ __global__ void permute_features_kernel(const float* __restrict__ in, long in_st
 
 // ----------------------------------------------------------------------------------------------- SIMT checkers
 __global__ void igemm_fwd_simt_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
-                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, es_conv_geom g,
+                                      const float* __restrict__ bias, long bias_stride, __nv_bfloat16* __restrict__ y, es_conv_geom g,
                                       const es_group* __restrict__ grp, int n_groups, long total) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -622,7 +622,7 @@ __global__ void igemm_fwd_simt_kernel(const __nv_bfloat16* __restrict__ x, const
   const int slot = grp[gi].slot;
   const long KK = (long)g.KH * g.KW * g.C;
   const float sy_sc = (float)g.Hs / (float)g.Hu, sx_sc = (float)g.Ws / (float)g.Wu;
-  float acc = bias ? bias[slot * g.N + n] : 0.f;
+  float acc = bias ? bias[slot * bias_stride + n] : 0.f;
   for (int ky = 0; ky < g.KH; ++ky)
     for (int kx = 0; kx < g.KW; ++kx) {
       const int uy = oy + ky - g.pad, ux = ox + kx - g.pad;
@@ -826,12 +826,12 @@ extern "C" int es_permute_features(const float* in, long in_stride, const int32_
   return ES_OK;
 }
 
-extern "C" int es_igemm_fwd_simt(const void* x, const void* w, const float* bias, void* y, const es_conv_geom* g,
-                                 const es_group* grp, int n_groups, int total_rows, void* stream) {
+extern "C" int es_igemm_fwd_simt(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
+                                 const es_conv_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
   ES_REQUIRE(x && w && y && g && grp && total_rows > 0, "bad arguments");
   const long total = (long)total_rows * g->Ho * g->Wo * g->N;
   igemm_fwd_simt_kernel<<<(unsigned)ceil_div_l(total, 256), 256, 0, as_stream(stream)>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)y, *g, grp, n_groups, total);
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, bias_slot_stride, (__nv_bfloat16*)y, *g, grp, n_groups, total);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }

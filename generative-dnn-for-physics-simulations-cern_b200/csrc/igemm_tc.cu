@@ -481,8 +481,8 @@ static int pick_bn(int n) { return n >= 256 ? 256 : n; }
 
 using namespace es;
 
-extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, void* y, const es_conv_geom* g,
-                            const es_group* grp, int n_groups, int total_rows, void* stream) {
+extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
+                            const es_conv_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
   ES_REQUIRE(x && w && y && grp, "null pointer");
   ES_REQUIRE(check_geom(g), "unsupported geometry (need C % 64 == 0, Hu,Wu <= 64, stride-1 window)");
   ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad group count / rows");
@@ -493,7 +493,7 @@ extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, voi
   ES_REQUIRE(g->N % 32 == 0 && g->N % p.BN == 0, "N must be a multiple of 32 and of the 256-wide tile");
   p.splits = 1;
   p.a_src = (const __nv_bfloat16*)x; p.b_src = (const __nv_bfloat16*)w; p.b_slot_stride = (long)g->N * p.KK;
-  p.bias = bias; p.bias_slot_stride = g->N; p.out = y; p.err_flag = err_flag_ptr();
+  p.bias = bias; p.bias_slot_stride = bias_slot_stride; p.out = y; p.err_flag = err_flag_ptr();
   const long mt = ceil_div_l((long)total_rows * p.P, kBM) + n_groups;
   ES_REQUIRE(mt < 2147483647L, "too many tiles");
   return launch_igemm<FWD>(p, dim3((unsigned)mt, g->N / p.BN), as_stream(stream));
@@ -544,8 +544,8 @@ extern "C" int es_dense_dgrad(const void* dy, const void* w, float* dx, int N, i
   return launch_igemm<DENSE_DGRAD>(p, dim3(mt, splits), as_stream(stream));
 }
 
-extern "C" int es_dense_wgrad(const void* dy, const void* x, float* dw, int N, int K, const int32_t* row_map,
-                              const es_group* grp, int n_groups, int total_rows, void* stream) {
+extern "C" int es_dense_wgrad(const void* dy, const void* x, float* dw, long dw_slot_stride, int N, int K,
+                              const int32_t* row_map, const es_group* grp, int n_groups, int total_rows, void* stream) {
   ES_REQUIRE(dy && x && dw && grp, "null pointer");
   ES_REQUIRE(N % kBM == 0 && K % 64 == 0 && K <= 256, "need N % 128 == 0 and K in {64,...,256}");
   ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad group count / rows");
@@ -555,6 +555,6 @@ extern "C" int es_dense_wgrad(const void* dy, const void* x, float* dw, int N, i
   p.grp = grp; p.n_groups = n_groups;
   p.Nout = N; p.KK = K; p.BN = K; p.splits = 1;
   p.a_src = (const __nv_bfloat16*)dy; p.b_src = (const __nv_bfloat16*)x;
-  p.out = dw; p.out_slot_stride = (long)N * K; p.row_map = row_map; p.err_flag = err_flag_ptr();
+  p.out = dw; p.out_slot_stride = dw_slot_stride; p.row_map = row_map; p.err_flag = err_flag_ptr();
   return launch_igemm<DENSE_WGRAD>(p, dim3(N / kBM, n_groups), as_stream(stream));
 }

@@ -503,9 +503,10 @@ spectral_norm_fwd_kernel(const float* __restrict__ w_orig, float* __restrict__ u
 __global__ void __launch_bounds__(256)
 spectral_norm_bwd_kernel(const float* __restrict__ dw_sn, const float* __restrict__ w_sn, const float* __restrict__ u_used,
                          const float* __restrict__ v_used, const float* __restrict__ sigma, long ssn, int O, int I,
-                         float* __restrict__ dw_orig, long sw) {
+                         float* __restrict__ dw_orig, long sw, const es_group* __restrict__ grp) {
   __shared__ float red[32];
   const int slot = blockIdx.x;
+  if (grp && grp[slot].rows == 0) return;   // skipped expert: its w_sn / sigma were never produced
   const float* D = dw_sn + slot * ssn;
   const float* WS = w_sn + slot * ssn;
   float dot = 0.f;
@@ -766,10 +767,10 @@ extern "C" int es_spectral_norm_fwd(const float* w_orig, float* u, float* v, lon
 
 extern "C" int es_spectral_norm_bwd(const float* dw_sn, const float* w_sn, const float* u_used, const float* v_used,
                                     const float* sigma, long slot_stride_sn, int slots, int O, int I, float* dw_orig,
-                                    long slot_stride_w, void* stream) {
+                                    long slot_stride_w, const es_group* grp, void* stream) {
   ES_REQUIRE(dw_sn && w_sn && u_used && v_used && sigma && dw_orig && slots >= 1, "bad arguments");
   spectral_norm_bwd_kernel<<<slots, 256, 0, as_stream(stream)>>>(dw_sn, w_sn, u_used, v_used, sigma, slot_stride_sn, O, I,
-                                                                dw_orig, slot_stride_w);
+                                                                dw_orig, slot_stride_w, grp);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }

@@ -114,6 +114,9 @@ def stream_ptr() -> int:
 
 
 n_calls = 0  # kernels-launching C-ABI calls made so far (bench.py reports it as gpu_launches evidence)
+# Optional per-call device timing (bench.py's roofline leg): {"names": set of entry points, "log": []}.  When set, calls to
+# the named entry points are bracketed by CUDA events on the launching stream; log rows are (name, args, start, end).
+profile = None
 
 
 def call(name: str, *args):
@@ -132,7 +135,14 @@ def call(name: str, *args):
         else:
             conv.append(float(a))
     conv.append(stream_ptr())
+    timed = profile is not None and name in profile["names"]
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = getattr(lib, name)(*conv)
+    if timed:
+        ev1.record()
+        profile["log"].append((name, tuple(a for a in args if not isinstance(a, torch.Tensor)), ev0, ev1))
     n_calls += 1
     if rc != 0:
         raise RuntimeError(f"{name} failed with status {rc}: {last_error()}")

@@ -85,7 +85,7 @@ class GenEngineProton:
         L.call("es_gen_fc1_fwd", z1, z2, cond, a.addr("fc1.0.weight"), a.addr("fc1.0.bias"), a.addr("fc1.1.weight"),
                a.addr("fc1.1.bias"), a.n, a.n, grp, E, R, int(two_pass), s["x0"], s["lin1"], s["h1"])
         s["y2"] = empty(R, self.F2, dtype=BF)
-        L.call("es_igemm_fwd", s["h1"], self.w_fc2, self.b_fc2, s["y2"], conv_geom(1, 1, 256, 1, 1, 1, 1, 0, self.F2), grp, E, R)
+        L.call("es_igemm_fwd", s["h1"], self.w_fc2, self.b_fc2, self.F2, s["y2"], conv_geom(1, 1, 256, 1, 1, 1, 1, 0, self.F2), grp, E, R)
         act, s["st2"] = empty(R, self.F2, dtype=BF), empty(R, 2)
         L.call("es_ln_lrelu_fwd", s["y2"], self.g_fc2, self.z_fc2, self.F2, self.F2, grp, E, R, act, s["st2"])
         s["a2"] = act
@@ -94,7 +94,7 @@ class GenEngineProton:
             g = conv_geom(*geo)
             P = g.Ho * g.Wo
             y = empty(R, P, N, dtype=BF)
-            L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), y, g, grp, E, R)
+            L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R)
             nxt, st = empty(R, P, N, dtype=BF), empty(R, groups, 2)
             L.call("es_gn_lrelu_fwd", y, a.addr(norm + ".weight"), a.addr(norm + ".bias"), a.n, P, N, groups, grp, E, R, nxt, st)
             s[f"y{i + 3}"], s[f"st{i + 3}"], s[f"a{i + 3}"] = y, st, nxt
@@ -128,13 +128,13 @@ class GenEngineProton:
             # weight gradient (packed fp32, unpacked below) and data gradient on the upsampled input grid
             L.call("es_igemm_wgrad", s[f"a{i + 2}"], dy, self.dw_p[name], g, grp, E, R)
             da = empty(R, Hu * Wu, C, dtype=BF)
-            L.call("es_igemm_fwd", dy, self.w_dg[name], None, da, conv_geom(g.Ho, g.Wo, N, g.Ho, g.Wo, KH, KW, KH - 1 - pad, C), grp, E, R)
+            L.call("es_igemm_fwd", dy, self.w_dg[name], None, 0, da, conv_geom(g.Ho, g.Wo, N, g.Ho, g.Wo, KH, KW, KH - 1 - pad, C), grp, E, R)
             up = (Hu, Wu)
         dy2 = empty(R, self.F2, dtype=BF)
         L.call("es_ln_lrelu_bwd", da, 18, 10, 36, 20, 512, s["y2"], s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R, dy2)
         L.call("es_ln_affine_bwd", da, 18, 10, 36, 20, 512, s["y2"], dy2, s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R,
                self.row_map, a.n, a.gaddr("fc2.1.weight"), a.gaddr("fc2.1.bias"), a.gaddr("fc2.0.bias"))
-        L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), self.F2, 256, self.row_map, grp, E, R)
+        L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), a.n, self.F2, 256, self.row_map, grp, E, R)
         dh1 = zeros(R, 256)
         L.call("es_dense_dgrad", dy2, self.w_fc2, dh1, self.F2, 256, grp, E, R)
         L.call("es_gen_fc1_bwd", dh1, s["x0"], s["lin1"], a.addr("fc1.1.weight"), a.addr("fc1.1.bias"), a.n, a.n, grp, E, R,
@@ -266,7 +266,7 @@ class DiscEngine:
             for name in self.SN:
                 O, I = self.dims[name]
                 wsn, sig, uu, vu = sn[name]
-                L.call("es_spectral_norm_bwd", dsn[name], wsn, uu, vu, sig, O * I, E, O, I, a.gaddr(name + ".weight_orig"), n)
+                L.call("es_spectral_norm_bwd", dsn[name], wsn, uu, vu, sig, O * I, E, O, I, a.gaddr(name + ".weight_orig"), n, grp)
 
 
 # =====================================================================================================================

@@ -43,5 +43,9 @@ class ArenaModule(nn.Module):
         return new
 
 
-def one_group(rows: int, slot: int, device):
-    return torch.tensor([[0, rows, slot, rows]], dtype=torch.int32, device=device)
+def one_group(rows: int, slot: int, device, n_slots: int = 1):
+    """Group table with one entry per arena slot in which only ``slot`` owns rows (a module used on its own)."""
+    t = torch.zeros(n_slots, 4, dtype=torch.int32)
+    t[:, 2] = torch.arange(n_slots)
+    t[slot] = torch.tensor([0, rows, slot, rows], dtype=torch.int32)
+    return t.to(device)

@@ -25,7 +25,7 @@ class AuxRegNeutron(ArenaModule):
         arena = self._home()
         eng = engine_for(arena, self.ARCH, self.KIND)
         R = x.shape[0]
-        grp = one_group(R, self._slot, x.device)
+        grp = one_group(R, self._slot, x.device, arena.E)
         coords, _ = eng.forward(x.float().reshape(R, -1).contiguous(), grp, R, self.training, None)
         return coords
 

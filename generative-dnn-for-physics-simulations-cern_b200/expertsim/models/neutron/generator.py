@@ -25,7 +25,7 @@ class GeneratorNeutron(ArenaModule):
         arena = self._home()
         eng = engine_for(arena, self.ARCH, self.KIND)
         R = noise.shape[0]
-        grp = one_group(R, self._slot, noise.device)
+        grp = one_group(R, self._slot, noise.device, arena.E)
         img, _, _ = eng.forward(noise.float().contiguous(), None, cond.float().contiguous(), grp, R, False, keep=False,
                                 training=self.training)
         return img.view(R, 1, *self.IMAGE_SHAPE)

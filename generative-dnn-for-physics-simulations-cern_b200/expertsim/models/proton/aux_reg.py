@@ -25,7 +25,7 @@ class AuxReg(ArenaModule):
         arena = self._home()
         eng = engine_for(arena, self.ARCH, self.KIND)
         R = x.shape[0]
-        grp = one_group(R, self._slot, x.device)
+        grp = one_group(R, self._slot, x.device, arena.E)
         masks = None
         if self.training:
             masks = ((torch.rand(R, 128, device=x.device) >= 0.3).float(), (torch.rand(R, 64, device=x.device) >= 0.3).float())

@@ -20,7 +20,7 @@ class Discriminator(ArenaModule):
         arena = self._home()
         eng = engine_for(arena, self.ARCH, self.KIND)
         R = img.shape[0]
-        grp = one_group(R, self._slot, img.device)
+        grp = one_group(R, self._slot, img.device, arena.E)
         sn = eng.spectral(grp, self.training)   # one power iteration per forward in training mode, as the hook does
         score, latent, _ = eng.forward(img.float().reshape(R, -1).contiguous(), cond.float().contiguous(), grp, R, sn)
         return score, latent

@@ -25,6 +25,6 @@ class Generator(ArenaModule):
         arena = self._home()
         eng = engine_for(arena, self.ARCH, self.KIND)
         R = noise.shape[0]
-        grp = one_group(R, self._slot, noise.device)
+        grp = one_group(R, self._slot, noise.device, arena.E)
         img, _, _ = eng.forward(noise.float().contiguous(), None, cond.float().contiguous(), grp, R, False, keep=False)
         return img.view(R, 1, *self.IMAGE_SHAPE)

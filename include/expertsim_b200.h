@@ -147,9 +147,10 @@ typedef struct {
 } es_conv_geom;
 
 /* y[row, oy, ox, n] = sum_{ky,kx,c} x_up[row, oy+ky-pad, ox+kx-pad, c] * w[slot][n][ky][kx][c] (+ bias[slot][n])
- * x: bf16 [rows,Hs,Ws,C]; w: bf16 packed [slots][N][KH*KW*C]; bias fp32 [slots][N] or NULL; y: bf16 [rows,Ho,Wo,N].
- * Used for the forward convs, for their data gradients (with transposed/flipped packed weights) and for fc2. */
-int es_igemm_fwd(const void* x, const void* w, const float* bias, void* y, const es_conv_geom* g,
+ * x: bf16 [rows,Hs,Ws,C]; w: bf16 packed [slots][N][KH*KW*C]; bias fp32, slot s at bias + s*bias_slot_stride, or NULL;
+ * y: bf16 [rows,Ho,Wo,N].  Used for the forward convs, for their data gradients (with transposed/flipped packed
+ * weights) and for fc2. */
+int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_conv_geom* g,
                  const es_group* grp, int n_groups, int total_rows, void* stream);
 /* dw[slot][n][ky][kx][c] += sum_{row,oy,ox} dy[row,oy,ox,n] * x_up[row,oy+ky-pad,ox+kx-pad,c]   (fp32, packed layout,
  * split-K with fp32 atomics; dw must be zeroed by the caller). */
@@ -159,13 +160,13 @@ int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es_conv_geom*
  * (fc2: N=92160, K=256; split over n with fp32 atomics; dx fp32 [rows,K] zeroed by the caller). */
 int es_dense_dgrad(const void* dy, const void* w, float* dx, int N, int K,
                    const es_group* grp, int n_groups, int total_rows, void* stream);
-/* dense weight gradient: dw[slot][row_map[n]][k] = sum_row dy[row,n] * x[row,k]  (fp32, direct store; row_map (nullable)
- * un-permutes the channels-last feature order back to the reference's NCHW flattening). */
-int es_dense_wgrad(const void* dy, const void* x, float* dw, int N, int K, const int32_t* row_map,
+/* dense weight gradient: dw[slot*dw_slot_stride + row_map[n]*K + k] = sum_row dy[row,n] * x[row,k]  (fp32, direct store;
+ * row_map (nullable) un-permutes the channels-last feature order back to the reference's NCHW flattening). */
+int es_dense_wgrad(const void* dy, const void* x, float* dw, long dw_slot_stride, int N, int K, const int32_t* row_map,
                    const es_group* grp, int n_groups, int total_rows, void* stream);
 /* Test-only SIMT (CUDA-core, fp32 accumulate) versions of the two implicit GEMMs; same arguments.  They exist so the
  * tcgen05 path can be cross-checked on the device at sizes the CPU oracle cannot reach.  Never called by the product. */
-int es_igemm_fwd_simt(const void* x, const void* w, const float* bias, void* y, const es_conv_geom* g,
+int es_igemm_fwd_simt(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_conv_geom* g,
                       const es_group* grp, int n_groups, int total_rows, void* stream);
 int es_igemm_wgrad_simt(const void* x, const void* dy, float* dw, const es_conv_geom* g,
                         const es_group* grp, int n_groups, int total_rows, void* stream);
@@ -271,9 +272,11 @@ int es_linear_bwd_weight(const float* x, int ldx, const float* dy, int I, int O,
 int es_spectral_norm_fwd(const float* w_orig, float* u, float* v, long slot_stride_w, long slot_stride_u, long slot_stride_v,
                          int slots, int O, int I, int do_power_iter, const es_group* grp, float* w_sn, long slot_stride_sn,
                          float* sigma_out, float* u_used, float* v_used, void* stream);
-/* dw_orig += (dw_sn - <dw_sn, w_sn> u v^T) / sigma */
+/* dw_orig += (dw_sn - <dw_sn, w_sn> u v^T) / sigma; slots whose grp[slot].rows == 0 are skipped (grp nullable: all slots,
+ * where grp[s] must describe slot s as produced by es_router_partition) */
 int es_spectral_norm_bwd(const float* dw_sn, const float* w_sn, const float* u_used, const float* v_used, const float* sigma,
-                         long slot_stride_sn, int slots, int O, int I, float* dw_orig, long slot_stride_w, void* stream);
+                         long slot_stride_sn, int slots, int O, int I, float* dw_orig, long slot_stride_w,
+                         const es_group* grp, void* stream);
 /* elementwise helpers: y = a + b then ReLU (residual join), its backward mask, mean over HW, dropout with a given keep-mask */
 int es_add_relu_fwd(const float* a, const float* b, long n, float* y, void* stream);
 int es_relu_bwd(const float* dy, const float* y, long n, float* dx, void* stream);

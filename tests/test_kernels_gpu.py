@@ -251,7 +251,7 @@ def test_igemm_fwd(name, impl):
     bias = torch.randn(2, N, generator=g) * 0.1
     want = ref_conv(x, w, bias, geo, counts, slots)
     y = torch.zeros(R, want.shape[1], want.shape[2], N, dtype=BF, device=DEV)
-    L.call(impl, cuda(x, BF), cuda(w, BF), cuda(bias), y, conv_geom(*geo), grp, len(counts), R)
+    L.call(impl, cuda(x, BF), cuda(w, BF), cuda(bias), N, y, conv_geom(*geo), grp, len(counts), R)
     torch.cuda.synchronize()
     check(f"{impl} {name}", y.float(), want, 6e-3, 3e-2)
 
@@ -266,7 +266,7 @@ def test_igemm_fwd_fc2_fullsize():
     w = bf16_round(torch.randn(3, N, K, generator=g) / 16)
     bias = torch.randn(3, N, generator=g) * 0.1
     y = torch.zeros(R, N, dtype=BF, device=DEV)
-    L.call("es_igemm_fwd", cuda(x, BF), cuda(w, BF), cuda(bias), y, conv_geom(1, 1, K, 1, 1, 1, 1, 0, N), grp, 3, R)
+    L.call("es_igemm_fwd", cuda(x, BF), cuda(w, BF), cuda(bias), N, y, conv_geom(1, 1, K, 1, 1, 1, 1, 0, N), grp, 3, R)
     want = torch.cat([x[:150] @ w[0].T + bias[0], x[150:] @ w[2].T + bias[2]])
     check("es_igemm_fwd fc2 92160x256", y.float(), want, 6e-3, 3e-2)
 
@@ -305,7 +305,7 @@ def test_dense_dgrad_wgrad():
     check("es_dense_dgrad fc2", dx, want, 3e-3, 1e-2)
     row_map = torch.randperm(N, generator=g).to(torch.int32)
     dw = torch.zeros(3, N, K, device=DEV)
-    L.call("es_dense_wgrad", cuda(dy, BF), cuda(x, BF), dw, N, K, cuda(row_map), grp, 3, R)
+    L.call("es_dense_wgrad", cuda(dy, BF), cuda(x, BF), dw, N * K, N, K, cuda(row_map), grp, 3, R)
     want_w = torch.zeros(3, N, K)
     want_w[2][row_map.long()] = dy[:140].T @ x[:140]
     want_w[0][row_map.long()] = dy[140:].T @ x[140:]
@@ -643,7 +643,7 @@ def test_spectral_norm(O, I):
     L.call("es_spectral_norm_fwd", cuda(w), du, dv, O * I, O, I, S, O, I, 1, grp, wsn, O * I, sig, uu, vu)
     dwsn = torch.randn(S, O, I, generator=g)
     dwo = torch.zeros(S, O, I, device=DEV)
-    L.call("es_spectral_norm_bwd", cuda(dwsn), wsn, uu, vu, sig, O * I, S, O, I, dwo, O * I)
+    L.call("es_spectral_norm_bwd", cuda(dwsn), wsn, uu, vu, sig, O * I, S, O, I, dwo, O * I, None)
     for s in (0, 2):
         sd = {"l.weight_orig": w[s].clone().requires_grad_(True), "l.weight_u": u[s].clone(), "l.weight_v": v[s].clone()}
         ws = orc.spectral_norm_weight(sd, "l", True)
