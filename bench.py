@@ -239,6 +239,18 @@ def run_b200(args):
 
     for i in range(args.warmup):
         step(i)
+    if args.ncu_step:
+        # profiling aid: `ncu --profile-from-start off ... bench.py --ncu-step` captures exactly one train step (and one
+        # inference batch); nothing measured under the profiler is ever reported as a bench value
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(args.warmup)
+        if args.ncu_step > 1:
+            moe.eval()
+            moe.generate(torch.randn(args.infer_batch, 9, device=dev), chunk=args.infer_batch)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     # ---- timed region: K steps, inputs resident in HBM
     names = {"es_igemm_fwd", "es_igemm_wgrad", "es_dense_dgrad", "es_dense_wgrad"}
     L.profile = {"names": names, "log": []}
@@ -368,6 +380,7 @@ def main():
     ap.add_argument("--infer-iters", type=int, default=5)
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", type=int, default=0, help="1: cudaProfilerStart/Stop around one train step; 2: + one inference batch")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

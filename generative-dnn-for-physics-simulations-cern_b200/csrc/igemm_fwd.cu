@@ -1,0 +1,349 @@
+// K2 (forward kind) — persistent, warp-specialised grouped implicit GEMM on tcgen05:  y[pix, n] = sum_k im2col(x)[pix, k] w[n, k].
+// Used by the generator's forward convolutions (nearest upsample folded into the gather), by their data gradients (same
+// kernel, transposed + flipped packed weights) and by fc2.
+//
+// Why this shape (r01 ncu of the first, non-persistent kernel: L1TEX 82 % busy, L2 50 %, tensor pipe 16 %): every operand
+// byte went through per-thread 16-byte cp.async, 32 different lines per warp instruction.  Here
+//   * B (weights, K-major [slots*N][KK] bf16) arrives by TMA — one elected thread, 128B-swizzled box {64 k, BN n}, no
+//     L1TEX traffic at all;
+//   * A (im2col rows: one output pixel x 64 channels = one 128-byte line) is still a gather, because the nearest upsample
+//     and the per-expert ragged row ranges are not expressible as a TMA box, but 8 consecutive lanes now copy ONE line
+//     (4 full lines per warp instruction), through L1 (.ca), and the reduction runs channel-block-major / tap-minor so
+//     the KH*KW shifted re-reads of a source line hit L1 instead of L2;
+//   * the CTA is persistent (one per SM, static tile striding) with a double-buffered TMEM accumulator, so the epilogue
+//     of tile i (TMEM -> registers -> +bias -> bf16 -> global) overlaps the main loop of tile i+1.
+// Warp roles: 0-3 A gather, 4 TMA producer (B), 5 MMA issuer + TMEM owner, 6-9 epilogue (TMEM lane quarter = warp % 4).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace es {
+
+namespace {
+
+constexpr int kFStages = 4;
+constexpr int kFLag = 2;
+constexpr int kFLoaders = 128;
+constexpr int kFThreads = 320;
+constexpr int kFStageA = kBM * 128;            // 16 KB
+constexpr int kFStageB = 256 * 128;            // 32 KB (BN <= 256)
+constexpr int kFStage = kFStageA + kFStageB;
+constexpr int kFMaxGroups = 64;
+constexpr size_t kFSmem = (size_t)kFStages * kFStage + 1024 /*align*/ + 2048 /*barriers + tables*/;
+
+struct FwdParams {
+  const es_group* grp;
+  int n_groups;
+  int Hs, Ws, C, Hu, Wu, Ho, Wo, KH, KW, pad, P;
+  int Nout, BN, KK, n_tiles_n;
+  unsigned char ymap[64], xmap[64];
+  const __nv_bfloat16* a_src;
+  const float* bias;
+  long bias_slot_stride;
+  __nv_bfloat16* out;
+  int* err_flag;
+};
+
+struct TileInfo {
+  int g, m0, n0, rows, row_start, slot;
+};
+
+// tile t -> (group, m0, n0).  s_tiles[i] = number of M tiles of group i (shared memory).
+__device__ __forceinline__ bool decode_tile(int t, const FwdParams& p, const int* s_tiles, const es_group* s_grp, TileInfo& ti) {
+  int mt = t / p.n_tiles_n;
+  const int nt = t - mt * p.n_tiles_n;
+  for (int i = 0; i < p.n_groups; ++i) {
+    const int n = s_tiles[i];
+    if (mt < n) {
+      ti.g = i; ti.m0 = mt * kBM; ti.n0 = nt * p.BN;
+      ti.rows = s_grp[i].rows; ti.row_start = s_grp[i].row_start; ti.slot = s_grp[i].slot;
+      return true;
+    }
+    mt -= n;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(kFThreads, 1)
+igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CUtensorMap tmap_w) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kFStages * kFStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kFStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kFStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kFStages + 2 + b); };
+  uint8_t* gen = smem_raw + (bar_base - raw);                 // generic pointer to the barrier/table area
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * (2 * kFStages + 4));
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kFStages + 4);
+  int* s_tiles = reinterpret_cast<int*>(gen + 128);            // [64]
+  es_group* s_grp = reinterpret_cast<es_group*>(gen + 384);    // [64] x 16 B
+  unsigned char* s_ymap = gen + 384 + 1024;                    // 64
+  unsigned char* s_xmap = s_ymap + 64;                         // 64
+
+  const int BN = p.BN;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
+
+  // ---- one-time setup
+  if (tid < p.n_groups) {
+    const es_group gq = p.grp[tid];
+    s_grp[tid] = gq;
+    s_tiles[tid] = ceil_div(gq.rows * p.P, kBM);
+  }
+  if (tid < 64) { s_ymap[tid] = p.ymap[tid]; s_xmap[tid] = p.xmap[tid]; }
+  if (tid == 0) {
+    for (int s = 0; s < kFStages; ++s) {
+      mbar_init(full_bar(s), kFLoaders + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  int total_tiles = 0;
+  for (int i = 0; i < p.n_groups; ++i) total_tiles += s_tiles[i];
+  total_tiles *= p.n_tiles_n;
+  const int taps = p.KH * p.KW;
+  const int cblks = p.C / kBK;
+  const int nkb = taps * cblks;
+
+  if (warp < 4) {
+    // =========================================================================== A GATHER (128 threads)
+    // lane group of 8 threads copies one 128-byte row; thread handles rows (tid>>3) + 16*j, j = 0..7, chunk tid&7
+    const int chunk = tid & 7, rsub = tid >> 3;
+    uint32_t it = 0, signalled = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileInfo ti;
+      decode_tile(tile, p, s_tiles, s_grp, ti);
+      int r_base[8];      // pixel index of the sample's first source pixel, or -1 for rows past the group's end
+      int r_oyx[8];       // oy << 8 | ox
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int m = ti.m0 + rsub + 16 * j;
+        const bool valid = m < ti.rows * p.P;
+        const int sample = valid ? m / p.P : 0;
+        const int pix = valid ? m - sample * p.P : 0;
+        const int oy = pix / p.Wo;
+        r_oyx[j] = (oy << 8) | (pix - oy * p.Wo);
+        r_base[j] = valid ? (ti.row_start + sample) * p.Hs * p.Ws : -1;
+      }
+      int cb = 0, ky = 0, kx = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kFStages;
+        if (it >= kFStages) mbar_wait(empty_bar(s), ((it / kFStages) - 1) & 1, p.err_flag, 1);
+        const uint32_t sa = base + s * kFStage;
+        const int c0 = cb * kBK + chunk * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = rsub + 16 * j;
+          const int uy = (r_oyx[j] >> 8) + ky - p.pad, ux = (r_oyx[j] & 255) + kx - p.pad;
+          const bool inb = r_base[j] >= 0 && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
+          const int sy = inb ? s_ymap[uy] : 0, sx = inb ? s_xmap[ux] : 0;
+          const __nv_bfloat16* src = p.a_src + (inb ? ((long)(r_base[j] + sy * p.Ws + sx) * p.C + c0) : 0L);
+          cp_async16_ca(sa + (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4), src, inb);
+        }
+        cp_async_commit();
+        if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++cb; } }
+        if (it - signalled >= (uint32_t)kFLag) {
+          cp_async_wait<kFLag>();
+          fence_proxy_async();
+          mbar_arrive(full_bar(signalled % kFStages));
+          ++signalled;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    while (signalled < it) {
+      mbar_arrive(full_bar(signalled % kFStages));
+      ++signalled;
+    }
+  } else if (warp == 4) {
+    // =========================================================================== TMA PRODUCER (weights)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileInfo ti;
+        decode_tile(tile, p, s_tiles, s_grp, ti);
+        const int wrow = ti.slot * p.Nout + ti.n0;
+        int cb = 0, tap = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kFStages;
+          if (it >= kFStages) mbar_wait(empty_bar(s), ((it / kFStages) - 1) & 1, p.err_flag, 4);
+          mbar_arrive_expect_tx(full_bar(s), (uint32_t)BN * 128u);
+          tma_load_2d(base + s * kFStage + kFStageA, &tmap_w, tap * p.C + cb * kBK, wrow, full_bar(s));
+          if (++tap == taps) { tap = 0; ++cb; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =========================================================================== MMA ISSUER
+    const uint32_t idesc = make_idesc(BN, false, false);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1;
+      if (tcount >= 2) mbar_wait(tempty_bar(buf), ((tcount >> 1) - 1) & 1, p.err_flag, 5);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kFStages;
+        mbar_wait(full_bar(s), (it / kFStages) & 1, p.err_flag, 2);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + s * kFStage;
+          const uint32_t sb = sa + kFStageA;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16(tacc, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+          if (kb == nkb - 1) umma_commit(tfull_bar(buf));
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+  } else {
+    // =========================================================================== EPILOGUE (warps 6-9)
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      TileInfo ti;
+      decode_tile(tile, p, s_tiles, s_grp, ti);
+      const uint32_t buf = tcount & 1;
+      mbar_wait(tfull_bar(buf), (tcount >> 1) & 1, p.err_flag, 3);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+      const int m = ti.m0 + q * 32 + lane;
+      const bool ok = m < ti.rows * p.P;
+      __nv_bfloat16* yrow = p.out + (((long)ti.row_start * p.P + m) * p.Nout + ti.n0);
+      const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
+      uint32_t r[32];
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(t_lane + c, r);
+        if (ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) dst[qq] = pack8(f + 8 * qq);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int* fwd_err_flag() {
+  static int* flag = nullptr;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) flag = nullptr;
+    else cudaMemset(flag, 0, sizeof(int));
+  }
+  return flag;
+}
+
+}  // namespace
+
+void fill_maps_uc(int Hs, int Ws, int Hu, int Wu, unsigned char* ymap, unsigned char* xmap) {
+  // torch 'nearest': src = min(floor(dst * (in/out as float)), in-1)
+  const float sy = (float)Hs / (float)Hu, sx = (float)Ws / (float)Wu;
+  for (int i = 0; i < 64; ++i) {
+    const int y = (int)floorf((float)i * sy), x = (int)floorf((float)i * sx);
+    ymap[i] = (unsigned char)(y < Hs - 1 ? y : Hs - 1);
+    xmap[i] = (unsigned char)(x < Ws - 1 ? x : Ws - 1);
+  }
+}
+
+}  // namespace es
+
+using namespace es;
+
+extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
+                            const es_conv_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
+  ES_REQUIRE(x && w && y && grp && g, "null pointer");
+  ES_REQUIRE(g->C > 0 && g->C % 64 == 0 && g->Hu <= 64 && g->Wu <= 64 && g->Hu >= g->Hs && g->Wu >= g->Ws &&
+                 g->Ho == g->Hu + 2 * g->pad - g->KH + 1 && g->Wo == g->Wu + 2 * g->pad - g->KW + 1 && g->Ho > 0 &&
+                 g->Wo > 0 && g->Ho < 256 && g->Wo < 256,
+             "unsupported geometry (need C % 64 == 0, Hu,Wu <= 64, stride-1 window)");
+  ES_REQUIRE(n_groups >= 1 && n_groups <= kFMaxGroups && total_rows > 0, "bad group count / rows");
+  FwdParams p{};
+  p.grp = grp; p.n_groups = n_groups;
+  p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
+  p.KH = g->KH; p.KW = g->KW; p.pad = g->pad; p.P = g->Ho * g->Wo;
+  p.KK = g->KH * g->KW * g->C;
+  p.Nout = g->N; p.BN = g->N >= 256 ? 256 : g->N;
+  ES_REQUIRE(g->N % 32 == 0 && g->N % p.BN == 0 && (p.BN & (p.BN - 1)) == 0, "N must be 32/64/128 or a multiple of 256");
+  ES_REQUIRE((long)total_rows * p.Hs * p.Ws < 2147483647L, "too many source pixels");
+  p.n_tiles_n = g->N / p.BN;
+  fill_maps_uc(p.Hs, p.Ws, p.Hu, p.Wu, p.ymap, p.xmap);
+  p.a_src = (const __nv_bfloat16*)x; p.bias = bias; p.bias_slot_stride = bias_slot_stride;
+  p.out = (__nv_bfloat16*)y; p.err_flag = fwd_err_flag();
+
+  // weights as a 2-D tensor [slots*N rows][KK] bf16; the number of slots is not known here, so the row extent is the
+  // largest one the group table can address (TMA never reads rows the kernel does not ask for)
+  EncodeTiledFn enc = encode_fn();
+  ES_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  alignas(64) CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)g->N};
+  const cuuint64_t strides[1] = {(cuuint64_t)p.KK * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (weights must be 16-byte aligned, KK*2 a multiple of 16)");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    ES_CUDA(cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long max_tiles = (ceil_div_l((long)total_rows * p.P, kBM) + n_groups) * p.n_tiles_n;
+  const int grid = (int)(max_tiles < sms ? max_tiles : sms);
+  igemm_fwd_kernel<<<grid, kFThreads, kFSmem, as_stream(stream)>>>(p, tmap);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}

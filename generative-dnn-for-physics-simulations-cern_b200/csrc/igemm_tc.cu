@@ -16,13 +16,12 @@
 // Pipeline: kStages smem stages, full[] barriers (128 loader arrivals after cp.async.wait_group + fence.proxy.async),
 // empty[] barriers (tcgen05.commit), one tmem_full barrier for the epilogue.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace es {
 
 enum IgemmMode { FWD = 0, WGRAD_CONV = 1, DENSE_DGRAD = 2, DENSE_WGRAD = 3 };
 
-constexpr int kBM = 128;
-constexpr int kBK = 64;
 constexpr int kStages = 4;
 constexpr int kLag = 2;
 constexpr int kLoaderThreads = 128;
@@ -53,93 +52,6 @@ struct IgemmParams {
   const int* row_map;
   int* err_flag;
 };
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a pipeline bug must surface as an error, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      if (err_flag) atomicExch(err_flag, tag);
-      __threadfence_system();
-      asm volatile("trap;");
-    }
-  }
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const uint32_t n = valid ? 16u : 0u;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), SWIZZLE_128B, version 1 (Blackwell).
-//   K-major : rows of 64 k (128 B); 8-row groups 1024 B apart (SBO); LBO unused.
-//   MN-major: rows of 64 m/n (128 B) per k; 8-k groups 1024 B apart (SBO); next 64 m/n block `lbo_bytes` away (LBO).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128, N=BN, optional MN-major operands.
-__device__ __forceinline__ uint32_t make_idesc(int bn, bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-}
 
 // write one 128-byte row (8 x 16 B) of a swizzled tile; `row` is the row index inside its 64/128/256-row block
 __device__ __forceinline__ void load_row128(uint32_t block_base, int row, const __nv_bfloat16* src, bool valid) {
@@ -475,29 +387,10 @@ int launch_igemm(const IgemmParams& p, dim3 grid, cudaStream_t st) {
   return ES_OK;
 }
 
-static int pick_bn(int n) { return n >= 256 ? 256 : n; }
 
 }  // namespace es
 
 using namespace es;
-
-extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
-                            const es_conv_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
-  ES_REQUIRE(x && w && y && grp, "null pointer");
-  ES_REQUIRE(check_geom(g), "unsupported geometry (need C % 64 == 0, Hu,Wu <= 64, stride-1 window)");
-  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad group count / rows");
-  IgemmParams p{};
-  geom_to_params(g, p);
-  p.grp = grp; p.n_groups = n_groups;
-  p.Nout = g->N; p.BN = pick_bn(g->N);
-  ES_REQUIRE(g->N % 32 == 0 && g->N % p.BN == 0, "N must be a multiple of 32 and of the 256-wide tile");
-  p.splits = 1;
-  p.a_src = (const __nv_bfloat16*)x; p.b_src = (const __nv_bfloat16*)w; p.b_slot_stride = (long)g->N * p.KK;
-  p.bias = bias; p.bias_slot_stride = bias_slot_stride; p.out = y; p.err_flag = err_flag_ptr();
-  const long mt = ceil_div_l((long)total_rows * p.P, kBM) + n_groups;
-  ES_REQUIRE(mt < 2147483647L, "too many tiles");
-  return launch_igemm<FWD>(p, dim3((unsigned)mt, g->N / p.BN), as_stream(stream));
-}
 
 extern "C" int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es_conv_geom* g, const es_group* grp,
                               int n_groups, int total_rows, void* stream) {
