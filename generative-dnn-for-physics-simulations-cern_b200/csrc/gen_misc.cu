@@ -316,7 +316,15 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
   const int r = blockIdx.x;
   const int g = find_group(grp, n_groups, r);
-  if (g < 0) return;
+  if (g < 0) {
+    // rows of skipped experts: the gradient tensor is read by the weight-gradient GEMM through TMA boxes that may
+    // straddle a group's end, where it is multiplied by zero-filled im2col rows — it must be finite there
+    if (BWD) {
+      uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)r * Hs * Ws * C);
+      for (int i = threadIdx.x; i < Hs * Ws * C / 8; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
   const int slot = grp[g].slot;
   const int P = Hs * Ws, c4 = C / 8, cpg = C / groups;
   const int tid = threadIdx.x;

@@ -253,6 +253,232 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient of a convolution:  dw[slot][n][kk] += sum_pix dy[pix, n] * im2col(x)[pix, kk]   (kk = (tap, channel))
+// D tile = 128 kk (M) x N (<= 256); the reduction runs over the group's pixels in blocks of 64.  Both operands are
+// MN-major (rows = pixels): A rows are gathered 128-byte channel slices of x (line-coalesced cp.async, zero-filled for
+// padding and past the group's end), B rows are dy, fetched by TMA as N/64 boxes of {64 n, 64 pixels}.
+// Work units = (group, split of the pixel range, 128-wide kk tile); units with the same pixel range are adjacent so
+// that the CTAs running together share dy in L2.  fp32 atomics (RED) combine the splits.
+struct WgParams {
+  const es_group* grp;
+  int n_groups;
+  int Hs, Ws, C, Hu, Wu, Ho, Wo, KH, KW, pad, P;
+  int N, KK, tiles_m, splits;
+  unsigned char ymap[64], xmap[64];
+  const __nv_bfloat16* x;
+  float* dw;
+  long dw_slot_stride;
+  int* err_flag;
+};
+
+struct WgTile {
+  int m0, rows, row_start, slot, kb0, kb1;
+};
+
+__device__ __forceinline__ bool wg_decode(int t, const WgParams& p, const es_group* s_grp, WgTile& ti) {
+  const int per_g = p.splits * p.tiles_m;
+  const int g = t / per_g, rem = t - g * per_g;
+  const int sp = rem / p.tiles_m, mt = rem - sp * p.tiles_m;
+  ti.m0 = mt * kBM;
+  ti.rows = s_grp[g].rows; ti.row_start = s_grp[g].row_start; ti.slot = s_grp[g].slot;
+  const int nkb = ceil_div(ti.rows * p.P, kBK);
+  const int per = ceil_div(nkb, p.splits);
+  ti.kb0 = sp * per;
+  ti.kb1 = min(nkb, ti.kb0 + per);
+  return ti.kb1 > ti.kb0;
+}
+
+__global__ void __launch_bounds__(kFThreads, 1)
+igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ CUtensorMap tmap_dy) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kFStages * kFStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kFStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kFStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kFStages + 2 + b); };
+  uint8_t* gen = smem_raw + (bar_base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * (2 * kFStages + 4));
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kFStages + 4);
+  es_group* s_grp = reinterpret_cast<es_group*>(gen + 384);
+  unsigned char* s_ymap = gen + 384 + 1024;
+  unsigned char* s_xmap = s_ymap + 64;
+
+  const int BN = p.N;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
+
+  if (tid < p.n_groups) s_grp[tid] = p.grp[tid];
+  if (tid < 64) { s_ymap[tid] = p.ymap[tid]; s_xmap[tid] = p.xmap[tid]; }
+  if (tid == 0) {
+    for (int s = 0; s < kFStages; ++s) {
+      mbar_init(full_bar(s), kFLoaders + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&tmap_dy);
+  if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int total_tiles = p.n_groups * p.splits * p.tiles_m;
+  const int nseg = BN >> 6;
+
+  if (warp < 4) {
+    // =========================================================================== A GATHER
+    const int chunk = tid & 7, rsub = tid >> 3;     // pixel rows rsub + 16 i (i < 4), both 64-wide kk segments
+    uint32_t it = 0, signalled = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      WgTile ti;
+      if (!wg_decode(tile, p, s_grp, ti)) continue;
+      int kyv[2], kxv[2], cv[2];
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        const int kk = ti.m0 + sg * 64;
+        const int tap = kk / p.C;
+        cv[sg] = kk - tap * p.C + chunk * 8;
+        kyv[sg] = tap / p.KW - p.pad;
+        kxv[sg] = tap % p.KW - p.pad;
+      }
+      const int hw = p.Hs * p.Ws;
+      const long src_base = (long)ti.row_start * hw;
+      // (sample, oy, ox) of this thread's 4 pixel rows: a mixed-radix counter advanced by 64 pixels per k-block, so the
+      // main loop has no integer division
+      int smp[4], oyv[4], oxv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pidx = ti.kb0 * kBK + rsub + 16 * i;
+        smp[i] = pidx / p.P;
+        const int pix = pidx - smp[i] * p.P;
+        oyv[i] = pix / p.Wo;
+        oxv[i] = pix - oyv[i] * p.Wo;
+      }
+      const int dy64 = kBK / p.Wo, dx64 = kBK - dy64 * p.Wo;
+      for (int kb = ti.kb0; kb < ti.kb1; ++kb, ++it) {
+        const int s = it % kFStages;
+        if (it >= kFStages) mbar_wait(empty_bar(s), ((it / kFStages) - 1) & 1, p.err_flag, 1);
+        const uint32_t sa = base + s * kFStage;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int prow = rsub + 16 * i;
+          const bool v = smp[i] < ti.rows;
+          const int oy = oyv[i], ox = oxv[i];
+          const long sbase = src_base + (long)smp[i] * hw;
+          const uint32_t doff = (uint32_t)prow * 128u + (uint32_t)((chunk ^ (prow & 7)) << 4);
+#pragma unroll
+          for (int sg = 0; sg < 2; ++sg) {
+            const int uy = oy + kyv[sg], ux = ox + kxv[sg];
+            const bool inb = v && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
+            const int sy = inb ? s_ymap[uy] : 0, sx = inb ? s_xmap[ux] : 0;
+            const __nv_bfloat16* src = p.x + (inb ? ((sbase + sy * p.Ws + sx) * p.C + cv[sg]) : 0L);
+            cp_async16(sa + sg * 8192u + doff, src, inb);
+          }
+          oxv[i] += dx64;
+          oyv[i] += dy64;
+          if (oxv[i] >= p.Wo) { oxv[i] -= p.Wo; ++oyv[i]; }
+          while (oyv[i] >= p.Ho) { oyv[i] -= p.Ho; ++smp[i]; }
+        }
+        cp_async_commit();
+        if (it - signalled >= (uint32_t)kFLag) {
+          cp_async_wait<kFLag>();
+          fence_proxy_async();
+          mbar_arrive(full_bar(signalled % kFStages));
+          ++signalled;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    while (signalled < it) {
+      mbar_arrive(full_bar(signalled % kFStages));
+      ++signalled;
+    }
+  } else if (warp == 4) {
+    // =========================================================================== TMA PRODUCER (dy)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        WgTile ti;
+        if (!wg_decode(tile, p, s_grp, ti)) continue;
+        const int prow0 = ti.row_start * p.P;
+        for (int kb = ti.kb0; kb < ti.kb1; ++kb, ++it) {
+          const int s = it % kFStages;
+          if (it >= kFStages) mbar_wait(empty_bar(s), ((it / kFStages) - 1) & 1, p.err_flag, 4);
+          mbar_arrive_expect_tx(full_bar(s), (uint32_t)BN * 128u);
+          const uint32_t sb = base + s * kFStage + kFStageA;
+          for (int sg = 0; sg < nseg; ++sg) tma_load_2d(sb + sg * 8192u, &tmap_dy, sg * 64, prow0 + kb * kBK, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =========================================================================== MMA ISSUER
+    const uint32_t idesc = make_idesc(BN, true, true);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      WgTile ti;
+      if (!wg_decode(tile, p, s_grp, ti)) continue;
+      const uint32_t buf = tcount & 1;
+      if (tcount >= 2) mbar_wait(tempty_bar(buf), ((tcount >> 1) - 1) & 1, p.err_flag, 5);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
+      for (int kb = ti.kb0; kb < ti.kb1; ++kb, ++it) {
+        const int s = it % kFStages;
+        mbar_wait(full_bar(s), (it / kFStages) & 1, p.err_flag, 2);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + s * kFStage;
+          const uint32_t sb = sa + kFStageA;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16(tacc, make_desc(sa + k * 2048, 8192, 1024), make_desc(sb + k * 2048, 8192, 1024), idesc,
+                      (kb > ti.kb0 || k) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+          if (kb == ti.kb1 - 1) umma_commit(tfull_bar(buf));
+        }
+        __syncwarp();
+      }
+      ++tcount;
+    }
+    tc_fence_before();
+  } else {
+    // =========================================================================== EPILOGUE (warps 6-9): RED into dw
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      WgTile ti;
+      if (!wg_decode(tile, p, s_grp, ti)) continue;
+      const uint32_t buf = tcount & 1;
+      mbar_wait(tfull_bar(buf), (tcount >> 1) & 1, p.err_flag, 3);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+      float* dw = p.dw + (long)ti.slot * p.dw_slot_stride + ti.m0 + q * 32 + lane;
+      uint32_t r[32];
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(t_lane + c, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dw + (long)(c + j) * p.KK, __uint_as_float(r[j]));
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+      ++tcount;
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -344,6 +570,56 @@ extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, lon
   const long max_tiles = (ceil_div_l((long)total_rows * p.P, kBM) + n_groups) * p.n_tiles_n;
   const int grid = (int)(max_tiles < sms ? max_tiles : sms);
   igemm_fwd_kernel<<<grid, kFThreads, kFSmem, as_stream(stream)>>>(p, tmap);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es_conv_geom* g, const es_group* grp,
+                              int n_groups, int total_rows, void* stream) {
+  ES_REQUIRE(x && dy && dw && grp && g, "null pointer");
+  ES_REQUIRE(g->C > 0 && g->C % 64 == 0 && g->Hu <= 64 && g->Wu <= 64 && g->Hu >= g->Hs && g->Wu >= g->Ws &&
+                 g->Ho == g->Hu + 2 * g->pad - g->KH + 1 && g->Wo == g->Wu + 2 * g->pad - g->KW + 1 && g->Ho > 0 && g->Wo > 0,
+             "unsupported geometry");
+  ES_REQUIRE(n_groups >= 1 && n_groups <= kFMaxGroups && total_rows > 0, "bad group count / rows");
+  ES_REQUIRE(g->N % 64 == 0 && g->N <= 256 && (g->N & (g->N - 1)) == 0, "dy channels must be 64, 128 or 256");
+  WgParams p{};
+  p.grp = grp; p.n_groups = n_groups;
+  p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
+  p.KH = g->KH; p.KW = g->KW; p.pad = g->pad; p.P = g->Ho * g->Wo;
+  p.KK = g->KH * g->KW * g->C; p.N = g->N;
+  ES_REQUIRE(p.KK % kBM == 0, "KH*KW*C must be a multiple of 128");
+  ES_REQUIRE((long)total_rows * p.P < 2147483647L && (long)total_rows * p.Hs * p.Ws * p.C < (1L << 40), "too many pixels");
+  p.tiles_m = p.KK / kBM;
+  int splits = ceil_div(1024, p.tiles_m * n_groups);
+  const long kblocks = ceil_div_l((long)total_rows * p.P, kBK);
+  if (splits > kblocks) splits = (int)kblocks;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  p.splits = splits;
+  fill_maps_uc(p.Hs, p.Ws, p.Hu, p.Wu, p.ymap, p.xmap);
+  p.x = (const __nv_bfloat16*)x; p.dw = dw; p.dw_slot_stride = (long)g->N * p.KK; p.err_flag = fwd_err_flag();
+
+  EncodeTiledFn enc = encode_fn();
+  ES_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  alignas(64) CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)g->N, (cuuint64_t)total_rows * (cuuint64_t)p.P};
+  const cuuint64_t strides[1] = {(cuuint64_t)g->N * 2};
+  const cuuint32_t box[2] = {64, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dy), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for dy");
+  static bool attr_set = false;
+  if (!attr_set) {
+    ES_CUDA(cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int total = n_groups * p.splits * p.tiles_m;
+  igemm_wgrad_kernel<<<total < sms ? total : sms, kFThreads, kFSmem, as_stream(stream)>>>(p, tmap);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }

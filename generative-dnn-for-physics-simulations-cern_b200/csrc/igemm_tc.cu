@@ -392,30 +392,6 @@ int launch_igemm(const IgemmParams& p, dim3 grid, cudaStream_t st) {
 
 using namespace es;
 
-extern "C" int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es_conv_geom* g, const es_group* grp,
-                              int n_groups, int total_rows, void* stream) {
-  ES_REQUIRE(x && dy && dw && grp, "null pointer");
-  ES_REQUIRE(check_geom(g), "unsupported geometry");
-  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad group count / rows");
-  ES_REQUIRE(g->N % 64 == 0 && g->N <= 256, "dy channels must be 64, 128 or 256");
-  IgemmParams p{};
-  geom_to_params(g, p);
-  ES_REQUIRE(p.KK % kBM == 0, "KH*KW*C must be a multiple of 128");
-  p.grp = grp; p.n_groups = n_groups;
-  p.Nout = g->N; p.BN = g->N;
-  // split the pixel reduction so that every SM gets work: tiles = KK/128 per group
-  const int tiles = p.KK / kBM;
-  const long kblocks = ceil_div_l((long)total_rows * p.P, kBK);
-  int splits = ceil_div(2 * 148, tiles * (n_groups > 0 ? 1 : 1));
-  if (splits > kblocks) splits = (int)kblocks;
-  if (splits < 1) splits = 1;
-  if (splits > 64) splits = 64;
-  p.splits = splits;
-  p.a_src = (const __nv_bfloat16*)x; p.b_src = (const __nv_bfloat16*)dy;
-  p.out = dw; p.out_slot_stride = (long)g->N * p.KK; p.err_flag = err_flag_ptr();
-  return launch_igemm<WGRAD_CONV>(p, dim3(tiles, n_groups * splits), as_stream(stream));
-}
-
 extern "C" int es_dense_dgrad(const void* dy, const void* w, float* dx, int N, int K, const es_group* grp,
                               int n_groups, int total_rows, void* stream) {
   ES_REQUIRE(dy && w && dx && grp, "null pointer");
