@@ -312,6 +312,7 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
                 float* __restrict__ stats, float* __restrict__ dgamma, float* __restrict__ dbeta,
                 float* __restrict__ dbias) {
   __shared__ float s_a[256], s_b[256];     // per-channel accumulators
+  __shared__ float s_dg[256], s_db[256];   // per-channel affine-gradient accumulators (backward)
   __shared__ float s_g1[64], s_g2[64];     // per-group results
   __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
   const int r = blockIdx.x;
@@ -331,7 +332,7 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   const int cu = tid % c4, c8 = cu * 8, pstep = 256 / c4, p0 = tid / c4;
   const float cnt = (float)(cpg * P);
   if (BWD && tid == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
-  s_a[tid] = 0.f; s_b[tid] = 0.f;
+  s_a[tid] = 0.f; s_b[tid] = 0.f; s_dg[tid] = 0.f; s_db[tid] = 0.f;
   __syncthreads();
   const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * P * C);
   float gk[8], bk[8];
@@ -412,14 +413,14 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) { atomicAdd(&s_a[c8 + k], a1[k]); atomicAdd(&s_b[c8 + k], a2[k]); }
-    // per-channel affine gradients: combine the threads that share a channel octet through shuffles is not possible
-    // (they sit in different warps), so go straight to global atomics, one per channel per thread
+    // per-channel affine gradients: combined per CTA in shared memory, then ONE global atomic per channel per CTA
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      atomicAdd(&dgamma[slot * slot_stride + c8 + k], ag[k]);
-      atomicAdd(&dbeta[slot * slot_stride + c8 + k], ab[k]);
-    }
+    for (int k = 0; k < 8; ++k) { atomicAdd(&s_dg[c8 + k], ag[k]); atomicAdd(&s_db[c8 + k], ab[k]); }
     __syncthreads();
+    if (tid < C) {
+      atomicAdd(&dgamma[slot * slot_stride + tid], s_dg[tid]);
+      atomicAdd(&dbeta[slot * slot_stride + tid], s_db[tid]);
+    }
     if (tid < groups) {
       float s1 = 0.f, s2 = 0.f;
       for (int k = 0; k < cpg; ++k) { s1 += s_a[tid * cpg + k]; s2 += s_b[tid * cpg + k]; }
@@ -446,8 +447,13 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
       dx4[(size_t)pix * c4 + cu] = pack8(o);
     }
     if (dbias) {
+      __syncthreads();                 // s_dg is free again: reuse it for the conv-bias gradient
+      if (tid < C) s_dg[tid] = 0.f;
+      __syncthreads();
 #pragma unroll
-      for (int k = 0; k < 8; ++k) atomicAdd(&dbias[slot * slot_stride + c8 + k], al[k]);
+      for (int k = 0; k < 8; ++k) atomicAdd(&s_dg[c8 + k], al[k]);
+      __syncthreads();
+      if (tid < C) atomicAdd(&dbias[slot * slot_stride + tid], s_dg[tid]);
     }
   }
 }

@@ -195,6 +195,74 @@ conv2d_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ 
   (void)red;
 }
 
+// Few-tap variant (Ci*KH*KW <= 9, e.g. the discriminator's first conv 1->32 k3): the generic kernel gives one thread per
+// tap, i.e. 9 busy threads.  Here threads own PIXELS, keep all T x 8 partial sums in registers over the CTA's samples and
+// combine them once at the end (warp shuffles + shared memory), then one atomic per weight per CTA.
+template <int T>
+__global__ void __launch_bounds__(256)
+conv2d_bwd_weight_fewtaps_kernel(const float* __restrict__ x, const float* __restrict__ dy, es_conv2d g,
+                                 const es_group* __restrict__ grp, int n_groups, int per, float* __restrict__ dw,
+                                 float* __restrict__ db, long sw, long sb) {
+  extern __shared__ float sm[];
+  __shared__ float s_red[8][(T + 1) * kCoT];
+  int gi, row0, ns;
+  if (!chunk_of(grp, n_groups, per, blockIdx.x, gi, row0, ns)) return;
+  const int slot = grp[gi].slot, co0 = blockIdx.y * kCoT;
+  const int in_sz = g.Ci * g.Hi * g.Wi, HWo = g.Ho * g.Wo, taps = g.Ci * g.KH * g.KW;
+  float* s_x = sm;
+  float* s_d = sm + ((in_sz + 3) & ~3);
+  float acc[T + 1][kCoT];
+#pragma unroll
+  for (int j = 0; j <= T; ++j)
+#pragma unroll
+    for (int c = 0; c < kCoT; ++c) acc[j][c] = 0.f;
+  for (int s = 0; s < ns; ++s) {
+    __syncthreads();
+    const size_t row = row0 + s;
+    for (int i = threadIdx.x; i < in_sz; i += blockDim.x) s_x[i] = x[row * in_sz + i];
+    for (int i = threadIdx.x; i < HWo * kCoT; i += blockDim.x) {
+      const int c = i / HWo, p = i % HWo;
+      s_d[p * kCoT + c] = dy[(row * g.Co + co0 + c) * HWo + p];
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < HWo; p += blockDim.x) {
+      const int oy = p / g.Wo, ox = p - oy * g.Wo;
+      const float4* dv = reinterpret_cast<const float4*>(s_d + p * kCoT);
+      const float4 d0 = dv[0], d1 = dv[1];
+      const float d[kCoT] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int c = 0; c < kCoT; ++c) acc[T][c] += d[c];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        if (t < taps) {
+          const int kx = t % g.KW, ky = (t / g.KW) % g.KH, ci = t / (g.KW * g.KH);
+          const int iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
+          const float xv = (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi) ? s_x[(ci * g.Hi + iy) * g.Wi + ix] : 0.f;
+#pragma unroll
+          for (int c = 0; c < kCoT; ++c) acc[t][c] = fmaf(xv, d[c], acc[t][c]);
+        }
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j <= T; ++j)
+#pragma unroll
+    for (int c = 0; c < kCoT; ++c) {
+      const float v = warp_sum(acc[j][c]);
+      if (lane == 0) s_red[warp][j * kCoT + c] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (T + 1) * kCoT; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_red[w][i];
+    const int j = i / kCoT, c = i % kCoT;
+    if (j < taps) atomicAdd(&dw[slot * sw + (size_t)(co0 + c) * taps + j], v);
+    else if (j == T && db) atomicAdd(&db[slot * sb + co0 + c], v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm (NCHW fp32)
 __global__ void __launch_bounds__(128)
 groupnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -500,6 +568,118 @@ spectral_norm_fwd_kernel(const float* __restrict__ w_orig, float* __restrict__ u
   if (v_used) for (int i = threadIdx.x; i < I; i += blockDim.x) v_used[(size_t)slot * I + i] = s_v[i];
 }
 
+// Multi-CTA power iteration for the large matrices (fc1.0: 128 x 2313 per expert): three launches, no inter-CTA waits.
+//   phase 1: t = W^T u      (threads along i: coalesced rows of W), |t|^2 by atomics
+//   phase 2: s = W t        (one warp per row),                     |s|^2 by atomics
+//   phase 3: v = t/|t|, u = (s/|t|)/|s/|t||, sigma = u.(W v) = |s|/|t|, w_sn = W / sigma (elementwise, all CTAs)
+// scratch per slot: t[I], s[O], n2[2].
+__global__ void __launch_bounds__(256)
+sn_phase1_kernel(const float* __restrict__ w_orig, const float* __restrict__ u, long sw, long su, int O, int I,
+                 const es_group* __restrict__ grp, float* __restrict__ scratch) {
+  __shared__ float red[32];
+  __shared__ float s_u[512];
+  const int slot = blockIdx.y;
+  if (grp && grp[slot].rows == 0) return;
+  const float* W = w_orig + slot * sw;
+  float* T = scratch + (size_t)slot * (I + O + 2);
+  for (int o = threadIdx.x; o < O; o += blockDim.x) s_u[o] = u[slot * su + o];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (i < I) {
+    int o = 0;
+    for (; o + 4 <= O; o += 4) {
+      a0 = fmaf(W[(size_t)o * I + i], s_u[o], a0);
+      a1 = fmaf(W[(size_t)(o + 1) * I + i], s_u[o + 1], a1);
+      a2 = fmaf(W[(size_t)(o + 2) * I + i], s_u[o + 2], a2);
+      a3 = fmaf(W[(size_t)(o + 3) * I + i], s_u[o + 3], a3);
+    }
+    for (; o < O; ++o) a0 = fmaf(W[(size_t)o * I + i], s_u[o], a0);
+    a0 = (a0 + a1) + (a2 + a3);
+    T[i] = a0;
+  }
+  const float n = block_sum(i < I ? a0 * a0 : 0.f, red);
+  if (threadIdx.x == 0) atomicAdd(&T[I + O], n);
+}
+
+__global__ void __launch_bounds__(256)
+sn_phase2_kernel(const float* __restrict__ w_orig, long sw, int O, int I, const es_group* __restrict__ grp,
+                 float* __restrict__ scratch) {
+  const int slot = blockIdx.y;
+  if (grp && grp[slot].rows == 0) return;
+  const float* W = w_orig + slot * sw;
+  float* T = scratch + (size_t)slot * (I + O + 2);
+  const int lane = threadIdx.x & 31, o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= O) return;
+  float a = 0.f;
+  for (int i = lane; i < I; i += 32) a = fmaf(W[(size_t)o * I + i], T[i], a);
+  a = warp_sum(a);
+  if (lane == 0) {
+    T[I + o] = a;
+    atomicAdd(&T[I + O + 1], a * a);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sn_phase3_kernel(const float* __restrict__ w_orig, float* __restrict__ u, float* __restrict__ v, long sw, long su, long sv,
+                 int O, int I, const es_group* __restrict__ grp, const float* __restrict__ scratch, float* __restrict__ w_sn,
+                 long ssn, float* __restrict__ sigma_out, float* __restrict__ u_used, float* __restrict__ v_used) {
+  const int slot = blockIdx.y;
+  if (grp && grp[slot].rows == 0) return;
+  const float* T = scratch + (size_t)slot * (I + O + 2);
+  const float nt = fmaxf(sqrtf(T[I + O]), 1e-12f);          // |W^T u|
+  const float nsp = sqrtf(T[I + O + 1]) / nt;                // |W v|
+  const float inv_u = 1.f / (fmaxf(nsp, 1e-12f) * nt);       // u = s * inv_u
+  const float sg = nsp * nsp / fmaxf(nsp, 1e-12f);           // sigma = u . (W v)
+  const float inv = 1.f / sg;
+  const float* W = w_orig + slot * sw;
+  float* WS = w_sn + slot * ssn;
+  const int n = O * I;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) WS[i] = W[i] * inv;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) sigma_out[slot] = sg;
+    for (int i = threadIdx.x; i < I; i += blockDim.x) {
+      const float x = T[i] / nt;
+      v[slot * sv + i] = x;
+      if (v_used) v_used[(size_t)slot * I + i] = x;
+    }
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+      const float x = T[I + o] * inv_u;
+      u[slot * su + o] = x;
+      if (u_used) u_used[(size_t)slot * O + o] = x;
+    }
+  }
+}
+
+// backward, multi-CTA: dot[slot] = <dw_sn, w_sn> by atomics, then the elementwise update
+__global__ void __launch_bounds__(256)
+sn_bwd_dot_kernel(const float* __restrict__ dw_sn, const float* __restrict__ w_sn, long ssn, int n,
+                  const es_group* __restrict__ grp, float* __restrict__ dot) {
+  __shared__ float red[32];
+  const int slot = blockIdx.y;
+  if (grp && grp[slot].rows == 0) return;
+  const float* D = dw_sn + slot * ssn;
+  const float* WS = w_sn + slot * ssn;
+  float a = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a = fmaf(D[i], WS[i], a);
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) atomicAdd(&dot[slot], a);
+}
+__global__ void __launch_bounds__(256)
+sn_bwd_apply_kernel(const float* __restrict__ dw_sn, const float* __restrict__ u_used, const float* __restrict__ v_used,
+                    const float* __restrict__ sigma, const float* __restrict__ dot, long ssn, int O, int I,
+                    float* __restrict__ dw_orig, long sw, const es_group* __restrict__ grp) {
+  const int slot = blockIdx.y;
+  if (grp && grp[slot].rows == 0) return;
+  const float* D = dw_sn + slot * ssn;
+  const float inv = 1.f / sigma[slot], dt = dot[slot];
+  const int n = O * I;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int o = i / I, k = i - o * I;
+    dw_orig[slot * sw + i] += (D[i] - dt * u_used[(size_t)slot * O + o] * v_used[(size_t)slot * I + k]) * inv;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 spectral_norm_bwd_kernel(const float* __restrict__ dw_sn, const float* __restrict__ w_sn, const float* __restrict__ u_used,
                          const float* __restrict__ v_used, const float* __restrict__ sigma, long ssn, int O, int I,
@@ -649,6 +829,13 @@ extern "C" int es_conv2d_bwd_weight(const float* x, const float* dy, const es_co
   ES_REQUIRE(smem <= 220 * 1024, "sample does not fit in shared memory");
   int per = ceil_div(total_rows * (g->Co / kCoT), 4 * 148);
   if (per < 1) per = 1;
+  if (g->Ci * g->KH * g->KW <= 9) {
+    ES_CUDA(cudaFuncSetAttribute(conv2d_bwd_weight_fewtaps_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    conv2d_bwd_weight_fewtaps_kernel<9><<<dim3(ceil_div(total_rows, per) + n_groups, g->Co / kCoT), 256, smem, as_stream(stream)>>>(
+        x, dy, *g, grp, n_groups, per, dw, db, slot_stride_w, slot_stride_b);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   ES_CUDA(cudaFuncSetAttribute(conv2d_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   conv2d_bwd_weight_kernel<<<dim3(ceil_div(total_rows, per) + n_groups, g->Co / kCoT), 256, smem, as_stream(stream)>>>(
       x, dy, *g, grp, n_groups, per, dw, db, slot_stride_w, slot_stride_b);
@@ -754,8 +941,20 @@ extern "C" int es_linear_bwd_weight(const float* x, int ldx, const float* dy, in
 extern "C" int es_spectral_norm_fwd(const float* w_orig, float* u, float* v, long slot_stride_w, long slot_stride_u,
                                     long slot_stride_v, int slots, int O, int I, int do_power_iter, const es_group* grp,
                                     float* w_sn, long slot_stride_sn, float* sigma_out, float* u_used, float* v_used,
-                                    void* stream) {
+                                    float* scratch, void* stream) {
   ES_REQUIRE(w_orig && u && v && w_sn && sigma_out && slots >= 1 && O > 0 && I > 0, "bad arguments");
+  if (scratch && do_power_iter && O <= 512 && (long)O * I >= 16384) {
+    cudaStream_t st = as_stream(stream);
+    const size_t per = (size_t)I + O + 2;
+    ES_CUDA(cudaMemsetAsync(scratch, 0, per * slots * sizeof(float), st));
+    sn_phase1_kernel<<<dim3(ceil_div(I, 256), slots), 256, 0, st>>>(w_orig, u, slot_stride_w, slot_stride_u, O, I, grp, scratch);
+    sn_phase2_kernel<<<dim3(ceil_div(O, 8), slots), 256, 0, st>>>(w_orig, slot_stride_w, O, I, grp, scratch);
+    const int nb = min(64, ceil_div(O * I, 2048));
+    sn_phase3_kernel<<<dim3(nb, slots), 256, 0, st>>>(w_orig, u, v, slot_stride_w, slot_stride_u, slot_stride_v, O, I, grp,
+                                                       scratch, w_sn, slot_stride_sn, sigma_out, u_used, v_used);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   const size_t smem = ((size_t)I + 2 * O) * sizeof(float);
   ES_REQUIRE(smem <= 48 * 1024, "spectral norm vectors do not fit in shared memory");
   spectral_norm_fwd_kernel<<<slots, 256, smem, as_stream(stream)>>>(w_orig, u, v, slot_stride_w, slot_stride_u,
@@ -767,8 +966,18 @@ extern "C" int es_spectral_norm_fwd(const float* w_orig, float* u, float* v, lon
 
 extern "C" int es_spectral_norm_bwd(const float* dw_sn, const float* w_sn, const float* u_used, const float* v_used,
                                     const float* sigma, long slot_stride_sn, int slots, int O, int I, float* dw_orig,
-                                    long slot_stride_w, const es_group* grp, void* stream) {
+                                    long slot_stride_w, const es_group* grp, float* scratch, void* stream) {
   ES_REQUIRE(dw_sn && w_sn && u_used && v_used && sigma && dw_orig && slots >= 1, "bad arguments");
+  if (scratch && (long)O * I >= 16384) {
+    cudaStream_t st = as_stream(stream);
+    ES_CUDA(cudaMemsetAsync(scratch, 0, slots * sizeof(float), st));
+    const int nb = min(64, ceil_div(O * I, 2048));
+    sn_bwd_dot_kernel<<<dim3(nb, slots), 256, 0, st>>>(dw_sn, w_sn, slot_stride_sn, O * I, grp, scratch);
+    sn_bwd_apply_kernel<<<dim3(nb, slots), 256, 0, st>>>(dw_sn, u_used, v_used, sigma, scratch, slot_stride_sn, O, I, dw_orig,
+                                                          slot_stride_w, grp);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   spectral_norm_bwd_kernel<<<slots, 256, 0, as_stream(stream)>>>(dw_sn, w_sn, u_used, v_used, sigma, slot_stride_sn, O, I,
                                                                 dw_orig, slot_stride_w, grp);
   ES_LAUNCH_CHECK();

@@ -171,7 +171,8 @@ class DiscEngine:
             wsn, sig = empty(E, O * I), empty(E)
             uu, vu = empty(E, O), empty(E, I)
             L.call("es_spectral_norm_fwd", a.addr(name + ".weight_orig"), a.baddr(name + ".weight_u"), a.baddr(name + ".weight_v"),
-                   a.n, a.nb, a.nb, E, O, I, int(training), grp if training else None, wsn, O * I, sig, uu, vu)
+                   a.n, a.nb, a.nb, E, O, I, int(training), grp if training else None, wsn, O * I, sig, uu, vu,
+                   empty(E, I + O + 2))
             out[name] = (wsn, sig, uu, vu)
         return out
 
@@ -266,7 +267,7 @@ class DiscEngine:
             for name in self.SN:
                 O, I = self.dims[name]
                 wsn, sig, uu, vu = sn[name]
-                L.call("es_spectral_norm_bwd", dsn[name], wsn, uu, vu, sig, O * I, E, O, I, a.gaddr(name + ".weight_orig"), n, grp)
+                L.call("es_spectral_norm_bwd", dsn[name], wsn, uu, vu, sig, O * I, E, O, I, a.gaddr(name + ".weight_orig"), n, grp, empty(E))
 
 
 # =====================================================================================================================

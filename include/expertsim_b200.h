@@ -268,15 +268,17 @@ int es_linear_bwd_data(const float* dy, const float* w, long slot_stride_w, int 
 int es_linear_bwd_weight(const float* x, int ldx, const float* dy, int I, int O, const es_group* grp, int n_groups, int total_rows,
                          float* dw, float* db, long slot_stride_w, long slot_stride_b, void* stream);
 /* Spectral norm (hook-based torch.nn.utils.spectral_norm, torch/nn/utils/spectral_norm.py:62-113): per slot, one power
- * iteration in place on u[O], v[I] (if do_power_iter), sigma = u.(W v), w_sn = w_orig / sigma.  sigma_out[slot]. */
+ * iteration in place on u[O], v[I] (if do_power_iter), sigma = u.(W v), w_sn = w_orig / sigma.  sigma_out[slot].
+ * scratch (nullable): slots*(I+O+2) floats (fwd) / slots floats (bwd); when given, matrices of >= 16384 elements run the
+ * multi-CTA path (three launches, partial norms by atomics) instead of one CTA per slot. */
 int es_spectral_norm_fwd(const float* w_orig, float* u, float* v, long slot_stride_w, long slot_stride_u, long slot_stride_v,
                          int slots, int O, int I, int do_power_iter, const es_group* grp, float* w_sn, long slot_stride_sn,
-                         float* sigma_out, float* u_used, float* v_used, void* stream);
+                         float* sigma_out, float* u_used, float* v_used, float* scratch, void* stream);
 /* dw_orig += (dw_sn - <dw_sn, w_sn> u v^T) / sigma; slots whose grp[slot].rows == 0 are skipped (grp nullable: all slots,
  * where grp[s] must describe slot s as produced by es_router_partition) */
 int es_spectral_norm_bwd(const float* dw_sn, const float* w_sn, const float* u_used, const float* v_used, const float* sigma,
                          long slot_stride_sn, int slots, int O, int I, float* dw_orig, long slot_stride_w,
-                         const es_group* grp, void* stream);
+                         const es_group* grp, float* scratch, void* stream);
 /* elementwise helpers: y = a + b then ReLU (residual join), its backward mask, mean over HW, dropout with a given keep-mask */
 int es_add_relu_fwd(const float* a, const float* b, long n, float* y, void* stream);
 int es_relu_bwd(const float* dy, const float* y, long n, float* dx, void* stream);

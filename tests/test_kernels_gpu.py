@@ -629,9 +629,12 @@ def test_linear(I, O):
     check(f"linear bwd bias {I}->{O}", db, lb.grad, 2e-5)
 
 
+@pytest.mark.parametrize("multi_cta", [False, True])
 @pytest.mark.parametrize("O,I", [(32, 9), (16, 288), (128, 2313), (64, 128), (1, 64)])
-def test_spectral_norm(O, I):
+def test_spectral_norm(O, I, multi_cta):
     S = 3
+    sc_f = torch.empty(S, I + O + 2, device=DEV) if multi_cta else None
+    sc_b = torch.empty(S, device=DEV) if multi_cta else None
     g = G(O * I)
     w = torch.randn(S, O, I, generator=g) / math.sqrt(I)
     u = F.normalize(torch.randn(S, O, generator=g), dim=1)
@@ -640,10 +643,10 @@ def test_spectral_norm(O, I):
     du, dv = cuda(u.clone()), cuda(v.clone())
     wsn = torch.zeros(S, O, I, device=DEV)
     sig, uu, vu = torch.zeros(S, device=DEV), torch.zeros(S, O, device=DEV), torch.zeros(S, I, device=DEV)
-    L.call("es_spectral_norm_fwd", cuda(w), du, dv, O * I, O, I, S, O, I, 1, grp, wsn, O * I, sig, uu, vu)
+    L.call("es_spectral_norm_fwd", cuda(w), du, dv, O * I, O, I, S, O, I, 1, grp, wsn, O * I, sig, uu, vu, sc_f)
     dwsn = torch.randn(S, O, I, generator=g)
     dwo = torch.zeros(S, O, I, device=DEV)
-    L.call("es_spectral_norm_bwd", cuda(dwsn), wsn, uu, vu, sig, O * I, S, O, I, dwo, O * I, None)
+    L.call("es_spectral_norm_bwd", cuda(dwsn), wsn, uu, vu, sig, O * I, S, O, I, dwo, O * I, grp, sc_b)
     for s in (0, 2):
         sd = {"l.weight_orig": w[s].clone().requires_grad_(True), "l.weight_u": u[s].clone(), "l.weight_v": v[s].clone()}
         ws = orc.spectral_norm_weight(sd, "l", True)
