@@ -3,25 +3,9 @@
 // 64->1 convolution + ReLU, weight (re)packing, and CUDA-core (SIMT) reference versions of the implicit GEMMs.
 // Reference: Generator.forward (expertsim/models/proton/generator.py:13-52).
 #include "common.cuh"
+#include "gen_common.cuh"
 
 namespace es {
-
-// row r of a generator batch -> (group, pass, half-batch row j)
-struct RowMap { int g, pass, j; };
-__device__ __forceinline__ RowMap map_row(const es_group* grp, int E, int r, int two_pass) {
-  RowMap m{-1, 0, 0};
-  m.g = find_group(grp, E, r);
-  if (m.g < 0) return m;
-  const es_group G = grp[m.g];
-  const int local = r - G.row_start;
-  if (two_pass) {
-    m.pass = local >= G.pass_rows ? 1 : 0;
-    m.j = G.row_start / 2 + local - m.pass * G.pass_rows;
-  } else {
-    m.j = r;
-  }
-  return m;
-}
 
 // ----------------------------------------------------------------------------------------------- fc1 (19 -> 256)
 constexpr int kF1 = 256, kIn = 19, kNz = 10, kNc = 9;
@@ -53,7 +37,12 @@ gen_fc1_fwd_kernel(const float* __restrict__ z1, const float* __restrict__ z2, c
     for (int k = 0; k < kIn; ++k) acc = fmaf(W[o * kIn + k], __shfl_sync(0xffffffffu, xin, k), acc);
     v[q] = acc;
     s += acc;
-    lin[(size_t)r * kF1 + o] = acc;
+    if (lin) lin[(size_t)r * kF1 + o] = acc;
+  }
+  if (!gamma) {     // linear head only (neutron: BatchNorm follows as its own pass)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) h[(size_t)r * kF1 + lane + 32 * q] = f2bf(v[q]);
+    return;
   }
   const float mean = warp_sum(s) * (1.f / kF1);
   float ss = 0.f;
@@ -86,6 +75,17 @@ gen_fc1_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ x0, c
   const int slot = G.slot;
   for (int i = ch * 8 + warp; i < G.rows; i += chunks * 8) {
     const int r = G.row_start + i;
+    if (!gamma) {   // linear head only: dh is the gradient w.r.t. the linear output
+      const float xin0 = lane < kIn ? x0[(size_t)r * kIn + lane] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int o = lane + 32 * q;
+        const float dl = dh[(size_t)r * kF1 + o];
+        atomicAdd(&s_v[0][o], dl);
+        for (int k = 0; k < kIn; ++k) atomicAdd(&s_dw[o * kIn + k], dl * __shfl_sync(0xffffffffu, xin0, k));
+      }
+      continue;
+    }
     float v[8], xh[8], dyn[8];
     float s = 0.f;
 #pragma unroll
@@ -124,8 +124,10 @@ gen_fc1_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ x0, c
   for (int i = threadIdx.x; i < kF1 * kIn; i += 256) atomicAdd(&dw[slot * sw + i], s_dw[i]);
   for (int i = threadIdx.x; i < kF1; i += 256) {
     atomicAdd(&db[slot * sv + i], s_v[0][i]);
-    atomicAdd(&dgamma[slot * sv + i], s_v[1][i]);
-    atomicAdd(&dbeta[slot * sv + i], s_v[2][i]);
+    if (gamma) {
+      atomicAdd(&dgamma[slot * sv + i], s_v[1][i]);
+      atomicAdd(&dbeta[slot * sv + i], s_v[2][i]);
+    }
   }
 }
 
@@ -170,32 +172,6 @@ ln_lrelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
     for (int k = 0; k < 8; ++k) f[k] = lrelu((f[k] - mean) * rstd * gg[k] + be[k]);
     y4[i] = pack8(f);
   }
-}
-
-// nearest-upsample fan-in tables: source index s receives upsampled indices [lo[s], hi[s])
-__device__ __forceinline__ void build_fanin(int Ns, int Nu, int* lo, int* hi) {
-  const float sc = (float)Ns / (float)Nu;
-  for (int s = 0; s < Ns; ++s) { lo[s] = Nu; hi[s] = 0; }
-  for (int u = 0; u < Nu; ++u) {
-    int s = (int)floorf((float)u * sc);
-    s = s < Ns - 1 ? s : Ns - 1;
-    if (u < lo[s]) lo[s] = u;
-    if (u + 1 > hi[s]) hi[s] = u + 1;
-  }
-}
-
-// gradient arriving at source pixel (sy,sx), channels [c8, c8+8): sum over its upsample fan-out
-__device__ __forceinline__ void load_da8(const __nv_bfloat16* __restrict__ dy_row, int Wu, int C, int c8, const int* ylo,
-                                         const int* yhi, const int* xlo, const int* xhi, int sy, int sx, float* out) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) out[k] = 0.f;
-  float f[8];
-  for (int uy = ylo[sy]; uy < yhi[sy]; ++uy)
-    for (int ux = xlo[sx]; ux < xhi[sx]; ++ux) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dy_row + ((size_t)uy * Wu + ux) * C + c8)), f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) out[k] += f[k];
-    }
 }
 
 __global__ void __launch_bounds__(512)
@@ -686,7 +662,7 @@ extern "C" int es_gen_fc1_fwd(const float* z1, const float* z2, const float* con
                               const float* gamma, const float* beta, long slot_stride_w, long slot_stride_v,
                               const es_group* grp_gen, int E, int total_rows, int two_pass, float* x0, float* lin,
                               void* h, void* stream) {
-  ES_REQUIRE(z1 && cond && w && b && gamma && beta && grp_gen && x0 && lin && h, "null pointer");
+  ES_REQUIRE(z1 && cond && w && b && grp_gen && x0 && h && (gamma ? (beta && lin) : true), "null pointer");
   ES_REQUIRE(!two_pass || z2, "two-pass batch needs z2");
   ES_REQUIRE(E >= 1 && E <= kMaxGroups && total_rows > 0, "bad sizes");
   gen_fc1_fwd_kernel<<<ceil_div(total_rows, 8), 256, 0, as_stream(stream)>>>(
@@ -699,7 +675,7 @@ extern "C" int es_gen_fc1_fwd(const float* z1, const float* z2, const float* con
 extern "C" int es_gen_fc1_bwd(const float* dh, const float* x0, const float* lin, const float* gamma,
                               const float* beta, long slot_stride_w, long slot_stride_v, const es_group* grp_gen,
                               int E, int total_rows, float* dw, float* db, float* dgamma, float* dbeta, void* stream) {
-  ES_REQUIRE(dh && x0 && lin && gamma && beta && grp_gen && dw && db && dgamma && dbeta, "null pointer");
+  ES_REQUIRE(dh && x0 && grp_gen && dw && db && (gamma ? (lin && beta && dgamma && dbeta) : true), "null pointer");
   ES_REQUIRE(E >= 1 && E <= kMaxGroups && total_rows > 0, "bad sizes");
   const int chunks = max(1, min(32, ceil_div(total_rows, 8 * 4 * E)));
   gen_fc1_bwd_kernel<<<E * chunks, 256, 0, as_stream(stream)>>>(dh, x0, lin, gamma, beta, slot_stride_w,

@@ -537,8 +537,10 @@ extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, lon
   p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
   p.KH = g->KH; p.KW = g->KW; p.pad = g->pad; p.P = g->Ho * g->Wo;
   p.KK = g->KH * g->KW * g->C;
-  p.Nout = g->N; p.BN = g->N >= 256 ? 256 : g->N;
-  ES_REQUIRE(g->N % 32 == 0 && g->N % p.BN == 0 && (p.BN & (p.BN - 1)) == 0, "N must be 32/64/128 or a multiple of 256");
+  p.Nout = g->N;
+  p.BN = 256;                                   // widest N tile (power of two, >= 32) that divides N
+  while (p.BN > 32 && g->N % p.BN != 0) p.BN >>= 1;
+  ES_REQUIRE(g->N % p.BN == 0, "N must be a multiple of 32");
   ES_REQUIRE((long)total_rows * p.Hs * p.Ws < 2147483647L, "too many source pixels");
   p.n_tiles_n = g->N / p.BN;
   fill_maps_uc(p.Hs, p.Ws, p.Hu, p.Wu, p.ymap, p.xmap);

@@ -75,7 +75,9 @@ conv2d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
 }
 
 // ------------------------------------------------------------------------------------------------ conv data gradient
-template <int CIT>
+// STAGED = false: the gradient sample does not fit in shared memory (neutron aux conv1: 32 x 42 x 42 floats); dy is then
+// read straight from global memory / L2 and only the weight tile is staged.
+template <int CIT, bool STAGED = true>
 __global__ void __launch_bounds__(256)
 conv2d_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, long sw, es_conv2d g,
                        const es_group* __restrict__ grp, int n_groups, int S, float* __restrict__ dx, int accumulate) {
@@ -85,8 +87,8 @@ conv2d_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w
   const int slot = grp[gi].slot, ci0 = blockIdx.y * CIT;
   const int out_sz = g.Co * g.Ho * g.Wo, ktaps = g.KH * g.KW, HWi = g.Hi * g.Wi;
   float* s_dy = sm;                    // [S][Co][Ho][Wo]
-  float* s_w = sm + S * out_sz;        // [Co][KH][KW][CIT]
-  for (int i = threadIdx.x; i < ns * out_sz; i += blockDim.x) s_dy[i] = dy[(size_t)row0 * out_sz + i];
+  float* s_w = sm + (STAGED ? S * out_sz : 0);        // [Co][KH][KW][CIT]
+  if (STAGED) for (int i = threadIdx.x; i < ns * out_sz; i += blockDim.x) s_dy[i] = dy[(size_t)row0 * out_sz + i];
   for (int i = threadIdx.x; i < g.Co * ktaps * CIT; i += blockDim.x) {
     const int c = i % CIT, t = (i / CIT) % ktaps, co = i / (CIT * ktaps);
     s_w[i] = w[slot * sw + ((size_t)co * g.Ci + ci0 + c) * ktaps + t];
@@ -97,7 +99,7 @@ conv2d_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w
     float acc[CIT];
 #pragma unroll
     for (int c = 0; c < CIT; ++c) acc[c] = 0.f;
-    const float* ds = s_dy + s * out_sz;
+    const float* ds = STAGED ? s_dy + s * out_sz : dy + (size_t)(row0 + s) * out_sz;
     for (int ky = 0; ky < g.KH; ++ky) {
       const int ty = iy + g.pad - ky;
       if (ty < 0 || ty % g.stride != 0) continue;
@@ -805,7 +807,14 @@ extern "C" int es_conv2d_bwd_data(const float* dy, const float* w, long slot_str
   const int out_sz = g->Co * g->Ho * g->Wo, wt = g->Co * g->KH * g->KW * cit;
   const int S = pick_samples(out_sz, g->Hi * g->Wi, wt);
   const size_t smem = ((size_t)S * out_sz + wt) * sizeof(float);
-  ES_REQUIRE(smem <= 220 * 1024, "gradient sample does not fit in shared memory");
+  if (smem > 220 * 1024) {      // unstaged variant
+    ES_REQUIRE(wt * sizeof(float) <= 48 * 1024, "weight tile does not fit in shared memory");
+    const dim3 grid1(total_rows + n_groups, g->Ci / cit);
+    if (cit == 1) conv2d_bwd_data_kernel<1, false><<<grid1, 256, wt * sizeof(float), as_stream(stream)>>>(dy, w, slot_stride_w, *g, grp, n_groups, 1, dx, accumulate);
+    else conv2d_bwd_data_kernel<8, false><<<grid1, 256, wt * sizeof(float), as_stream(stream)>>>(dy, w, slot_stride_w, *g, grp, n_groups, 1, dx, accumulate);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   const dim3 grid(ceil_div(total_rows, S) + n_groups, g->Ci / cit);
   if (cit == 1) {
     ES_CUDA(cudaFuncSetAttribute(conv2d_bwd_data_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

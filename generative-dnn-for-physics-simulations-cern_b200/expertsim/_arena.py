@@ -149,6 +149,7 @@ class Arena:
         self.off: Dict[str, int] = OrderedDict()
         self.boff: Dict[str, int] = OrderedDict()
         self.shape: Dict[str, tuple] = {}
+        self.ioff: Dict[str, int] = OrderedDict()     # int64 buffers (BatchNorm num_batches_tracked)
         n = nb = 0
         for name, shape, kind, _ in spec:
             self.shape[name] = shape
@@ -159,12 +160,15 @@ class Arena:
             elif kind != "nbt":
                 self.boff[name] = nb
                 nb += _round4(numel)
-        self.n, self.nb = n, max(nb, 4)
+            else:
+                self.ioff[name] = len(self.ioff)
+        self.n, self.nb, self.ni = n, max(nb, 4), max(len(self.ioff), 1)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=self.device)
         self.P, self.G = z(n_slots, n), z(n_slots, n)
         self.M, self.V = z(n_slots, n), z(n_slots, n)
         self.steps = z(n_slots, dt=torch.int32)
         self.Bf = z(n_slots, self.nb)
+        self.Bi = z(n_slots, self.ni, dt=torch.int64)
         self.modules: List[nn.Module] = []
         self.version = 0      # bumped whenever parameters change (optimizer step, load_state_dict)
         self.engine = None    # compute engine bound to this arena (created by the owner)
@@ -178,6 +182,9 @@ class Arena:
 
     def baddr(self, name):
         return self.Bf.data_ptr() + 4 * self.boff[name]
+
+    def iaddr(self, name):
+        return self.Bi.data_ptr() + 8 * self.ioff[name]
 
     def numel(self, name):
         return int(math.prod(self.shape[name])) if self.shape[name] else 1
@@ -198,7 +205,9 @@ class Arena:
                     p.data = v
                     p.grad = None
                 elif kind == "nbt":
-                    holder._buffers[leaf] = holder._buffers[leaf].to(self.device)
+                    v = self.Bi[slot, self.ioff[name]]
+                    v.copy_(holder._buffers[leaf].to(self.device))
+                    holder._buffers[leaf] = v
                 else:
                     v = self.view(self.Bf, name, slot)
                     v.copy_(holder._buffers[leaf].to(self.device))

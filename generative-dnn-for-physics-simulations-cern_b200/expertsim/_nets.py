@@ -74,7 +74,7 @@ class GenEngineProton:
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
             L.call("es_pack_conv_weight", a.addr(name + ".weight"), a.n, E, N, C, KH, KW, self.w_fwd[name], self.w_dg[name])
 
-    def forward(self, z1, z2, cond, grp, R, two_pass, keep=True, training=True, drop=None):
+    def forward(self, z1, z2, cond, grp, R, two_pass, keep=True, training=True, drop=None, dp=None):
         """z1,z2 [B,10], cond [B,9] in expert-sorted order; grp = generator group table; R = total rows.
         Returns (img1 [B,HW], img2 or None, saved).  The proton generator has no train/eval difference (LayerNorm /
         GroupNorm only, no dropout), so ``training`` and ``drop`` are accepted for interface symmetry and unused."""
@@ -322,7 +322,7 @@ class AuxEngineProton:
         return dx
 
     # -- forward / backward -----------------------------------------------------------------------------------------
-    def forward(self, img, grp, R, training, masks=None):
+    def forward(self, img, grp, R, training, masks=None, dp=None):
         """img [R, 1680] -> coords [R,2].  masks = (keep128 [R,128], keep64 [R,64]) in training mode."""
         a, E, fe = self.a, self.a.E, self.FE
         s = {"img": img, "R": R, "grp": grp, "training": training, "masks": masks}
@@ -419,6 +419,263 @@ class AuxEngineProton:
 
 
 # =====================================================================================================================
+# neutron: BatchNorm (+ Dropout) networks.  Batch statistics are per (expert, pass) "stat group" and only fp64 partial
+# sums cross kernels, so the optional ``allreduce`` callback (data parallelism) turns them into SyncBN.
+# =====================================================================================================================
+def _noop(t):
+    return t
+
+
+def _seed():
+    """fresh 62-bit seed from torch's CPU generator (no device sync; honours torch.manual_seed)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+class GenEngineNeutron:
+    H, W = 44, 44
+    SP = (13, 13, 128)                           # fc2 output viewed as [128, 13, 13]
+    F2 = 21632
+    P_DROP = 0.2
+    # (conv name, fwd geometry (Hs,Ws,C,Hu,Wu,KH,KW,pad,N), BatchNorm name, dropout site)
+    CONVS = (("conv_layers.0", (13, 13, 128, 26, 26, 3, 3, 0, 256), "conv_layers.1", "conv_layers.2"),
+             ("conv_layers.5", (24, 24, 256, 48, 48, 3, 3, 0, 128), "conv_layers.6", "conv_layers.7"),
+             ("conv_layers.9", (46, 46, 128, 46, 46, 2, 2, 0, 64), "conv_layers.10", "conv_layers.11"))
+
+    def __init__(self, arena: Arena):
+        self.a = arena
+        E, dev = arena.E, arena.device
+        fp = torch.arange(self.F2, device=dev)
+        # packed feature f' = (y*13+x)*128 + c  <-  reference feature f = c*169 + y*13 + x   (view(-1,128,13,13))
+        self.row_map = ((fp % 128) * 169 + fp // 128).to(torch.int32).contiguous()
+        self.w_fc2 = torch.empty(E, self.F2, 256, dtype=BF, device=dev)
+        self.b_fc2 = torch.empty(E, self.F2, device=dev)
+        self.w_fwd, self.w_dg, self.dw_p = {}, {}, {}
+        for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
+            self.w_fwd[name] = torch.empty(E, N, KH, KW, C, dtype=BF, device=dev)
+            self.w_dg[name] = torch.empty(E, C, KH, KW, N, dtype=BF, device=dev)
+            self.dw_p[name] = torch.empty(E, N, KH, KW, C, device=dev)
+
+    def repack(self):
+        a, E = self.a, self.a.E
+        L.call("es_pack_dense_weight", a.addr("fc2.0.weight"), a.n, E, self.F2, 256, self.row_map, self.w_fc2)
+        L.call("es_permute_features", a.addr("fc2.0.bias"), a.n, self.row_map, E, self.F2, self.b_fc2, self.F2, 0)
+        for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
+            L.call("es_pack_conv_weight", a.addr(name + ".weight"), a.n, E, N, C, KH, KW, self.w_fwd[name], self.w_dg[name])
+
+    # ---- one BatchNorm (+dropout +LeakyReLU) layer on bf16 NHWC rows
+    def _bn_fwd(self, x, bn, geo, feat, chmap, site, ctx):
+        a, E = self.a, self.a.E
+        Hs, Ws, C = geo
+        CS = Hs * Ws * C if feat else C
+        passes = 2 if ctx["two_pass"] else 1
+        stats = empty(2 * E, CS, 2)
+        sums = None
+        if ctx["training"]:
+            sums = zeros(2 * E, CS, 2, dtype=torch.float64)
+            L.call("es_bn_stats_nhwc", x, Hs, Ws, C, int(feat), ctx["grp"], E, ctx["R"], int(ctx["two_pass"]), sums)
+            ctx["allreduce"](sums)
+        n_sg = (ctx["n_rows"] * (1 if feat else Hs * Ws)).contiguous()
+        L.call("es_bn_finalize", sums, n_sg, CS, passes, int(ctx["training"]), 0.1, chmap, a.baddr(bn + ".running_mean"),
+               a.baddr(bn + ".running_var"), a.nb, a.iaddr(bn + ".num_batches_tracked"), a.ni,
+               ctx["grp_slots"] if ctx["training"] else None, E, stats)
+        mask, seed = ctx["drop"](site)
+        p = self.P_DROP if ctx["training"] else 0.0
+        y = empty(*x.shape, dtype=BF)
+        L.call("es_bn_apply_fwd_nhwc", x, Hs, Ws, C, int(feat), stats, a.addr(bn + ".weight"), a.addr(bn + ".bias"), a.n, chmap,
+               mask, seed, p, ctx["grp"], E, ctx["R"], int(ctx["two_pass"]), y)
+        return y, dict(stats=stats, n_sg=n_sg, mask=mask, seed=seed, p=p)
+
+    def _bn_bwd(self, da, up, x, sv, bn, geo, feat, chmap, ctx):
+        """da: gradient on the consumer's (upsampled) grid ``up``; returns dx (bf16) w.r.t. the pre-BatchNorm tensor."""
+        a, E = self.a, self.a.E
+        Hs, Ws, C = geo
+        CS = Hs * Ws * C if feat else C
+        passes = 2 if ctx["two_pass"] else 1
+        sums2 = zeros(2 * E, CS, 2, dtype=torch.float64)
+        args = (da, Hs, Ws, up[0], up[1], C, int(feat), x, sv["stats"])
+        tail = (a.addr(bn + ".weight"), a.addr(bn + ".bias"), a.n, chmap, sv["mask"], sv["seed"], sv["p"], ctx["grp"], E, ctx["R"],
+                int(ctx["two_pass"]))
+        L.call("es_bn_bwd_reduce_nhwc", *args, *tail, sums2)
+        ctx["allreduce"](sums2)
+        L.call("es_bn_affine_grads", sums2, CS, passes, 1.0 / ctx["world"], chmap, ctx["grp_slots"], E, a.gaddr(bn + ".weight"),
+               a.gaddr(bn + ".bias"), a.n)
+        dx = empty(*x.shape, dtype=BF)
+        L.call("es_bn_bwd_apply_nhwc", *args, sums2, sv["n_sg"], *tail, dx)
+        return dx
+
+    def _ctx(self, grp, R, two_pass, training, drop, dp):
+        """drop: None (hash-based dropout, fresh seed per site) or dict site -> keep mask in the batch's row order."""
+        E = self.a.E
+        g = grp.view(E, 4)
+        rows_pass = (g[:, 3] if two_pass else g[:, 1]).to(torch.float32)
+        n_rows = dp["rows_global"] if dp and dp.get("rows_global") is not None else rows_pass
+        sites = {}
+
+        def dropf(site):
+            if site not in sites:
+                sites[site] = (drop[site], 0) if drop is not None else (None, _seed())
+            return sites[site]
+
+        return dict(grp=grp, grp_slots=grp, R=R, two_pass=two_pass, training=training, drop=dropf,
+                    n_rows=n_rows.repeat_interleave(2).contiguous(), allreduce=(dp or {}).get("allreduce", _noop),
+                    world=(dp or {}).get("world", 1))
+
+    def forward(self, z1, z2, cond, grp, R, two_pass, keep=True, training=True, drop=None, dp=None):
+        a, E = self.a, self.a.E
+        B = R // 2 if two_pass else R
+        ctx = self._ctx(grp, R, two_pass, training, drop, dp)
+        s = {"R": R, "two_pass": two_pass, "grp": grp, "ctx": ctx}
+        s["x0"], lin1 = empty(R, 19), empty(R, 256, dtype=BF)
+        L.call("es_gen_fc1_fwd", z1, z2, cond, a.addr("fc1.0.weight"), a.addr("fc1.0.bias"), None, None, a.n, a.n, grp, E, R,
+               int(two_pass), s["x0"], None, lin1)
+        s["lin1"] = lin1
+        s["h1"], s["bn1"] = self._bn_fwd(lin1, "fc1.1", (1, 1, 256), False, None, "fc1.2", ctx)
+        y2 = empty(R, self.F2, dtype=BF)
+        L.call("es_igemm_fwd", s["h1"], self.w_fc2, self.b_fc2, self.F2, y2, conv_geom(1, 1, 256, 1, 1, 1, 1, 0, self.F2), grp, E, R)
+        s["y2"] = y2
+        act, s["bn2"] = self._bn_fwd(y2, "fc2.1", self.SP, True, self.row_map, "fc2.2", ctx)
+        s["a2"] = act
+        for i, (name, geo, bn, site) in enumerate(self.CONVS):
+            g = conv_geom(*geo)
+            y = empty(R, g.Ho * g.Wo, g.N, dtype=BF)
+            L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R)
+            act, s[f"bn{i + 3}"] = self._bn_fwd(y, bn, (g.Ho, g.Wo, g.N), False, None, site, ctx)
+            s[f"y{i + 3}"], s[f"a{i + 3}"] = y, act
+        img1 = zeros(B, self.H * self.W)
+        img2 = zeros(B, self.H * self.W) if two_pass else None
+        L.call("es_gen_out_fwd", act, a.addr("conv_layers.13.weight"), a.addr("conv_layers.13.bias"), a.n, a.n, 45, 45, 64, 2, 2, 0,
+               grp, E, R, int(two_pass), img1, img2)
+        s["img1"], s["img2"] = img1, img2
+        return img1, img2, (s if keep else None)
+
+    def backward(self, s, dimg1, dimg2):
+        a, E, R, grp, ctx = self.a, self.a.E, s["R"], s["grp"], s["ctx"]
+        for t in self.dw_p.values():
+            t.zero_()
+        da = empty(R, 45 * 45, 64, dtype=BF)
+        L.call("es_gen_out_bwd", s["a5"], a.addr("conv_layers.13.weight"), a.n, a.n, 45, 45, 64, 2, 2, 0, s["img1"], s["img2"],
+               dimg1, dimg2, grp, E, R, int(s["two_pass"]), da, a.gaddr("conv_layers.13.weight"), a.gaddr("conv_layers.13.bias"))
+        up = (45, 45)
+        for i in (2, 1, 0):
+            name, geo, bn, _ = self.CONVS[i]
+            Hs, Ws, C, Hu, Wu, KH, KW, pad, N = geo
+            g = conv_geom(*geo)
+            dy = self._bn_bwd(da, up, s[f"y{i + 3}"], s[f"bn{i + 3}"], bn, (g.Ho, g.Wo, N), False, None, ctx)
+            # the conv bias sits in front of a BatchNorm: its gradient is identically zero and is left at zero
+            L.call("es_igemm_wgrad", s[f"a{i + 2}"], dy, self.dw_p[name], g, grp, E, R)
+            da = empty(R, Hu * Wu, C, dtype=BF)
+            L.call("es_igemm_fwd", dy, self.w_dg[name], None, 0, da, conv_geom(g.Ho, g.Wo, N, g.Ho, g.Wo, KH, KW, KH - 1 - pad, C), grp, E, R)
+            up = (Hu, Wu)
+        dy2 = self._bn_bwd(da, up, s["y2"], s["bn2"], "fc2.1", self.SP, True, self.row_map, ctx)
+        L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), a.n, self.F2, 256, self.row_map, grp, E, R)
+        dh1 = zeros(R, 256)
+        L.call("es_dense_dgrad", dy2, self.w_fc2, dh1, self.F2, 256, grp, E, R)
+        dlin = self._bn_bwd(dh1.to(BF), (1, 1), s["lin1"], s["bn1"], "fc1.1", (1, 1, 256), False, None, ctx)
+        L.call("es_gen_fc1_bwd", dlin.float(), s["x0"], None, None, None, a.n, a.n, grp, E, R, a.gaddr("fc1.0.weight"),
+               a.gaddr("fc1.0.bias"), None, None)
+        for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
+            L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
+
+
+class AuxEngineNeutron:
+    """AuxRegNeutron (reference neutron/aux_reg.py:8-80): 4 x [Conv k3 -> BatchNorm2d -> LeakyReLU -> Dropout(.2) (-> MaxPool)],
+    1x1 reduce (no bias) -> BatchNorm2d -> LeakyReLU, global average pool, Linear(64, 2).  fp32 NCHW."""
+    FE = "feature_extractor"
+    P_DROP = 0.2
+
+    def __init__(self, arena: Arena):
+        self.a = arena
+        fe = self.FE
+        self.layers = []            # (conv name, conv geometry, bn name, dropout site or None, pool (kh,kw) or None)
+        H, W, Ci = 44, 44, 1
+        for i, (Co, pool) in enumerate(((32, (2, 2)), (64, (2, 1)), (128, (2, 1)), (256, None)), start=1):
+            c = conv2d(Ci, H, W, Co, 3, 3, 1, 0)
+            self.layers.append((f"{fe}.conv{i}", c, f"{fe}.conv{i}_bd.0", f"conv{i}_bd.2", pool))
+            H, W, Ci = c.Ho, c.Wo, Co
+            if pool:
+                H, W = H // pool[0], W // pool[1]
+        c = conv2d(Ci, H, W, 64, 1, 1, 1, 0)
+        self.layers.append((f"{fe}.reduce.0", c, f"{fe}.reduce.1", None, None))
+        self.Hf, self.Wf = c.Ho, c.Wo
+
+    def forward(self, img, grp, R, training, masks=None, dp=None):
+        """masks: None (hash dropout) or dict site -> keep mask [R, C, H, W]."""
+        a, E, n = self.a, self.a.E, self.a.n
+        dp = dp or {}
+        allreduce, world = dp.get("allreduce", _noop), dp.get("world", 1)
+        g = grp.view(E, 4)
+        n_rows = dp["rows_global"] if dp.get("rows_global") is not None else g[:, 1].to(torch.float32)
+        n_rows = n_rows.repeat_interleave(2).contiguous()
+        s = {"R": R, "grp": grp, "layers": [], "allreduce": allreduce, "world": world}
+        x = img
+        for name, c, bn, site, pool in self.layers:
+            has_bias = (name + ".bias") in a.off
+            y = empty(R, c.Co, c.Ho, c.Wo)
+            L.call("es_conv2d_fwd", x, a.addr(name + ".weight"), a.addr(name + ".bias") if has_bias else None, n, n, c, grp, E, R, y)
+            P = c.Ho * c.Wo
+            stats, sums = empty(2 * E, c.Co, 2), None
+            if training:
+                sums = zeros(2 * E, c.Co, 2, dtype=torch.float64)
+                L.call("es_bn2d_stats", y, c.Co, P, grp, E, R, sums)
+                allreduce(sums)
+            n_sg = (n_rows * P).contiguous()
+            L.call("es_bn_finalize", sums, n_sg, c.Co, 1, int(training), 0.1, None, a.baddr(bn + ".running_mean"),
+                   a.baddr(bn + ".running_var"), a.nb, a.iaddr(bn + ".num_batches_tracked"), a.ni, grp if training else None, E, stats)
+            p = self.P_DROP if (training and site) else 0.0
+            mask, seed = (masks[site], 0) if (masks is not None and site) else (None, _seed() if p else 0)
+            act = empty(R, c.Co, c.Ho, c.Wo)
+            L.call("es_bn2d_apply_fwd", y, c.Co, P, stats, a.addr(bn + ".weight"), a.addr(bn + ".bias"), n, mask, seed, p, grp, E, R, act)
+            rec = dict(x=x, y=y, stats=stats, n_sg=n_sg, mask=mask, seed=seed, p=p, idx=None)
+            if pool:
+                kh, kw = pool
+                po = empty(R, c.Co, c.Ho // kh, c.Wo // kw)
+                rec["idx"] = empty(R, c.Co, c.Ho // kh, c.Wo // kw, dtype=torch.uint8)
+                L.call("es_maxpool_fwd", act, c.Co, c.Ho, c.Wo, kh, kw, kh, kw, R, po, rec["idx"])
+                act = po
+            s["layers"].append(rec)
+            x = act
+        feat = empty(R, 64)
+        L.call("es_gap_fwd", x, 64, self.Hf * self.Wf, R, feat)
+        coords = zeros(R, 2)
+        L.call("es_linear_fwd", feat, 64, a.addr("dense.weight"), a.addr("dense.bias"), n, n, 64, 2, grp, E, R, coords)
+        s["feat"] = feat
+        return coords, s
+
+    def backward(self, s, d_coords, d_img, accumulate=True):
+        a, E, n, R, grp = self.a, self.a.E, self.a.n, s["R"], s["grp"]
+        L.call("es_linear_bwd_weight", s["feat"], 64, d_coords, 64, 2, grp, E, R, a.gaddr("dense.weight"), a.gaddr("dense.bias"), n, n)
+        dfeat = zeros(R, 64)
+        L.call("es_linear_bwd_data", d_coords, a.addr("dense.weight"), n, 64, 2, grp, E, R, dfeat, 64)
+        d = empty(R, 64, self.Hf, self.Wf)
+        L.call("es_gap_bwd", dfeat, 64, self.Hf * self.Wf, R, d)
+        for li in range(len(self.layers) - 1, -1, -1):
+            name, c, bn, site, pool = self.layers[li]
+            rec = s["layers"][li]
+            P = c.Ho * c.Wo
+            if pool:
+                kh, kw = pool
+                dact = empty(R, c.Co, c.Ho, c.Wo)
+                L.call("es_maxpool_bwd", d, rec["idx"], c.Co, c.Ho, c.Wo, kh, kw, kh, kw, R, dact)
+                d = dact
+            sums2 = zeros(2 * E, c.Co, 2, dtype=torch.float64)
+            common = (a.addr(bn + ".weight"), a.addr(bn + ".bias"), n, rec["mask"], rec["seed"], rec["p"], grp, E, R)
+            L.call("es_bn2d_bwd_reduce", d, rec["y"], c.Co, P, rec["stats"], *common, sums2)
+            s["allreduce"](sums2)
+            L.call("es_bn_affine_grads", sums2, c.Co, 1, 1.0 / s["world"], None, grp, E, a.gaddr(bn + ".weight"), a.gaddr(bn + ".bias"), n)
+            dy = zeros(R, c.Co, c.Ho, c.Wo)
+            L.call("es_bn2d_bwd_apply", d, rec["y"], c.Co, P, rec["stats"], sums2, rec["n_sg"], *common, dy)
+            has_bias = (name + ".bias") in a.off
+            # (a conv bias in front of a BatchNorm has an identically-zero gradient; db is still accumulated: it is free)
+            L.call("es_conv2d_bwd_weight", rec["x"], dy, c, grp, E, R, a.gaddr(name + ".weight"),
+                   a.gaddr(name + ".bias") if has_bias else None, n, n)
+            if li == 0:
+                L.call("es_conv2d_bwd_data", dy, a.addr(name + ".weight"), n, c, grp, E, R, d_img, int(accumulate))
+            else:
+                d = zeros(*rec["x"].shape)
+                L.call("es_conv2d_bwd_data", dy, a.addr(name + ".weight"), n, c, grp, E, R, d, 0)
+
+
+# =====================================================================================================================
 def engine_for(arena: Arena, arch: str, kind: str):
     """The compute engine bound to ``arena`` (created on first use).  Generator engines keep bf16 kernel-layout
     copies of the weights and are re-packed whenever ``arena.version`` moved (optimizer step, load_state_dict)."""
@@ -431,8 +688,12 @@ def engine_for(arena: Arena, arch: str, kind: str):
             arena.engine = GenEngineProton(arena)
         elif (arch, kind) == ("proton", "aux_reg"):
             arena.engine = AuxEngineProton(arena)
+        elif (arch, kind) == ("neutron", "generator"):
+            arena.engine = GenEngineNeutron(arena)
+        elif (arch, kind) == ("neutron", "aux_reg"):
+            arena.engine = AuxEngineNeutron(arena)
         else:
-            raise NotImplementedError(f"no sm_100a engine for {arch}.{kind} yet")
+            raise NotImplementedError(f"no sm_100a engine for {arch}.{kind}")
     eng = arena.engine
     if hasattr(eng, "repack") and getattr(eng, "packed_version", -1) != arena.version:
         eng.repack()

@@ -110,6 +110,7 @@ class MoEWrapper(nn.Module):
         for arena in self._arenas.values():
             dist.broadcast(arena.P, 0, group=process_group)
             dist.broadcast(arena.Bf, 0, group=process_group)
+            dist.broadcast(arena.Bi, 0, group=process_group)
             arena.version += 1
         return self
 
@@ -213,10 +214,14 @@ class MoEWrapper(nn.Module):
             z2 = self._gather(f32(noise["z2"], 10), perm, 10)
         else:   # i.i.d. rows: drawing directly in sorted order is the same distribution as randn(B_e, 10) per expert
             z1, z2 = torch.randn(B, 10, device=dev), torch.randn(B, 10, device=dev)
-        drop = self._dropout_masks(noise, perm, B, dev)
+        drop = self._dropout_masks(noise, r, B, dev)
+        # data-parallel context of the BatchNorm layers (neutron): SyncBN over the global per-expert rows
+        dp = None
+        if world > 1:
+            dp = {"allreduce": self._allreduce, "world": world, "rows_global": counts_g * (counts_g >= 2).to(torch.float32)}
 
         # ---- G(z1) and G(z2): one two-pass batch of 2B rows (moe.py:143-145,535-538)
-        img1, img2, sg = gen.forward(z1, z2, cond_s, gg, 2 * B, True, training=self.training, drop=drop.get("g"))
+        img1, img2, sg = gen.forward(z1, z2, cond_s, gg, 2 * B, True, training=self.training, drop=drop.get("g"), dp=dp)
         if "img1_sorted" in noise:
             # parity harness only: replace the generated images (expert-sorted rows) by the oracle's fp32 images, so that
             # everything downstream of the generator can be compared at fp32 tolerance.  The networks' gradients are
@@ -245,7 +250,7 @@ class MoEWrapper(nn.Module):
         score1, lat1, sv1 = disc.forward(img1, cond_s, gh, B, sn_c)
         sn_d = disc.spectral(gh, self.training)
         _, lat2, sv2 = disc.forward(img2, cond_s, gh, B, sn_d)
-        coords, sv_a = aux.forward(img1, gh, B, self.training, drop.get("a"))
+        coords, sv_a = aux.forward(img1, gh, B, self.training, drop.get("a"), dp=dp)
         sums = torch.zeros(E, 8, dtype=torch.float64, device=dev)
         s_out, div_out = torch.zeros(B, device=dev), torch.zeros(B, device=dev)
         L.call("es_gen_loss_reduce", img1, HW, lat1, lat2, z1, z2, std_s, int_s, coords, pos_s, score1, gh, E, B,
@@ -327,17 +332,36 @@ class MoEWrapper(nn.Module):
                       "logits": r["logits"]}
         return m
 
-    def _dropout_masks(self, noise, perm, B, dev):
-        """keep-masks of every nn.Dropout on the path, in expert-sorted order.  Proton: the aux-regressor head
-        (proton/aux_reg.py:25,29; p=0.3)."""
+    def _dropout_masks(self, noise, r, B, dev):
+        """keep-masks of every nn.Dropout on the path when the parity harness injects them ('drop.<net>.<site>' indexed
+        by ORIGINAL sample), re-ordered to the kernels' row order; otherwise None = counter-hash dropout inside the
+        kernels (neutron) / torch-drawn masks for the two small proton aux-regressor sites.
+        Proton: aux head (proton/aux_reg.py:25,29; p=0.3).  Neutron: generator (neutron/generator.py:14-36) and aux
+        feature extractor (neutron/aux_reg.py:17-41), p=0.2."""
         if not self.training:
             return {}
+        perm = r["perm"]
+        g = lambda k: self._gather(noise[k].to(dev).float().reshape(B, -1).contiguous(), perm, noise[k][0].numel())
         if self.arch == "proton":
             if "drop.a.regressor.3" in noise:
-                g = lambda k, w: self._gather(noise[k].to(dev).float().reshape(B, w).contiguous(), perm, w)
-                return {"a": (g("drop.a.regressor.3", 128), g("drop.a.regressor.7", 64))}
+                return {"a": (g("drop.a.regressor.3"), g("drop.a.regressor.7"))}
             return {"a": ((torch.rand(B, 128, device=dev) >= 0.3).float(), (torch.rand(B, 64, device=dev) >= 0.3).float())}
-        raise NotImplementedError("neutron training path")
+        if not any(k.startswith("drop.") for k in noise):
+            return {}
+        # parity path (host sync is fine here): the generator's two-pass batch holds, per expert, its z1 rows then its z2 rows
+        off = r["offsets"].cpu().tolist()
+        segs = []
+        for e in range(self.n_experts):
+            segs += [(0, off[e], off[e + 1]), (1, off[e], off[e + 1])]
+        out = {"g": {}, "a": {}}
+        for k in noise:
+            if k.startswith("drop.g1."):
+                site = k[len("drop.g1."):]
+                m1, m2 = g(k), g("drop.g2." + site)
+                out["g"][site] = torch.cat([(m2 if ps else m1)[lo:hi] for ps, lo, hi in segs]).contiguous()
+            elif k.startswith("drop.a."):
+                out["a"][k[len("drop.a."):]] = g(k)
+        return out
 
     # ------------------------------------------------------------------------------------------------ inference
     @torch.no_grad()
@@ -360,7 +384,7 @@ class MoEWrapper(nn.Module):
             z = noise[s:s + chunk].to(dev).float().contiguous() if noise is not None else torch.randn(B, 10, device=dev)
             cs = self._gather(c, r["perm"], 9)
             zs = self._gather(z, r["perm"], 10)
-            img, _, _ = gen.forward(zs, None, cs, r["grp_half"], B, False, keep=False, training=False)
+            img, _, _ = gen.forward(zs, None, cs, r["grp_half"], B, False, keep=False, training=False)   # eval: running BN stats
             o64 = torch.empty(B, H, W, dtype=torch.float64, device=dev) if out_dtype == torch.float64 else None
             o32 = torch.empty(B, H, W, device=dev) if o64 is None else None
             L.call("es_expm1_scatter", img, r["perm"], B, H * W, o64, o32)

@@ -173,7 +173,9 @@ int es_igemm_wgrad_simt(const void* x, const void* dy, float* dw, const es_conv_
 
 /* generator head: x0 = [z | cond] (19) -> Linear(19,256) + LayerNorm(256) + LeakyReLU(0.1) (proton/generator.py:13-17).
  * In the two-pass training batch, row r of group e takes z from z1 (first pass_rows rows) or z2 and cond from the
- * half-batch row offsets.  lin[rows,256] fp32 (pre-norm, kept for backward), h[rows,256] bf16. */
+ * half-batch row offsets.  lin[rows,256] fp32 (pre-norm, kept for backward), h[rows,256] bf16.
+ * gamma == NULL selects the linear head only (neutron: h = bf16(x0 W^T + b), BatchNorm follows as its own pass; in the
+ * backward dh is then the gradient w.r.t. the linear output and lin/beta/dgamma/dbeta may be NULL). */
 int es_gen_fc1_fwd(const float* z1, const float* z2, const float* cond, const float* w, const float* b,
                    const float* gamma, const float* beta, long slot_stride_w, long slot_stride_v,
                    const es_group* grp_gen, int E, int total_rows, int two_pass, float* x0, float* lin, void* h, void* stream);
@@ -287,6 +289,55 @@ int es_gap_bwd(const float* dy, int C, int HW, int total_rows, float* dx, void* 
 int es_dropout(const float* x, const float* keep_mask, float p, long n, float* y, void* stream);
 int es_axpy(float alpha, const float* x, long n, float* y, void* stream);   /* y += alpha * x */
 int es_copy_cols(const float* src, int lds, int cols, int rows, float* dst, int ldd, int col0, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm (+ Dropout + LeakyReLU) of the neutron networks (expertsim/models/neutron/generator.py:11-40,
+ * expertsim/models/neutron/aux_reg.py:11-49), forward and backward, grouped by expert.
+ * A stat group sg = 2*slot + pass is what one reference forward call normalises over (the generator's two-pass batch
+ * = two calls).  sums / sums2: double [2*slots][CS][2]  ((sum x, sum x^2) / (sum g, sum g*xhat)), zeroed by the caller and,
+ * under data parallelism, all-reduced by the caller between the reduce and the apply call (SyncBN).
+ * n_sg: float [2*slots] GLOBAL element count of a stat group (rows * pixels).  stats: float [2*slots][CS][2] (mean, rstd).
+ * chmap (nullable): stat channel -> parameter index.  Dropout: keep_mask (nullable; reference NCHW activation layout,
+ * element (row*C + c)*P + p) or a counter hash of (seed, element index); p_drop = 0 disables it.
+ * NHWC entry points (generator, bf16): a row is [Hs*Ws][C]; feat_stats != 0 = BatchNorm1d over the flattened map
+ * (CS = Hs*Ws*C), else BatchNorm2d (CS = C); order BN -> Dropout -> LeakyReLU.  dy_up lives on the (Hu,Wu) grid of the
+ * consumer (nearest-upsample backward folded in).  NCHW entry points (aux regressor, fp32): BN -> LeakyReLU -> Dropout.
+ * ---------------------------------------------------------------------------------------------- */
+int es_bn_stats_nhwc(const void* x, int Hs, int Ws, int C, int feat_stats, const es_group* grp, int E, int total_rows,
+                     int two_pass, double* sums, void* stream);
+/* training: sums -> stats, running_mean/var <- momentum update per pass (unbiased variance), num_batches_tracked += passes;
+ * eval (training == 0): stats <- running buffers.  Slots with grp[slot].rows == 0 are untouched. */
+int es_bn_finalize(const double* sums, const float* n_sg, int CS, int passes, int training, float momentum,
+                   const int32_t* chmap, float* running_mean, float* running_var, long buf_slot_stride,
+                   int64_t* num_batches_tracked, long nbt_slot_stride, const es_group* grp, int slots, float* stats,
+                   void* stream);
+int es_bn_apply_fwd_nhwc(const void* x, int Hs, int Ws, int C, int feat_stats, const float* stats, const float* gamma,
+                         const float* beta, long slot_stride, const int32_t* chmap, const float* keep_mask,
+                         unsigned long long seed, float p_drop, const es_group* grp, int E, int total_rows, int two_pass,
+                         void* y, void* stream);
+int es_bn_bwd_reduce_nhwc(const void* dy_up, int Hs, int Ws, int Hu, int Wu, int C, int feat_stats, const void* x,
+                          const float* stats, const float* gamma, const float* beta, long slot_stride, const int32_t* chmap,
+                          const float* keep_mask, unsigned long long seed, float p_drop, const es_group* grp, int E,
+                          int total_rows, int two_pass, double* sums2, void* stream);
+int es_bn_bwd_apply_nhwc(const void* dy_up, int Hs, int Ws, int Hu, int Wu, int C, int feat_stats, const void* x,
+                         const float* stats, const double* sums2, const float* n_sg, const float* gamma, const float* beta,
+                         long slot_stride, const int32_t* chmap, const float* keep_mask, unsigned long long seed,
+                         float p_drop, const es_group* grp, int E, int total_rows, int two_pass, void* dx, void* stream);
+/* dgamma[slot][chmap[c]] += scale * sum_pass sums2[.][c][1],  dbeta += scale * sum_pass sums2[.][c][0]
+ * (scale = 1/world when sums2 was all-reduced and the gradient arena is sum-all-reduced afterwards) */
+int es_bn_affine_grads(const double* sums2, int CS, int passes, float scale, const int32_t* chmap, const es_group* grp,
+                       int slots, float* dgamma, float* dbeta, long slot_stride, void* stream);
+int es_bn2d_stats(const float* x, int C, int P, const es_group* grp, int E, int total_rows, double* sums, void* stream);
+int es_bn2d_apply_fwd(const float* x, int C, int P, const float* stats, const float* gamma, const float* beta,
+                      long slot_stride, const float* keep_mask, unsigned long long seed, float p_drop, const es_group* grp,
+                      int E, int total_rows, float* y, void* stream);
+int es_bn2d_bwd_reduce(const float* dy, const float* x, int C, int P, const float* stats, const float* gamma,
+                       const float* beta, long slot_stride, const float* keep_mask, unsigned long long seed, float p_drop,
+                       const es_group* grp, int E, int total_rows, double* sums2, void* stream);
+int es_bn2d_bwd_apply(const float* dy, const float* x, int C, int P, const float* stats, const double* sums2,
+                      const float* n_sg, const float* gamma, const float* beta, long slot_stride, const float* keep_mask,
+                      unsigned long long seed, float p_drop, const es_group* grp, int E, int total_rows, float* dx,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fused multi-tensor Adam (torch.optim.Adam defaults; expertsim/train/training_setup.py:20-40, stepped at
