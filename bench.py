@@ -275,6 +275,13 @@ def run_b200(args):
     value = args.steps * B * world / (ms / 1e3)
 
     # ---- roofline of the dominant kernel family (tcgen05 grouped implicit GEMM), per launch, inside the timed region
+    if args.per_launch and rank == 0:      # tuning aid: every timed GEMM launch of the last step, to stderr
+        per = len(plog) // args.steps
+        for name, a, s, e in plog[-per:]:
+            g = next((x for x in a if hasattr(x, "Ho")), None)
+            geo = f"Hs{g.Hs} C{g.C} {g.KH}x{g.KW} N{g.N} Ho{g.Ho}" if g is not None else str([x for x in a if isinstance(x, int)][:3])
+            t = s.elapsed_time(e)
+            print(f"  {name:16s} {geo:34s} {t:8.3f} ms {igemm_flops(name, a) / t / 1e9:8.1f} TFLOP/s", file=sys.stderr)
     fam = {}
     for name, a, s, e in plog:
         key = name
@@ -380,6 +387,7 @@ def main():
     ap.add_argument("--infer-iters", type=int, default=5)
     ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-launch", action="store_true", help="print every timed GEMM launch of the last step to stderr")
     ap.add_argument("--ncu-step", type=int, default=0, help="1: cudaProfilerStart/Stop around one train step; 2: + one inference batch")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -1,0 +1,317 @@
+// K3 convolutions as fp32 SIMT implicit GEMMs (discriminator + auxiliary regressor, forward / data gradient / weight
+// gradient), grouped by expert.  The channel counts of these networks (1..256, mostly 32/64) and their fp32 parity bar
+// keep them off the tensor cores; the first direct kernels (one thread = one pixel x 8 channels, a whole sample staged in
+// shared memory) ran at 0.5-3 TFLOP/s (r01 launch list: 27 ms of an 89 ms step).  Here every conv is a register-tiled
+// GEMM: CTA tile 64 (pixels, sample-major inside one expert group) x BN (channels) x 16 (reduction), 256 threads, thread
+// tile 4 x BN/16, operands gathered into shared memory with lanes along the pixel axis (coalesced NCHW reads/writes),
+// reduction index -> (channel, ky, kx) through a per-CTA lookup table.
+//   FWD       y[m, co]  = sum_k xcol[m, k]  w[co, k]              k = (ci, ky, kx)
+//   BWD_DATA  dx[m, ci] = sum_k dycol[m, k] w[co, ci, ky, kx]     k = (co, ky, kx), m = input pixel
+//   BWD_W     dw[co, k] += sum_m dy[m, co] xcol[m, k]             split over m, fp32 atomics
+#include "common.cuh"
+
+namespace es {
+int conv2d_bwd_weight_fewtaps(const float* x, const float* dy, const es_conv2d* g, const es_group* grp, int n_groups,
+                              int total_rows, float* dw, float* db, long slot_stride_w, long slot_stride_b, void* stream);
+int conv2d_bwd_data_ci1(const float* dy, const float* w, long slot_stride_w, const es_conv2d* g, const es_group* grp,
+                        int n_groups, int total_rows, float* dx, int accumulate, void* stream);
+namespace {
+
+constexpr int kCM = 64, kCK = 16;
+
+struct KEnt { int off; short ky, kx; };   // source offset of reduction index k relative to the window origin
+
+__device__ __forceinline__ bool tile_of(const es_group* grp, int n_groups, int px_per_row, int tile_px, int t, int& g,
+                                        int& m0, int& mtot) {
+  for (int i = 0; i < n_groups; ++i) {
+    const int tot = grp[i].rows * px_per_row;
+    const int nt = ceil_div(tot, tile_px);
+    if (t < nt) { g = i; m0 = t * tile_px; mtot = tot; return true; }
+    t -= nt;
+  }
+  return false;
+}
+
+// MODE 0: forward.  MODE 1: data gradient (src = dy, "output" = dx over input pixels).
+template <int MODE, int BN>
+__global__ void __launch_bounds__(256)
+conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, const float* __restrict__ bias, long sw,
+                 long sb, es_conv2d g, const es_group* __restrict__ grp, int n_groups, float* __restrict__ dst,
+                 int accumulate) {
+  extern __shared__ float sm[];
+  constexpr int TN = BN / 16;
+  const int KHW = g.KH * g.KW;
+  const int K = (MODE == 0 ? g.Ci : g.Co) * KHW;                 // reduction length
+  const int Nn = MODE == 0 ? g.Co : g.Ci;                        // GEMM N extent
+  const int Hm = MODE == 0 ? g.Ho : g.Hi, Wm = MODE == 0 ? g.Wo : g.Wi;      // pixel grid of the M axis
+  const int Hs = MODE == 0 ? g.Hi : g.Ho, Ws = MODE == 0 ? g.Wi : g.Wo;      // pixel grid of the source
+  const int Cs = MODE == 0 ? g.Ci : g.Co;
+  const int PXm = Hm * Wm, PXs = Hs * Ws;
+  KEnt* ktab = reinterpret_cast<KEnt*>(sm);                       // [K]
+  float* As = sm + 2 * ((K + 1) & ~1);                            // [kCK][kCM + 4]
+  float* Bs = As + kCK * (kCM + 4);                               // [kCK][BN + 4]
+  int gi, m0, mtot;
+  if (!tile_of(grp, n_groups, PXm, kCM, blockIdx.x, gi, m0, mtot)) return;
+  const int slot = grp[gi].slot, row_start = grp[gi].row_start;
+  const int n0 = blockIdx.y * BN;
+  const int tid = threadIdx.x;
+  for (int k = tid; k < K; k += 256) {
+    const int c = k / KHW, t = k - c * KHW, ky = t / g.KW, kx = t - ky * g.KW;
+    KEnt e;
+    e.ky = (short)ky; e.kx = (short)kx;
+    e.off = c * PXs;
+    ktab[k] = e;
+  }
+  // this thread's gather row (fixed): m = m0 + (tid & 63)
+  const int ml = tid & 63, kl = tid >> 6;                         // kl in 0..3: reduction rows kl, kl+4, kl+8, kl+12
+  const int m = m0 + ml;
+  const bool mv = m < mtot;
+  const int smp = mv ? m / PXm : 0, pm = mv ? m - smp * PXm : 0;
+  const int py = pm / Wm, px = pm - py * Wm;
+  const float* sbase = src + (size_t)(row_start + smp) * Cs * PXs;
+  const float* wslot = w + slot * sw;
+  const int tm = tid & 15, tn = tid >> 4;
+  float acc[4][TN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  __syncthreads();
+  for (int k0 = 0; k0 < K; k0 += kCK) {
+    // ---- A tile: gathered source values
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = kl + 4 * j, k = k0 + kk;
+      float v = 0.f;
+      if (mv && k < K) {
+        const KEnt e = ktab[k];
+        if (MODE == 0) {
+          const int iy = py * g.stride + e.ky - g.pad, ix = px * g.stride + e.kx - g.pad;
+          if (iy >= 0 && iy < Hs && ix >= 0 && ix < Ws) v = __ldg(sbase + e.off + iy * Ws + ix);
+        } else {
+          const int ty = py + g.pad - e.ky, tx = px + g.pad - e.kx;
+          if (ty >= 0 && tx >= 0) {
+            const int oy = ty / g.stride, ox = tx / g.stride;
+            if (oy * g.stride == ty && ox * g.stride == tx && oy < Hs && ox < Ws) v = __ldg(sbase + e.off + oy * Ws + ox);
+          }
+        }
+      }
+      As[kk * (kCM + 4) + ml] = v;
+    }
+    // ---- B tile: weights  Bs[kk][n]
+    for (int i = tid; i < kCK * BN; i += 256) {
+      const int kk = i % kCK, n = i / kCK, k = k0 + kk;
+      float v = 0.f;
+      if (k < K && n0 + n < Nn) {
+        if (MODE == 0) v = __ldg(wslot + (size_t)(n0 + n) * K + k);
+        else {
+          const int co = k / KHW, t = k - co * KHW;
+          v = __ldg(wslot + ((size_t)co * g.Ci + n0 + n) * KHW + t);
+        }
+      }
+      Bs[kk * (BN + 4) + n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kCK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(As + kk * (kCM + 4) + tm * 4);
+      float b[TN];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk * (BN + 4) + tn * TN + j];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+        acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+        acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+        acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- epilogue: NCHW store, lanes along pixels
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mm = m0 + tm * 4 + i;
+    if (mm >= mtot) continue;
+    const int s2 = mm / PXm, p2 = mm - s2 * PXm;
+    float* o = dst + (size_t)(row_start + s2) * Nn * PXm + p2;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tn * TN + j;
+      if (n >= Nn) continue;
+      float v = acc[i][j];
+      if (MODE == 0 && bias) v += bias[slot * sb + n];
+      if (accumulate) o[(size_t)n * PXm] += v;
+      else o[(size_t)n * PXm] = v;
+    }
+  }
+}
+
+// weight gradient: CTA = (64-wide k tile, chunk of `mper` group pixels); D[k, co] += sum_m xcol[m, k] dy[m, co]
+template <int BN>
+__global__ void __launch_bounds__(256)
+conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy, es_conv2d g,
+                       const es_group* __restrict__ grp, int n_groups, int mper, float* __restrict__ dw,
+                       float* __restrict__ db, long sw, long sb) {
+  __shared__ __align__(16) float As[kCK][kCM + 4];     // [m chunk][k tile]
+  __shared__ __align__(16) float Bs[kCK][BN + 4];      // [m chunk][co]
+  constexpr int TN = BN / 16;
+  const int KHW = g.KH * g.KW, K = g.Ci * KHW, PXo = g.Ho * g.Wo, PXi = g.Hi * g.Wi;
+  int gi, mbeg, mtot;
+  if (!tile_of(grp, n_groups, PXo, mper, blockIdx.y, gi, mbeg, mtot)) return;
+  const int mend = min(mtot, mbeg + mper);
+  const int slot = grp[gi].slot, row_start = grp[gi].row_start;
+  const int k0 = blockIdx.x * kCM, n0 = blockIdx.z * BN;
+  const int tid = threadIdx.x;
+  // gather column owned by this thread: k = k0 + (tid >> 2) for the A tile (64 k x 16 m, 4 m per thread)
+  const int ka = k0 + (tid >> 2), ma = (tid & 3) * 4;
+  const bool kv = ka < K;
+  const int ci = kv ? ka / KHW : 0, t = kv ? ka - ci * KHW : 0, ky = t / g.KW, kx = t - ky * g.KW;
+  const int tm = tid & 15, tn = tid >> 4;
+  float acc[4][TN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  for (int mc = mbeg; mc < mend; mc += kCK) {
+    // A tile: xcol[m, k] for 16 consecutive m, 64 k
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int mm = mc + ma + j;
+      float v = 0.f;
+      if (kv && mm < mend) {
+        const int s2 = mm / PXo, p2 = mm - s2 * PXo, oy = p2 / g.Wo, ox = p2 - oy * g.Wo;
+        const int iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
+        if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
+          v = __ldg(x + ((size_t)(row_start + s2) * g.Ci + ci) * PXi + iy * g.Wi + ix);
+      }
+      As[ma + j][tid >> 2] = v;
+    }
+    // B tile: dy[m, co]: lanes along m
+    for (int i = tid; i < kCK * BN; i += 256) {
+      const int mm = i % kCK, n = i / kCK, m = mc + mm;
+      float v = 0.f;
+      if (m < mend && n0 + n < g.Co) {
+        const int s2 = m / PXo, p2 = m - s2 * PXo;
+        v = __ldg(dy + ((size_t)(row_start + s2) * g.Co + n0 + n) * PXo + p2);
+      }
+      Bs[mm][n] = v;
+    }
+    __syncthreads();
+    if (db && blockIdx.x == 0 && tid < BN) {
+#pragma unroll
+      for (int mm = 0; mm < kCK; ++mm) bsum += Bs[mm][tid];
+    }
+#pragma unroll
+    for (int mm = 0; mm < kCK; ++mm) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[mm][tm * 4]);
+      float b[TN];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[mm][tn * TN + j];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+        acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+        acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+        acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + tm * 4 + i;
+    if (k >= K) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tn * TN + j;
+      if (n < g.Co) atomicAdd(&dw[slot * sw + (size_t)n * K + k], acc[i][j]);
+    }
+  }
+  if (db && blockIdx.x == 0 && tid < BN && n0 + tid < g.Co) atomicAdd(&db[slot * sb + n0 + tid], bsum);
+}
+
+bool geom_ok(const es_conv2d* g) {
+  return g && g->Ci > 0 && g->Co > 0 && g->KH > 0 && g->KW > 0 && g->stride > 0 && g->pad >= 0 &&
+         g->Ho == (g->Hi + 2 * g->pad - g->KH) / g->stride + 1 && g->Wo == (g->Wi + 2 * g->pad - g->KW) / g->stride + 1 &&
+         g->Ho > 0 && g->Wo > 0;
+}
+
+template <int MODE>
+int launch_conv_gemm(const float* src, const float* w, const float* b, long sw, long sb, const es_conv2d* g,
+                     const es_group* grp, int n_groups, int total_rows, float* dst, int accumulate, cudaStream_t st) {
+  const int KHW = g->KH * g->KW;
+  const int K = (MODE == 0 ? g->Ci : g->Co) * KHW, Nn = MODE == 0 ? g->Co : g->Ci;
+  const int PXm = MODE == 0 ? g->Ho * g->Wo : g->Hi * g->Wi;
+  const long tiles = ceil_div_l((long)total_rows * PXm, kCM) + n_groups;
+  if (tiles >= 2147483647L) { set_error("conv gemm: too many tiles"); return ES_ERR_INVALID; }
+  const int BN = Nn > 32 ? 64 : (Nn > 16 ? 32 : 16);
+  const size_t smem = (2 * (size_t)((K + 1) & ~1) + kCK * (kCM + 4) + kCK * (BN + 4)) * sizeof(float);
+  if (smem > 200 * 1024) { set_error("conv gemm: reduction table does not fit in shared memory"); return ES_ERR_INVALID; }
+  const dim3 grid((unsigned)tiles, ceil_div(Nn, BN));
+#define ES_LAUNCH_CG(BNV)                                                                                              \
+  {                                                                                                                    \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(conv_gemm_kernel<MODE, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    conv_gemm_kernel<MODE, BNV><<<grid, 256, smem, st>>>(src, w, b, sw, sb, *g, grp, n_groups, dst, accumulate);       \
+  }
+  if (BN == 64) ES_LAUNCH_CG(64) else if (BN == 32) ES_LAUNCH_CG(32) else ES_LAUNCH_CG(16)
+#undef ES_LAUNCH_CG
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error(std::string("conv gemm launch: ") + cudaGetErrorString(e)); return ES_ERR_CUDA; }
+  return ES_OK;
+}
+
+}  // namespace
+}  // namespace es
+
+using namespace es;
+
+extern "C" int es_conv2d_fwd(const float* x, const float* w, const float* b, long slot_stride_w, long slot_stride_b,
+                             const es_conv2d* g, const es_group* grp, int n_groups, int total_rows, float* y,
+                             void* stream) {
+  ES_REQUIRE(x && w && grp && y, "null pointer");
+  ES_REQUIRE(geom_ok(g), "bad conv geometry");
+  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad sizes");
+  return launch_conv_gemm<0>(x, w, b, slot_stride_w, slot_stride_b, g, grp, n_groups, total_rows, y, 0, as_stream(stream));
+}
+
+extern "C" int es_conv2d_bwd_data(const float* dy, const float* w, long slot_stride_w, const es_conv2d* g,
+                                  const es_group* grp, int n_groups, int total_rows, float* dx, int accumulate,
+                                  void* stream) {
+  ES_REQUIRE(dy && w && grp && dx, "null pointer");
+  ES_REQUIRE(geom_ok(g), "bad conv geometry");
+  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad sizes");
+  if (g->Ci == 1)    // gradient w.r.t. the 1-channel image: a GEMM with N = 1 wastes the tile; direct kernel instead
+    return conv2d_bwd_data_ci1(dy, w, slot_stride_w, g, grp, n_groups, total_rows, dx, accumulate, stream);
+  return launch_conv_gemm<1>(dy, w, nullptr, slot_stride_w, 0, g, grp, n_groups, total_rows, dx, accumulate, as_stream(stream));
+}
+
+extern "C" int es_conv2d_bwd_weight(const float* x, const float* dy, const es_conv2d* g, const es_group* grp,
+                                    int n_groups, int total_rows, float* dw, float* db, long slot_stride_w,
+                                    long slot_stride_b, void* stream) {
+  ES_REQUIRE(x && dy && grp && dw, "null pointer");
+  ES_REQUIRE(geom_ok(g), "bad conv geometry");
+  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad sizes");
+  const int K = g->Ci * g->KH * g->KW, PXo = g->Ho * g->Wo;
+  if (K <= 9 && g->Co % 8 == 0)   // a 64-wide k tile would be 86 % padding: pixel-parallel register kernel instead
+    return conv2d_bwd_weight_fewtaps(x, dy, g, grp, n_groups, total_rows, dw, db, slot_stride_w, slot_stride_b, stream);
+  const int ktiles = ceil_div(K, kCM);
+  const int BN = g->Co > 32 ? 64 : (g->Co > 16 ? 32 : 16);
+  const int ntiles = ceil_div(g->Co, BN);
+  // split the pixel reduction so that ~4 waves of CTAs exist, but keep >= 256 pixels per CTA
+  const long total_px = (long)total_rows * PXo;
+  long chunks = ceil_div_l(4L * 148, (long)ktiles * ntiles);
+  long mper = ceil_div_l(total_px, chunks);
+  if (mper < 256) mper = 256;
+  mper = ceil_div_l(mper, kCK) * kCK;
+  const long ychunks = ceil_div_l(total_px, mper) + n_groups;
+  ES_REQUIRE(ychunks < 65535 && mper < 2147483647L, "too many reduction chunks");
+  const dim3 grid(ktiles, (unsigned)ychunks, ntiles);
+  cudaStream_t st = as_stream(stream);
+  if (BN == 64) conv_wgrad_gemm_kernel<64><<<grid, 256, 0, st>>>(x, dy, *g, grp, n_groups, (int)mper, dw, db, slot_stride_w, slot_stride_b);
+  else if (BN == 32) conv_wgrad_gemm_kernel<32><<<grid, 256, 0, st>>>(x, dy, *g, grp, n_groups, (int)mper, dw, db, slot_stride_w, slot_stride_b);
+  else conv_wgrad_gemm_kernel<16><<<grid, 256, 0, st>>>(x, dy, *g, grp, n_groups, (int)mper, dw, db, slot_stride_w, slot_stride_b);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}

@@ -14,6 +14,7 @@
 //     of tile i (TMEM -> registers -> +bias -> bf16 -> global) overlaps the main loop of tile i+1.
 // Warp roles: 0-3 A gather, 4 TMA producer (B), 5 MMA issuer + TMEM owner, 6-9 epilogue (TMEM lane quarter = warp % 4).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -50,13 +51,14 @@ struct TileInfo {
 };
 
 // tile t -> (group, m0, n0).  s_tiles[i] = number of M tiles of group i (shared memory).
-__device__ __forceinline__ bool decode_tile(int t, const FwdParams& p, const int* s_tiles, const es_group* s_grp, TileInfo& ti) {
+__device__ __forceinline__ bool decode_tile(int t, const FwdParams& p, const int* s_tiles, const es_group* s_grp, int tile_m,
+                                            TileInfo& ti) {
   int mt = t / p.n_tiles_n;
   const int nt = t - mt * p.n_tiles_n;
   for (int i = 0; i < p.n_groups; ++i) {
     const int n = s_tiles[i];
     if (mt < n) {
-      ti.g = i; ti.m0 = mt * kBM; ti.n0 = nt * p.BN;
+      ti.g = i; ti.m0 = mt * tile_m; ti.n0 = nt * p.BN;
       ti.rows = s_grp[i].rows; ti.row_start = s_grp[i].row_start; ti.slot = s_grp[i].slot;
       return true;
     }
@@ -65,39 +67,53 @@ __device__ __forceinline__ bool decode_tile(int t, const FwdParams& p, const int
   return false;
 }
 
+// MT  = 128-row M sub-tiles per CTA tile (1 or 2).  Two sub-tiles share every weight (B) tile, which halves the L2->SM
+//       weight traffic per FLOP — the bound of the N = 256 layers (r01: B alone was 7.4 TB/s of L2 reads at 948 TFLOP/s).
+// G4  = A rows arrive by TMA tile::gather4 (four 128-byte rows per instruction, row indices computed per tap, -1 = zero
+//       padding) issued by one warp, instead of per-thread cp.async.  cp.async moves 64 B/clk/SM through L1TEX, which is
+//       exactly what a 128 x 128 x 64 k-block needs at tensor peak, so the N <= 128 layers were gather-bound at ~50 %;
+//       gather4 bypasses L1TEX (at the price of re-reading shifted taps from L2 instead of L1).
+template <int MT, bool G4>
 __global__ void __launch_bounds__(kFThreads, 1)
-igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CUtensorMap tmap_w) {
+igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_a) {
+  constexpr int kStages = MT == 1 ? 4 : 3;
+  constexpr int kStageA = MT * kFStageA;
+  constexpr int kStage = kStageA + kFStageB;
+  constexpr int kTileM = MT * kBM;
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bar_base = base + kFStages * kFStage;
+  const uint32_t bar_base = base + kStages * kStage;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kFStages + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kFStages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kFStages + 2 + b); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (8 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (10 + b); };
   uint8_t* gen = smem_raw + (bar_base - raw);                 // generic pointer to the barrier/table area
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * (2 * kFStages + 4));
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kFStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * 12);
+  const uint32_t tmem_slot = bar_base + 8u * 12;
   int* s_tiles = reinterpret_cast<int*>(gen + 128);            // [64]
   es_group* s_grp = reinterpret_cast<es_group*>(gen + 384);    // [64] x 16 B
   unsigned char* s_ymap = gen + 384 + 1024;                    // 64
   unsigned char* s_xmap = s_ymap + 64;                         // 64
 
   const int BN = p.BN;
+  const int acc_cols = MT * BN;                                // TMEM columns of one accumulator set
+  const uint32_t nbuf = 2 * acc_cols <= 512 ? 2u : 1u;         // double-buffer the accumulators when TMEM allows
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
+  while ((int)tmem_cols < (int)nbuf * acc_cols) tmem_cols <<= 1;
 
   // ---- one-time setup
   if (tid < p.n_groups) {
     const es_group gq = p.grp[tid];
     s_grp[tid] = gq;
-    s_tiles[tid] = ceil_div(gq.rows * p.P, kBM);
+    s_tiles[tid] = ceil_div(gq.rows * p.P, kTileM);
   }
   if (tid < 64) { s_ymap[tid] = p.ymap[tid]; s_xmap[tid] = p.xmap[tid]; }
   if (tid == 0) {
-    for (int s = 0; s < kFStages; ++s) {
-      mbar_init(full_bar(s), kFLoaders + 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), G4 ? 2 : kFLoaders + 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -106,7 +122,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4 && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmap_w); if (G4) tma_prefetch_desc(&tmap_a); }
   if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -121,55 +137,97 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
   const int nkb = taps * cblks;
 
   if (warp < 4) {
-    // =========================================================================== A GATHER (128 threads)
-    // lane group of 8 threads copies one 128-byte row; thread handles rows (tid>>3) + 16*j, j = 0..7, chunk tid&7
-    const int chunk = tid & 7, rsub = tid >> 3;
-    uint32_t it = 0, signalled = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      TileInfo ti;
-      decode_tile(tile, p, s_tiles, s_grp, ti);
-      int r_base[8];      // pixel index of the sample's first source pixel, or -1 for rows past the group's end
-      int r_oyx[8];       // oy << 8 | ox
+    if (!G4) {
+      // ========================================================================= A GATHER by cp.async (128 threads)
+      // lane group of 8 threads copies one 128-byte row; thread handles rows (tid>>3) + 16*j, chunk tid&7
+      constexpr int RPT = 8 * MT;
+      const int chunk = tid & 7, rsub = tid >> 3;
+      uint32_t it = 0, signalled = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileInfo ti;
+        decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+        int r_base[RPT];    // pixel index of the sample's first source pixel, or -1 for rows past the group's end
+        int r_oyx[RPT];     // oy << 8 | ox
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int m = ti.m0 + rsub + 16 * j;
-        const bool valid = m < ti.rows * p.P;
-        const int sample = valid ? m / p.P : 0;
-        const int pix = valid ? m - sample * p.P : 0;
-        const int oy = pix / p.Wo;
-        r_oyx[j] = (oy << 8) | (pix - oy * p.Wo);
-        r_base[j] = valid ? (ti.row_start + sample) * p.Hs * p.Ws : -1;
-      }
-      int cb = 0, ky = 0, kx = 0;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % kFStages;
-        if (it >= kFStages) mbar_wait(empty_bar(s), ((it / kFStages) - 1) & 1, p.err_flag, 1);
-        const uint32_t sa = base + s * kFStage;
-        const int c0 = cb * kBK + chunk * 8;
+        for (int j = 0; j < RPT; ++j) {
+          const int m = ti.m0 + rsub + 16 * j;
+          const bool valid = m < ti.rows * p.P;
+          const int sample = valid ? m / p.P : 0;
+          const int pix = valid ? m - sample * p.P : 0;
+          const int oy = pix / p.Wo;
+          r_oyx[j] = (oy << 8) | (pix - oy * p.Wo);
+          r_base[j] = valid ? (ti.row_start + sample) * p.Hs * p.Ws : -1;
+        }
+        int cb = 0, ky = 0, kx = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 1);
+          const uint32_t sa = base + s * kStage;
+          const int c0 = cb * kBK + chunk * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = rsub + 16 * j;
-          const int uy = (r_oyx[j] >> 8) + ky - p.pad, ux = (r_oyx[j] & 255) + kx - p.pad;
-          const bool inb = r_base[j] >= 0 && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
-          const int sy = inb ? s_ymap[uy] : 0, sx = inb ? s_xmap[ux] : 0;
-          const __nv_bfloat16* src = p.a_src + (inb ? ((long)(r_base[j] + sy * p.Ws + sx) * p.C + c0) : 0L);
-          cp_async16_ca(sa + (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4), src, inb);
-        }
-        cp_async_commit();
-        if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++cb; } }
-        if (it - signalled >= (uint32_t)kFLag) {
-          cp_async_wait<kFLag>();
-          fence_proxy_async();
-          mbar_arrive(full_bar(signalled % kFStages));
-          ++signalled;
+          for (int j = 0; j < RPT; ++j) {
+            const int r = rsub + 16 * j;
+            const int uy = (r_oyx[j] >> 8) + ky - p.pad, ux = (r_oyx[j] & 255) + kx - p.pad;
+            const bool inb = r_base[j] >= 0 && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
+            const int sy = inb ? s_ymap[uy] : 0, sx = inb ? s_xmap[ux] : 0;
+            const __nv_bfloat16* src = p.a_src + (inb ? ((long)(r_base[j] + sy * p.Ws + sx) * p.C + c0) : 0L);
+            cp_async16_ca(sa + (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4), src, inb);
+          }
+          cp_async_commit();
+          if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++cb; } }
+          if (it - signalled >= (uint32_t)kFLag) {
+            cp_async_wait<kFLag>();
+            fence_proxy_async();
+            mbar_arrive(full_bar(signalled % kStages));
+            ++signalled;
+          }
         }
       }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    while (signalled < it) {
-      mbar_arrive(full_bar(signalled % kFStages));
-      ++signalled;
+      cp_async_wait<0>();
+      fence_proxy_async();
+      while (signalled < it) {
+        mbar_arrive(full_bar(signalled % kStages));
+        ++signalled;
+      }
+    } else if (warp == 0) {
+      // ========================================================================= A GATHER by TMA gather4 (one warp)
+      // lane l owns tile rows 4l .. 4l+3 of every 128-row sub-tile: one gather4 (512 B) per sub-tile per k-block
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileInfo ti;
+        decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+        int r_base[4 * MT], r_oyx[4 * MT];
+#pragma unroll
+        for (int j = 0; j < 4 * MT; ++j) {
+          const int m = ti.m0 + (j >> 2) * kBM + lane * 4 + (j & 3);
+          const bool valid = m < ti.rows * p.P;
+          const int sample = valid ? m / p.P : 0;
+          const int pix = valid ? m - sample * p.P : 0;
+          const int oy = pix / p.Wo;
+          r_oyx[j] = (oy << 8) | (pix - oy * p.Wo);
+          r_base[j] = valid ? (ti.row_start + sample) * p.Hs * p.Ws : -1;
+        }
+        int cb = 0, ky = 0, kx = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 1);
+          const uint32_t sa = base + s * kStage;
+          if (lane == 0) mbar_arrive_expect_tx(full_bar(s), (uint32_t)kStageA);
+          __syncwarp();
+          int idx[4 * MT];
+#pragma unroll
+          for (int j = 0; j < 4 * MT; ++j) {
+            const int uy = (r_oyx[j] >> 8) + ky - p.pad, ux = (r_oyx[j] & 255) + kx - p.pad;
+            const bool inb = r_base[j] >= 0 && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
+            idx[j] = inb ? r_base[j] + s_ymap[uy] * p.Ws + s_xmap[ux] : -1;     // -1: out of bounds -> zero rows
+          }
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tma_gather4(sa + mt * kFStageA + lane * 512u, &tmap_a, cb * kBK, idx[4 * mt], idx[4 * mt + 1], idx[4 * mt + 2],
+                        idx[4 * mt + 3], full_bar(s));
+          if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++cb; } }
+        }
+      }
     }
   } else if (warp == 4) {
     // =========================================================================== TMA PRODUCER (weights)
@@ -177,14 +235,14 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         TileInfo ti;
-        decode_tile(tile, p, s_tiles, s_grp, ti);
+        decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
         const int wrow = ti.slot * p.Nout + ti.n0;
         int cb = 0, tap = 0;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % kFStages;
-          if (it >= kFStages) mbar_wait(empty_bar(s), ((it / kFStages) - 1) & 1, p.err_flag, 4);
+          const int s = it % kStages;
+          if (it >= kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
           mbar_arrive_expect_tx(full_bar(s), (uint32_t)BN * 128u);
-          tma_load_2d(base + s * kFStage + kFStageA, &tmap_w, tap * p.C + cb * kBK, wrow, full_bar(s));
+          tma_load_2d(base + s * kStage + kStageA, &tmap_w, tap * p.C + cb * kBK, wrow, full_bar(s));
           if (++tap == taps) { tap = 0; ++cb; }
         }
       }
@@ -194,20 +252,25 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     const uint32_t idesc = make_idesc(BN, false, false);
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t buf = tcount & 1;
-      if (tcount >= 2) mbar_wait(tempty_bar(buf), ((tcount >> 1) - 1) & 1, p.err_flag, 5);
+      const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+      const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;      // how many times this buffer was used before
+      if (use >= 1) mbar_wait(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
+      const uint32_t tacc = tmem_base + buf * (uint32_t)acc_cols;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % kFStages;
-        mbar_wait(full_bar(s), (it / kFStages) & 1, p.err_flag, 2);
+        const int s = it % kStages;
+        mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = base + s * kFStage;
-          const uint32_t sb = sa + kFStageA;
+          const uint32_t sa = base + s * kStage;
+          const uint32_t sb = sa + kStageA;
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16(tacc, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t bd = make_desc(sb + k * 32, 16, 1024);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              umma_bf16(tacc + mt * BN, make_desc(sa + mt * kFStageA + k * 32, 16, 1024), bd, idesc, (kb | k) ? 1u : 0u);
+          }
           umma_commit(empty_bar(s));
           if (kb == nkb - 1) umma_commit(tfull_bar(buf));
         }
@@ -221,25 +284,29 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       TileInfo ti;
-      decode_tile(tile, p, s_tiles, s_grp, ti);
-      const uint32_t buf = tcount & 1;
-      mbar_wait(tfull_bar(buf), (tcount >> 1) & 1, p.err_flag, 3);
+      decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+      const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+      const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+      mbar_wait(tfull_bar(buf), use & 1, p.err_flag, 3);
       tc_fence_after();
-      const uint32_t t_lane = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
-      const int m = ti.m0 + q * 32 + lane;
-      const bool ok = m < ti.rows * p.P;
-      __nv_bfloat16* yrow = p.out + (((long)ti.row_start * p.P + m) * p.Nout + ti.n0);
       const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
       uint32_t r[32];
-      for (int c = 0; c < BN; c += 32) {
-        tmem_ld32(t_lane + c, r);
-        if (ok) {
-          float f[32];
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t t_lane = tmem_base + buf * (uint32_t)acc_cols + mt * BN + ((uint32_t)(q * 32) << 16);
+        const int m = ti.m0 + mt * kBM + q * 32 + lane;
+        const bool ok = m < ti.rows * p.P;
+        __nv_bfloat16* yrow = p.out + (((long)ti.row_start * p.P + m) * p.Nout + ti.n0);
+        for (int c = 0; c < BN; c += 32) {
+          tmem_ld32(t_lane + c, r);
+          if (ok) {
+            float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
-          uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
+            uint4* dst = reinterpret_cast<uint4*>(yrow + c);
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) dst[qq] = pack8(f + 8 * qq);
+            for (int qq = 0; qq < 4; ++qq) dst[qq] = pack8(f + 8 * qq);
+          }
         }
       }
       tc_fence_before();
@@ -551,27 +618,56 @@ extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, lon
   // largest one the group table can address (TMA never reads rows the kernel does not ask for)
   EncodeTiledFn enc = encode_fn();
   ES_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
-  alignas(64) CUtensorMap tmap;
-  const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)g->N};
-  const cuuint64_t strides[1] = {(cuuint64_t)p.KK * 2};
-  const cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
+  alignas(64) CUtensorMap tmap, tmap_a;
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult rc = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (weights must be 16-byte aligned, KK*2 a multiple of 16)");
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)g->N};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.KK * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
+    const CUresult rc = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (weights must be 16-byte aligned, KK*2 a multiple of 16)");
+  }
+  {  // activations as [source pixels][C] for tile::gather4 (box = one row of 64 channels)
+    const cuuint64_t dims[2] = {(cuuint64_t)p.C, (cuuint64_t)total_rows * p.Hs * p.Ws};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.C * 2};
+    const cuuint32_t box[2] = {64, 1};
+    const CUresult rc = enc(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the activations");
+  }
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    ES_CUDA(cudaFuncSetAttribute(igemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem));
-    attr_set = true;
+  // Variant.  Measured on B200 (r01, per-launch CUDA events, batch 1024, E = 8; TFLOP/s for MT=1/cp.async, MT=2/cp.async,
+  // MT=2/gather4): conv1 fwd 959 / 748 / 528, conv2 fwd 503 / 469 / 259, conv3 fwd 236 / 229 / 129, conv1 dgrad 927 / 731 /
+  // 525.  The 128-row tile with double-buffered accumulators and the cp.async gather wins everywhere (the 3-stage pipeline
+  // and the exposed epilogue of MT=2 cost more than the halved weight traffic saves; the TMA gather engine sustains about
+  // half the row rate of cp.async), so it is the default; the other variants stay selectable for tuning.
+  int mt = 1, g4 = 0;
+  if (const char* ov = getenv("ES_IGEMM_FWD_VARIANT")) {   // "mt,g4" — tuning aid
+    int a = 0, b = 0;
+    if (sscanf(ov, "%d,%d", &a, &b) == 2 && (a == 1 || a == 2) && (b == 0 || b == 1)) { mt = a; g4 = b; }
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long max_tiles = (ceil_div_l((long)total_rows * p.P, kBM) + n_groups) * p.n_tiles_n;
+  const long max_tiles = (ceil_div_l((long)total_rows * p.P, (long)mt * kBM) + n_groups) * p.n_tiles_n;
   const int grid = (int)(max_tiles < sms ? max_tiles : sms);
-  igemm_fwd_kernel<<<grid, kFThreads, kFSmem, as_stream(stream)>>>(p, tmap);
+#define ES_FWD_LAUNCH(MTV, G4V)                                                                                          \
+  {                                                                                                                      \
+    static bool attr_set = false;                                                                                        \
+    if (!attr_set) {                                                                                                     \
+      ES_CUDA(cudaFuncSetAttribute(igemm_fwd_kernel<MTV, G4V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem)); \
+      attr_set = true;                                                                                                   \
+    }                                                                                                                    \
+    igemm_fwd_kernel<MTV, G4V><<<grid, kFThreads, kFSmem, as_stream(stream)>>>(p, tmap, tmap_a);                         \
+  }
+  if (mt == 1 && !g4) ES_FWD_LAUNCH(1, false)
+  else if (mt == 1) ES_FWD_LAUNCH(1, true)
+  else if (!g4) ES_FWD_LAUNCH(2, false)
+  else ES_FWD_LAUNCH(2, true)
+#undef ES_FWD_LAUNCH
   ES_LAUNCH_CHECK();
   return ES_OK;
 }

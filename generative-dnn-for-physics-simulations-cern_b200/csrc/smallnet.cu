@@ -3,8 +3,8 @@
 // (expertsim/models/proton/discriminator.py:121-155), AuxReg / FeatureExtractor / ResidualBlock
 // (expertsim/models/proton/aux_reg.py:11-131) and the hook-based spectral norm of torch.
 //
-// The convolutions are direct CUDA-core kernels: a CTA stages S input samples and one 8-channel weight tile in shared
-// memory; each thread produces 8 output channels of one pixel (1 LDS for x, 2 broadcast LDS.128 for w per 8 FMAs).
+// The convolutions live in conv_simt.cu (fp32 SIMT implicit GEMMs); this file keeps the few-tap weight-gradient kernel,
+// the norms, pools, linears, spectral norm, Adam and the elementwise helpers.
 #include "common.cuh"
 
 namespace es {
@@ -26,55 +26,7 @@ __device__ __forceinline__ bool chunk_of(const es_group* grp, int n_groups, int 
   return false;
 }
 
-// ------------------------------------------------------------------------------------------------ conv forward
-__global__ void __launch_bounds__(256)
-conv2d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, long sw, long sb,
-                  es_conv2d g, const es_group* __restrict__ grp, int n_groups, int S, float* __restrict__ y) {
-  extern __shared__ float sm[];
-  int gi, row0, ns;
-  if (!chunk_of(grp, n_groups, S, blockIdx.x, gi, row0, ns)) return;
-  const int slot = grp[gi].slot, co0 = blockIdx.y * kCoT;
-  const int in_sz = g.Ci * g.Hi * g.Wi, taps = g.Ci * g.KH * g.KW, HWo = g.Ho * g.Wo;
-  float* s_x = sm;                 // [S][Ci][Hi][Wi]
-  float* s_w = sm + ((S * in_sz + 3) & ~3);     // [taps][8], 16-byte aligned
-  for (int i = threadIdx.x; i < ns * in_sz; i += blockDim.x) s_x[i] = x[(size_t)row0 * in_sz + i];
-  for (int i = threadIdx.x; i < taps * kCoT; i += blockDim.x) {
-    const int t = i / kCoT, c = i % kCoT;
-    s_w[i] = w[slot * sw + (size_t)(co0 + c) * taps + t];
-  }
-  __syncthreads();
-  float bias[kCoT];
-#pragma unroll
-  for (int c = 0; c < kCoT; ++c) bias[c] = b ? b[slot * sb + co0 + c] : 0.f;
-  for (int idx = threadIdx.x; idx < ns * HWo; idx += blockDim.x) {
-    const int s = idx / HWo, p = idx % HWo, oy = p / g.Wo, ox = p % g.Wo;
-    float acc[kCoT];
-#pragma unroll
-    for (int c = 0; c < kCoT; ++c) acc[c] = bias[c];
-    const float* xs = s_x + s * in_sz;
-    for (int ci = 0; ci < g.Ci; ++ci)
-      for (int ky = 0; ky < g.KH; ++ky) {
-        const int iy = oy * g.stride + ky - g.pad;
-        if (iy < 0 || iy >= g.Hi) continue;
-        for (int kx = 0; kx < g.KW; ++kx) {
-          const int ix = ox * g.stride + kx - g.pad;
-          if (ix < 0 || ix >= g.Wi) continue;
-          const float xv = xs[(ci * g.Hi + iy) * g.Wi + ix];
-          const float4* wv = reinterpret_cast<const float4*>(s_w + ((ci * g.KH + ky) * g.KW + kx) * kCoT);
-          const float4 w0 = wv[0], w1 = wv[1];
-          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-          acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-          acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
-        }
-      }
-    float* yo = y + ((size_t)(row0 + s) * g.Co + co0) * HWo + p;
-#pragma unroll
-    for (int c = 0; c < kCoT; ++c) yo[(size_t)c * HWo] = acc[c];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ conv data gradient
+// ------------------------------------------------------------------------------------------------ conv data gradient, single input channel (direct)
 // STAGED = false: the gradient sample does not fit in shared memory (neutron aux conv1: 32 x 42 x 42 floats); dy is then
 // read straight from global memory / L2 and only the weight tile is staged.
 template <int CIT, bool STAGED = true>
@@ -125,76 +77,6 @@ conv2d_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w
       else o[(size_t)c * HWi] = acc[c];
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------ conv weight gradient
-// CTA = (group, chunk of `per` samples, 8-channel tile).  Threads own (ci,ky,kx) entries (up to 8 each) and keep
-// 8 accumulators per entry in registers; samples are staged one at a time in shared memory.
-constexpr int kMaxEnt = 7;
-__global__ void __launch_bounds__(256)
-conv2d_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, es_conv2d g,
-                         const es_group* __restrict__ grp, int n_groups, int per, float* __restrict__ dw,
-                         float* __restrict__ db, long sw, long sb) {
-  extern __shared__ float sm[];
-  __shared__ float red[32];
-  int gi, row0, ns;
-  if (!chunk_of(grp, n_groups, per, blockIdx.x, gi, row0, ns)) return;
-  const int slot = grp[gi].slot, co0 = blockIdx.y * kCoT;
-  const int in_sz = g.Ci * g.Hi * g.Wi, HWo = g.Ho * g.Wo, taps = g.Ci * g.KH * g.KW;
-  float* s_x = sm;              // [Ci][Hi][Wi]
-  float* s_d = sm + ((in_sz + 3) & ~3);      // [HWo][8], 16-byte aligned
-  float acc[kMaxEnt][kCoT];
-#pragma unroll
-  for (int j = 0; j < kMaxEnt; ++j)
-#pragma unroll
-    for (int c = 0; c < kCoT; ++c) acc[j][c] = 0.f;
-  float bsum = 0.f;
-  for (int s = 0; s < ns; ++s) {
-    __syncthreads();
-    const size_t row = row0 + s;
-    for (int i = threadIdx.x; i < in_sz; i += blockDim.x) s_x[i] = x[row * in_sz + i];
-    for (int i = threadIdx.x; i < HWo * kCoT; i += blockDim.x) {
-      const int c = i / HWo, p = i % HWo;   // coalesced global read, transposed smem write
-      s_d[p * kCoT + c] = dy[(row * g.Co + co0 + c) * HWo + p];
-    }
-    __syncthreads();
-    if (threadIdx.x < kCoT) {
-      float t = 0.f;
-      for (int p = 0; p < HWo; ++p) t += s_d[p * kCoT + threadIdx.x];
-      bsum += t;
-    }
-#pragma unroll
-    for (int j = 0; j < kMaxEnt; ++j) {
-      const int e = threadIdx.x + j * 256;
-      if (e >= taps) break;
-      const int kx = e % g.KW, ky = (e / g.KW) % g.KH, ci = e / (g.KW * g.KH);
-      const float* xs = s_x + ci * g.Hi * g.Wi;
-      for (int oy = 0; oy < g.Ho; ++oy) {
-        const int iy = oy * g.stride + ky - g.pad;
-        if (iy < 0 || iy >= g.Hi) continue;
-        for (int ox = 0; ox < g.Wo; ++ox) {
-          const int ix = ox * g.stride + kx - g.pad;
-          if (ix < 0 || ix >= g.Wi) continue;
-          const float xv = xs[iy * g.Wi + ix];
-          const float4* dv = reinterpret_cast<const float4*>(s_d + (oy * g.Wo + ox) * kCoT);
-          const float4 d0 = dv[0], d1 = dv[1];
-          acc[j][0] = fmaf(xv, d0.x, acc[j][0]); acc[j][1] = fmaf(xv, d0.y, acc[j][1]);
-          acc[j][2] = fmaf(xv, d0.z, acc[j][2]); acc[j][3] = fmaf(xv, d0.w, acc[j][3]);
-          acc[j][4] = fmaf(xv, d1.x, acc[j][4]); acc[j][5] = fmaf(xv, d1.y, acc[j][5]);
-          acc[j][6] = fmaf(xv, d1.z, acc[j][6]); acc[j][7] = fmaf(xv, d1.w, acc[j][7]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < kMaxEnt; ++j) {
-    const int e = threadIdx.x + j * 256;
-    if (e >= taps) break;
-#pragma unroll
-    for (int c = 0; c < kCoT; ++c) atomicAdd(&dw[slot * sw + (size_t)(co0 + c) * taps + e], acc[j][c]);
-  }
-  if (db && threadIdx.x < kCoT) atomicAdd(&db[slot * sb + co0 + threadIdx.x], bsum);
-  (void)red;
 }
 
 // Few-tap variant (Ci*KH*KW <= 9, e.g. the discriminator's first conv 1->32 k3): the generic kernel gives one thread per
@@ -383,12 +265,13 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 }
 
 // ------------------------------------------------------------------------------------------------ max pooling
-__global__ void maxpool_fwd_kernel(const float* __restrict__ x, int C, int Hi, int Wi, int kh, int kw, int sh, int sw_,
-                                   int Ho, int Wo, long total, float* __restrict__ y, uint8_t* __restrict__ idx) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int ox = i % Wo, oy = (i / Wo) % Ho;
-  const long rc = i / ((long)Wo * Ho);
+// grid = (rows*C planes, plane chunks): 32-bit index math only (a flat 64-bit index costs three 64-bit divisions per thread)
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, int Hi, int Wi, int kh, int kw, int sh, int sw_,
+                                   int Ho, int Wo, float* __restrict__ y, uint8_t* __restrict__ idx) {
+  const int p = blockIdx.y * blockDim.x + threadIdx.x;
+  if (p >= Ho * Wo) return;
+  const int oy = p / Wo, ox = p - oy * Wo;
+  const size_t rc = blockIdx.x;
   const float* xs = x + rc * Hi * Wi;
   float best = -INFINITY;
   int bi = 0;
@@ -397,16 +280,18 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, int C, int Hi, i
       const float v = xs[(oy * sh + ky) * Wi + ox * sw_ + kx];
       if (v > best) { best = v; bi = ky * kw + kx; }
     }
-  y[i] = best;
-  idx[i] = (uint8_t)bi;
+  y[rc * Ho * Wo + p] = best;
+  idx[rc * Ho * Wo + p] = (uint8_t)bi;
 }
 
 __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, int Hi, int Wi, int kh,
-                                   int kw, int sh, int sw_, int Ho, int Wo, long total, float* __restrict__ dx) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int ix = i % Wi, iy = (i / Wi) % Hi;
-  const long rc = i / ((long)Wi * Hi);
+                                   int kw, int sh, int sw_, int Ho, int Wo, float* __restrict__ dx) {
+  const int p = blockIdx.y * blockDim.x + threadIdx.x;
+  if (p >= Hi * Wi) return;
+  const int iy = p / Wi, ix = p - iy * Wi;
+  const size_t rc = blockIdx.x;
+  const float* dys = dy + rc * Ho * Wo;
+  const uint8_t* ids = idx + rc * Ho * Wo;
   float acc = 0.f;
   for (int ky = 0; ky < kh; ++ky) {
     const int ty = iy - ky;
@@ -418,11 +303,11 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* 
       if (tx < 0 || tx % sw_ != 0) continue;
       const int ox = tx / sw_;
       if (ox >= Wo) continue;
-      const long o = (rc * Ho + oy) * Wo + ox;
-      if (idx[o] == ky * kw + kx) acc += dy[o];
+      const int o = oy * Wo + ox;
+      if (ids[o] == ky * kw + kx) acc += dys[o];
     }
   }
-  dx[i] = acc;
+  dx[rc * Hi * Wi + p] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ small SGEMMs (linear)
@@ -780,28 +665,13 @@ static int pick_samples(int per_sample_floats, int pixels, int extra_floats) {
   return S < 1 ? 1 : S;
 }
 
-extern "C" int es_conv2d_fwd(const float* x, const float* w, const float* b, long slot_stride_w, long slot_stride_b,
-                             const es_conv2d* g, const es_group* grp, int n_groups, int total_rows, float* y,
-                             void* stream) {
-  ES_REQUIRE(x && w && grp && y, "null pointer");
-  ES_REQUIRE(conv_ok(g) && g->Co % kCoT == 0, "bad conv geometry (Co must be a multiple of 8)");
-  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad sizes");
-  const int in_sz = g->Ci * g->Hi * g->Wi, wt = g->Ci * g->KH * g->KW * kCoT;
-  const int S = pick_samples(in_sz, g->Ho * g->Wo, wt);
-  const size_t smem = ((size_t)S * in_sz + wt + 4) * sizeof(float);
-  ES_REQUIRE(smem <= 220 * 1024, "input sample does not fit in shared memory");
-  ES_CUDA(cudaFuncSetAttribute(conv2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  conv2d_fwd_kernel<<<dim3(ceil_div(total_rows, S) + n_groups, g->Co / kCoT), 256, smem, as_stream(stream)>>>(
-      x, w, b, slot_stride_w, slot_stride_b, *g, grp, n_groups, S, y);
-  ES_LAUNCH_CHECK();
-  return ES_OK;
-}
-
-extern "C" int es_conv2d_bwd_data(const float* dy, const float* w, long slot_stride_w, const es_conv2d* g,
+namespace es {
+// direct data gradient for Ci == 1 (gradient w.r.t. the image); called by es_conv2d_bwd_data (conv_simt.cu)
+int conv2d_bwd_data_ci1(const float* dy, const float* w, long slot_stride_w, const es_conv2d* g,
                                   const es_group* grp, int n_groups, int total_rows, float* dx, int accumulate,
                                   void* stream) {
   ES_REQUIRE(dy && w && grp && dx, "null pointer");
-  ES_REQUIRE(conv_ok(g) && (g->Ci == 1 || g->Ci % 8 == 0), "bad conv geometry (Ci must be 1 or a multiple of 8)");
+  ES_REQUIRE(conv_ok(g) && g->Ci == 1, "direct data-gradient path is for Ci == 1");
   ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad sizes");
   const int cit = g->Ci == 1 ? 1 : 8;
   const int out_sz = g->Co * g->Ho * g->Wo, wt = g->Co * g->KH * g->KW * cit;
@@ -826,31 +696,24 @@ extern "C" int es_conv2d_bwd_data(const float* dy, const float* w, long slot_str
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
+}  // namespace es
 
-extern "C" int es_conv2d_bwd_weight(const float* x, const float* dy, const es_conv2d* g, const es_group* grp,
-                                    int n_groups, int total_rows, float* dw, float* db, long slot_stride_w,
-                                    long slot_stride_b, void* stream) {
-  ES_REQUIRE(x && dy && grp && dw, "null pointer");
-  ES_REQUIRE(conv_ok(g) && g->Co % kCoT == 0, "bad conv geometry");
-  ES_REQUIRE(g->Ci * g->KH * g->KW <= kMaxEnt * 256, "too many taps per output channel");
-  ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad sizes");
+// few-tap weight gradient (Ci*KH*KW <= 9); called by es_conv2d_bwd_weight (conv_simt.cu)
+namespace es {
+int conv2d_bwd_weight_fewtaps(const float* x, const float* dy, const es_conv2d* g, const es_group* grp, int n_groups,
+                              int total_rows, float* dw, float* db, long slot_stride_w, long slot_stride_b, void* stream) {
+  ES_REQUIRE(g->Co % kCoT == 0 && g->Ci * g->KH * g->KW <= 9, "few-tap path needs Co % 8 == 0 and <= 9 taps");
   const size_t smem = ((size_t)g->Ci * g->Hi * g->Wi + (size_t)g->Ho * g->Wo * kCoT + 4) * sizeof(float);
   ES_REQUIRE(smem <= 220 * 1024, "sample does not fit in shared memory");
   int per = ceil_div(total_rows * (g->Co / kCoT), 4 * 148);
   if (per < 1) per = 1;
-  if (g->Ci * g->KH * g->KW <= 9) {
-    ES_CUDA(cudaFuncSetAttribute(conv2d_bwd_weight_fewtaps_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    conv2d_bwd_weight_fewtaps_kernel<9><<<dim3(ceil_div(total_rows, per) + n_groups, g->Co / kCoT), 256, smem, as_stream(stream)>>>(
-        x, dy, *g, grp, n_groups, per, dw, db, slot_stride_w, slot_stride_b);
-    ES_LAUNCH_CHECK();
-    return ES_OK;
-  }
-  ES_CUDA(cudaFuncSetAttribute(conv2d_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  conv2d_bwd_weight_kernel<<<dim3(ceil_div(total_rows, per) + n_groups, g->Co / kCoT), 256, smem, as_stream(stream)>>>(
+  ES_CUDA(cudaFuncSetAttribute(conv2d_bwd_weight_fewtaps_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  conv2d_bwd_weight_fewtaps_kernel<9><<<dim3(ceil_div(total_rows, per) + n_groups, g->Co / kCoT), 256, smem, as_stream(stream)>>>(
       x, dy, *g, grp, n_groups, per, dw, db, slot_stride_w, slot_stride_b);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
+}  // namespace es
 
 extern "C" int es_groupnorm_fwd(const float* x, const float* gamma, const float* beta, long slot_stride, int C, int HW,
                                 int groups, int act, const es_group* grp, int n_groups, int total_rows, float* y,
@@ -902,8 +765,8 @@ extern "C" int es_maxpool_fwd(const float* x, int C, int Hi, int Wi, int kh, int
                               float* y, uint8_t* idx, void* stream) {
   ES_REQUIRE(x && y && idx && C > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && total_rows > 0, "bad arguments");
   const int Ho = (Hi - kh) / sh + 1, Wo = (Wi - kw) / sw + 1;
-  const long total = (long)total_rows * C * Ho * Wo;
-  maxpool_fwd_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(x, C, Hi, Wi, kh, kw, sh, sw, Ho, Wo, total, y, idx);
+  ES_REQUIRE((long)total_rows * C < 2147483647L, "too many planes");
+  maxpool_fwd_kernel<<<dim3(total_rows * C, ceil_div(Ho * Wo, 128)), 128, 0, as_stream(stream)>>>(x, Hi, Wi, kh, kw, sh, sw, Ho, Wo, y, idx);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
@@ -912,8 +775,8 @@ extern "C" int es_maxpool_bwd(const float* dy, const uint8_t* idx, int C, int Hi
                               int total_rows, float* dx, void* stream) {
   ES_REQUIRE(dy && dx && idx && C > 0 && total_rows > 0, "bad arguments");
   const int Ho = (Hi - kh) / sh + 1, Wo = (Wi - kw) / sw + 1;
-  const long total = (long)total_rows * C * Hi * Wi;
-  maxpool_bwd_kernel<<<blocks_for(total), 256, 0, as_stream(stream)>>>(dy, idx, Hi, Wi, kh, kw, sh, sw, Ho, Wo, total, dx);
+  ES_REQUIRE((long)total_rows * C < 2147483647L, "too many planes");
+  maxpool_bwd_kernel<<<dim3(total_rows * C, ceil_div(Hi * Wi, 128)), 128, 0, as_stream(stream)>>>(dy, idx, Hi, Wi, kh, kw, sh, sw, Ho, Wo, dx);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }

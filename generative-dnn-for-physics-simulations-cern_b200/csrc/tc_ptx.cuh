@@ -105,6 +105,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int 
       ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// four rows (row indices r0..r3, out-of-range = zero fill) x one 64-element box column block -> 4 consecutive 128-byte rows
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void* tmap, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
