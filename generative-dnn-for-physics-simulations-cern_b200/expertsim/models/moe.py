@@ -140,6 +140,16 @@ class MoEWrapper(nn.Module):
                r["grp_half"], r["grp_gen"], scratch)
         return r
 
+    def _side_streams(self, dev):
+        """two side streams per device; with ``overlap_streams = False`` everything runs on the caller's stream"""
+        if not getattr(self, "overlap_streams", True):
+            cur = torch.cuda.current_stream()
+            return cur, cur
+        key = (dev.index if dev.index is not None else torch.cuda.current_device())
+        if getattr(self, "_streams", None) is None or self._streams[0] != key:
+            self._streams = (key, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        return self._streams[1], self._streams[2]
+
     @staticmethod
     def _gather(x, perm, width):
         B = perm.shape[0]
@@ -220,6 +230,20 @@ class MoEWrapper(nn.Module):
         if world > 1:
             dp = {"allreduce": self._allreduce, "world": world, "rows_global": counts_g * (counts_g >= 2).to(torch.float32)}
 
+        # Independent chains of small kernels run on side streams (they are latency-bound, not throughput-bound):
+        #   D(real) forward            || generator forward
+        #   D'(fake2) fwd / bwd, aux regressor fwd / bwd   || D'(fake1) fwd / bwd
+        # Spectral-norm power iterations keep their reference order a -> b -> c -> d through events.
+        main = torch.cuda.current_stream()
+        s1, s2 = self._side_streams(dev)
+        ev0 = main.record_event()
+        with torch.cuda.stream(s1):
+            s1.wait_event(ev0)
+            sn_a = disc.spectral(gh, self.training)
+            ev_a = s1.record_event()
+            s_real, _, sv_real = disc.forward(real_s, cond_s, gh, B, sn_a)
+            ev_real = s1.record_event()
+
         # ---- G(z1) and G(z2): one two-pass batch of 2B rows (moe.py:143-145,535-538)
         img1, img2, sg = gen.forward(z1, z2, cond_s, gg, 2 * B, True, training=self.training, drop=drop.get("g"), dp=dp)
         if "img1_sorted" in noise:
@@ -231,10 +255,10 @@ class MoEWrapper(nn.Module):
             img2.copy_(noise["img2_sorted"].to(dev).reshape(B, HW))
 
         # ---- discriminator step (moe.py:506-527)
-        sn_a = disc.spectral(gh, self.training)
-        s_real, _, sv_real = disc.forward(real_s, cond_s, gh, B, sn_a)
+        main.wait_event(ev_a)
         sn_b = disc.spectral(gh, self.training)
         s_fake, _, sv_fake = disc.forward(img1, cond_s, gh, B, sn_b)
+        main.wait_event(ev_real)
         d_real, d_fake = torch.zeros(B, device=dev), torch.zeros(B, device=dev)
         loss_d = torch.zeros(E, device=dev)
         L.call("es_hinge_d", s_real, s_fake, gh, E, counts_g, Bg, d_real, d_fake, loss_d)
@@ -247,10 +271,19 @@ class MoEWrapper(nn.Module):
 
         # ---- generator step (moe.py:529-571): D carries its UPDATED weights
         sn_c = disc.spectral(gh, self.training)
+        ev_c = main.record_event()
+        with torch.cuda.stream(s1):
+            s1.wait_event(ev_c)
+            sn_d = disc.spectral(gh, self.training)
+            _, lat2, sv2 = disc.forward(img2, cond_s, gh, B, sn_d)
+            ev_f2 = s1.record_event()
+        with torch.cuda.stream(s2):
+            s2.wait_event(ev_c)
+            coords, sv_a = aux.forward(img1, gh, B, self.training, drop.get("a"), dp=dp)
+            ev_ax = s2.record_event()
         score1, lat1, sv1 = disc.forward(img1, cond_s, gh, B, sn_c)
-        sn_d = disc.spectral(gh, self.training)
-        _, lat2, sv2 = disc.forward(img2, cond_s, gh, B, sn_d)
-        coords, sv_a = aux.forward(img1, gh, B, self.training, drop.get("a"), dp=dp)
+        main.wait_event(ev_f2)
+        main.wait_event(ev_ax)
         sums = torch.zeros(E, 8, dtype=torch.float64, device=dev)
         s_out, div_out = torch.zeros(B, device=dev), torch.zeros(B, device=dev)
         L.call("es_gen_loss_reduce", img1, HW, lat1, lat2, z1, z2, std_s, int_s, coords, pos_s, score1, gh, E, B,
@@ -259,15 +292,27 @@ class MoEWrapper(nn.Module):
         d_score1, d_coords = torch.zeros(B, device=dev), torch.zeros(B, 2, device=dev)
         d_lat1, d_lat2 = torch.zeros(B, 64, device=dev), torch.zeros(B, 64, device=dev)
         d_img1, d_img2 = torch.zeros(B, HW, device=dev), torch.zeros(B, HW, device=dev)
+        d_img1_aux = torch.zeros(B, HW, device=dev)
+        d_score2 = torch.zeros(B, device=dev)
         losses = torch.zeros(E, 6, device=dev)
         gcfg, stren_a = cfgm.generator, float(cfgm.aux_reg.strength)
         L.call("es_gen_loss_grads", img1, HW, lat1, lat2, z1, z2, std_s, int_s, coords, pos_s, s_out, div_out, gh, E, B,
                sums, Bg, float(gcfg.di_strength), float(gcfg.in_strength), stren_a, d_score1, d_lat1, d_lat2, d_coords,
                d_img1, losses)
+        ev_l = main.record_event()
+        with torch.cuda.stream(s1):
+            s1.wait_event(ev_l)
+            disc.backward(sv2, sn_d, d_score2, d_lat2, want_w=False, d_img=d_img2, accumulate=False)
+            ev_b2 = s1.record_event()
+        with torch.cuda.stream(s2):
+            s2.wait_event(ev_l)
+            a_a.G.zero_()
+            aux.backward(sv_a, d_coords, d_img1_aux, accumulate=False)
+            ev_ba = s2.record_event()
         disc.backward(sv1, sn_c, d_score1, d_lat1, want_w=False, d_img=d_img1, accumulate=True)
-        disc.backward(sv2, sn_d, torch.zeros(B, device=dev), d_lat2, want_w=False, d_img=d_img2, accumulate=False)
-        a_a.G.zero_()
-        aux.backward(sv_a, d_coords, d_img1, accumulate=True)
+        main.wait_event(ev_b2)
+        main.wait_event(ev_ba)
+        L.call("es_axpy", 1.0, d_img1_aux, B * HW, d_img1)
         a_g.G.zero_()
         gen.backward(sg, d_img1, d_img2)
         del sg, sv1, sv2, sv_a
