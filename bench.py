@@ -166,6 +166,11 @@ def workload_cfg(args, note=None):
 def igemm_flops(name, a):
     """algorithmic FLOPs of one grouped GEMM launch from its logged scalar arguments."""
     ints = [x for x in a if isinstance(x, int)]
+    if name in ("es_igemm_taps_fwd", "es_igemm_taps_wgrad"):
+        # phase-folded x2-upsample conv: ALGORITHMIC = the un-folded direct convolution (SURVEY.md §8d); executed MACs are
+        # n_taps*C per output instead of KH*KW*C
+        g = next(x for x in a if hasattr(x, "n_taps"))
+        return g.alg_flops_per_row * ints[-1]
     if name in ("es_igemm_fwd", "es_igemm_wgrad"):
         g = next(x for x in a if hasattr(x, "Ho"))
         rows = ints[-1]
@@ -252,7 +257,7 @@ def run_b200(args):
         torch.cuda.profiler.stop()
         return
     # ---- timed region: K steps, inputs resident in HBM
-    names = {"es_igemm_fwd", "es_igemm_wgrad", "es_dense_dgrad", "es_dense_wgrad"}
+    names = {"es_igemm_fwd", "es_igemm_wgrad", "es_igemm_taps_fwd", "es_igemm_taps_wgrad", "es_dense_dgrad", "es_dense_wgrad"}
     L.profile = {"names": names, "log": []}
     clocks = ClockSampler(local)
     if rank == 0:
@@ -279,7 +284,12 @@ def run_b200(args):
         per = len(plog) // args.steps
         for name, a, s, e in plog[-per:]:
             g = next((x for x in a if hasattr(x, "Ho")), None)
-            geo = f"Hs{g.Hs} C{g.C} {g.KH}x{g.KW} N{g.N} Ho{g.Ho}" if g is not None else str([x for x in a if isinstance(x, int)][:3])
+            if g is not None and hasattr(g, "n_taps"):
+                geo = f"Hs{g.Hs} C{g.C} taps{g.n_taps} N{g.N} Ho{g.Ho} (folded)"
+            elif g is not None:
+                geo = f"Hs{g.Hs} C{g.C} {g.KH}x{g.KW} N{g.N} Ho{g.Ho}"
+            else:
+                geo = str([x for x in a if isinstance(x, int)][:3])
             t = s.elapsed_time(e)
             print(f"  {name:16s} {geo:34s} {t:8.3f} ms {igemm_flops(name, a) / t / 1e9:8.1f} TFLOP/s", file=sys.stderr)
     fam = {}
@@ -289,10 +299,10 @@ def run_b200(args):
         f[0] += igemm_flops(name, a)
         f[1] += s.elapsed_time(e)
         f[2] += 1
-    tc = [fam[k] for k in ("es_igemm_fwd", "es_igemm_wgrad") if k in fam]
+    tc = [fam[k] for k in ("es_igemm_fwd", "es_igemm_wgrad", "es_igemm_taps_fwd", "es_igemm_taps_wgrad") if k in fam]
     tc_flops, tc_ms, tc_n = (sum(x[i] for x in tc) for i in range(3))
     pk = peaks()
-    roof = {"bound": "tensor", "kernel": "igemm_tc (grouped bf16 tcgen05 implicit GEMM: es_igemm_fwd + es_igemm_wgrad)",
+    roof = {"bound": "tensor", "kernel": "igemm_persist (grouped bf16 tcgen05 implicit GEMM family: igemm_fwd_kernel + igemm_wgrad_kernel, incl. the x2-upsample-folded tap-table launches; algorithmic = un-folded direct-conv FLOPs)",
             "achieved": round(tc_flops / (tc_ms * 1e-3) / 1e12, 2) if tc_ms else None, "peak": pk["tflops"], "unit": "TFLOP/s",
             "frac": round(tc_flops / (tc_ms * 1e-3) / 1e12 / pk["tflops"], 4) if tc_ms else None, "traffic": None,
             "peak_source": f"{pk['src']} sustained bf16 (MEASURED_PEAKS.json)", "launches": tc_n,

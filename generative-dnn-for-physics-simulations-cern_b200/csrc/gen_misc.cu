@@ -658,6 +658,86 @@ __global__ void igemm_wgrad_simt_kernel(const __nv_bfloat16* __restrict__ x, con
 
 using namespace es;
 
+// ----------------------------------------------------------------------------------------------- x2-upsample folding
+// A conv that follows a x2 nearest upsample sees, for output phase (py, px) = (oy & 1, ox & 1), only the distinct source
+// rows a + dy with dy = floor((py + ky - pad) / 2): taps that land on the same source pixel are pre-summed.  Folded tap
+// t = (py, px, dy, dx) of the table; forward layout [slot][n][t][c], data-gradient layout [slot][c][t][n] (both bf16),
+// folded weight gradient [slot][n][t][c] (fp32) unfolded back to the reference's [n][c][ky][kx].
+namespace es {
+__device__ __forceinline__ int floor_half(int v) { return v >= 0 ? v / 2 : -((1 - v) / 2); }
+
+__global__ void fold_up2_kernel(const float* __restrict__ w, long sw, int N, int C, int KH, int KW, int pad, es_fold_table t,
+                                __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const int slot = blockIdx.y;
+  const long total = (long)N * t.n_taps * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), tt = (int)((i / C) % t.n_taps), n = (int)(i / ((long)C * t.n_taps));
+    float acc = 0.f;
+    for (int ky = 0; ky < KH; ++ky) {
+      if (floor_half(t.py[tt] + ky - pad) != t.dy[tt]) continue;
+      for (int kx = 0; kx < KW; ++kx)
+        if (floor_half(t.px[tt] + kx - pad) == t.dx[tt]) acc += w[slot * sw + (((size_t)n * C + c) * KH + ky) * KW + kx];
+    }
+    const __nv_bfloat16 v = f2bf(acc);
+    if (wf) wf[(size_t)slot * total + ((size_t)n * t.n_taps + tt) * C + c] = v;
+    if (wd) wd[(size_t)slot * total + ((size_t)c * t.n_taps + tt) * N + n] = v;
+  }
+}
+
+__global__ void unfold_up2_kernel(const float* __restrict__ dwf, int N, int C, int KH, int KW, int pad, es_fold_table t,
+                                  float* __restrict__ dw, long sw) {
+  const int slot = blockIdx.y;
+  const long total = (long)N * C * KH * KW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int kx = (int)(i % KW), ky = (int)((i / KW) % KH), c = (int)((i / ((long)KW * KH)) % C), n = (int)(i / ((long)KW * KH * C));
+    float acc = 0.f;
+    for (int tt = 0; tt < t.n_taps; ++tt)
+      if (floor_half(t.py[tt] + ky - pad) == t.dy[tt] && floor_half(t.px[tt] + kx - pad) == t.dx[tt])
+        acc += dwf[((size_t)slot * N + n) * t.n_taps * C + (size_t)tt * C + c];
+    dw[slot * sw + i] += acc;
+  }
+}
+
+// dst[row, a*Wo + b, :] = src[row, (a*my + oy)*Wf + b*mx + ox, :]   (one output phase of an NHWC bf16 map, 16-byte chunks)
+__global__ void pick_pixels_kernel(const __nv_bfloat16* __restrict__ src, int Pf, int Wf, int C, int my, int oy, int mx, int ox,
+                                   int Ho, int Wo, __nv_bfloat16* __restrict__ dst) {
+  const int row = blockIdx.x, c8 = C / 8, n = Ho * Wo * c8;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)row * Pf * C);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + (size_t)row * Ho * Wo * C);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int pix = i / c8, ch = i - pix * c8, a = pix / Wo, b = pix - a * Wo;
+    d4[i] = s4[(size_t)((a * my + oy) * Wf + b * mx + ox) * c8 + ch];
+  }
+}
+}  // namespace es
+
+extern "C" int es_fold_up2_weights(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW, int pad,
+                                   const es_fold_table* t, void* w_fwd, void* w_dgrad, void* stream) {
+  ES_REQUIRE(w && t && (w_fwd || w_dgrad) && slots >= 1 && N > 0 && C > 0 && t->n_taps >= 1 && t->n_taps <= 32, "bad arguments");
+  es::fold_up2_kernel<<<dim3(512, slots), 256, 0, es::as_stream(stream)>>>(w, slot_stride, N, C, KH, KW, pad, *t,
+                                                                            (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_unfold_up2_wgrad(const float* dw_folded, int slots, int N, int C, int KH, int KW, int pad,
+                                   const es_fold_table* t, float* dw_ref, long slot_stride, void* stream) {
+  ES_REQUIRE(dw_folded && t && dw_ref && slots >= 1 && t->n_taps >= 1 && t->n_taps <= 32, "bad arguments");
+  es::unfold_up2_kernel<<<dim3(512, slots), 256, 0, es::as_stream(stream)>>>(dw_folded, N, C, KH, KW, pad, *t, dw_ref, slot_stride);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_pick_pixels(const void* src, int Ho_full, int Wo_full, int C, int my, int oy, int mx, int ox, int Ho, int Wo,
+                              int total_rows, void* dst, void* stream) {
+  ES_REQUIRE(src && dst && C % 8 == 0 && total_rows > 0 && Ho > 0 && Wo > 0, "bad arguments");
+  ES_REQUIRE((Ho - 1) * my + oy < Ho_full && (Wo - 1) * mx + ox < Wo_full, "pixel selection out of range");
+  es::pick_pixels_kernel<<<total_rows, 256, 0, es::as_stream(stream)>>>((const __nv_bfloat16*)src, Ho_full * Wo_full, Wo_full, C, my,
+                                                                        oy, mx, ox, Ho, Wo, (__nv_bfloat16*)dst);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
 extern "C" int es_gen_fc1_fwd(const float* z1, const float* z2, const float* cond, const float* w, const float* b,
                               const float* gamma, const float* beta, long slot_stride_w, long slot_stride_v,
                               const es_group* grp_gen, int E, int total_rows, int two_pass, float* x0, float* lin,

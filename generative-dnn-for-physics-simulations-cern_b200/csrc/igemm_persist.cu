@@ -33,10 +33,18 @@ constexpr int kFStage = kFStageA + kFStageB;
 constexpr int kFMaxGroups = 64;
 constexpr size_t kFSmem = (size_t)kFStages * kFStage + 1024 /*align*/ + 2048 /*barriers + tables*/;
 
+// The reduction is a TAP TABLE: tap t reads the (virtually upsampled) source at (oy*my + tdy[t], ox*mx + tdx[t]) and its C
+// weights start at column tkoff[t] of the packed weight row.  A plain conv is tdy = ky - pad, tdx = kx - pad, tkoff = t*C,
+// my = mx = 1.  The phase-folded x2-upsample convs and their combined data gradient use other tables (see
+// es_igemm_taps_fwd).  Output pixel (a, b) of the M-space grid [Ho, Wo] is stored at ((a*o_my + o_oy)*Wo_full + b*o_mx + o_ox).
 struct FwdParams {
   const es_group* grp;
   int n_groups;
-  int Hs, Ws, C, Hu, Wu, Ho, Wo, KH, KW, pad, P;
+  int Hs, Ws, C, Hu, Wu, Ho, Wo, P;
+  int n_taps, my, mx;
+  signed char tdy[32], tdx[32];
+  int tkoff[32];
+  int o_my, o_oy, o_mx, o_ox, Wo_full, P_full;
   int Nout, BN, KK, n_tiles_n;
   unsigned char ymap[64], xmap[64];
   const __nv_bfloat16* a_src;
@@ -97,6 +105,9 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
   es_group* s_grp = reinterpret_cast<es_group*>(gen + 384);    // [64] x 16 B
   unsigned char* s_ymap = gen + 384 + 1024;                    // 64
   unsigned char* s_xmap = s_ymap + 64;                         // 64
+  signed char* s_tdy = reinterpret_cast<signed char*>(s_xmap + 64);   // 32
+  signed char* s_tdx = s_tdy + 32;                             // 32
+  int* s_tkoff = reinterpret_cast<int*>(s_tdx + 32);           // 32 ints
 
   const int BN = p.BN;
   const int acc_cols = MT * BN;                                // TMEM columns of one accumulator set
@@ -111,6 +122,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     s_tiles[tid] = ceil_div(gq.rows * p.P, kTileM);
   }
   if (tid < 64) { s_ymap[tid] = p.ymap[tid]; s_xmap[tid] = p.xmap[tid]; }
+  if (tid < 32) { s_tdy[tid] = p.tdy[tid]; s_tdx[tid] = p.tdx[tid]; s_tkoff[tid] = p.tkoff[tid]; }
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), G4 ? 2 : kFLoaders + 1);
@@ -132,7 +144,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
   int total_tiles = 0;
   for (int i = 0; i < p.n_groups; ++i) total_tiles += s_tiles[i];
   total_tiles *= p.n_tiles_n;
-  const int taps = p.KH * p.KW;
+  const int taps = p.n_taps;
   const int cblks = p.C / kBK;
   const int nkb = taps * cblks;
 
@@ -158,23 +170,24 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
           r_oyx[j] = (oy << 8) | (pix - oy * p.Wo);
           r_base[j] = valid ? (ti.row_start + sample) * p.Hs * p.Ws : -1;
         }
-        int cb = 0, ky = 0, kx = 0;
+        int cb = 0, tap = 0;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           if (it >= kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 1);
           const uint32_t sa = base + s * kStage;
           const int c0 = cb * kBK + chunk * 8;
+          const int ty = s_tdy[tap], tx = s_tdx[tap];
 #pragma unroll
           for (int j = 0; j < RPT; ++j) {
             const int r = rsub + 16 * j;
-            const int uy = (r_oyx[j] >> 8) + ky - p.pad, ux = (r_oyx[j] & 255) + kx - p.pad;
+            const int uy = (r_oyx[j] >> 8) * p.my + ty, ux = (r_oyx[j] & 255) * p.mx + tx;
             const bool inb = r_base[j] >= 0 && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
             const int sy = inb ? s_ymap[uy] : 0, sx = inb ? s_xmap[ux] : 0;
             const __nv_bfloat16* src = p.a_src + (inb ? ((long)(r_base[j] + sy * p.Ws + sx) * p.C + c0) : 0L);
             cp_async16_ca(sa + (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4), src, inb);
           }
           cp_async_commit();
-          if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++cb; } }
+          if (++tap == taps) { tap = 0; ++cb; }
           if (it - signalled >= (uint32_t)kFLag) {
             cp_async_wait<kFLag>();
             fence_proxy_async();
@@ -207,17 +220,18 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
           r_oyx[j] = (oy << 8) | (pix - oy * p.Wo);
           r_base[j] = valid ? (ti.row_start + sample) * p.Hs * p.Ws : -1;
         }
-        int cb = 0, ky = 0, kx = 0;
+        int cb = 0, tap = 0;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           if (it >= kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 1);
           const uint32_t sa = base + s * kStage;
           if (lane == 0) mbar_arrive_expect_tx(full_bar(s), (uint32_t)kStageA);
           __syncwarp();
+          const int ty = s_tdy[tap], tx = s_tdx[tap];
           int idx[4 * MT];
 #pragma unroll
           for (int j = 0; j < 4 * MT; ++j) {
-            const int uy = (r_oyx[j] >> 8) + ky - p.pad, ux = (r_oyx[j] & 255) + kx - p.pad;
+            const int uy = (r_oyx[j] >> 8) * p.my + ty, ux = (r_oyx[j] & 255) * p.mx + tx;
             const bool inb = r_base[j] >= 0 && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
             idx[j] = inb ? r_base[j] + s_ymap[uy] * p.Ws + s_xmap[ux] : -1;     // -1: out of bounds -> zero rows
           }
@@ -225,7 +239,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
           for (int mt = 0; mt < MT; ++mt)
             tma_gather4(sa + mt * kFStageA + lane * 512u, &tmap_a, cb * kBK, idx[4 * mt], idx[4 * mt + 1], idx[4 * mt + 2],
                         idx[4 * mt + 3], full_bar(s));
-          if (++kx == p.KW) { kx = 0; if (++ky == p.KH) { ky = 0; ++cb; } }
+          if (++tap == taps) { tap = 0; ++cb; }
         }
       }
     }
@@ -242,7 +256,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
           const int s = it % kStages;
           if (it >= kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
           mbar_arrive_expect_tx(full_bar(s), (uint32_t)BN * 128u);
-          tma_load_2d(base + s * kStage + kStageA, &tmap_w, tap * p.C + cb * kBK, wrow, full_bar(s));
+          tma_load_2d(base + s * kStage + kStageA, &tmap_w, s_tkoff[tap] + cb * kBK, wrow, full_bar(s));
           if (++tap == taps) { tap = 0; ++cb; }
         }
       }
@@ -296,7 +310,10 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
         const uint32_t t_lane = tmem_base + buf * (uint32_t)acc_cols + mt * BN + ((uint32_t)(q * 32) << 16);
         const int m = ti.m0 + mt * kBM + q * 32 + lane;
         const bool ok = m < ti.rows * p.P;
-        __nv_bfloat16* yrow = p.out + (((long)ti.row_start * p.P + m) * p.Nout + ti.n0);
+        const int smp = ok ? m / p.P : 0, pix = ok ? m - smp * p.P : 0;
+        const int oa = pix / p.Wo, ob = pix - oa * p.Wo;
+        const long opix = (long)(ti.row_start + smp) * p.P_full + (oa * p.o_my + p.o_oy) * p.Wo_full + ob * p.o_mx + p.o_ox;
+        __nv_bfloat16* yrow = p.out + (opix * p.Nout + ti.n0);
         for (int c = 0; c < BN; c += 32) {
           tmem_ld32(t_lane + c, r);
           if (ok) {
@@ -330,7 +347,11 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
 struct WgParams {
   const es_group* grp;
   int n_groups;
-  int Hs, Ws, C, Hu, Wu, Ho, Wo, KH, KW, pad, P;
+  int Hs, Ws, C, Hu, Wu, Ho, Wo, P;
+  int n_taps;                       // tap t gathers x at (oy + tdy[t], ox + tdx[t]); its C columns start at tcol[t] of a dw row
+  signed char tdy[32], tdx[32];
+  int tcol[32];
+  int dw_ld;                        // length of a dw row (all taps of all phases)
   int N, KK, tiles_m, splits;
   unsigned char ymap[64], xmap[64];
   const __nv_bfloat16* x;
@@ -413,8 +434,8 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
         const int kk = ti.m0 + sg * 64;
         const int tap = kk / p.C;
         cv[sg] = kk - tap * p.C + chunk * 8;
-        kyv[sg] = tap / p.KW - p.pad;
-        kxv[sg] = tap % p.KW - p.pad;
+        kyv[sg] = p.tdy[tap];
+        kxv[sg] = p.tdx[tap];
       }
       const int hw = p.Hs * p.Ws;
       const long src_base = (long)ti.row_start * hw;
@@ -527,12 +548,14 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1, p.err_flag, 3);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
-      float* dw = p.dw + (long)ti.slot * p.dw_slot_stride + ti.m0 + q * 32 + lane;
+      const int kk = ti.m0 + q * 32 + lane;                    // this thread's reduction column inside the launch's KK
+      const int tap = kk / p.C;
+      float* dw = p.dw + (long)ti.slot * p.dw_slot_stride + p.tcol[tap] + (kk - tap * p.C);
       uint32_t r[32];
       for (int c = 0; c < BN; c += 32) {
         tmem_ld32(t_lane + c, r);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dw + (long)(c + j) * p.KK, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; ++j) atomicAdd(dw + (long)(c + j) * p.dw_ld, __uint_as_float(r[j]));
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
@@ -591,28 +614,21 @@ void fill_maps_uc(int Hs, int Ws, int Hu, int Wu, unsigned char* ymap, unsigned 
 
 using namespace es;
 
-extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
-                            const es_conv_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
-  ES_REQUIRE(x && w && y && grp && g, "null pointer");
-  ES_REQUIRE(g->C > 0 && g->C % 64 == 0 && g->Hu <= 64 && g->Wu <= 64 && g->Hu >= g->Hs && g->Wu >= g->Ws &&
-                 g->Ho == g->Hu + 2 * g->pad - g->KH + 1 && g->Wo == g->Wu + 2 * g->pad - g->KW + 1 && g->Ho > 0 &&
-                 g->Wo > 0 && g->Ho < 256 && g->Wo < 256,
-             "unsupported geometry (need C % 64 == 0, Hu,Wu <= 64, stride-1 window)");
+static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows, int n_groups, void* stream) {
+  ES_REQUIRE(p.C > 0 && p.C % 64 == 0 && p.Hu <= 64 && p.Wu <= 64 && p.Hu >= p.Hs && p.Wu >= p.Ws && p.Ho > 0 && p.Wo > 0 &&
+                 p.Ho < 256 && p.Wo < 256 && p.n_taps >= 1 && p.n_taps <= 32 && p.KK % 8 == 0,
+             "unsupported geometry (need C % 64 == 0, Hu,Wu <= 64, <= 32 taps)");
   ES_REQUIRE(n_groups >= 1 && n_groups <= kFMaxGroups && total_rows > 0, "bad group count / rows");
-  FwdParams p{};
-  p.grp = grp; p.n_groups = n_groups;
-  p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
-  p.KH = g->KH; p.KW = g->KW; p.pad = g->pad; p.P = g->Ho * g->Wo;
-  p.KK = g->KH * g->KW * g->C;
-  p.Nout = g->N;
+  p.n_groups = n_groups;
+  p.P = p.Ho * p.Wo;
   p.BN = 256;                                   // widest N tile (power of two, >= 32) that divides N
-  while (p.BN > 32 && g->N % p.BN != 0) p.BN >>= 1;
-  ES_REQUIRE(g->N % p.BN == 0, "N must be a multiple of 32");
-  ES_REQUIRE((long)total_rows * p.Hs * p.Ws < 2147483647L, "too many source pixels");
-  p.n_tiles_n = g->N / p.BN;
+  while (p.BN > 32 && p.Nout % p.BN != 0) p.BN >>= 1;
+  ES_REQUIRE(p.Nout % p.BN == 0, "N must be a multiple of 32");
+  ES_REQUIRE((long)total_rows * p.Hs * p.Ws < 2147483647L && (long)total_rows * p.P_full < 2147483647L, "too many pixels");
+  p.n_tiles_n = p.Nout / p.BN;
   fill_maps_uc(p.Hs, p.Ws, p.Hu, p.Wu, p.ymap, p.xmap);
-  p.a_src = (const __nv_bfloat16*)x; p.bias = bias; p.bias_slot_stride = bias_slot_stride;
-  p.out = (__nv_bfloat16*)y; p.err_flag = fwd_err_flag();
+  p.a_src = (const __nv_bfloat16*)x;
+  p.err_flag = fwd_err_flag();
 
   // weights as a 2-D tensor [slots*N rows][KK] bf16; the number of slots is not known here, so the row extent is the
   // largest one the group table can address (TMA never reads rows the kernel does not ask for)
@@ -621,7 +637,7 @@ extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, lon
   alignas(64) CUtensorMap tmap, tmap_a;
   const cuuint32_t estr[2] = {1, 1};
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)g->N};
+    const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)p.Nout};
     const cuuint64_t strides[1] = {(cuuint64_t)p.KK * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
     const CUresult rc = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
@@ -672,20 +688,57 @@ extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, lon
   return ES_OK;
 }
 
-extern "C" int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es_conv_geom* g, const es_group* grp,
-                              int n_groups, int total_rows, void* stream) {
-  ES_REQUIRE(x && dy && dw && grp && g, "null pointer");
-  ES_REQUIRE(g->C > 0 && g->C % 64 == 0 && g->Hu <= 64 && g->Wu <= 64 && g->Hu >= g->Hs && g->Wu >= g->Ws &&
-                 g->Ho == g->Hu + 2 * g->pad - g->KH + 1 && g->Wo == g->Wu + 2 * g->pad - g->KW + 1 && g->Ho > 0 && g->Wo > 0,
-             "unsupported geometry");
-  ES_REQUIRE(n_groups >= 1 && n_groups <= kFMaxGroups && total_rows > 0, "bad group count / rows");
-  ES_REQUIRE(g->N % 64 == 0 && g->N <= 256 && (g->N & (g->N - 1)) == 0, "dy channels must be 64, 128 or 256");
-  WgParams p{};
-  p.grp = grp; p.n_groups = n_groups;
+extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
+                            const es_conv_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
+  ES_REQUIRE(x && w && y && grp && g, "null pointer");
+  ES_REQUIRE(g->KH >= 1 && g->KW >= 1 && g->KH * g->KW <= 32 && g->Ho == g->Hu + 2 * g->pad - g->KH + 1 &&
+                 g->Wo == g->Wu + 2 * g->pad - g->KW + 1, "unsupported window (stride 1, <= 32 taps)");
+  FwdParams p{};
+  p.grp = grp;
   p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
-  p.KH = g->KH; p.KW = g->KW; p.pad = g->pad; p.P = g->Ho * g->Wo;
-  p.KK = g->KH * g->KW * g->C; p.N = g->N;
-  ES_REQUIRE(p.KK % kBM == 0, "KH*KW*C must be a multiple of 128");
+  p.n_taps = g->KH * g->KW; p.my = 1; p.mx = 1;
+  for (int ky = 0; ky < g->KH; ++ky)
+    for (int kx = 0; kx < g->KW; ++kx) {
+      const int t = ky * g->KW + kx;
+      p.tdy[t] = (signed char)(ky - g->pad); p.tdx[t] = (signed char)(kx - g->pad); p.tkoff[t] = t * g->C;
+    }
+  p.KK = g->KH * g->KW * g->C;
+  p.Nout = g->N;
+  p.o_my = 1; p.o_oy = 0; p.o_mx = 1; p.o_ox = 0; p.Wo_full = g->Wo; p.P_full = g->Ho * g->Wo;
+  p.bias = bias; p.bias_slot_stride = bias_slot_stride; p.out = (__nv_bfloat16*)y;
+  return launch_fwd(p, x, w, total_rows, n_groups, stream);
+}
+
+extern "C" int es_igemm_taps_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
+                                 const es_tap_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
+  ES_REQUIRE(x && w && y && grp && g, "null pointer");
+  ES_REQUIRE(g->n_taps >= 1 && g->n_taps <= 32 && g->my >= 1 && g->mx >= 1 && g->o_my >= 1 && g->o_mx >= 1, "bad tap table");
+  ES_REQUIRE((g->Ho - 1) * g->o_my + g->o_oy < g->Ho_full && (g->Wo - 1) * g->o_mx + g->o_ox < g->Wo_full, "output scatter out of range");
+  FwdParams p{};
+  p.grp = grp;
+  p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
+  p.n_taps = g->n_taps; p.my = g->my; p.mx = g->mx;
+  for (int t = 0; t < g->n_taps; ++t) {
+    p.tdy[t] = g->tap_dy[t]; p.tdx[t] = g->tap_dx[t]; p.tkoff[t] = g->tap_koff[t];
+    ES_REQUIRE(g->tap_koff[t] >= 0 && g->tap_koff[t] % 64 == 0 && g->tap_koff[t] + g->C <= g->KK, "tap weight offset out of range");
+  }
+  p.KK = g->KK;
+  p.Nout = g->N;
+  p.o_my = g->o_my; p.o_oy = g->o_oy; p.o_mx = g->o_mx; p.o_ox = g->o_ox; p.Wo_full = g->Wo_full; p.P_full = g->Ho_full * g->Wo_full;
+  p.bias = bias; p.bias_slot_stride = bias_slot_stride; p.out = (__nv_bfloat16*)y;
+  return launch_fwd(p, x, w, total_rows, n_groups, stream);
+}
+
+static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, long dw_slot_stride, int total_rows,
+                        int n_groups, void* stream) {
+  ES_REQUIRE(p.C > 0 && p.C % 64 == 0 && p.Hu <= 64 && p.Wu <= 64 && p.Hu >= p.Hs && p.Wu >= p.Ws && p.Ho > 0 && p.Wo > 0 &&
+                 p.n_taps >= 1 && p.n_taps <= 32, "unsupported geometry");
+  ES_REQUIRE(n_groups >= 1 && n_groups <= kFMaxGroups && total_rows > 0, "bad group count / rows");
+  ES_REQUIRE(p.N % 64 == 0 && p.N <= 256 && (p.N & (p.N - 1)) == 0, "dy channels must be 64, 128 or 256");
+  p.n_groups = n_groups;
+  p.P = p.Ho * p.Wo;
+  p.KK = p.n_taps * p.C;
+  ES_REQUIRE(p.KK % kBM == 0, "taps*C must be a multiple of 128");
   ES_REQUIRE((long)total_rows * p.P < 2147483647L && (long)total_rows * p.Hs * p.Ws * p.C < (1L << 40), "too many pixels");
   p.tiles_m = p.KK / kBM;
   int splits = ceil_div(1024, p.tiles_m * n_groups);
@@ -695,13 +748,13 @@ extern "C" int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es
   if (splits > 64) splits = 64;
   p.splits = splits;
   fill_maps_uc(p.Hs, p.Ws, p.Hu, p.Wu, p.ymap, p.xmap);
-  p.x = (const __nv_bfloat16*)x; p.dw = dw; p.dw_slot_stride = (long)g->N * p.KK; p.err_flag = fwd_err_flag();
+  p.x = (const __nv_bfloat16*)x; p.dw = dw; p.dw_slot_stride = dw_slot_stride; p.err_flag = fwd_err_flag();
 
   EncodeTiledFn enc = encode_fn();
   ES_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   alignas(64) CUtensorMap tmap;
-  const cuuint64_t dims[2] = {(cuuint64_t)g->N, (cuuint64_t)total_rows * (cuuint64_t)p.P};
-  const cuuint64_t strides[1] = {(cuuint64_t)g->N * 2};
+  const cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)total_rows * (cuuint64_t)p.P};
+  const cuuint64_t strides[1] = {(cuuint64_t)p.N * 2};
   const cuuint32_t box[2] = {64, 64};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult rc = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dy), dims, strides, box, estr,
@@ -720,4 +773,43 @@ extern "C" int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es
   igemm_wgrad_kernel<<<total < sms ? total : sms, kFThreads, kFSmem, as_stream(stream)>>>(p, tmap);
   ES_LAUNCH_CHECK();
   return ES_OK;
+}
+
+extern "C" int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es_conv_geom* g, const es_group* grp,
+                              int n_groups, int total_rows, void* stream) {
+  ES_REQUIRE(x && dy && dw && grp && g, "null pointer");
+  ES_REQUIRE(g->KH >= 1 && g->KW >= 1 && g->KH * g->KW <= 32 && g->Ho == g->Hu + 2 * g->pad - g->KH + 1 &&
+                 g->Wo == g->Wu + 2 * g->pad - g->KW + 1, "unsupported window (stride 1, <= 32 taps)");
+  WgParams p{};
+  p.grp = grp;
+  p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
+  p.n_taps = g->KH * g->KW;
+  for (int ky = 0; ky < g->KH; ++ky)
+    for (int kx = 0; kx < g->KW; ++kx) {
+      const int t = ky * g->KW + kx;
+      p.tdy[t] = (signed char)(ky - g->pad); p.tdx[t] = (signed char)(kx - g->pad); p.tcol[t] = t * g->C;
+    }
+  p.N = g->N;
+  p.dw_ld = g->KH * g->KW * g->C;
+  return launch_wgrad(p, x, dy, dw, (long)g->N * p.dw_ld, total_rows, n_groups, stream);
+}
+
+/* tap-table weight gradient: dy is [rows, Ho*Wo, N] (the pixels of ONE output phase, contiguous), x the low-resolution source;
+ * dw[slot][n][tap_koff[t] + c] += sum_pix dy[pix, n] * x[(oy + tap_dy[t], ox + tap_dx[t]), c];  a dw row has g->KK columns */
+extern "C" int es_igemm_taps_wgrad(const void* x, const void* dy, float* dw, const es_tap_geom* g, const es_group* grp,
+                                   int n_groups, int total_rows, void* stream) {
+  ES_REQUIRE(x && dy && dw && grp && g, "null pointer");
+  ES_REQUIRE(g->my == 1 && g->mx == 1, "the weight gradient gathers with unit pixel stride");
+  WgParams p{};
+  p.grp = grp;
+  p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
+  p.n_taps = g->n_taps;
+  ES_REQUIRE(g->n_taps >= 1 && g->n_taps <= 32, "bad tap table");
+  for (int t = 0; t < g->n_taps; ++t) {
+    p.tdy[t] = g->tap_dy[t]; p.tdx[t] = g->tap_dx[t]; p.tcol[t] = g->tap_koff[t];
+    ES_REQUIRE(g->tap_koff[t] >= 0 && g->tap_koff[t] + g->C <= g->KK, "tap column offset out of range");
+  }
+  p.N = g->N;
+  p.dw_ld = g->KK;
+  return launch_wgrad(p, x, dy, dw, (long)g->N * g->KK, total_rows, n_groups, stream);
 }

@@ -31,6 +31,17 @@ class ESConv2d(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("Ci", "Hi", "Wi", "Co", "Ho", "Wo", "KH", "KW", "stride", "pad")]
 
 
+class ESTapGeom(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_int32) for n in ("Hs", "Ws", "C", "Hu", "Wu", "Ho", "Wo", "my", "mx", "n_taps")]
+                + [("tap_dy", ctypes.c_int8 * 32), ("tap_dx", ctypes.c_int8 * 32), ("tap_koff", ctypes.c_int32 * 32)]
+                + [(n, ctypes.c_int32) for n in ("KK", "N", "o_my", "o_oy", "o_mx", "o_ox", "Ho_full", "Wo_full")])
+
+
+class ESFoldTable(ctypes.Structure):
+    _fields_ = [("n_taps", ctypes.c_int32), ("py", ctypes.c_int8 * 32), ("px", ctypes.c_int8 * 32), ("dy", ctypes.c_int8 * 32),
+                ("dx", ctypes.c_int8 * 32)]
+
+
 def parse_header(path: str = HEADER_PATH) -> Dict[str, Tuple[str, List[Tuple[str, str]]]]:
     """-> {function name: (return type, [(ctype kind, arg name), ...])} for every prototype in the header."""
     src = open(path).read()

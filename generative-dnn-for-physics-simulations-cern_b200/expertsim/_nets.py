@@ -39,6 +39,83 @@ def conv2d(Ci, Hi, Wi, Co, KH, KW, stride, pad):
 
 
 # =====================================================================================================================
+# x2 nearest upsample folded into the following conv (see es_igemm_taps_fwd in include/expertsim_b200.h)
+# =====================================================================================================================
+class Up2Conv:
+    """Tap tables of a stride-1 conv (KHxKW, pad) applied to a x2 nearest-upsampled [Hs,Ws,C] map -> [Ho,Wo,N].
+    Output phase (py,px) = (oy&1, ox&1) reads source rows a+dy, dy in {floor((py+ky-pad)/2)}: taps landing on the same source
+    pixel are pre-summed, e.g. k4/p1: 9+6+6+4 = 25 folded taps per 4 outputs instead of 64 (2.56x fewer MACs), k3/p0: 16
+    instead of 36 (2.25x).  Forward = one table-conv per phase (strided output), data gradient = ONE table-conv over dy writing
+    the low-resolution gradient, weight gradient = one table-GEMM per phase on a contiguous copy of that phase's dy pixels,
+    un-folded afterwards."""
+
+    def __init__(self, Hs, Ws, C, KH, KW, pad, N):
+        self.Hs, self.Ws, self.C, self.KH, self.KW, self.pad, self.N = Hs, Ws, C, KH, KW, pad, N
+        self.Ho, self.Wo = 2 * Hs + 2 * pad - KH + 1, 2 * Ws + 2 * pad - KW + 1
+        fl = lambda v: v // 2          # python floor division
+        dl = lambda p_, K: sorted({fl(p_ + k - pad) for k in range(K)})
+        self.taps = []                  # global folded taps (py, px, dy, dx)
+        self.phases = []                # (py, px, first global tap, [(dy, dx)...], Ho', Wo')
+        for py in (0, 1):
+            for px in (0, 1):
+                lst = [(dy, dx) for dy in dl(py, KH) for dx in dl(px, KW)]
+                self.phases.append((py, px, len(self.taps), lst, (self.Ho - py + 1) // 2, (self.Wo - px + 1) // 2))
+                self.taps += [(py, px, dy, dx) for dy, dx in lst]
+        self.T = len(self.taps)
+        assert self.T <= 32
+        self.table = L.ESFoldTable()
+        self.table.n_taps = self.T
+        for t, (py, px, dy, dx) in enumerate(self.taps):
+            self.table.py[t], self.table.px[t], self.table.dy[t], self.table.dx[t] = py, px, dy, dx
+        self.g_fwd, self.g_wg = [], []
+        for py, px, t0, lst, Hp, Wp in self.phases:
+            for store, kk_c in ((self.g_fwd, C), (self.g_wg, C)):
+                g = L.ESTapGeom()
+                g.Hs, g.Ws, g.C, g.Hu, g.Wu, g.Ho, g.Wo, g.my, g.mx = Hs, Ws, C, Hs, Ws, Hp, Wp, 1, 1
+                g.n_taps = len(lst)
+                for i, (dy, dx) in enumerate(lst):
+                    g.tap_dy[i], g.tap_dx[i], g.tap_koff[i] = dy, dx, (t0 + i) * C
+                g.KK, g.N = self.T * C, N
+                g.o_my, g.o_oy, g.o_mx, g.o_ox, g.Ho_full, g.Wo_full = 2, py, 2, px, self.Ho, self.Wo
+                g.alg_flops_per_row = 2.0 * Hp * Wp * N * KH * KW * C     # un-folded direct-conv FLOPs of this phase's pixels
+                store.append(g)
+        g = L.ESTapGeom()                # data gradient: M-space = source pixels, "source" = dy on the [Ho,Wo] grid
+        g.Hs, g.Ws, g.C, g.Hu, g.Wu, g.Ho, g.Wo, g.my, g.mx = self.Ho, self.Wo, N, self.Ho, self.Wo, Hs, Ws, 2, 2
+        g.n_taps = self.T
+        for t, (py, px, dy, dx) in enumerate(self.taps):
+            g.tap_dy[t], g.tap_dx[t], g.tap_koff[t] = py - 2 * dy, px - 2 * dx, t * N
+        g.KK, g.N = self.T * N, C
+        g.o_my, g.o_oy, g.o_mx, g.o_ox, g.Ho_full, g.Wo_full = 1, 0, 1, 0, Hs, Ws
+        g.alg_flops_per_row = 2.0 * self.Ho * self.Wo * N * KH * KW * C
+        self.g_dgrad = g
+
+    def alloc(self, E, dev):
+        self.w_f = torch.empty(E, self.N, self.T * self.C, dtype=BF, device=dev)
+        self.w_d = torch.empty(E, self.C, self.T * self.N, dtype=BF, device=dev)
+        self.dw_f = torch.empty(E, self.N, self.T * self.C, device=dev)
+
+    def fold(self, w_addr, slot_stride, E):
+        L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, self.pad, self.table, self.w_f, self.w_d)
+
+    def forward(self, x, bias_addr, bias_stride, y, grp, E, R):
+        for g in self.g_fwd:
+            L.call("es_igemm_taps_fwd", x, self.w_f, bias_addr, bias_stride, y, g, grp, E, R)
+
+    def wgrad(self, x, dy, dw_addr, slot_stride, grp, E, R):
+        """dy [R, Ho*Wo, N] -> parameter gradient in the reference layout (accumulated at dw_addr)."""
+        self.dw_f.zero_()
+        for (py, px, t0, lst, Hp, Wp), g in zip(self.phases, self.g_wg):
+            dyp = empty(R, Hp * Wp, self.N, dtype=BF)
+            L.call("es_pick_pixels", dy, self.Ho, self.Wo, self.N, 2, py, 2, px, Hp, Wp, R, dyp)
+            L.call("es_igemm_taps_wgrad", x, dyp, self.dw_f, g, grp, E, R)
+        L.call("es_unfold_up2_wgrad", self.dw_f, E, self.N, self.C, self.KH, self.KW, self.pad, self.table, dw_addr, slot_stride)
+
+    def dgrad(self, dy, dx, grp, E, R):
+        """dy [R, Ho*Wo, N] -> dx [R, Hs*Ws, C] on the LOW-resolution grid (the upsample's backward is folded in)."""
+        L.call("es_igemm_taps_fwd", dy, self.w_d, None, 0, dx, self.g_dgrad, grp, E, R)
+
+
+# =====================================================================================================================
 # generator (proton): bf16 NHWC activations, tcgen05 implicit GEMMs
 # =====================================================================================================================
 class GenEngineProton:
@@ -59,8 +136,12 @@ class GenEngineProton:
         self.b_fc2 = torch.empty(E, self.F2, device=dev)
         self.g_fc2 = torch.empty(E, self.F2, device=dev)
         self.z_fc2 = torch.empty(E, self.F2, device=dev)
-        self.w_fwd, self.w_dg, self.dw_p = {}, {}, {}
+        self.w_fwd, self.w_dg, self.dw_p, self.up2 = {}, {}, {}, {}
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
+            if (Hu, Wu) == (2 * Hs, 2 * Ws):      # exact x2 nearest upsample in front of the conv: fold it away
+                self.up2[name] = Up2Conv(Hs, Ws, C, KH, KW, pad, N)
+                self.up2[name].alloc(E, dev)
+                continue
             self.w_fwd[name] = torch.empty(E, N, KH, KW, C, dtype=BF, device=dev)
             self.w_dg[name] = torch.empty(E, C, KH, KW, N, dtype=BF, device=dev)
             self.dw_p[name] = torch.empty(E, N, KH, KW, C, device=dev)
@@ -72,7 +153,10 @@ class GenEngineProton:
         for src, dst in (("fc2.0.bias", self.b_fc2), ("fc2.1.weight", self.g_fc2), ("fc2.1.bias", self.z_fc2)):
             L.call("es_permute_features", a.addr(src), a.n, self.row_map, E, self.F2, dst, self.F2, 0)
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
-            L.call("es_pack_conv_weight", a.addr(name + ".weight"), a.n, E, N, C, KH, KW, self.w_fwd[name], self.w_dg[name])
+            if name in self.up2:
+                self.up2[name].fold(a.addr(name + ".weight"), a.n, E)
+            else:
+                L.call("es_pack_conv_weight", a.addr(name + ".weight"), a.n, E, N, C, KH, KW, self.w_fwd[name], self.w_dg[name])
 
     def forward(self, z1, z2, cond, grp, R, two_pass, keep=True, training=True, drop=None, dp=None):
         """z1,z2 [B,10], cond [B,9] in expert-sorted order; grp = generator group table; R = total rows.
@@ -94,7 +178,10 @@ class GenEngineProton:
             g = conv_geom(*geo)
             P = g.Ho * g.Wo
             y = empty(R, P, N, dtype=BF)
-            L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R)
+            if name in self.up2:
+                self.up2[name].forward(act, a.addr(name + ".bias"), a.n, y, grp, E, R)
+            else:
+                L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R)
             nxt, st = empty(R, P, N, dtype=BF), empty(R, groups, 2)
             L.call("es_gn_lrelu_fwd", y, a.addr(norm + ".weight"), a.addr(norm + ".bias"), a.n, P, N, groups, grp, E, R, nxt, st)
             s[f"y{i + 3}"], s[f"st{i + 3}"], s[f"a{i + 3}"] = y, st, nxt
@@ -125,14 +212,22 @@ class GenEngineProton:
             L.call("es_gn_lrelu_bwd", da, g.Ho, g.Wo, up[0], up[1], s[f"y{i + 3}"], s[f"st{i + 3}"], a.addr(norm + ".weight"),
                    a.addr(norm + ".bias"), a.n, N, groups, grp, E, R, dy, a.gaddr(norm + ".weight"), a.gaddr(norm + ".bias"),
                    a.gaddr(name + ".bias"))
+            if name in self.up2:
+                # folded x2 upsample: the data gradient comes out on the LOW-resolution grid (no fan-in left for the norm backward)
+                u = self.up2[name]
+                u.wgrad(s[f"a{i + 2}"], dy, a.gaddr(name + ".weight"), a.n, grp, E, R)
+                da = empty(R, Hs * Ws, C, dtype=BF)
+                u.dgrad(dy, da, grp, E, R)
+                up = (Hs, Ws)
+                continue
             # weight gradient (packed fp32, unpacked below) and data gradient on the upsampled input grid
             L.call("es_igemm_wgrad", s[f"a{i + 2}"], dy, self.dw_p[name], g, grp, E, R)
             da = empty(R, Hu * Wu, C, dtype=BF)
             L.call("es_igemm_fwd", dy, self.w_dg[name], None, 0, da, conv_geom(g.Ho, g.Wo, N, g.Ho, g.Wo, KH, KW, KH - 1 - pad, C), grp, E, R)
             up = (Hu, Wu)
         dy2 = empty(R, self.F2, dtype=BF)
-        L.call("es_ln_lrelu_bwd", da, 18, 10, 36, 20, 512, s["y2"], s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R, dy2)
-        L.call("es_ln_affine_bwd", da, 18, 10, 36, 20, 512, s["y2"], dy2, s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R,
+        L.call("es_ln_lrelu_bwd", da, 18, 10, up[0], up[1], 512, s["y2"], s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R, dy2)
+        L.call("es_ln_affine_bwd", da, 18, 10, up[0], up[1], 512, s["y2"], dy2, s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R,
                self.row_map, a.n, a.gaddr("fc2.1.weight"), a.gaddr("fc2.1.bias"), a.gaddr("fc2.0.bias"))
         L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), a.n, self.F2, 256, self.row_map, grp, E, R)
         dh1 = zeros(R, 256)
@@ -140,7 +235,8 @@ class GenEngineProton:
         L.call("es_gen_fc1_bwd", dh1, s["x0"], s["lin1"], a.addr("fc1.1.weight"), a.addr("fc1.1.bias"), a.n, a.n, grp, E, R,
                a.gaddr("fc1.0.weight"), a.gaddr("fc1.0.bias"), a.gaddr("fc1.1.weight"), a.gaddr("fc1.1.bias"))
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
-            L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
+            if name not in self.up2:
+                L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
 
 
 # =====================================================================================================================
@@ -449,8 +545,12 @@ class GenEngineNeutron:
         self.row_map = ((fp % 128) * 169 + fp // 128).to(torch.int32).contiguous()
         self.w_fc2 = torch.empty(E, self.F2, 256, dtype=BF, device=dev)
         self.b_fc2 = torch.empty(E, self.F2, device=dev)
-        self.w_fwd, self.w_dg, self.dw_p = {}, {}, {}
+        self.w_fwd, self.w_dg, self.dw_p, self.up2 = {}, {}, {}, {}
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
+            if (Hu, Wu) == (2 * Hs, 2 * Ws):      # exact x2 nearest upsample in front of the conv: fold it away
+                self.up2[name] = Up2Conv(Hs, Ws, C, KH, KW, pad, N)
+                self.up2[name].alloc(E, dev)
+                continue
             self.w_fwd[name] = torch.empty(E, N, KH, KW, C, dtype=BF, device=dev)
             self.w_dg[name] = torch.empty(E, C, KH, KW, N, dtype=BF, device=dev)
             self.dw_p[name] = torch.empty(E, N, KH, KW, C, device=dev)
@@ -460,7 +560,10 @@ class GenEngineNeutron:
         L.call("es_pack_dense_weight", a.addr("fc2.0.weight"), a.n, E, self.F2, 256, self.row_map, self.w_fc2)
         L.call("es_permute_features", a.addr("fc2.0.bias"), a.n, self.row_map, E, self.F2, self.b_fc2, self.F2, 0)
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
-            L.call("es_pack_conv_weight", a.addr(name + ".weight"), a.n, E, N, C, KH, KW, self.w_fwd[name], self.w_dg[name])
+            if name in self.up2:
+                self.up2[name].fold(a.addr(name + ".weight"), a.n, E)
+            else:
+                L.call("es_pack_conv_weight", a.addr(name + ".weight"), a.n, E, N, C, KH, KW, self.w_fwd[name], self.w_dg[name])
 
     # ---- one BatchNorm (+dropout +LeakyReLU) layer on bf16 NHWC rows
     def _bn_fwd(self, x, bn, geo, feat, chmap, site, ctx):
@@ -538,7 +641,10 @@ class GenEngineNeutron:
         for i, (name, geo, bn, site) in enumerate(self.CONVS):
             g = conv_geom(*geo)
             y = empty(R, g.Ho * g.Wo, g.N, dtype=BF)
-            L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R)
+            if name in self.up2:
+                self.up2[name].forward(act, a.addr(name + ".bias"), a.n, y, grp, E, R)
+            else:
+                L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R)
             act, s[f"bn{i + 3}"] = self._bn_fwd(y, bn, (g.Ho, g.Wo, g.N), False, None, site, ctx)
             s[f"y{i + 3}"], s[f"a{i + 3}"] = y, act
         img1 = zeros(B, self.H * self.W)
@@ -562,6 +668,13 @@ class GenEngineNeutron:
             g = conv_geom(*geo)
             dy = self._bn_bwd(da, up, s[f"y{i + 3}"], s[f"bn{i + 3}"], bn, (g.Ho, g.Wo, N), False, None, ctx)
             # the conv bias sits in front of a BatchNorm: its gradient is identically zero and is left at zero
+            if name in self.up2:
+                u = self.up2[name]
+                u.wgrad(s[f"a{i + 2}"], dy, a.gaddr(name + ".weight"), a.n, grp, E, R)
+                da = empty(R, Hs * Ws, C, dtype=BF)
+                u.dgrad(dy, da, grp, E, R)
+                up = (Hs, Ws)
+                continue
             L.call("es_igemm_wgrad", s[f"a{i + 2}"], dy, self.dw_p[name], g, grp, E, R)
             da = empty(R, Hu * Wu, C, dtype=BF)
             L.call("es_igemm_fwd", dy, self.w_dg[name], None, 0, da, conv_geom(g.Ho, g.Wo, N, g.Ho, g.Wo, KH, KW, KH - 1 - pad, C), grp, E, R)
@@ -574,7 +687,8 @@ class GenEngineNeutron:
         L.call("es_gen_fc1_bwd", dlin.float(), s["x0"], None, None, None, a.n, a.n, grp, E, R, a.gaddr("fc1.0.weight"),
                a.gaddr("fc1.0.bias"), None, None)
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
-            L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
+            if name not in self.up2:
+                L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
 
 
 class AuxEngineNeutron:

@@ -152,6 +152,49 @@ typedef struct {
  * weights) and for fc2. */
 int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_conv_geom* g,
                  const es_group* grp, int n_groups, int total_rows, void* stream);
+/* Generalised reduction of the same kernel: a TAP TABLE instead of a dense KHxKW window.  Tap t reads the (virtually
+ * nearest-upsampled [Hs,Ws]->[Hu,Wu]) source at (oy*my + tap_dy[t], ox*mx + tap_dx[t]) (outside [0,Hu)x[0,Wu) = zero) and
+ * multiplies it with the C weights starting at column tap_koff[t] of the packed weight row of length KK.  (oy, ox) runs
+ * over the M-space grid [Ho, Wo]; the result is stored at pixel ((oy*o_my + o_oy), (ox*o_mx + o_ox)) of a [Ho_full, Wo_full]
+ * map.  This is how the x2 nearest upsample in front of a conv is folded away: output phase (py, px) of such a conv only
+ * sees ceil((KH+1-py)/2)-ish distinct source rows, so four phase convs with pre-summed taps (es_fold_up2_weights) do
+ * 25 instead of 64 tap-MACs per 4 outputs for k4/p1 (2.56x fewer), and the data gradient is ONE table-conv over dy
+ * (my = mx = 2) writing the low-resolution gradient directly. */
+typedef struct {
+  int32_t Hs, Ws, C;
+  int32_t Hu, Wu;
+  int32_t Ho, Wo;
+  int32_t my, mx;
+  int32_t n_taps;
+  int8_t tap_dy[32], tap_dx[32];
+  int32_t tap_koff[32];
+  int32_t KK;
+  int32_t N;
+  int32_t o_my, o_oy, o_mx, o_ox, Ho_full, Wo_full;
+} es_tap_geom;
+int es_igemm_taps_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_tap_geom* g,
+                      const es_group* grp, int n_groups, int total_rows, void* stream);
+
+/* folded-tap table of a conv behind a x2 nearest upsample: folded tap t belongs to output phase (py, px) and source offset
+ * (dy, dx); original tap (ky, kx) folds into it iff floor((py+ky-pad)/2) == dy and floor((px+kx-pad)/2) == dx */
+typedef struct {
+  int32_t n_taps;
+  int8_t py[32], px[32], dy[32], dx[32];
+} es_fold_table;
+/* w fp32 [slots][N][C][KH][KW] -> w_fwd bf16 [slots][N][n_taps][C] and/or w_dgrad bf16 [slots][C][n_taps][N] (pre-summed) */
+int es_fold_up2_weights(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW, int pad,
+                        const es_fold_table* t, void* w_fwd, void* w_dgrad, void* stream);
+/* dw_ref[slot][n][c][ky][kx] += sum over the folded taps (ky, kx) folds into, of dw_folded[slot][n][t][c] */
+int es_unfold_up2_wgrad(const float* dw_folded, int slots, int N, int C, int KH, int KW, int pad, const es_fold_table* t,
+                        float* dw_ref, long slot_stride, void* stream);
+/* dst[row, a*Wo + b, :] = src[row, (a*my + oy)*Wo_full + b*mx + ox, :]  (NHWC bf16; one output phase made contiguous) */
+int es_pick_pixels(const void* src, int Ho_full, int Wo_full, int C, int my, int oy, int mx, int ox, int Ho, int Wo,
+                   int total_rows, void* dst, void* stream);
+/* weight gradient with a tap table (see es_igemm_taps_fwd): dy is [rows, Ho*Wo, N], x the source map;
+ * dw[slot][n][tap_koff[t] + c] += sum_pix dy[pix, n] * x[(oy + tap_dy[t], ox + tap_dx[t]), c]; a dw row has KK columns */
+int es_igemm_taps_wgrad(const void* x, const void* dy, float* dw, const es_tap_geom* g, const es_group* grp, int n_groups,
+                        int total_rows, void* stream);
+
 /* dw[slot][n][ky][kx][c] += sum_{row,oy,ox} dy[row,oy,ox,n] * x_up[row,oy+ky-pad,ox+kx-pad,c]   (fp32, packed layout,
  * split-K with fp32 atomics; dw must be zeroed by the caller). */
 int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es_conv_geom* g,

@@ -701,3 +701,48 @@ def test_expm1_scatter():
     want = torch.zeros(R, HW, dtype=torch.float64)
     want[perm.long()] = torch.expm1(img).double()
     check("expm1 + scatter (f64)", o64, want, 1e-6)
+
+
+# ------------------------------------------------------------------------------------- x2-upsample folding (tap tables)
+@pytest.mark.parametrize("Hs,Ws,C,KH,KW,pad,N", [(18, 10, 512, 4, 4, 1, 256), (13, 13, 128, 3, 3, 0, 256), (24, 24, 256, 3, 3, 0, 128),
+                                                  (5, 4, 128, 4, 4, 1, 64)])
+def test_up2_folded_conv_fwd_dgrad_wgrad(Hs, Ws, C, KH, KW, pad, N):
+    """conv(upsample_x2_nearest(x)) computed as four phase convs with pre-summed taps, its data gradient as ONE table-conv over
+    dy on the low-resolution grid and its weight gradient per phase + unfold — against fp32 torch autograd on the same
+    (bf16-rounded) x and dy.  Weights are folded in fp32 and rounded once, so the bound is the bf16 tolerance."""
+    from expertsim._nets import Up2Conv
+    counts, slots = [3, 0, 2], [2, 0, 1]
+    E = 3
+    grp, R = groups(counts, slots)
+    g = G(Hs * 1000 + C + KH)
+    x = bf16_round(torch.randn(R, Hs, Ws, C, generator=g))
+    w = torch.randn(E, N, C, KH, KW, generator=g) / math.sqrt(KH * KW * C)
+    bias = torch.randn(E, N, generator=g) * 0.1
+    u = Up2Conv(Hs, Ws, C, KH, KW, pad, N)
+    u.alloc(E, DEV)
+    dw_ref = cuda(w)
+    u.fold(dw_ref, N * C * KH * KW, E)
+    y = torch.zeros(R, u.Ho * u.Wo, N, dtype=BF, device=DEV)
+    u.forward(cuda(x, BF), cuda(bias), N, y, grp, E, R)
+    dy = bf16_round(torch.randn(R, u.Ho, u.Wo, N, generator=g))
+    want_y, want_dx, want_dw, off = [], [], torch.zeros_like(w), 0
+    for c, s in zip(counts, slots):
+        if c == 0:
+            continue
+        xi = x[off:off + c].permute(0, 3, 1, 2).clone().requires_grad_(True)
+        wi = w[s].clone().requires_grad_(True)
+        yi = F.conv2d(F.interpolate(xi, scale_factor=2, mode="nearest"), wi, bias[s], padding=pad)
+        (yi * dy[off:off + c].permute(0, 3, 1, 2)).sum().backward()
+        want_y.append(yi.detach().permute(0, 2, 3, 1))
+        want_dx.append(xi.grad.permute(0, 2, 3, 1))
+        want_dw[s] = wi.grad
+        off += c
+    check(f"up2 folded fwd {Hs}x{Ws}x{C} k{KH} N{N}", y.float().view(R, u.Ho, u.Wo, N), torch.cat(want_y), 8e-3, 4e-2)
+    dx = torch.zeros(R, Hs * Ws, C, dtype=BF, device=DEV)
+    u.dgrad(cuda(dy, BF), dx, grp, E, R)
+    check(f"up2 folded dgrad {Hs}x{Ws}x{C}", dx.float().view(R, Hs, Ws, C), torch.cat(want_dx), 8e-3, 4e-2)
+    dw = torch.zeros(E, N, C, KH, KW, device=DEV)
+    u.wgrad(cuda(x, BF), cuda(dy, BF), dw, N * C * KH * KW, grp, E, R)
+    for s in (1, 2):
+        check(f"up2 folded wgrad slot {s} {Hs}x{Ws}x{C}", dw[s], want_dw[s], 5e-3, 2e-2)
+    assert float(dw[0].abs().max()) == 0.0
