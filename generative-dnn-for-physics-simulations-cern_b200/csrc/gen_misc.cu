@@ -280,7 +280,8 @@ ln_affine_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, in
 // ----------------------------------------------------------------------------------------------- GroupNorm (NHWC bf16)
 // One CTA (256 threads) per sample.  Thread t always owns channel octet (t % (C/8)), so per-channel partial sums stay in
 // registers; group statistics are combined through shared memory.
-template <bool BWD>
+// FAN = the consumer reads a nearest-upsampled copy (gradient fan-in over the upsample); without it dy is read directly
+template <bool BWD, bool FAN>
 __global__ void __launch_bounds__(256)
 gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int Hu,
                 int Wu, const float* __restrict__ gamma, const float* __restrict__ beta, long slot_stride, int C,
@@ -307,7 +308,7 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   const int tid = threadIdx.x;
   const int cu = tid % c4, c8 = cu * 8, pstep = 256 / c4, p0 = tid / c4;
   const float cnt = (float)(cpg * P);
-  if (BWD && tid == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+  if (BWD && FAN && tid == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
   s_a[tid] = 0.f; s_b[tid] = 0.f; s_dg[tid] = 0.f; s_db[tid] = 0.f;
   __syncthreads();
   const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * P * C);
@@ -374,7 +375,8 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
     float ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float da[8];
     for (int pix = p0; pix < P; pix += pstep) {
-      load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+      if (FAN) load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+      else unpack8(__ldg(reinterpret_cast<const uint4*>(dyr) + (size_t)pix * c4 + cu), da);
       unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -409,7 +411,8 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
     for (int k = 0; k < 8; ++k) { m1[k] = s_g1[(c8 + k) / cpg]; m2[k] = s_g2[(c8 + k) / cpg]; }
     uint4* dx4 = reinterpret_cast<uint4*>(out + (size_t)r * P * C);
     for (int pix = p0; pix < P; pix += pstep) {
-      load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+      if (FAN) load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+      else unpack8(__ldg(reinterpret_cast<const uint4*>(dyr) + (size_t)pix * c4 + cu), da);
       unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
       float o[8];
 #pragma unroll
@@ -664,37 +667,34 @@ using namespace es;
 // t = (py, px, dy, dx) of the table; forward layout [slot][n][t][c], data-gradient layout [slot][c][t][n] (both bf16),
 // folded weight gradient [slot][n][t][c] (fp32) unfolded back to the reference's [n][c][ky][kx].
 namespace es {
-__device__ __forceinline__ int floor_half(int v) { return v >= 0 ? v / 2 : -((1 - v) / 2); }
-
-__global__ void fold_up2_kernel(const float* __restrict__ w, long sw, int N, int C, int KH, int KW, int pad, es_fold_table t,
+__global__ void fold_up2_kernel(const float* __restrict__ w, long sw, int N, int C, int KHW, es_fold_table t,
                                 __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
   const int slot = blockIdx.y;
   const long total = (long)N * t.n_taps * C;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C), tt = (int)((i / C) % t.n_taps), n = (int)(i / ((long)C * t.n_taps));
+    const float* src = w + slot * sw + ((size_t)n * C + c) * KHW;
     float acc = 0.f;
-    for (int ky = 0; ky < KH; ++ky) {
-      if (floor_half(t.py[tt] + ky - pad) != t.dy[tt]) continue;
-      for (int kx = 0; kx < KW; ++kx)
-        if (floor_half(t.px[tt] + kx - pad) == t.dx[tt]) acc += w[slot * sw + (((size_t)n * C + c) * KH + ky) * KW + kx];
-    }
+    for (uint32_t m = t.mask[tt]; m; m &= m - 1) acc += src[__ffs(m) - 1];
     const __nv_bfloat16 v = f2bf(acc);
     if (wf) wf[(size_t)slot * total + ((size_t)n * t.n_taps + tt) * C + c] = v;
     if (wd) wd[(size_t)slot * total + ((size_t)c * t.n_taps + tt) * N + n] = v;
   }
 }
 
-__global__ void unfold_up2_kernel(const float* __restrict__ dwf, int N, int C, int KH, int KW, int pad, es_fold_table t,
+// thread = (n, c): reads of the folded gradient are coalesced over c, each thread writes its KH*KW contiguous outputs
+__global__ void unfold_up2_kernel(const float* __restrict__ dwf, int N, int C, int KHW, es_fold_table t,
                                   float* __restrict__ dw, long sw) {
   const int slot = blockIdx.y;
-  const long total = (long)N * C * KH * KW;
+  const long total = (long)N * C;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int kx = (int)(i % KW), ky = (int)((i / KW) % KH), c = (int)((i / ((long)KW * KH)) % C), n = (int)(i / ((long)KW * KH * C));
-    float acc = 0.f;
-    for (int tt = 0; tt < t.n_taps; ++tt)
-      if (floor_half(t.py[tt] + ky - pad) == t.dy[tt] && floor_half(t.px[tt] + kx - pad) == t.dx[tt])
-        acc += dwf[((size_t)slot * N + n) * t.n_taps * C + (size_t)tt * C + c];
-    dw[slot * sw + i] += acc;
+    const int c = (int)(i % C), n = (int)(i / C);
+    const float* src = dwf + ((size_t)slot * N + n) * t.n_taps * C + c;
+    float* dst = dw + slot * sw + (size_t)i * KHW;
+    for (int tt = 0; tt < t.n_taps; ++tt) {
+      const float v = src[(size_t)tt * C];
+      for (uint32_t m = t.mask[tt]; m; m &= m - 1) dst[__ffs(m) - 1] += v;
+    }
   }
 }
 
@@ -711,19 +711,20 @@ __global__ void pick_pixels_kernel(const __nv_bfloat16* __restrict__ src, int Pf
 }
 }  // namespace es
 
-extern "C" int es_fold_up2_weights(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW, int pad,
+extern "C" int es_fold_up2_weights(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW,
                                    const es_fold_table* t, void* w_fwd, void* w_dgrad, void* stream) {
   ES_REQUIRE(w && t && (w_fwd || w_dgrad) && slots >= 1 && N > 0 && C > 0 && t->n_taps >= 1 && t->n_taps <= 32, "bad arguments");
-  es::fold_up2_kernel<<<dim3(512, slots), 256, 0, es::as_stream(stream)>>>(w, slot_stride, N, C, KH, KW, pad, *t,
+  ES_REQUIRE(KH * KW <= 32, "at most 32 original taps");
+  es::fold_up2_kernel<<<dim3(512, slots), 256, 0, es::as_stream(stream)>>>(w, slot_stride, N, C, KH * KW, *t,
                                                                             (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
 
-extern "C" int es_unfold_up2_wgrad(const float* dw_folded, int slots, int N, int C, int KH, int KW, int pad,
+extern "C" int es_unfold_up2_wgrad(const float* dw_folded, int slots, int N, int C, int KH, int KW,
                                    const es_fold_table* t, float* dw_ref, long slot_stride, void* stream) {
-  ES_REQUIRE(dw_folded && t && dw_ref && slots >= 1 && t->n_taps >= 1 && t->n_taps <= 32, "bad arguments");
-  es::unfold_up2_kernel<<<dim3(512, slots), 256, 0, es::as_stream(stream)>>>(dw_folded, N, C, KH, KW, pad, *t, dw_ref, slot_stride);
+  ES_REQUIRE(dw_folded && t && dw_ref && slots >= 1 && t->n_taps >= 1 && t->n_taps <= 32 && KH * KW <= 32, "bad arguments");
+  es::unfold_up2_kernel<<<dim3(512, slots), 256, 0, es::as_stream(stream)>>>(dw_folded, N, C, KH * KW, *t, dw_ref, slot_stride);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
@@ -808,7 +809,7 @@ extern "C" int es_gn_lrelu_fwd(const void* x, const float* gamma, const float* b
   ES_REQUIRE(x && gamma && beta && grp && y && stats, "null pointer");
   ES_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && groups <= 64 && C % groups == 0, "bad channels/groups");
   ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups && P > 0, "bad sizes");
-  gn_lrelu_kernel<false><<<total_rows, 256, 0, as_stream(stream)>>>(
+  gn_lrelu_kernel<false, false><<<total_rows, 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, nullptr, P, 1, P, 1, gamma, beta, slot_stride, C, groups, grp, n_groups,
       (__nv_bfloat16*)y, stats, nullptr, nullptr, nullptr);
   ES_LAUNCH_CHECK();
@@ -823,9 +824,14 @@ extern "C" int es_gn_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu
   ES_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && groups <= 64 && C % groups == 0, "bad channels/groups");
   ES_REQUIRE(Hs <= 64 && Ws <= 64 && Hu <= 64 && Wu <= 64 && Hu >= Hs && Wu >= Ws, "bad geometry");
   ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups, "bad sizes");
-  gn_lrelu_kernel<true><<<total_rows, 256, 0, as_stream(stream)>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, gamma, beta, slot_stride, C, groups, grp,
-      n_groups, (__nv_bfloat16*)dx, const_cast<float*>(stats), dgamma, dbeta, dbias_conv);
+  if (Hu == Hs && Wu == Ws)
+    gn_lrelu_kernel<true, false><<<total_rows, 256, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, gamma, beta, slot_stride, C, groups, grp,
+        n_groups, (__nv_bfloat16*)dx, const_cast<float*>(stats), dgamma, dbeta, dbias_conv);
+  else
+    gn_lrelu_kernel<true, true><<<total_rows, 256, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, gamma, beta, slot_stride, C, groups, grp,
+        n_groups, (__nv_bfloat16*)dx, const_cast<float*>(stats), dgamma, dbeta, dbias_conv);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }

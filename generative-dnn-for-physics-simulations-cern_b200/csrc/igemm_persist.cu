@@ -348,7 +348,7 @@ struct WgParams {
   const es_group* grp;
   int n_groups;
   int Hs, Ws, C, Hu, Wu, Ho, Wo, P;
-  int n_taps;                       // tap t gathers x at (oy + tdy[t], ox + tdx[t]); its C columns start at tcol[t] of a dw row
+  int n_taps, my, mx;               // tap t gathers x at (oy*my + tdy[t], ox*mx + tdx[t]); its C columns start at tcol[t] of a dw row
   signed char tdy[32], tdx[32];
   int tcol[32];
   int dw_ld;                        // length of a dw row (all taps of all phases)
@@ -464,7 +464,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
           const uint32_t doff = (uint32_t)prow * 128u + (uint32_t)((chunk ^ (prow & 7)) << 4);
 #pragma unroll
           for (int sg = 0; sg < 2; ++sg) {
-            const int uy = oy + kyv[sg], ux = ox + kxv[sg];
+            const int uy = oy * p.my + kyv[sg], ux = ox * p.mx + kxv[sg];
             const bool inb = v && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
             const int sy = inb ? s_ymap[uy] : 0, sx = inb ? s_xmap[ux] : 0;
             const __nv_bfloat16* src = p.x + (inb ? ((sbase + sy * p.Ws + sx) * p.C + cv[sg]) : 0L);
@@ -783,7 +783,7 @@ extern "C" int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es
   WgParams p{};
   p.grp = grp;
   p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
-  p.n_taps = g->KH * g->KW;
+  p.n_taps = g->KH * g->KW; p.my = 1; p.mx = 1;
   for (int ky = 0; ky < g->KH; ++ky)
     for (int kx = 0; kx < g->KW; ++kx) {
       const int t = ky * g->KW + kx;
@@ -799,11 +799,11 @@ extern "C" int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es
 extern "C" int es_igemm_taps_wgrad(const void* x, const void* dy, float* dw, const es_tap_geom* g, const es_group* grp,
                                    int n_groups, int total_rows, void* stream) {
   ES_REQUIRE(x && dy && dw && grp && g, "null pointer");
-  ES_REQUIRE(g->my == 1 && g->mx == 1, "the weight gradient gathers with unit pixel stride");
+  ES_REQUIRE(g->my >= 1 && g->mx >= 1, "bad pixel stride");
   WgParams p{};
   p.grp = grp;
   p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
-  p.n_taps = g->n_taps;
+  p.n_taps = g->n_taps; p.my = g->my; p.mx = g->mx;
   ES_REQUIRE(g->n_taps >= 1 && g->n_taps <= 32, "bad tap table");
   for (int t = 0; t < g->n_taps; ++t) {
     p.tdy[t] = g->tap_dy[t]; p.tdx[t] = g->tap_dx[t]; p.tcol[t] = g->tap_koff[t];

@@ -38,8 +38,7 @@ class ESTapGeom(ctypes.Structure):
 
 
 class ESFoldTable(ctypes.Structure):
-    _fields_ = [("n_taps", ctypes.c_int32), ("py", ctypes.c_int8 * 32), ("px", ctypes.c_int8 * 32), ("dy", ctypes.c_int8 * 32),
-                ("dx", ctypes.c_int8 * 32)]
+    _fields_ = [("n_taps", ctypes.c_int32), ("mask", ctypes.c_uint32 * 32)]
 
 
 def parse_header(path: str = HEADER_PATH) -> Dict[str, Tuple[str, List[Tuple[str, str]]]]:

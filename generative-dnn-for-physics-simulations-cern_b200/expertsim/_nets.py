@@ -39,80 +39,114 @@ def conv2d(Ci, Hi, Wi, Co, KH, KW, stride, pad):
 
 
 # =====================================================================================================================
-# x2 nearest upsample folded into the following conv (see es_igemm_taps_fwd in include/expertsim_b200.h)
+# nearest upsample folded into the following conv (see es_igemm_taps_fwd in include/expertsim_b200.h)
 # =====================================================================================================================
-class Up2Conv:
-    """Tap tables of a stride-1 conv (KHxKW, pad) applied to a x2 nearest-upsampled [Hs,Ws,C] map -> [Ho,Wo,N].
-    Output phase (py,px) = (oy&1, ox&1) reads source rows a+dy, dy in {floor((py+ky-pad)/2)}: taps landing on the same source
-    pixel are pre-summed, e.g. k4/p1: 9+6+6+4 = 25 folded taps per 4 outputs instead of 64 (2.56x fewer MACs), k3/p0: 16
-    instead of 36 (2.25x).  Forward = one table-conv per phase (strided output), data gradient = ONE table-conv over dy writing
-    the low-resolution gradient, weight gradient = one table-GEMM per phase on a contiguous copy of that phase's dy pixels,
-    un-folded afterwards."""
+def _axis_classes(S, U, K, pad, O, fold):
+    """Output classes of one axis of conv_K(pad)(upsample_nearest S->U).  -> (per_o, mult, grid, [(p, count, [(off, [k...])])])
+    fold: outputs o = p + per_o*a (U/S = per_o/per_s in lowest terms) read source a*per_s + floor((p+k-pad)*S/U); taps k with
+    the same offset are pre-summed.  not fold: one class, taps k-pad on the upsampled grid (nearest map applied by the kernel)."""
+    from math import gcd
+    if not fold or U == S:
+        return 1, 1, U, [(0, O, [(k - pad, [k]) for k in range(K)])]
+    g = gcd(U, S)
+    per_o, per_s = U // g, S // g
+    classes = []
+    for p_ in range(min(per_o, O)):
+        offs = {}
+        for k in range(K):
+            offs.setdefault((p_ + k - pad) * S // U, []).append(k)      # python floor division
+        classes.append((p_, (O - p_ + per_o - 1) // per_o, sorted(offs.items())))
+    return per_o, per_s, S, classes
 
-    def __init__(self, Hs, Ws, C, KH, KW, pad, N):
+
+class FoldedConv:
+    """Tap tables of a stride-1 conv (KHxKW, pad) behind a nearest upsample [Hs,Ws,C] -> [Hu,Wu] -> [Ho,Wo,N], with the
+    upsample folded into the conv along the axes named in ``fold``: outputs of one class read the same pattern of distinct
+    source pixels, so the taps that land on the same source pixel are pre-summed.
+      x2 on both axes, k4/p1: 9+6+6+4 = 25 folded taps per 4 outputs instead of 64 (2.56x fewer MACs); k3/p0: 16 vs 36.
+      35->56 (= 5->8) along y only, k4/p1: 8 row classes with 2..3 distinct source rows instead of 4 (1.39x fewer MACs).
+    Forward = one table-conv per class (strided output); weight gradient = one table-GEMM per class on a contiguous copy of
+    the class's dy pixels, un-folded afterwards; for exact x2 folding the data gradient is ONE table-conv over dy that writes
+    the low-resolution gradient directly (``has_dgrad``)."""
+
+    def __init__(self, Hs, Ws, C, Hu, Wu, KH, KW, pad, N, fold=(True, True)):
         self.Hs, self.Ws, self.C, self.KH, self.KW, self.pad, self.N = Hs, Ws, C, KH, KW, pad, N
-        self.Ho, self.Wo = 2 * Hs + 2 * pad - KH + 1, 2 * Ws + 2 * pad - KW + 1
-        fl = lambda v: v // 2          # python floor division
-        dl = lambda p_, K: sorted({fl(p_ + k - pad) for k in range(K)})
-        self.taps = []                  # global folded taps (py, px, dy, dx)
-        self.phases = []                # (py, px, first global tap, [(dy, dx)...], Ho', Wo')
-        for py in (0, 1):
-            for px in (0, 1):
-                lst = [(dy, dx) for dy in dl(py, KH) for dx in dl(px, KW)]
-                self.phases.append((py, px, len(self.taps), lst, (self.Ho - py + 1) // 2, (self.Wo - px + 1) // 2))
-                self.taps += [(py, px, dy, dx) for dy, dx in lst]
-        self.T = len(self.taps)
-        assert self.T <= 32
-        self.table = L.ESFoldTable()
-        self.table.n_taps = self.T
-        for t, (py, px, dy, dx) in enumerate(self.taps):
-            self.table.py[t], self.table.px[t], self.table.dy[t], self.table.dx[t] = py, px, dy, dx
-        self.g_fwd, self.g_wg = [], []
-        for py, px, t0, lst, Hp, Wp in self.phases:
-            for store, kk_c in ((self.g_fwd, C), (self.g_wg, C)):
-                g = L.ESTapGeom()
-                g.Hs, g.Ws, g.C, g.Hu, g.Wu, g.Ho, g.Wo, g.my, g.mx = Hs, Ws, C, Hs, Ws, Hp, Wp, 1, 1
-                g.n_taps = len(lst)
-                for i, (dy, dx) in enumerate(lst):
-                    g.tap_dy[i], g.tap_dx[i], g.tap_koff[i] = dy, dx, (t0 + i) * C
-                g.KK, g.N = self.T * C, N
-                g.o_my, g.o_oy, g.o_mx, g.o_ox, g.Ho_full, g.Wo_full = 2, py, 2, px, self.Ho, self.Wo
-                g.alg_flops_per_row = 2.0 * Hp * Wp * N * KH * KW * C     # un-folded direct-conv FLOPs of this phase's pixels
-                store.append(g)
-        g = L.ESTapGeom()                # data gradient: M-space = source pixels, "source" = dy on the [Ho,Wo] grid
-        g.Hs, g.Ws, g.C, g.Hu, g.Wu, g.Ho, g.Wo, g.my, g.mx = self.Ho, self.Wo, N, self.Ho, self.Wo, Hs, Ws, 2, 2
-        g.n_taps = self.T
-        for t, (py, px, dy, dx) in enumerate(self.taps):
-            g.tap_dy[t], g.tap_dx[t], g.tap_koff[t] = py - 2 * dy, px - 2 * dx, t * N
-        g.KK, g.N = self.T * N, C
-        g.o_my, g.o_oy, g.o_mx, g.o_ox, g.Ho_full, g.Wo_full = 1, 0, 1, 0, Hs, Ws
-        g.alg_flops_per_row = 2.0 * self.Ho * self.Wo * N * KH * KW * C
-        self.g_dgrad = g
+        self.Ho, self.Wo = Hu + 2 * pad - KH + 1, Wu + 2 * pad - KW + 1
+        oy_per, my, gy, ycls = _axis_classes(Hs, Hu, KH, pad, self.Ho, fold[0])
+        ox_per, mx, gx, xcls = _axis_classes(Ws, Wu, KW, pad, self.Wo, fold[1])
+        self.classes = []       # dict(py, px, Hp, Wp, taps [(dy, dx, mask)], table, g_fwd, g_wg)
+        for py, Hp, ytaps in ycls:
+            for px, Wp, xtaps in xcls:
+                taps = [(dy, dx, sum(1 << (ky * KW + kx) for ky in kys for kx in kxs)) for dy, kys in ytaps for dx, kxs in xtaps]
+                assert len(taps) <= 32 and (len(taps) * C) % 128 == 0
+                tab = L.ESFoldTable()
+                tab.n_taps = len(taps)
+                geos = []
+                for _ in range(2):
+                    g = L.ESTapGeom()
+                    g.Hs, g.Ws, g.C, g.Hu, g.Wu, g.Ho, g.Wo, g.my, g.mx = Hs, Ws, C, gy, gx, Hp, Wp, my, mx
+                    g.n_taps = len(taps)
+                    for i, (dy, dx, mask) in enumerate(taps):
+                        g.tap_dy[i], g.tap_dx[i], g.tap_koff[i] = dy, dx, i * C
+                        tab.mask[i] = mask
+                    g.KK, g.N = len(taps) * C, N
+                    g.o_my, g.o_oy, g.o_mx, g.o_ox, g.Ho_full, g.Wo_full = oy_per, py, ox_per, px, self.Ho, self.Wo
+                    g.alg_flops_per_row = 2.0 * Hp * Wp * N * KH * KW * C     # un-folded direct-conv FLOPs of this class's pixels
+                    geos.append(g)
+                self.classes.append(dict(py=py, px=px, Hp=Hp, Wp=Wp, taps=taps, table=tab, g_fwd=geos[0], g_wg=geos[1]))
+        self.oy_per, self.ox_per = oy_per, ox_per
+        self.executed_ratio = sum(c["Hp"] * c["Wp"] * len(c["taps"]) for c in self.classes) / (self.Ho * self.Wo * KH * KW)
+        # combined data gradient: exact x2 on both axes (source row of tap = a + dy  <=>  dy pixel = 2*(s - dy) + py)
+        self.has_dgrad = fold[0] and fold[1] and Hu == 2 * Hs and Wu == 2 * Ws and sum(len(c["taps"]) for c in self.classes) <= 32
+        if self.has_dgrad:
+            g, tab, t = L.ESTapGeom(), L.ESFoldTable(), 0
+            g.Hs, g.Ws, g.C, g.Hu, g.Wu, g.Ho, g.Wo, g.my, g.mx = self.Ho, self.Wo, N, self.Ho, self.Wo, Hs, Ws, 2, 2
+            for c in self.classes:
+                for dy, dx, mask in c["taps"]:
+                    g.tap_dy[t], g.tap_dx[t], g.tap_koff[t] = c["py"] - 2 * dy, c["px"] - 2 * dx, t * N
+                    tab.mask[t] = mask
+                    t += 1
+            g.n_taps = tab.n_taps = t
+            g.KK, g.N = t * N, C
+            g.o_my, g.o_oy, g.o_mx, g.o_ox, g.Ho_full, g.Wo_full = 1, 0, 1, 0, Hs, Ws
+            g.alg_flops_per_row = 2.0 * self.Ho * self.Wo * N * KH * KW * C
+            self.g_dgrad, self.table_all = g, tab
 
     def alloc(self, E, dev):
-        self.w_f = torch.empty(E, self.N, self.T * self.C, dtype=BF, device=dev)
-        self.w_d = torch.empty(E, self.C, self.T * self.N, dtype=BF, device=dev)
-        self.dw_f = torch.empty(E, self.N, self.T * self.C, device=dev)
+        for c in self.classes:
+            T = len(c["taps"])
+            c["w_f"] = torch.empty(E, self.N, T * self.C, dtype=BF, device=dev)
+            c["dw_f"] = torch.empty(E, self.N, T * self.C, device=dev)
+        if self.has_dgrad:
+            self.w_d = torch.empty(E, self.C, self.table_all.n_taps * self.N, dtype=BF, device=dev)
 
     def fold(self, w_addr, slot_stride, E):
-        L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, self.pad, self.table, self.w_f, self.w_d)
+        for c in self.classes:
+            L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, c["table"], c["w_f"], None)
+        if self.has_dgrad:
+            L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, self.table_all, None, self.w_d)
 
     def forward(self, x, bias_addr, bias_stride, y, grp, E, R):
-        for g in self.g_fwd:
-            L.call("es_igemm_taps_fwd", x, self.w_f, bias_addr, bias_stride, y, g, grp, E, R)
+        for c in self.classes:
+            L.call("es_igemm_taps_fwd", x, c["w_f"], bias_addr, bias_stride, y, c["g_fwd"], grp, E, R)
 
     def wgrad(self, x, dy, dw_addr, slot_stride, grp, E, R):
         """dy [R, Ho*Wo, N] -> parameter gradient in the reference layout (accumulated at dw_addr)."""
-        self.dw_f.zero_()
-        for (py, px, t0, lst, Hp, Wp), g in zip(self.phases, self.g_wg):
-            dyp = empty(R, Hp * Wp, self.N, dtype=BF)
-            L.call("es_pick_pixels", dy, self.Ho, self.Wo, self.N, 2, py, 2, px, Hp, Wp, R, dyp)
-            L.call("es_igemm_taps_wgrad", x, dyp, self.dw_f, g, grp, E, R)
-        L.call("es_unfold_up2_wgrad", self.dw_f, E, self.N, self.C, self.KH, self.KW, self.pad, self.table, dw_addr, slot_stride)
+        for c in self.classes:
+            c["dw_f"].zero_()
+            dyp = empty(R, c["Hp"] * c["Wp"], self.N, dtype=BF)
+            L.call("es_pick_pixels", dy, self.Ho, self.Wo, self.N, self.oy_per, c["py"], self.ox_per, c["px"], c["Hp"], c["Wp"], R, dyp)
+            L.call("es_igemm_taps_wgrad", x, dyp, c["dw_f"], c["g_wg"], grp, E, R)
+            L.call("es_unfold_up2_wgrad", c["dw_f"], E, self.N, self.C, self.KH, self.KW, c["table"], dw_addr, slot_stride)
 
     def dgrad(self, dy, dx, grp, E, R):
         """dy [R, Ho*Wo, N] -> dx [R, Hs*Ws, C] on the LOW-resolution grid (the upsample's backward is folded in)."""
         L.call("es_igemm_taps_fwd", dy, self.w_d, None, 0, dx, self.g_dgrad, grp, E, R)
+
+
+def Up2Conv(Hs, Ws, C, KH, KW, pad, N):
+    """conv behind an exact x2 nearest upsample, folded on both axes"""
+    return FoldedConv(Hs, Ws, C, 2 * Hs, 2 * Ws, KH, KW, pad, N, (True, True))
 
 
 # =====================================================================================================================
@@ -140,7 +174,13 @@ class GenEngineProton:
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
             if (Hu, Wu) == (2 * Hs, 2 * Ws):      # exact x2 nearest upsample in front of the conv: fold it away
                 self.up2[name] = Up2Conv(Hs, Ws, C, KH, KW, pad, N)
+            elif (Hu, Wu) != (Hs, Ws):            # 35x19 -> 56x30: rows repeat with period 8 (5 source rows): fold along y
+                self.up2[name] = FoldedConv(Hs, Ws, C, Hu, Wu, KH, KW, pad, N, (True, False))
+            if name in self.up2:
                 self.up2[name].alloc(E, dev)
+                if self.up2[name].has_dgrad:
+                    continue
+                self.w_dg[name] = torch.empty(E, C, KH, KW, N, dtype=BF, device=dev)     # data gradient stays un-folded
                 continue
             self.w_fwd[name] = torch.empty(E, N, KH, KW, C, dtype=BF, device=dev)
             self.w_dg[name] = torch.empty(E, C, KH, KW, N, dtype=BF, device=dev)
@@ -155,6 +195,8 @@ class GenEngineProton:
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
             if name in self.up2:
                 self.up2[name].fold(a.addr(name + ".weight"), a.n, E)
+                if not self.up2[name].has_dgrad:
+                    L.call("es_pack_conv_weight", a.addr(name + ".weight"), a.n, E, N, C, KH, KW, None, self.w_dg[name])
             else:
                 L.call("es_pack_conv_weight", a.addr(name + ".weight"), a.n, E, N, C, KH, KW, self.w_fwd[name], self.w_dg[name])
 
@@ -213,15 +255,18 @@ class GenEngineProton:
                    a.addr(norm + ".bias"), a.n, N, groups, grp, E, R, dy, a.gaddr(norm + ".weight"), a.gaddr(norm + ".bias"),
                    a.gaddr(name + ".bias"))
             if name in self.up2:
-                # folded x2 upsample: the data gradient comes out on the LOW-resolution grid (no fan-in left for the norm backward)
                 u = self.up2[name]
                 u.wgrad(s[f"a{i + 2}"], dy, a.gaddr(name + ".weight"), a.n, grp, E, R)
-                da = empty(R, Hs * Ws, C, dtype=BF)
-                u.dgrad(dy, da, grp, E, R)
-                up = (Hs, Ws)
-                continue
-            # weight gradient (packed fp32, unpacked below) and data gradient on the upsampled input grid
-            L.call("es_igemm_wgrad", s[f"a{i + 2}"], dy, self.dw_p[name], g, grp, E, R)
+                if u.has_dgrad:
+                    # folded x2 upsample: the data gradient comes out on the LOW-resolution grid (no fan-in left for the norm backward)
+                    da = empty(R, Hs * Ws, C, dtype=BF)
+                    u.dgrad(dy, da, grp, E, R)
+                    up = (Hs, Ws)
+                    continue
+            else:
+                # weight gradient (packed fp32, unpacked below)
+                L.call("es_igemm_wgrad", s[f"a{i + 2}"], dy, self.dw_p[name], g, grp, E, R)
+            # data gradient on the (upsampled) input grid
             da = empty(R, Hu * Wu, C, dtype=BF)
             L.call("es_igemm_fwd", dy, self.w_dg[name], None, 0, da, conv_geom(g.Ho, g.Wo, N, g.Ho, g.Wo, KH, KW, KH - 1 - pad, C), grp, E, R)
             up = (Hu, Wu)

@@ -175,23 +175,25 @@ typedef struct {
 int es_igemm_taps_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_tap_geom* g,
                       const es_group* grp, int n_groups, int total_rows, void* stream);
 
-/* folded-tap table of a conv behind a x2 nearest upsample: folded tap t belongs to output phase (py, px) and source offset
- * (dy, dx); original tap (ky, kx) folds into it iff floor((py+ky-pad)/2) == dy and floor((px+kx-pad)/2) == dx */
+/* folded-tap table of a conv behind a nearest upsample: folded tap t is the SUM of the original taps (ky, kx) whose bit
+ * ky*KW + kx is set in mask[t] (they all read the same source pixel for the output class the tap belongs to; KH*KW <= 32).
+ * x2 upsample, class = output phase (py, px), source offset (dy, dx): (ky, kx) is in the mask iff
+ * floor((py+ky-pad)/2) == dy and floor((px+kx-pad)/2) == dx. */
 typedef struct {
   int32_t n_taps;
-  int8_t py[32], px[32], dy[32], dx[32];
+  uint32_t mask[32];
 } es_fold_table;
 /* w fp32 [slots][N][C][KH][KW] -> w_fwd bf16 [slots][N][n_taps][C] and/or w_dgrad bf16 [slots][C][n_taps][N] (pre-summed) */
-int es_fold_up2_weights(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW, int pad,
+int es_fold_up2_weights(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW,
                         const es_fold_table* t, void* w_fwd, void* w_dgrad, void* stream);
-/* dw_ref[slot][n][c][ky][kx] += sum over the folded taps (ky, kx) folds into, of dw_folded[slot][n][t][c] */
-int es_unfold_up2_wgrad(const float* dw_folded, int slots, int N, int C, int KH, int KW, int pad, const es_fold_table* t,
+/* dw_ref[slot][n][c][ky][kx] += sum over the folded taps whose mask contains (ky, kx), of dw_folded[slot][n][t][c] */
+int es_unfold_up2_wgrad(const float* dw_folded, int slots, int N, int C, int KH, int KW, const es_fold_table* t,
                         float* dw_ref, long slot_stride, void* stream);
 /* dst[row, a*Wo + b, :] = src[row, (a*my + oy)*Wo_full + b*mx + ox, :]  (NHWC bf16; one output phase made contiguous) */
 int es_pick_pixels(const void* src, int Ho_full, int Wo_full, int C, int my, int oy, int mx, int ox, int Ho, int Wo,
                    int total_rows, void* dst, void* stream);
 /* weight gradient with a tap table (see es_igemm_taps_fwd): dy is [rows, Ho*Wo, N], x the source map;
- * dw[slot][n][tap_koff[t] + c] += sum_pix dy[pix, n] * x[(oy + tap_dy[t], ox + tap_dx[t]), c]; a dw row has KK columns */
+ * dw[slot][n][tap_koff[t] + c] += sum_pix dy[pix, n] * x[(oy*my + tap_dy[t], ox*mx + tap_dx[t]), c]; a dw row has KK columns */
 int es_igemm_taps_wgrad(const void* x, const void* dy, float* dw, const es_tap_geom* g, const es_group* grp, int n_groups,
                         int total_rows, void* stream);
 

@@ -746,3 +746,41 @@ def test_up2_folded_conv_fwd_dgrad_wgrad(Hs, Ws, C, KH, KW, pad, N):
     for s in (1, 2):
         check(f"up2 folded wgrad slot {s} {Hs}x{Ws}x{C}", dw[s], want_dw[s], 5e-3, 2e-2)
     assert float(dw[0].abs().max()) == 0.0
+
+
+def test_y_folded_conv2_fwd_wgrad():
+    """proton conv2: 35x19 -> 56x30 nearest (rows repeat with period 8 <- 5 source rows), k4/p1.  Folded along y only:
+    8 row classes with 2..3 distinct source rows instead of 4; x keeps the nearest map.  Forward and weight gradient against
+    fp32 torch on bf16-rounded x / dy."""
+    from expertsim._nets import FoldedConv
+    Hs, Ws, C, Hu, Wu, KH, KW, pad, N = 35, 19, 256, 56, 30, 4, 4, 1, 128
+    counts, slots, E = [2, 0, 3], [2, 0, 1], 3
+    grp, R = groups(counts, slots)
+    g = G(4242)
+    x = bf16_round(torch.randn(R, Hs, Ws, C, generator=g))
+    w = torch.randn(E, N, C, KH, KW, generator=g) / math.sqrt(KH * KW * C)
+    bias = torch.randn(E, N, generator=g) * 0.1
+    f = FoldedConv(Hs, Ws, C, Hu, Wu, KH, KW, pad, N, (True, False))
+    assert len(f.classes) == 8 and abs(f.executed_ratio - 0.718) < 1e-3 and not f.has_dgrad
+    f.alloc(E, DEV)
+    f.fold(cuda(w), N * C * KH * KW, E)
+    y = torch.zeros(R, f.Ho * f.Wo, N, dtype=BF, device=DEV)
+    f.forward(cuda(x, BF), cuda(bias), N, y, grp, E, R)
+    dy = bf16_round(torch.randn(R, f.Ho, f.Wo, N, generator=g))
+    want_y, want_dw, off = [], torch.zeros_like(w), 0
+    for c, s in zip(counts, slots):
+        if c == 0:
+            continue
+        xi = x[off:off + c].permute(0, 3, 1, 2)
+        wi = w[s].clone().requires_grad_(True)
+        yi = F.conv2d(F.interpolate(xi, size=(Hu, Wu), mode="nearest"), wi, bias[s], padding=pad)
+        (yi * dy[off:off + c].permute(0, 3, 1, 2)).sum().backward()
+        want_y.append(yi.detach().permute(0, 2, 3, 1))
+        want_dw[s] = wi.grad
+        off += c
+    check("y-folded conv2 fwd", y.float().view(R, f.Ho, f.Wo, N), torch.cat(want_y), 8e-3, 4e-2)
+    dw = torch.zeros(E, N, C, KH, KW, device=DEV)
+    f.wgrad(cuda(x, BF), cuda(dy, BF), dw, N * C * KH * KW, grp, E, R)
+    for s in (1, 2):
+        check(f"y-folded conv2 wgrad slot {s}", dw[s], want_dw[s], 5e-3, 2e-2)
+    assert float(dw[0].abs().max()) == 0.0
