@@ -27,6 +27,11 @@ constexpr int kFStages = 4;
 constexpr int kFLag = 2;
 constexpr int kFLoaders = 128;
 constexpr int kFThreads = 320;
+// forward kernel: 8 gather warps (r01 ncu: tensor 21-39 %, L1TEX <= 50 %, L2 <= 27 % — the gather was bound by the latency of
+// its own address-generation instruction stream per warp, not by any memory pipe), then TMA, MMA and 4 epilogue warps
+constexpr int kGW = 8;
+constexpr int kGLoaders = kGW * 32;
+constexpr int kGThreads = (kGW + 6) * 32;
 constexpr int kFStageA = kBM * 128;            // 16 KB
 constexpr int kFStageB = 256 * 128;            // 32 KB (BN <= 256)
 constexpr int kFStage = kFStageA + kFStageB;
@@ -82,7 +87,7 @@ __device__ __forceinline__ bool decode_tile(int t, const FwdParams& p, const int
 //       exactly what a 128 x 128 x 64 k-block needs at tensor peak, so the N <= 128 layers were gather-bound at ~50 %;
 //       gather4 bypasses L1TEX (at the price of re-reading shifted taps from L2 instead of L1).
 template <int MT, bool G4>
-__global__ void __launch_bounds__(kFThreads, 1)
+__global__ void __launch_bounds__(kGThreads, 1)
 igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_a) {
   constexpr int kStages = MT == 1 ? 4 : 3;
@@ -125,7 +130,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
   if (tid < 32) { s_tdy[tid] = p.tdy[tid]; s_tdx[tid] = p.tdx[tid]; s_tkoff[tid] = p.tkoff[tid]; }
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), G4 ? 2 : kFLoaders + 1);
+      mbar_init(full_bar(s), G4 ? 2 : kGLoaders + 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -134,8 +139,8 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmap_w); if (G4) tma_prefetch_desc(&tmap_a); }
-  if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == kGW && lane == 0) { tma_prefetch_desc(&tmap_w); if (G4) tma_prefetch_desc(&tmap_a); }
+  if (warp == kGW + 1) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -148,11 +153,12 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
   const int cblks = p.C / kBK;
   const int nkb = taps * cblks;
 
-  if (warp < 4) {
+  if (warp < kGW) {
     if (!G4) {
       // ========================================================================= A GATHER by cp.async (128 threads)
       // lane group of 8 threads copies one 128-byte row; thread handles rows (tid>>3) + 16*j, chunk tid&7
-      constexpr int RPT = 8 * MT;
+      constexpr int RPT = MT * kBM / (kGLoaders / 8);       // rows per thread: 8 lanes per row
+      constexpr int RSTEP = kGLoaders / 8;
       const int chunk = tid & 7, rsub = tid >> 3;
       uint32_t it = 0, signalled = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -162,7 +168,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
         int r_oyx[RPT];     // oy << 8 | ox
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
-          const int m = ti.m0 + rsub + 16 * j;
+          const int m = ti.m0 + rsub + RSTEP * j;
           const bool valid = m < ti.rows * p.P;
           const int sample = valid ? m / p.P : 0;
           const int pix = valid ? m - sample * p.P : 0;
@@ -179,7 +185,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
           const int ty = s_tdy[tap], tx = s_tdx[tap];
 #pragma unroll
           for (int j = 0; j < RPT; ++j) {
-            const int r = rsub + 16 * j;
+            const int r = rsub + RSTEP * j;
             const int uy = (r_oyx[j] >> 8) * p.my + ty, ux = (r_oyx[j] & 255) * p.mx + tx;
             const bool inb = r_base[j] >= 0 && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
             const int sy = inb ? s_ymap[uy] : 0, sx = inb ? s_xmap[ux] : 0;
@@ -243,7 +249,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kGW) {
     // =========================================================================== TMA PRODUCER (weights)
     if (lane == 0) {
       uint32_t it = 0;
@@ -261,7 +267,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kGW + 1) {
     // =========================================================================== MMA ISSUER
     const uint32_t idesc = make_idesc(BN, false, false);
     uint32_t it = 0, tcount = 0;
@@ -293,7 +299,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     }
     tc_fence_before();
   } else {
-    // =========================================================================== EPILOGUE (warps 6-9)
+    // =========================================================================== EPILOGUE (last 4 warps)
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -331,7 +337,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
     }
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kGW + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -677,7 +683,7 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
       ES_CUDA(cudaFuncSetAttribute(igemm_fwd_kernel<MTV, G4V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFSmem)); \
       attr_set = true;                                                                                                   \
     }                                                                                                                    \
-    igemm_fwd_kernel<MTV, G4V><<<grid, kFThreads, kFSmem, as_stream(stream)>>>(p, tmap, tmap_a);                         \
+    igemm_fwd_kernel<MTV, G4V><<<grid, kGThreads, kFSmem, as_stream(stream)>>>(p, tmap, tmap_a);                         \
   }
   if (mt == 1 && !g4) ES_FWD_LAUNCH(1, false)
   else if (mt == 1) ES_FWD_LAUNCH(1, true)
