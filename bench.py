@@ -177,8 +177,8 @@ def igemm_flops(name, a):
         return 2.0 * rows * g.Ho * g.Wo * g.N * g.KH * g.KW * g.C
     if name == "es_dense_dgrad":       # (N, K, n_groups, total_rows)
         return 2.0 * ints[-1] * ints[0] * ints[1]
-    if name == "es_dense_wgrad":       # (dw_slot_stride, N, K, n_groups, total_rows)
-        return 2.0 * ints[-1] * ints[1] * ints[2]
+    if name == "es_dense_wgrad":       # (..., N, K, n_groups, total_rows) — leading ints may be raw addresses / strides
+        return 2.0 * ints[-1] * ints[-4] * ints[-3]
     return 0.0
 
 

@@ -383,7 +383,7 @@ __device__ __forceinline__ bool wg_decode(int t, const WgParams& p, const es_gro
   return ti.kb1 > ti.kb0;
 }
 
-__global__ void __launch_bounds__(kFThreads, 1)
+__global__ void __launch_bounds__(kGThreads, 1)
 igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ CUtensorMap tmap_dy) {
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -409,7 +409,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
   if (tid < 64) { s_ymap[tid] = p.ymap[tid]; s_xmap[tid] = p.xmap[tid]; }
   if (tid == 0) {
     for (int s = 0; s < kFStages; ++s) {
-      mbar_init(full_bar(s), kFLoaders + 1);
+      mbar_init(full_bar(s), kGLoaders + 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -418,8 +418,8 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4 && lane == 0) tma_prefetch_desc(&tmap_dy);
-  if (warp == 5) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == kGW && lane == 0) tma_prefetch_desc(&tmap_dy);
+  if (warp == kGW + 1) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -427,9 +427,11 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
   const int total_tiles = p.n_groups * p.splits * p.tiles_m;
   const int nseg = BN >> 6;
 
-  if (warp < 4) {
-    // =========================================================================== A GATHER
-    const int chunk = tid & 7, rsub = tid >> 3;     // pixel rows rsub + 16 i (i < 4), both 64-wide kk segments
+  if (warp < kGW) {
+    // =========================================================================== A GATHER (8 warps, see igemm_fwd_kernel)
+    constexpr int PR = 64 / (kGLoaders / 8);        // pixel rows per thread
+    constexpr int PSTEP = kGLoaders / 8;
+    const int chunk = tid & 7, rsub = tid >> 3;     // pixel rows rsub + PSTEP*i (i < PR), both 64-wide kk segments
     uint32_t it = 0, signalled = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       WgTile ti;
@@ -447,10 +449,10 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
       const long src_base = (long)ti.row_start * hw;
       // (sample, oy, ox) of this thread's 4 pixel rows: a mixed-radix counter advanced by 64 pixels per k-block, so the
       // main loop has no integer division
-      int smp[4], oyv[4], oxv[4];
+      int smp[PR], oyv[PR], oxv[PR];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int pidx = ti.kb0 * kBK + rsub + 16 * i;
+      for (int i = 0; i < PR; ++i) {
+        const int pidx = ti.kb0 * kBK + rsub + PSTEP * i;
         smp[i] = pidx / p.P;
         const int pix = pidx - smp[i] * p.P;
         oyv[i] = pix / p.Wo;
@@ -462,8 +464,8 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
         if (it >= kFStages) mbar_wait(empty_bar(s), ((it / kFStages) - 1) & 1, p.err_flag, 1);
         const uint32_t sa = base + s * kFStage;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int prow = rsub + 16 * i;
+        for (int i = 0; i < PR; ++i) {
+          const int prow = rsub + PSTEP * i;
           const bool v = smp[i] < ti.rows;
           const int oy = oyv[i], ox = oxv[i];
           const long sbase = src_base + (long)smp[i] * hw;
@@ -496,7 +498,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
       mbar_arrive(full_bar(signalled % kFStages));
       ++signalled;
     }
-  } else if (warp == 4) {
+  } else if (warp == kGW) {
     // =========================================================================== TMA PRODUCER (dy)
     if (lane == 0) {
       uint32_t it = 0;
@@ -513,7 +515,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kGW + 1) {
     // =========================================================================== MMA ISSUER
     const uint32_t idesc = make_idesc(BN, true, true);
     uint32_t it = 0, tcount = 0;
@@ -569,7 +571,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
     }
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kGW + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -776,7 +778,7 @@ static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, l
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int total = n_groups * p.splits * p.tiles_m;
-  igemm_wgrad_kernel<<<total < sms ? total : sms, kFThreads, kFSmem, as_stream(stream)>>>(p, tmap);
+  igemm_wgrad_kernel<<<total < sms ? total : sms, kGThreads, kFSmem, as_stream(stream)>>>(p, tmap);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
