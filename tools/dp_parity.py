@@ -7,6 +7,7 @@ the sharded step must equal the single-device global-batch step
 the comparison runs at fp32 / bf16-kernel tolerance (see tests/test_step_gpu.py for why)."""
 import copy
 import os
+import re
 import sys
 
 import torch
@@ -28,11 +29,14 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     from expertsim.config import Config
     from expertsim.train.loop import setup_moe_system
-    arch, E, B, seed = "proton", 3, 24 * world // 2 * 2 // world * world, 7
+    arch = sys.argv[1] if len(sys.argv) > 1 else "proton"
+    E, seed = 3, 7
     B = 24 if 24 % world == 0 else 8 * world
+    H, W = orc.IMAGE_SHAPE[arch]
     ocfg = copy.deepcopy(orc.DEFAULT_CFG)
     ocfg["model"]["n_experts"] = E
-    ocfg["dataset"] = {"input_image_shape": [56, 30]}
+    ocfg["model"]["architecture"] = arch
+    ocfg["dataset"] = {"input_image_shape": [H, W]}
     st = orc.make_state(arch, E, seed, ocfg)
     moe = setup_moe_system(Config(ocfg), dev)
     for e in range(E):
@@ -53,7 +57,7 @@ def main():
         rows = []
         for e in range(E):
             sel = (masks[e] % world) == rank
-            src = aux[key][e].reshape(-1, 56 * 30) if e in aux[key] else torch.zeros(masks[e].numel(), 56 * 30)
+            src = aux[key][e].reshape(-1, H * W) if e in aux[key] else torch.zeros(masks[e].numel(), H * W)
             rows.append(src[sel])
         nz[name] = torch.cat(rows).to(dev)
     b = sh(batch)
@@ -73,6 +77,10 @@ def main():
             for name, gw in collect.get(f"{kind}_{e}", {}).items():
                 if float(gw.abs().max()) < 1e-9:
                     continue
+                if arch == "neutron" and ((key == "g" and name in ("fc1.0.bias", "fc2.0.bias", "conv_layers.0.bias", "conv_layers.5.bias",
+                                                                   "conv_layers.9.bias"))
+                                          or (key == "a" and re.fullmatch(r"feature_extractor\.conv\d\.bias", name))):
+                    continue          # a bias in front of a BatchNorm: identically-zero gradient, autograd returns rounding noise
                 gg = arena.view(arena.G, name, e).double().cpu()
                 r = float((gg - gw.double()).norm() / gw.double().norm())
                 worst[key] = max(worst[key], r)
@@ -88,7 +96,7 @@ def main():
     ok = torch.tensor([0 if fails else 1], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"dp parity world={world} B={B}: worst relL2 g={worst['g']:.3e} d={worst['d']:.3e} a={worst['a']:.3e}; "
+        print(f"dp parity {arch} world={world} B={B}: worst relL2 g={worst['g']:.3e} d={worst['d']:.3e} a={worst['a']:.3e}; "
               f"gen_loss {float(got['gen_loss']):.6f} vs oracle {want['gen_loss']:.6f}")
     for f in fails:
         print(f"[rank {rank}] FAIL {f}")
