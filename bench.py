@@ -40,6 +40,15 @@ F_R = 23_296
 TRAIN_FLOPS = {a: 6 * F_G[a] + 12 * F_D[a] + 3 * F_A[a] + 3 * F_R for a in F_G}   # as executed by the reference
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) per launch of the dominant kernel family, from the committed `ncu --set full` capture
+    (profiles/roofline_traffic.json, written by tools/ncu_summary.py); None if no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -304,7 +313,9 @@ def run_b200(args):
     pk = peaks()
     roof = {"bound": "tensor", "kernel": "igemm_persist (grouped bf16 tcgen05 implicit GEMM family: igemm_fwd_kernel + igemm_wgrad_kernel, incl. the x2-upsample-folded tap-table launches; algorithmic = un-folded direct-conv FLOPs)",
             "achieved": round(tc_flops / (tc_ms * 1e-3) / 1e12, 2) if tc_ms else None, "peak": pk["tflops"], "unit": "TFLOP/s",
-            "frac": round(tc_flops / (tc_ms * 1e-3) / 1e12 / pk["tflops"], 4) if tc_ms else None, "traffic": None,
+            "frac": round(tc_flops / (tc_ms * 1e-3) / 1e12 / pk["tflops"], 4) if tc_ms else None,
+            "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_source": (ncu_traffic() or {}).get("source"),
+            "algorithmic_flops_per_launch": round(tc_flops / max(tc_n, 1)),
             "peak_source": f"{pk['src']} sustained bf16 (MEASURED_PEAKS.json)", "launches": tc_n,
             "share_of_step": round(tc_ms / (e0.elapsed_time(e1)), 4),
             "families": {k: {"tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 2) if v[1] else None, "ms_per_step": round(v[1] / args.steps, 3),
@@ -386,7 +397,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arch", default="proton", choices=["proton", "neutron"])
