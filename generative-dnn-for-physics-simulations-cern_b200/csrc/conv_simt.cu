@@ -147,13 +147,15 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
   }
 }
 
-// weight gradient: CTA = (64-wide k tile, chunk of `mper` group pixels); D[k, co] += sum_m xcol[m, k] dy[m, co]
+// weight gradient: CTA = (64-wide k tile, chunk of `mper` group pixels); D[k, co] += sum_m xcol[m, k] dy[m, co].
+// The gather walks pixels with an incremental (sample, oy, ox) counter — no integer division in the reduction loop.
 template <int BN>
 __global__ void __launch_bounds__(256)
 conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy, es_conv2d g,
                        const es_group* __restrict__ grp, int n_groups, int mper, float* __restrict__ dw,
                        float* __restrict__ db, long sw, long sb) {
-  __shared__ __align__(16) float As[kCK][kCM + 4];     // [m chunk][k tile]
+  constexpr int kWK = 64;                                  // k tile
+  __shared__ __align__(16) float As[kCK][kWK + 4];     // [m chunk][k tile]
   __shared__ __align__(16) float Bs[kCK][BN + 4];      // [m chunk][co]
   constexpr int TN = BN / 16;
   const int KHW = g.KH * g.KW, K = g.Ci * KHW, PXo = g.Ho * g.Wo, PXi = g.Hi * g.Wi;
@@ -161,12 +163,28 @@ conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy
   if (!tile_of(grp, n_groups, PXo, mper, blockIdx.y, gi, mbeg, mtot)) return;
   const int mend = min(mtot, mbeg + mper);
   const int slot = grp[gi].slot, row_start = grp[gi].row_start;
-  const int k0 = blockIdx.x * kCM, n0 = blockIdx.z * BN;
+  const int k0 = blockIdx.x * kWK, n0 = blockIdx.z * BN;
   const int tid = threadIdx.x;
-  // gather column owned by this thread: k = k0 + (tid >> 2) for the A tile (64 k x 16 m, 4 m per thread)
+  // A gather: thread owns reduction column ka = k0 + (tid >> 2) and the 4 consecutive pixels ma .. ma+3 of every chunk
   const int ka = k0 + (tid >> 2), ma = (tid & 3) * 4;
   const bool kv = ka < K;
   const int ci = kv ? ka / KHW : 0, t = kv ? ka - ci * KHW : 0, ky = t / g.KW, kx = t - ky * g.KW;
+  int a_s, a_oy, a_ox;                                     // (sample, oy, ox) of pixel mbeg + ma
+  {
+    const int mm = mbeg + ma;
+    a_s = mm / PXo;
+    const int p2 = mm - a_s * PXo;
+    a_oy = p2 / g.Wo;
+    a_ox = p2 - a_oy * g.Wo;
+  }
+  // B gather: thread owns channel nb = tid >> 4 (+16, ...) and pixel mb = tid & 15 of every chunk
+  const int mb = tid & 15;
+  int b_s, b_p;
+  {
+    const int mm = mbeg + mb;
+    b_s = mm / PXo;
+    b_p = mm - b_s * PXo;
+  }
   const int tm = tid & 15, tn = tid >> 4;
   float acc[4][TN];
 #pragma unroll
@@ -176,28 +194,32 @@ conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy
   float bsum = 0.f;
   for (int mc = mbeg; mc < mend; mc += kCK) {
     // A tile: xcol[m, k] for 16 consecutive m, 64 k
+    {
+      int s2 = a_s, oy = a_oy, ox = a_ox;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int mm = mc + ma + j;
-      float v = 0.f;
-      if (kv && mm < mend) {
-        const int s2 = mm / PXo, p2 = mm - s2 * PXo, oy = p2 / g.Wo, ox = p2 - oy * g.Wo;
-        const int iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
-        if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
-          v = __ldg(x + ((size_t)(row_start + s2) * g.Ci + ci) * PXi + iy * g.Wi + ix);
+      for (int j = 0; j < 4; ++j) {
+        float v = 0.f;
+        if (kv && mc + ma + j < mend) {
+          const int iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
+          if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
+            v = __ldg(x + ((size_t)(row_start + s2) * g.Ci + ci) * PXi + iy * g.Wi + ix);
+        }
+        As[ma + j][tid >> 2] = v;
+        if (++ox == g.Wo) { ox = 0; if (++oy == g.Ho) { oy = 0; ++s2; } }
       }
-      As[ma + j][tid >> 2] = v;
+      // advance the base counter by one chunk (16 pixels)
+      a_ox += kCK;
+      while (a_ox >= g.Wo) { a_ox -= g.Wo; if (++a_oy == g.Ho) { a_oy = 0; ++a_s; } }
     }
     // B tile: dy[m, co]: lanes along m
-    for (int i = tid; i < kCK * BN; i += 256) {
-      const int mm = i % kCK, n = i / kCK, m = mc + mm;
+#pragma unroll
+    for (int nn = tid >> 4; nn < BN; nn += 16) {
       float v = 0.f;
-      if (m < mend && n0 + n < g.Co) {
-        const int s2 = m / PXo, p2 = m - s2 * PXo;
-        v = __ldg(dy + ((size_t)(row_start + s2) * g.Co + n0 + n) * PXo + p2);
-      }
-      Bs[mm][n] = v;
+      if (mc + mb < mend && n0 + nn < g.Co) v = __ldg(dy + ((size_t)(row_start + b_s) * g.Co + n0 + nn) * PXo + b_p);
+      Bs[mb][nn] = v;
     }
+    b_p += kCK;
+    while (b_p >= PXo) { b_p -= PXo; ++b_s; }
     __syncthreads();
     if (db && blockIdx.x == 0 && tid < BN) {
 #pragma unroll
@@ -296,7 +318,7 @@ extern "C" int es_conv2d_bwd_weight(const float* x, const float* dy, const es_co
   const int K = g->Ci * g->KH * g->KW, PXo = g->Ho * g->Wo;
   if (K <= 9 && g->Co % 8 == 0)   // a 64-wide k tile would be 86 % padding: pixel-parallel register kernel instead
     return conv2d_bwd_weight_fewtaps(x, dy, g, grp, n_groups, total_rows, dw, db, slot_stride_w, slot_stride_b, stream);
-  const int ktiles = ceil_div(K, kCM);
+  const int ktiles = ceil_div(K, 64);
   const int BN = g->Co > 32 ? 64 : (g->Co > 16 ? 32 : 16);
   const int ntiles = ceil_div(g->Co, BN);
   // split the pixel reduction so that ~4 waves of CTAs exist, but keep >= 256 pixels per CTA

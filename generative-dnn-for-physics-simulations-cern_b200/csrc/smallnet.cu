@@ -568,7 +568,7 @@ sn_bwd_apply_kernel(const float* __restrict__ dw_sn, const float* __restrict__ u
   const int n = O * I;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int o = i / I, k = i - o * I;
-    dw_orig[slot * sw + i] += (D[i] - dt * u_used[(size_t)slot * O + o] * v_used[(size_t)slot * I + k]) * inv;
+    atomicAdd(&dw_orig[slot * sw + i], (D[i] - dt * u_used[(size_t)slot * O + o] * v_used[(size_t)slot * I + k]) * inv);
   }
 }
 
@@ -587,7 +587,8 @@ spectral_norm_bwd_kernel(const float* __restrict__ dw_sn, const float* __restric
   const float inv = 1.f / sigma[slot];
   for (int i = threadIdx.x; i < O * I; i += blockDim.x) {
     const int o = i / I, k = i % I;
-    dw_orig[slot * sw + i] += (D[i] - dot * u_used[(size_t)slot * O + o] * v_used[(size_t)slot * I + k]) * inv;
+    // atomic: the two backward passes of a discriminator step (real / fake batch) may run concurrently on two streams
+    atomicAdd(&dw_orig[slot * sw + i], (D[i] - dot * u_used[(size_t)slot * O + o] * v_used[(size_t)slot * I + k]) * inv);
   }
 }
 

@@ -263,8 +263,13 @@ class MoEWrapper(nn.Module):
         loss_d = torch.zeros(E, device=dev)
         L.call("es_hinge_d", s_real, s_fake, gh, E, counts_g, Bg, d_real, d_fake, loss_d)
         a_d.G.zero_()
-        disc.backward(sv_real, sn_a, d_real, None, want_w=True)
+        ev_h = main.record_event()
+        with torch.cuda.stream(s1):     # the two passes only meet in atomic accumulations into the gradient arena
+            s1.wait_event(ev_h)
+            disc.backward(sv_real, sn_a, d_real, None, want_w=True)
+            ev_br = s1.record_event()
         disc.backward(sv_fake, sn_b, d_fake, None, want_w=True)
+        main.wait_event(ev_br)
         self._allreduce(a_d.G)
         self._adam(a_d, self._lr(discriminator_optimizers, cfgm.discriminator.lr_d), gh)
         del sv_real, sv_fake
