@@ -380,9 +380,9 @@ def run_b200(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, dt = cpu_train_samples_per_s(arch, E, args.cpu_batch, 1, 1, threads)
+        v, dt = cpu_train_samples_per_s(arch, E, args.cpu_batch, 4, 1, threads)
         cpu = {"value": round(v, 3), "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"1 timed MoE train step (after 1 warm-up) at batch {args.cpu_batch}, E={E}, {arch}: fp32 PyTorch "
+               "sample": f"4 timed MoE train steps (after 1 warm-up) at batch {args.cpu_batch}, E={E}, {arch}: fp32 PyTorch "
                          f"restatement of the reference (oracle/) on {threads} host threads, {dt:.1f} s/step"}
     line = {"metric": "train_samples_per_sec", "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
@@ -406,7 +406,7 @@ def main():
     ap.add_argument("--pool", type=int, default=16, help="distinct resident input batches cycled through")
     ap.add_argument("--infer-batch", type=int, default=8192)
     ap.add_argument("--infer-iters", type=int, default=5)
-    ap.add_argument("--cpu-batch", type=int, default=64, help="batch of the bounded CPU-reference sample")
+    ap.add_argument("--cpu-batch", type=int, default=128, help="batch of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-launch", action="store_true", help="print every timed GEMM launch of the last step to stderr")
     ap.add_argument("--ncu-step", type=int, default=0, help="1: cudaProfilerStart/Stop around one train step; 2: + one inference batch")
