@@ -197,9 +197,64 @@ __global__ void expm1_scatter_kernel(const float* __restrict__ img, const int32_
   }
 }
 
+// Evaluation metric front end (reference train/utils.py:18-78): the five "channel" sums of a shower —
+// the checkerboard cells (i%2 != j%2) of the bottom-left, bottom-right, top-left and top-right quadrants, and the
+// complementary checkerboard of the whole image — with the expm1 of the batch-inference tail fused in.  One warp per image,
+// fp64 accumulation (the reference sums float64 copies on the host).
+__global__ void __launch_bounds__(256)
+channel_sums_kernel(const float* __restrict__ img, int H, int W, int rows, int apply_expm1, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* p = img + (size_t)r * H * W;
+  const int mr = H / 2, mc = W / 2;
+  double s[5] = {0, 0, 0, 0, 0};
+  for (int i = lane; i < H * W; i += 32) {
+    const int y = i / W, x = i - y * W;
+    const float v = apply_expm1 ? expm1f(p[i]) : p[i];
+    if ((y & 1) != (x & 1)) s[(y >= mr ? 0 : 2) + (x >= mc ? 1 : 0)] += (double)v;
+    else s[4] += (double)v;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const double t = warp_sum_d(s[k]);
+    if (lane == 0) out[(size_t)r * 5 + k] = t;
+  }
+}
+
+// 1-D Wasserstein distance between two equally sized, already sorted samples: mean |a_i - b_i|
+__global__ void __launch_bounds__(256)
+w1_sorted_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, int stride, double* __restrict__ out) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += fabs(a[(size_t)i * stride] - b[(size_t)i * stride]);
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[blockIdx.x] = t / (double)n;
+  }
+}
+
 }  // namespace es
 
 using namespace es;
+
+extern "C" int es_channel_sums(const float* img, int H, int W, int rows, int apply_expm1, double* out5, void* stream) {
+  ES_REQUIRE(img && out5 && H > 1 && W > 1 && rows > 0, "bad arguments");
+  channel_sums_kernel<<<ceil_div(rows, 8), 256, 0, as_stream(stream)>>>(img, H, W, rows, apply_expm1, out5);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_w1_sorted(const double* a, const double* b, int n, int n_cols, double* out, void* stream) {
+  ES_REQUIRE(a && b && out && n > 0 && n_cols >= 1, "bad arguments");
+  for (int c = 0; c < n_cols; ++c)   // column c of row-major [n, n_cols] arrays
+    w1_sorted_kernel<<<1, 256, 0, as_stream(stream)>>>(a + c, b + c, n, n_cols, out + c);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
 
 extern "C" int es_hinge_d(const float* real_score, const float* fake_score, const es_group* grp, int E,
                           const float* counts_global, int B_global, float* d_real, float* d_fake, float* loss,

@@ -446,22 +446,44 @@ class MoEWrapper(nn.Module):
 
     @torch.no_grad()
     def evaluate(self, epoch, y_test, x_test, true_positions, std, intensity, cfg, device):
-        """Wasserstein metric of the reference (moe.py:644-692): 5 channel sums of real vs generated showers, overall and
-        per routed expert, repeated min(epoch//5+1, 5) times."""
-        from ..train.utils import calculate_joint_ws_across_experts, sum_channels_parallel
-        x_np = np.asarray(x_test.cpu() if isinstance(x_test, torch.Tensor) else x_test)
-        ch_org = np.array(list(sum_channels_parallel(np.expm1(x_np).reshape(-1, *self.image_shape))))
-        soft_gates, _ = self.router(y_test)
-        predicted = soft_gates.argmax(1).cpu().numpy()
-        idx_e = [np.where(predicted == i)[0] for i in range(self.n_experts)]
-        ch_org_e = [ch_org[ix] if len(ix) else np.zeros((0, 5)) for ix in idx_e]
-        y_e = [y_test[torch.as_tensor(ix, device=y_test.device)] for ix in idx_e]
-        ws_mean, ws_std, ws_mean_exp, ws_std_exp = calculate_joint_ws_across_experts(
-            min(epoch // 5 + 1, 5), [x_np[ix] for ix in idx_e], y_e, self.generators, ch_org, ch_org_e, self.noise_dim,
-            device, n_experts=self.n_experts, shape_images=self.image_shape)
-        log = {"ws_mean": ws_mean, "ws_std": ws_std, "epoch": epoch}
-        for i in range(self.n_experts):
-            log[f"ws_mean_{i}"], log[f"ws_std_{i}"] = ws_mean_exp[i], ws_std_exp[i]
+        """Wasserstein metric of the reference (moe.py:644-692 with train/utils.py:117-176): route the test conditionals
+        once (Gumbel noise at tau=1, as ``self.router(y_test)`` does), then ``min(epoch//5+1, 5)`` times generate every
+        sample with its expert's generator and compare the 5 channel sums of generated vs real showers, overall and per
+        expert.  Everything up to the per-channel distances stays on the device (grouped generation, expm1 + channel sums
+        fused, sort, mean |a-b| for the equally sized samples); the reference copies every image to the host, widens it to
+        float64 and calls scipy.  One host sync (expert offsets) and one readback of the distances per call."""
+        from ..train.utils import channel_sums_device, ws_device
+        gen, _, _ = self._engines()
+        E = self.n_experts
+        H, W = self.image_shape
+        dev = next(self.router.parameters()).device
+        cond = y_test.to(dev, torch.float32).contiguous()
+        N = cond.shape[0]
+        real = torch.as_tensor(np.asarray(x_test.cpu() if isinstance(x_test, torch.Tensor) else x_test)).to(dev, torch.float32)
+        real = real.reshape(N, H * W).contiguous()
+        gumbel = -torch.empty(N, E, device=dev).exponential_().log()
+        r = self._route(cond, gumbel, 1.0, 1)
+        off = r["offsets"].cpu().tolist()
+        cond_s = self._gather(cond, r["perm"], 9)
+        ch_org = channel_sums_device(self._gather(real, r["perm"], H * W), H, W, True)
+        org_all = ch_org.sort(dim=0).values
+        org_e = [ch_org[off[e]:off[e + 1]].sort(dim=0).values for e in range(E)]
+        n_calc = min(epoch // 5 + 1, 5)
+        ws = torch.zeros(n_calc, 5, dtype=torch.float64, device=dev)
+        ws_exp = torch.zeros(n_calc, E, 5, dtype=torch.float64, device=dev)
+        for j in range(n_calc):
+            z = torch.randn(N, 10, device=dev)
+            img, _, _ = gen.forward(z, None, cond_s, r["grp_half"], N, False, keep=False, training=False)
+            ch = channel_sums_device(img, H, W, True)
+            ws[j] = ws_device(org_all, ch)
+            for e in range(E):
+                if off[e + 1] > off[e]:
+                    ws_exp[j, e] = ws_device(org_e[e], ch[off[e]:off[e + 1]])
+        ws, ws_exp = ws.cpu().numpy(), ws_exp.cpu().numpy()
+        runs, runs_exp = ws.mean(axis=1), ws_exp.mean(axis=2)
+        log = {"ws_mean": runs.mean(), "ws_std": runs.std(), "epoch": epoch}
+        for i in range(E):
+            log[f"ws_mean_{i}"], log[f"ws_std_{i}"] = runs_exp.mean(axis=0)[i], runs_exp.std(axis=0)[i]
         return log
 
     def get_expert_assignment_counts(self, expert_assignments: torch.Tensor) -> torch.Tensor:

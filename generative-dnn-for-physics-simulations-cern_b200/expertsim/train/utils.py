@@ -48,6 +48,25 @@ def sum_channels_parallel(data: np.ndarray):
     return zip(*[(data * m).sum(axis=1).sum(axis=1) for m in masks])
 
 
+def channel_sums_device(img: torch.Tensor, H: int, W: int, apply_expm1: bool = True) -> torch.Tensor:
+    """[N, H*W] fp32 CUDA images -> [N, 5] fp64 channel sums on the device (expm1 fused; same masks as get_channel_masks)."""
+    from .. import _lib as L
+    n = img.shape[0]
+    out = torch.empty(n, 5, dtype=torch.float64, device=img.device)
+    L.call("es_channel_sums", img.reshape(n, H * W).contiguous(), H, W, n, int(apply_expm1), out)
+    return out
+
+
+def ws_device(ch_a_sorted: torch.Tensor, ch_b: torch.Tensor) -> torch.Tensor:
+    """1-D Wasserstein distance per channel between two equally sized samples ([n,5] fp64; ``ch_a_sorted`` already sorted per
+    column): for equal sizes scipy.stats.wasserstein_distance is mean |sort(a) - sort(b)|.  -> [5] fp64 on the device."""
+    from .. import _lib as L
+    assert ch_a_sorted.shape == ch_b.shape
+    out = torch.empty(ch_b.shape[1], dtype=torch.float64, device=ch_b.device)
+    L.call("es_w1_sorted", ch_a_sorted.contiguous(), ch_b.sort(dim=0).values.contiguous(), ch_b.shape[0], ch_b.shape[1], out)
+    return out
+
+
 def calculate_joint_ws_across_experts(n_calc, x_tests: List, y_tests: List, generators: List, ch_org, ch_org_expert,
                                       noise_dim, device, batch_size=64, n_experts=3, shape_images=(56, 30)):
     """Wasserstein distance between real and generated channel sums, overall and per expert, ``n_calc`` repetitions

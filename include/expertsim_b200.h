@@ -397,6 +397,16 @@ int es_adam_step(float* p, const float* g, float* m, float* v, long n, long slot
  * and widened to float64 as the reference's numpy result. */
 int es_expm1_scatter(const float* img, const int32_t* perm, int rows, int HW, double* out_f64, float* out_f32, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * evaluation metric front end: sum_channels_parallel (expertsim/train/utils.py:18-78) with the expm1
+ * of the inference tail fused in, and the 1-D Wasserstein distance of two equally sized sorted samples
+ * (scipy.stats.wasserstein_distance as called at train/utils.py:153-168).
+ * ---------------------------------------------------------------------------------------------- */
+/* out5[row][0..4] (fp64) = the five channel sums of img[row] ([H,W] fp32; expm1 applied first when apply_expm1 != 0) */
+int es_channel_sums(const float* img, int H, int W, int rows, int apply_expm1, double* out5, void* stream);
+/* a, b: row-major [n, n_cols] fp64, every column sorted ascending; out[c] = mean_i |a[i,c] - b[i,c]| */
+int es_w1_sorted(const double* a, const double* b, int n, int n_cols, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ import re
 
 import pytest
 import torch
+import numpy as np
 import torch.nn.functional as F
 
 import oracle.expertsim_oracle as orc
@@ -360,3 +361,36 @@ def test_modules_standalone_forward():
     gates, logits = router(cond.to(DEV))
     check("RouterNetwork.forward logits", logits, orc.router_forward(sd, cond, torch.zeros(B, 5))[1], 1e-5)
     assert torch.allclose(gates.sum(1).cpu(), torch.ones(B), atol=1e-5)
+
+
+def test_device_wasserstein_metric_matches_scipy():
+    """§8f row 1 (evaluation metric on the device): fused expm1 + 5 channel sums and the sorted-sample Wasserstein distance
+    against the reference's numpy masks + scipy.stats.wasserstein_distance on the same showers."""
+    import numpy as np
+    from scipy.stats import wasserstein_distance
+    from expertsim.train.utils import channel_sums_device, sum_channels_parallel, ws_device
+    for H, W in ((56, 30), (44, 44)):
+        g = torch.Generator().manual_seed(H)
+        a = torch.rand(300, H, W, generator=g) * (torch.rand(300, H, W, generator=g) < 0.05) * 5.0
+        b = torch.rand(300, H, W, generator=g) * (torch.rand(300, H, W, generator=g) < 0.05) * 5.0
+        ch_a = channel_sums_device(a.to(DEV).reshape(300, -1), H, W, True)
+        ch_b = channel_sums_device(b.to(DEV).reshape(300, -1), H, W, True)
+        want_a = np.array(list(sum_channels_parallel(np.expm1(a.numpy()).astype(np.float64))))
+        want_b = np.array(list(sum_channels_parallel(np.expm1(b.numpy()).astype(np.float64))))
+        _check(f"channel sums {H}x{W}", ch_a, torch.from_numpy(want_a), 1e-6)
+        got = ws_device(ch_a.sort(dim=0).values, ch_b).cpu().numpy()
+        for i in range(5):
+            w = wasserstein_distance(want_a[:, i], want_b[:, i])
+            assert abs(got[i] - w) <= 1e-6 * max(1.0, abs(w)), (i, got[i], w)
+
+
+def test_evaluate_returns_reference_keys():
+    arch, E = "proton", 3
+    ocfg, cfg = make_cfg(arch, E)
+    st = orc.make_state(arch, E, 2, ocfg)
+    moe = build_moe(arch, E, cfg, st).eval()
+    batch = orc.make_batch(arch, 64, 1)
+    out = moe.evaluate(7, batch["cond"].to(DEV), batch["real_images"][:, 0].numpy(), batch["true_positions"], batch["std"],
+                       batch["intensity"], cfg, torch.device(DEV))
+    assert set(out) == {"ws_mean", "ws_std", "epoch"} | {f"ws_mean_{i}" for i in range(E)} | {f"ws_std_{i}" for i in range(E)}
+    assert out["epoch"] == 7 and out["ws_mean"] > 0 and all(np.isfinite(float(v)) for v in out.values())
