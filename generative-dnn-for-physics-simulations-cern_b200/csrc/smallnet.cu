@@ -365,6 +365,26 @@ linear_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
              [&](int m, int n, float v) { y[(size_t)(row0 + m) * O + n] = v + (b ? b[slot * sb + n] : 0.f); });
 }
 
+// split-K variant for long reductions (discriminator fc1: I = 2313, O = 128, only 2 x 16 output tiles): grid.z splits
+// the reduction, partial tiles meet in fp32 atomics on a zeroed y; split 0 adds the bias.
+__global__ void __launch_bounds__(256)
+linear_fwd_splitk_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
+                         long sw, long sb, int I, int O, int kper, const es_group* __restrict__ grp, int n_groups,
+                         float* __restrict__ y) {
+  int gi, row0, ns;
+  if (!chunk_of(grp, n_groups, 64, blockIdx.x, gi, row0, ns)) return;
+  const int slot = grp[gi].slot;
+  const int kb = blockIdx.z * kper, kn = min(kper, I - kb);
+  if (kn <= 0) return;
+  const float* W = w + slot * sw + kb;
+  const float* X = x + kb;
+  const bool first = blockIdx.z == 0;
+  sgemm_tile(ns, O, kn, 0, blockIdx.y * 64,
+             [&](int m, int k) { return X[(size_t)(row0 + m) * ldx + k]; },
+             [&](int k, int n) { return W[(size_t)n * I + k]; },
+             [&](int m, int n, float v) { atomicAdd(&y[(size_t)(row0 + m) * O + n], v + ((first && b) ? b[slot * sb + n] : 0.f)); });
+}
+
 __global__ void __launch_bounds__(256)
 linear_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, long sw, int I, int O,
                        const es_group* __restrict__ grp, int n_groups, float* __restrict__ dx, int lddx) {
@@ -796,7 +816,18 @@ extern "C" int es_linear_fwd(const float* x, int ldx, const float* w, const floa
                              long slot_stride_b, int I, int O, const es_group* grp, int n_groups, int total_rows, float* y,
                              void* stream) {
   ES_REQUIRE(x && w && grp && y && I > 0 && O > 0 && ldx >= I && total_rows > 0 && n_groups <= kMaxGroups, "bad arguments");
-  linear_fwd_kernel<<<dim3(ceil_div(total_rows, 64) + n_groups, ceil_div(O, 64)), 256, 0, as_stream(stream)>>>(
+  const int chunks = ceil_div(total_rows, 64) + n_groups, ntiles = ceil_div(O, 64);
+  if (I >= 512 && chunks * ntiles < 2 * 148) {
+    int splits = min(ceil_div(4 * 148, chunks * ntiles), ceil_div(I, 128));
+    const int kper = ceil_div(ceil_div(I, splits), 16) * 16;
+    splits = ceil_div(I, kper);
+    ES_CUDA(cudaMemsetAsync(y, 0, (size_t)total_rows * O * sizeof(float), as_stream(stream)));
+    linear_fwd_splitk_kernel<<<dim3(chunks, ntiles, splits), 256, 0, as_stream(stream)>>>(
+        x, ldx, w, b, slot_stride_w, slot_stride_b, I, O, kper, grp, n_groups, y);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
+  linear_fwd_kernel<<<dim3(chunks, ntiles), 256, 0, as_stream(stream)>>>(
       x, ldx, w, b, slot_stride_w, slot_stride_b, I, O, grp, n_groups, y);
   ES_LAUNCH_CHECK();
   return ES_OK;

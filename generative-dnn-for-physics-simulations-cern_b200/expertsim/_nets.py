@@ -321,24 +321,15 @@ class DiscEngine:
         """img [R, H*W], cond [R, 9] (sorted order) -> score [R,1], latent [R,64], saved tensors."""
         a, E, n = self.a, self.a.E, self.a.n
         s = {"img": img, "R": R, "grp": grp}
-        y1 = empty(R, 32, self.c0.Ho, self.c0.Wo)
-        L.call("es_conv2d_fwd", img, sn["conv_layers.0"][0], a.addr("conv_layers.0.bias"), 32 * 9, n, self.c0, grp, E, R, y1)
-        a1, s["st1"] = empty(*y1.shape), empty(R, 8, 2)
-        L.call("es_groupnorm_fwd", y1, a.addr("conv_layers.1.weight"), a.addr("conv_layers.1.bias"), n, 32, self.c0.Ho * self.c0.Wo,
-               8, ACT_LRELU, grp, E, R, a1, s["st1"])
-        p1, s["i1"] = empty(R, 32, self.H1, self.W1), empty(R, 32, self.H1, self.W1, dtype=torch.uint8)
-        L.call("es_maxpool_fwd", a1, 32, self.c0.Ho, self.c0.Wo, 2, 2, 2, 2, R, p1, s["i1"])
-        y2 = empty(R, 16, self.c4.Ho, self.c4.Wo)
-        L.call("es_conv2d_fwd", p1, sn["conv_layers.4"][0], a.addr("conv_layers.4.bias"), 16 * 288, n, self.c4, grp, E, R, y2)
-        a2, s["st2"] = empty(*y2.shape), empty(R, 8, 2)
-        L.call("es_groupnorm_fwd", y2, a.addr("conv_layers.5.weight"), a.addr("conv_layers.5.bias"), n, 16, self.c4.Ho * self.c4.Wo,
-               8, ACT_LRELU, grp, E, R, a2, s["st2"])
-        kh, kw = self.pool2
-        p2, s["i2"] = empty(R, self.flat), empty(R, self.flat, dtype=torch.uint8)
-        L.call("es_maxpool_fwd", a2, 16, self.c4.Ho, self.c4.Wo, kh, kw, kh, kw, R, p2, s["i2"])
+        # fused trunk (csrc/disc_fused.cu): stem = conv0 + GN + LReLU + pool, stage 2 = conv4 + GN + LReLU + pool + concat
+        p1, s["st1"] = empty(R, 32, self.H1, self.W1), empty(R, 8, 2)
+        L.call("es_disc_stem_fwd", img, sn["conv_layers.0"][0], 32 * 9, a.addr("conv_layers.0.bias"), n,
+               a.addr("conv_layers.1.weight"), a.addr("conv_layers.1.bias"), n, self.H, self.W, grp, E, R, p1, s["st1"])
+        y2, s["st2"] = empty(R, 16, self.c4.Ho * self.c4.Wo), empty(R, 8, 2)
         fcin = empty(R, self.flat + 9)
-        L.call("es_copy_cols", p2, self.flat, self.flat, R, fcin, self.flat + 9, 0)
-        L.call("es_copy_cols", cond, 9, 9, R, fcin, self.flat + 9, self.flat)
+        L.call("es_disc_stage2_fwd", p1, sn["conv_layers.4"][0], 16 * 288, a.addr("conv_layers.4.bias"), n,
+               a.addr("conv_layers.5.weight"), a.addr("conv_layers.5.bias"), n, cond, self.H1, self.W1, self.pool2[1], grp, E, R,
+               y2, s["st2"], fcin, self.flat + 9)
         l1 = empty(R, 128)
         L.call("es_linear_fwd", fcin, self.flat + 9, sn["fc1.0"][0], a.addr("fc1.0.bias"), 128 * (self.flat + 9), n, self.flat + 9, 128, grp, E, R, l1)
         f1, s["s1"] = empty(R, 128), empty(R, 2)
@@ -349,7 +340,7 @@ class DiscEngine:
         L.call("es_layernorm_fwd", l2, a.addr("fc2.1.weight"), a.addr("fc2.1.bias"), n, 64, ACT_LRELU, grp, E, R, lat, s["s2"])
         score = zeros(R, 1)
         L.call("es_linear_fwd", lat, 64, sn["fc3"][0], a.addr("fc3.bias"), 64, n, 64, 1, grp, E, R, score)
-        s.update(y1=y1, p1=p1, y2=y2, fcin=fcin, l1=l1, f1=f1, l2=l2, lat=lat)
+        s.update(p1=p1, y2=y2, fcin=fcin, l1=l1, f1=f1, l2=l2, lat=lat)
         return score, lat, s
 
     def backward(self, s, sn, d_score, d_latent, want_w: bool, d_img=None, accumulate=False):
@@ -381,29 +372,18 @@ class DiscEngine:
         dfc = zeros(R, I1)
         L.call("es_linear_bwd_data", dl1, sn["fc1.0"][0], 128 * I1, I1, 128, grp, E, R, dfc, I1)
         lin_w(s["fcin"], I1, dl1, "fc1.0")
-        dp2 = empty(R, self.flat)
-        L.call("es_copy_cols", dfc, I1, self.flat, R, dp2, self.flat, 0)
-        kh, kw = self.pool2
-        da2 = empty(R, 16, self.c4.Ho, self.c4.Wo)
-        L.call("es_maxpool_bwd", dp2, s["i2"], 16, self.c4.Ho, self.c4.Wo, kh, kw, kh, kw, R, da2)
-        dy2 = zeros(*da2.shape)
-        L.call("es_groupnorm_bwd", da2, s["y2"], s["st2"], a.addr("conv_layers.5.weight"), a.addr("conv_layers.5.bias"), n, 16,
-               self.c4.Ho * self.c4.Wo, 8, ACT_LRELU, grp, E, R, dy2,
-               a.gaddr("conv_layers.5.weight") if want_w else None, a.gaddr("conv_layers.5.bias") if want_w else None)
-        if want_w:
-            L.call("es_conv2d_bwd_weight", s["p1"], dy2, self.c4, grp, E, R, dsn["conv_layers.4"], a.gaddr("conv_layers.4.bias"), 16 * 288, n)
-        dp1 = zeros(R, 32, self.H1, self.W1)
-        L.call("es_conv2d_bwd_data", dy2, sn["conv_layers.4"][0], 16 * 288, self.c4, grp, E, R, dp1, 0)
-        da1 = empty(R, 32, self.c0.Ho, self.c0.Wo)
-        L.call("es_maxpool_bwd", dp1, s["i1"], 32, self.c0.Ho, self.c0.Wo, 2, 2, 2, 2, R, da1)
-        dy1 = zeros(*da1.shape)
-        L.call("es_groupnorm_bwd", da1, s["y1"], s["st1"], a.addr("conv_layers.1.weight"), a.addr("conv_layers.1.bias"), n, 32,
-               self.c0.Ho * self.c0.Wo, 8, ACT_LRELU, grp, E, R, dy1,
-               a.gaddr("conv_layers.1.weight") if want_w else None, a.gaddr("conv_layers.1.bias") if want_w else None)
-        if want_w:
-            L.call("es_conv2d_bwd_weight", s["img"], dy1, self.c0, grp, E, R, dsn["conv_layers.0"], a.gaddr("conv_layers.0.bias"), 32 * 9, n)
-        if d_img is not None:
-            L.call("es_conv2d_bwd_data", dy1, sn["conv_layers.0"][0], 32 * 9, self.c0, grp, E, R, d_img, int(accumulate))
+        dp1 = empty(R, 32, self.H1, self.W1)
+        gw = (lambda name: a.gaddr(name)) if want_w else (lambda name: None)
+        L.call("es_disc_stage2_bwd", dfc, I1, s["y2"], s["st2"], s["p1"], sn["conv_layers.4"][0], 16 * 288,
+               a.addr("conv_layers.5.weight"), a.addr("conv_layers.5.bias"), n, self.H1, self.W1, self.pool2[1], grp, E, R, dp1,
+               dsn["conv_layers.4"] if want_w else None, 16 * 288, gw("conv_layers.4.bias"), n, gw("conv_layers.5.weight"),
+               gw("conv_layers.5.bias"))
+        if d_img is not None and not accumulate:
+            d_img.zero_()           # the stem's image gradient is accumulated with atomics (8 GroupNorm groups per sample)
+        L.call("es_disc_stem_bwd", dp1, s["img"], sn["conv_layers.0"][0], 32 * 9, a.addr("conv_layers.0.bias"), n,
+               a.addr("conv_layers.1.weight"), a.addr("conv_layers.1.bias"), n, s["st1"], self.H, self.W, grp, E, R, d_img,
+               dsn["conv_layers.0"] if want_w else None, 32 * 9, gw("conv_layers.0.bias"), gw("conv_layers.1.weight"),
+               gw("conv_layers.1.bias"))
         if want_w:
             for name in self.SN:
                 O, I = self.dims[name]

@@ -307,6 +307,31 @@ int es_maxpool_fwd(const float* x, int C, int Hi, int Wi, int kh, int kw, int sh
                    float* y, uint8_t* idx, void* stream);
 int es_maxpool_bwd(const float* dy, const uint8_t* idx, int C, int Hi, int Wi, int kh, int kw, int sh, int sw, int total_rows,
                    float* dx, void* stream);
+/* Fused discriminator trunk (expertsim/models/proton/discriminator.py:121-155, neutron/discriminator.py:11-48).
+ * Stem = SN-Conv(1->32,k3,valid) -> GroupNorm(8) -> LeakyReLU(0.1) -> MaxPool(2): one launch; only the pooled map
+ * p1 [rows][32][(H-2)/2][(W-2)/2] and the statistics stats [rows][8][2] are written.  w = normalised weights
+ * [slots][32*9] (slot stride slot_stride_w); bias / gamma / beta live in the arena (slot strides given).
+ * Backward re-computes the conv from the image: dp1 = gradient of p1; d_img [rows][H*W] is ACCUMULATED with atomics (the
+ * caller zeroes it) or NULL; dw [slots][32*9] (+ dbias, dgamma, dbeta, all accumulated) or NULL. */
+int es_disc_stem_fwd(const float* img, const float* w, long slot_stride_w, const float* bias, long slot_stride_b,
+                     const float* gamma, const float* beta, long slot_stride_n, int H, int W, const es_group* grp,
+                     int n_groups, int total_rows, float* p1, float* stats, void* stream);
+int es_disc_stem_bwd(const float* dp1, const float* img, const float* w, long slot_stride_w, const float* bias,
+                     long slot_stride_b, const float* gamma, const float* beta, long slot_stride_n, const float* stats, int H,
+                     int W, const es_group* grp, int n_groups, int total_rows, float* d_img, float* dw, long slot_stride_dw,
+                     float* dbias, float* dgamma, float* dbeta, void* stream);
+/* Stage 2 = SN-Conv(32->16,k3,valid) -> GroupNorm(8) -> LeakyReLU -> MaxPool(2, pool_kw) -> flatten, written straight into
+ * the fc1 input fcin [rows][ldf] (features 0..flat-1, then the 9 conditionals).  p1 [rows][32][H1][W1]; y2 (pre-norm conv
+ * output, [rows][16][(H1-2)*(W1-2)]) and stats [rows][8][2] are kept for the backward.  Backward: dfc = gradient of
+ * fcin (only the first `flat` columns are read); dp1 = gradient of p1 (written); dw [slots][16*288] etc. or NULL. */
+int es_disc_stage2_fwd(const float* p1, const float* w, long slot_stride_w, const float* bias, long slot_stride_b,
+                       const float* gamma, const float* beta, long slot_stride_n, const float* cond, int H1, int W1,
+                       int pool_kw, const es_group* grp, int n_groups, int total_rows, float* y2, float* stats, float* fcin,
+                       int ldf, void* stream);
+int es_disc_stage2_bwd(const float* dfc, int ldf, const float* y2, const float* stats, const float* p1, const float* w,
+                       long slot_stride_w, const float* gamma, const float* beta, long slot_stride_n, int H1, int W1,
+                       int pool_kw, const es_group* grp, int n_groups, int total_rows, float* dp1, float* dw,
+                       long slot_stride_dw, float* dbias, long slot_stride_b, float* dgamma, float* dbeta, void* stream);
 /* y[row, 0:O] = x[row, 0:I] . W[slot][O,I]^T + b   /  dx = dy . W  /  dW += dy^T x, db += sum dy */
 int es_linear_fwd(const float* x, int ldx, const float* w, const float* b, long slot_stride_w, long slot_stride_b, int I, int O,
                   const es_group* grp, int n_groups, int total_rows, float* y, void* stream);

@@ -532,6 +532,78 @@ def test_conv2d_fwd_bwd(name):
     check(f"conv2d bwd bias {name}", db, lb.grad, 2e-5)
 
 
+@pytest.mark.parametrize("arch", ["proton", "neutron"])
+def test_disc_fused_trunk(arch):
+    """Fused discriminator trunk (stem + stage 2, forward and backward) against torch autograd on sparse images (flat
+    regions make every pooling window a tie: the arg-max rule — first maximum in scan order — is what is tested)."""
+    H, W, pk = (56, 30, (2, 1)) if arch == "proton" else (44, 44, (2, 2))
+    counts, slots = [5, 0, 9, 1], [2, 1, 0, 3]
+    grp, R = groups(counts, slots)
+    S = 4
+    g = G(7 if arch == "proton" else 8)
+    img = torch.log1p((torch.rand(R, 1, H, W, generator=g) < 0.03).float() * torch.empty(R, 1, H, W).exponential_(generator=g) * 20)
+    cond = torch.randn(R, 9, generator=g)
+    w0 = torch.randn(S, 32, 1, 3, 3, generator=g) / 3
+    b0 = torch.randn(S, 32, generator=g) * .1
+    g0, be0 = 1 + .2 * torch.randn(S, 32, generator=g), .1 * torch.randn(S, 32, generator=g)
+    w1 = torch.randn(S, 16, 32, 3, 3, generator=g) / math.sqrt(288)
+    b1 = torch.randn(S, 16, generator=g) * .1
+    g1, be1 = 1 + .2 * torch.randn(S, 16, generator=g), .1 * torch.randn(S, 16, generator=g)
+    H1, W1 = (H - 2) // 2, (W - 2) // 2
+    Hp, Wp = (H1 - 2) // pk[0], (W1 - 2) // pk[1]
+    flat = 16 * Hp * Wp
+    ldf = flat + 9
+    dfc = torch.randn(R, ldf, generator=g)
+    leaves = [t.clone().requires_grad_(True) for t in (img, w0, b0, g0, be0, w1, b1, g1, be1)]
+    limg, lw0, lb0, lg0, lbe0, lw1, lb1, lg1, lbe1 = leaves
+    ref_p1, ref_fc, off = [], [], 0
+    for c, s in zip(counts, slots):
+        if c:
+            x = F.conv2d(limg[off:off + c], lw0[s], lb0[s])
+            x = F.max_pool2d(F.leaky_relu(F.group_norm(x, 8, lg0[s], lbe0[s]), 0.1), 2)
+            ref_p1.append(x.detach())
+            y = F.conv2d(x, lw1[s], lb1[s])
+            y = F.max_pool2d(F.leaky_relu(F.group_norm(y, 8, lg1[s], lbe1[s]), 0.1), pk).flatten(1)
+            ref_fc.append(y.detach())
+            (y * dfc[off:off + c, :flat]).sum().backward()
+        off += c
+    d = lambda t: cuda(t.reshape(t.shape[0], -1))
+    p1, st1 = torch.zeros(R, 32, H1, W1, device=DEV), torch.zeros(R, 8, 2, device=DEV)
+    L.call("es_disc_stem_fwd", d(img), d(w0), 288, d(b0), 32, d(g0), d(be0), 32, H, W, grp, len(counts), R, p1, st1)
+    check(f"disc stem fwd {arch}", p1, torch.cat(ref_p1), 1e-5)
+    y2, st2 = torch.zeros(R, 16, (H1 - 2) * (W1 - 2), device=DEV), torch.zeros(R, 8, 2, device=DEV)
+    fcin = torch.zeros(R, ldf, device=DEV)
+    L.call("es_disc_stage2_fwd", p1, d(w1), 16 * 288, d(b1), 16, d(g1), d(be1), 16, cuda(cond), H1, W1, pk[1], grp,
+           len(counts), R, y2, st2, fcin, ldf)
+    check(f"disc stage2 fwd {arch}", fcin[:, :flat], torch.cat(ref_fc), 2e-5)
+    assert torch.equal(fcin[:, flat:].cpu(), cond)
+    for want_w in (True, False):
+        dp1 = torch.zeros(R, 32, H1, W1, device=DEV)
+        dw1, db1 = torch.zeros(S, 16 * 288, device=DEV), torch.zeros(S, 16, device=DEV)
+        dg1, dbe1 = torch.zeros(S, 16, device=DEV), torch.zeros(S, 16, device=DEV)
+        L.call("es_disc_stage2_bwd", cuda(dfc), ldf, y2, st2, p1, d(w1), 16 * 288, d(g1), d(be1), 16, H1, W1, pk[1], grp,
+               len(counts), R, dp1, dw1 if want_w else None, 16 * 288, db1 if want_w else None, 16,
+               dg1 if want_w else None, dbe1 if want_w else None)
+        d_img = torch.zeros(R, H * W, device=DEV)
+        dw0, db0 = torch.zeros(S, 288, device=DEV), torch.zeros(S, 32, device=DEV)
+        dg0, dbe0 = torch.zeros(S, 32, device=DEV), torch.zeros(S, 32, device=DEV)
+        L.call("es_disc_stem_bwd", dp1, d(img), d(w0), 288, d(b0), 32, d(g0), d(be0), 32, st1, H, W, grp, len(counts), R,
+               d_img, dw0 if want_w else None, 288, db0 if want_w else None, dg0 if want_w else None,
+               dbe0 if want_w else None)
+        check(f"disc trunk d_img {arch} w={want_w}", d_img, limg.grad.reshape(R, -1), 2e-4)
+        if want_w:
+            for nm, got, ref in (("dw1", dw1, lw1.grad), ("db1", db1, lb1.grad), ("dgamma1", dg1, lg1.grad),
+                                 ("dbeta1", dbe1, lbe1.grad), ("dw0", dw0, lw0.grad), ("db0", db0, lb0.grad),
+                                 ("dgamma0", dg0, lg0.grad), ("dbeta0", dbe0, lbe0.grad)):
+                check(f"disc trunk {nm} {arch}", got, ref.reshape(S, -1), 2e-4)
+            # weight gradients only (discriminator step: no image gradient requested)
+            dw0b = torch.zeros(S, 288, device=DEV)
+            L.call("es_disc_stem_bwd", dp1, d(img), d(w0), 288, d(b0), 32, d(g0), d(be0), 32, st1, H, W, grp, len(counts),
+                   R, None, dw0b, 288, torch.zeros(S, 32, device=DEV), torch.zeros(S, 32, device=DEV),
+                   torch.zeros(S, 32, device=DEV))
+            check(f"disc stem dw0 (no d_img) {arch}", dw0b, lw0.grad.reshape(S, -1), 2e-4)
+
+
 @pytest.mark.parametrize("C,H,W,groups_n,act", [(32, 54, 28, 8, 2), (16, 25, 12, 8, 2), (32, 27, 14, 8, 1), (64, 6, 3, 32, 0)])
 def test_groupnorm_fwd_bwd(C, H, W, groups_n, act):
     counts, slots = [4, 5], [1, 0]
