@@ -41,12 +41,22 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
   extern __shared__ float sm[];
   constexpr int TN = BN / 16;
   const int KHW = g.KH * g.KW;
-  const int K = (MODE == 0 ? g.Ci : g.Co) * KHW;                 // reduction length
   const int Nn = MODE == 0 ? g.Co : g.Ci;                        // GEMM N extent
-  const int Hm = MODE == 0 ? g.Ho : g.Hi, Wm = MODE == 0 ? g.Wo : g.Wi;      // pixel grid of the M axis
+  const int Hf = MODE == 0 ? g.Ho : g.Hi, Wf = MODE == 0 ? g.Wo : g.Wi;      // full pixel grid of the destination
   const int Hs = MODE == 0 ? g.Hi : g.Ho, Ws = MODE == 0 ? g.Wi : g.Wo;      // pixel grid of the source
   const int Cs = MODE == 0 ? g.Ci : g.Co;
-  const int PXm = Hm * Wm, PXs = Hs * Ws;
+  // Data gradient of a strided conv: an input pixel (iy, ix) only meets the taps with ky = (iy + pad) mod stride (same in
+  // x) — 6.25 of 25 for k5/s2.  blockIdx.z walks the stride x stride parity classes; each is a dense GEMM over its own
+  // pixel sub-grid (iy = S*py + cy) and tap subset (ky = ky0 + S*i), so no reduction step multiplies by a structural zero.
+  const int S = MODE == 1 ? g.stride : 1;
+  const int cy = MODE == 1 ? (int)blockIdx.z / S : 0, cx = MODE == 1 ? (int)blockIdx.z % S : 0;
+  const int Hm = (Hf - cy + S - 1) / S, Wm = (Wf - cx + S - 1) / S;          // pixel grid of the M axis (this class)
+  const int ky0 = MODE == 1 ? (cy + g.pad) % S : 0, kx0 = MODE == 1 ? (cx + g.pad) % S : 0;
+  const int nky = (g.KH - ky0 + S - 1) / S, nkx = (g.KW - kx0 + S - 1) / S;
+  const int KHWc = nky * nkx;
+  const int K = Cs * KHWc;                                       // reduction length
+  const int PXm = Hm * Wm, PXs = Hs * Ws, PXf = Hf * Wf;
+  if (PXm <= 0) return;   // (a class without taps, e.g. 1x1 stride 2, still writes its zeros)
   KEnt* ktab = reinterpret_cast<KEnt*>(sm);                       // [K]
   float* As = sm + 2 * ((K + 1) & ~1);                            // [kCK][kCM + 4]
   float* Bs = As + kCK * (kCM + 4);                               // [kCK][BN + 4]
@@ -56,7 +66,7 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
   const int n0 = blockIdx.y * BN;
   const int tid = threadIdx.x;
   for (int k = tid; k < K; k += 256) {
-    const int c = k / KHW, t = k - c * KHW, ky = t / g.KW, kx = t - ky * g.KW;
+    const int c = k / KHWc, t = k - c * KHWc, ky = ky0 + (t / nkx) * S, kx = kx0 + (t % nkx) * S;
     KEnt e;
     e.ky = (short)ky; e.kx = (short)kx;
     e.off = c * PXs;
@@ -89,10 +99,10 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
           const int iy = py * g.stride + e.ky - g.pad, ix = px * g.stride + e.kx - g.pad;
           if (iy >= 0 && iy < Hs && ix >= 0 && ix < Ws) v = __ldg(sbase + e.off + iy * Ws + ix);
         } else {
-          const int ty = py + g.pad - e.ky, tx = px + g.pad - e.kx;
+          const int ty = py * S + cy + g.pad - e.ky, tx = px * S + cx + g.pad - e.kx;     // multiples of S by construction
           if (ty >= 0 && tx >= 0) {
-            const int oy = ty / g.stride, ox = tx / g.stride;
-            if (oy * g.stride == ty && ox * g.stride == tx && oy < Hs && ox < Ws) v = __ldg(sbase + e.off + oy * Ws + ox);
+            const int oy = ty / S, ox = tx / S;
+            if (oy < Hs && ox < Ws) v = __ldg(sbase + e.off + oy * Ws + ox);
           }
         }
       }
@@ -105,8 +115,8 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
       if (k < K && n0 + n < Nn) {
         if (MODE == 0) v = __ldg(wslot + (size_t)(n0 + n) * K + k);
         else {
-          const int co = k / KHW, t = k - co * KHW;
-          v = __ldg(wslot + ((size_t)co * g.Ci + n0 + n) * KHW + t);
+          const KEnt e = ktab[k];
+          v = __ldg(wslot + ((size_t)(k / KHWc) * g.Ci + n0 + n) * KHW + e.ky * g.KW + e.kx);
         }
       }
       Bs[kk * (BN + 4) + n] = v;
@@ -134,15 +144,16 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
     const int mm = m0 + tm * 4 + i;
     if (mm >= mtot) continue;
     const int s2 = mm / PXm, p2 = mm - s2 * PXm;
-    float* o = dst + (size_t)(row_start + s2) * Nn * PXm + p2;
+    const int pf = MODE == 0 ? p2 : ((p2 / Wm) * S + cy) * Wf + (p2 % Wm) * S + cx;
+    float* o = dst + (size_t)(row_start + s2) * Nn * PXf + pf;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tn * TN + j;
       if (n >= Nn) continue;
       float v = acc[i][j];
       if (MODE == 0 && bias) v += bias[slot * sb + n];
-      if (accumulate) o[(size_t)n * PXm] += v;
-      else o[(size_t)n * PXm] = v;
+      if (accumulate) o[(size_t)n * PXf] += v;
+      else o[(size_t)n * PXf] = v;
     }
   }
 }
@@ -265,13 +276,14 @@ int launch_conv_gemm(const float* src, const float* w, const float* b, long sw, 
                      const es_group* grp, int n_groups, int total_rows, float* dst, int accumulate, cudaStream_t st) {
   const int KHW = g->KH * g->KW;
   const int K = (MODE == 0 ? g->Ci : g->Co) * KHW, Nn = MODE == 0 ? g->Co : g->Ci;
-  const int PXm = MODE == 0 ? g->Ho * g->Wo : g->Hi * g->Wi;
+  const int S = MODE == 0 ? 1 : g->stride;
+  const int PXm = MODE == 0 ? g->Ho * g->Wo : ceil_div(g->Hi, S) * ceil_div(g->Wi, S);   // largest parity class
   const long tiles = ceil_div_l((long)total_rows * PXm, kCM) + n_groups;
   if (tiles >= 2147483647L) { set_error("conv gemm: too many tiles"); return ES_ERR_INVALID; }
   const int BN = Nn > 32 ? 64 : (Nn > 16 ? 32 : 16);
   const size_t smem = (2 * (size_t)((K + 1) & ~1) + kCK * (kCM + 4) + kCK * (BN + 4)) * sizeof(float);
   if (smem > 200 * 1024) { set_error("conv gemm: reduction table does not fit in shared memory"); return ES_ERR_INVALID; }
-  const dim3 grid((unsigned)tiles, ceil_div(Nn, BN));
+  const dim3 grid((unsigned)tiles, ceil_div(Nn, BN), S * S);
 #define ES_LAUNCH_CG(BNV)                                                                                              \
   {                                                                                                                    \
     if (smem > 48 * 1024) cudaFuncSetAttribute(conv_gemm_kernel<MODE, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \

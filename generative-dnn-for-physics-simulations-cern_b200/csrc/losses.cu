@@ -185,6 +185,17 @@ gen_loss_grads_kernel(const float* __restrict__ img, int HW, const float* __rest
   }
 }
 
+// gradient of the coordinate-regression loss alone (it needs nothing but the regressor's own output and the global batch
+// size), so the auxiliary regressor's backward can start before the discriminator passes of the generator step finish
+__global__ void aux_loss_grad_kernel(const float* __restrict__ coords, const float* __restrict__ pos,
+                                     const es_group* __restrict__ grp, int E, int total_rows, float scale,
+                                     float* __restrict__ d_coords) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_rows * 2) return;
+  const int g = find_group(grp, E, i >> 1);
+  d_coords[i] = g < 0 ? 0.f : scale * tanhf(coords[i] - pos[i]);
+}
+
 __global__ void expm1_scatter_kernel(const float* __restrict__ img, const int32_t* __restrict__ perm, int HW,
                                      double* __restrict__ out64, float* __restrict__ out32) {
   const int r = blockIdx.x;
@@ -294,6 +305,15 @@ extern "C" int es_gen_loss_grads(const float* img, int HW, const float* lat1, co
   gen_loss_grads_kernel<<<ceil_div(total_rows, 8), 256, 0, as_stream(stream)>>>(
       img, HW, lat1, lat2, z1, z2, intensity, coords, pos, s, divv, grp, E, total_rows, sums, B_global, di_strength,
       in_strength, aux_strength, d_score1, d_lat1, d_lat2, d_coords, d_img, losses);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_aux_loss_grad(const float* coords, const float* pos, const es_group* grp, int E, int total_rows,
+                                int B_global, float aux_strength, float* d_coords, void* stream) {
+  ES_REQUIRE(coords && pos && grp && d_coords && E >= 1 && E <= kMaxGroups && total_rows > 0 && B_global > 0, "bad arguments");
+  aux_loss_grad_kernel<<<ceil_div(total_rows * 2, 256), 256, 0, as_stream(stream)>>>(
+      coords, pos, grp, E, total_rows, aux_strength * 0.5f / (float)B_global, d_coords);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }

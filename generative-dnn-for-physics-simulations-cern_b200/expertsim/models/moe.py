@@ -254,6 +254,22 @@ class MoEWrapper(nn.Module):
             img1.copy_(noise["img1_sorted"].to(dev).reshape(B, HW))
             img2.copy_(noise["img2_sorted"].to(dev).reshape(B, HW))
 
+        # ---- auxiliary regressor (moe.py:557-559): forward AND backward need nothing but G(z1) — the gradient of the
+        # regression loss depends only on the regressor's own output — so the whole chain runs on a side stream under the
+        # discriminator step and the D' passes of the generator step; it joins before the generator backward.
+        gcfg, stren_a = cfgm.generator, float(cfgm.aux_reg.strength)
+        ev_g = main.record_event()
+        with torch.cuda.stream(s2):
+            s2.wait_event(ev_g)
+            coords, sv_a = aux.forward(img1, gh, B, self.training, drop.get("a"), dp=dp)
+            ev_ax = s2.record_event()
+            d_coords = torch.empty(B, 2, device=dev)
+            L.call("es_aux_loss_grad", coords, pos_s, gh, E, B, Bg, stren_a, d_coords)
+            d_img1_aux = torch.zeros(B, HW, device=dev)
+            a_a.G.zero_()
+            aux.backward(sv_a, d_coords, d_img1_aux, accumulate=False)
+            ev_ba = s2.record_event()
+
         # ---- discriminator step (moe.py:506-527)
         main.wait_event(ev_a)
         sn_b = disc.spectral(gh, self.training)
@@ -282,10 +298,6 @@ class MoEWrapper(nn.Module):
             sn_d = disc.spectral(gh, self.training)
             _, lat2, sv2 = disc.forward(img2, cond_s, gh, B, sn_d)
             ev_f2 = s1.record_event()
-        with torch.cuda.stream(s2):
-            s2.wait_event(ev_c)
-            coords, sv_a = aux.forward(img1, gh, B, self.training, drop.get("a"), dp=dp)
-            ev_ax = s2.record_event()
         score1, lat1, sv1 = disc.forward(img1, cond_s, gh, B, sn_c)
         main.wait_event(ev_f2)
         main.wait_event(ev_ax)
@@ -294,26 +306,19 @@ class MoEWrapper(nn.Module):
         L.call("es_gen_loss_reduce", img1, HW, lat1, lat2, z1, z2, std_s, int_s, coords, pos_s, score1, gh, E, B,
                s_out, div_out, sums)
         self._allreduce(sums)
-        d_score1, d_coords = torch.zeros(B, device=dev), torch.zeros(B, 2, device=dev)
+        d_score1, d_coords2 = torch.zeros(B, device=dev), torch.zeros(B, 2, device=dev)   # d_coords2: same values as d_coords
         d_lat1, d_lat2 = torch.zeros(B, 64, device=dev), torch.zeros(B, 64, device=dev)
         d_img1, d_img2 = torch.zeros(B, HW, device=dev), torch.zeros(B, HW, device=dev)
-        d_img1_aux = torch.zeros(B, HW, device=dev)
         d_score2 = torch.zeros(B, device=dev)
         losses = torch.zeros(E, 6, device=dev)
-        gcfg, stren_a = cfgm.generator, float(cfgm.aux_reg.strength)
         L.call("es_gen_loss_grads", img1, HW, lat1, lat2, z1, z2, std_s, int_s, coords, pos_s, s_out, div_out, gh, E, B,
-               sums, Bg, float(gcfg.di_strength), float(gcfg.in_strength), stren_a, d_score1, d_lat1, d_lat2, d_coords,
+               sums, Bg, float(gcfg.di_strength), float(gcfg.in_strength), stren_a, d_score1, d_lat1, d_lat2, d_coords2,
                d_img1, losses)
         ev_l = main.record_event()
         with torch.cuda.stream(s1):
             s1.wait_event(ev_l)
             disc.backward(sv2, sn_d, d_score2, d_lat2, want_w=False, d_img=d_img2, accumulate=False)
             ev_b2 = s1.record_event()
-        with torch.cuda.stream(s2):
-            s2.wait_event(ev_l)
-            a_a.G.zero_()
-            aux.backward(sv_a, d_coords, d_img1_aux, accumulate=False)
-            ev_ba = s2.record_event()
         disc.backward(sv1, sn_c, d_score1, d_lat1, want_w=False, d_img=d_img1, accumulate=True)
         main.wait_event(ev_b2)
         main.wait_event(ev_ba)

@@ -130,6 +130,11 @@ int es_gen_loss_grads(const float* img, int HW, const float* lat1, const float* 
                       float di_strength, float in_strength, float aux_strength,
                       float* d_score1, float* d_lat1, float* d_lat2, float* d_coords, float* d_img,
                       float* losses, void* stream);
+/* d_coords[r][j] = aux_strength * tanh(coords - pos) / (2 B_global) for rows of active groups, 0 elsewhere: the
+ * regression-loss gradient of es_gen_loss_grads on its own (proton/aux_reg.py:42-45 scaled as moe.py:559-562), so that the
+ * auxiliary regressor's backward does not have to wait for the discriminator passes of the generator step. */
+int es_aux_loss_grad(const float* coords, const float* pos, const es_group* grp, int E, int total_rows, int B_global,
+                     float aux_strength, float* d_coords, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2  generator: grouped (per-expert) bf16 tcgen05 GEMM / implicit GEMM
