@@ -371,24 +371,69 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
       rs[k] = stats[((size_t)r * groups + gi) * 2 + 1];
     }
     const __nv_bfloat16* dyr = dy_up + (size_t)r * Hu * Wu * C;
-    float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint4* d4 = reinterpret_cast<const uint4*>(dyr);
+    float a1[8], a2[8];
     float ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float da[8];
-    for (int pix = p0; pix < P; pix += pstep) {
-      if (FAN) load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
-      else unpack8(__ldg(reinterpret_cast<const uint4*>(dyr) + (size_t)pix * c4 + cu), da);
-      unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
+    // The loop is latency-bound unless several 16-byte loads per thread are in flight: U pixels are fetched before any
+    // is consumed (measured: 2.2 TB/s with one pixel in flight).  FAN: a source pixel sums its <= 2 x 2 fan-out pixels.
+    constexpr int U = FAN ? 2 : 4;
+    constexpr int NQ = FAN ? 4 : 1;
+    uint4 qx[U], qd[U][NQ];
+    int nq[U];
+    auto fetch = [&](int pix0) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float xh = (f[k] - mu[k]) * rs[k];
-        const float yv = xh * gk[k] + bk[k];
-        const float d = da[k] * (yv > 0.f ? 1.f : kLReLU);
-        ag[k] += d * xh;
-        ab[k] += d;
-        a1[k] += d * gk[k];
-        a2[k] += d * gk[k] * xh;
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * pstep;
+        nq[u] = 0;
+        if (pix < P) {
+          qx[u] = __ldg(x4 + (size_t)pix * c4 + cu);
+          if (FAN) {
+            const int sy = pix / Ws, sx = pix - sy * Ws;
+            const int y0 = ylo[sy], ny = yhi[sy] - y0, x0 = xlo[sx], nx = xhi[sx] - x0;
+            nq[u] = ny * nx;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j)
+              if (j < ny * nx) qd[u][j] = __ldg(d4 + ((size_t)(y0 + j / nx) * Wu + x0 + j % nx) * c4 + cu);
+          } else {
+            qd[u][0] = __ldg(d4 + (size_t)pix * c4 + cu);
+          }
+        }
+      }
+    };
+    auto grad_of = [&](int u, float* da) {
+      unpack8(qd[u][0], da);
+      if (FAN) {
+        float t[8];
+#pragma unroll
+        for (int j = 1; j < NQ; ++j)
+          if (j < nq[u]) {
+            unpack8(qd[u][j], t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) da[k] += t[k];
+          }
+      }
+    };
+    float da[8];
+    for (int pix0 = p0; pix0 < P; pix0 += U * pstep) {
+      fetch(pix0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (pix0 + u * pstep >= P) continue;
+        grad_of(u, da);
+        unpack8(qx[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (f[k] - mu[k]) * rs[k];
+          const float yv = xh * gk[k] + bk[k];
+          const float d = da[k] * (yv > 0.f ? 1.f : kLReLU);
+          ag[k] += d * xh;
+          ab[k] += d;
+        }
       }
     }
+    // gamma is constant per channel: sum(d * gamma) = gamma * sum(d)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a1[k] = gk[k] * ab[k]; a2[k] = gk[k] * ag[k]; }
 #pragma unroll
     for (int k = 0; k < 8; ++k) { atomicAdd(&s_a[c8 + k], a1[k]); atomicAdd(&s_b[c8 + k], a2[k]); }
     // per-channel affine gradients: combined per CTA in shared memory, then ONE global atomic per channel per CTA
@@ -410,20 +455,25 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 #pragma unroll
     for (int k = 0; k < 8; ++k) { m1[k] = s_g1[(c8 + k) / cpg]; m2[k] = s_g2[(c8 + k) / cpg]; }
     uint4* dx4 = reinterpret_cast<uint4*>(out + (size_t)r * P * C);
-    for (int pix = p0; pix < P; pix += pstep) {
-      if (FAN) load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
-      else unpack8(__ldg(reinterpret_cast<const uint4*>(dyr) + (size_t)pix * c4 + cu), da);
-      unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
-      float o[8];
+    for (int pix0 = p0; pix0 < P; pix0 += U * pstep) {
+      fetch(pix0);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float xh = (f[k] - mu[k]) * rs[k];
-        const float yv = xh * gk[k] + bk[k];
-        const float d = da[k] * (yv > 0.f ? 1.f : kLReLU) * gk[k];
-        o[k] = rs[k] * (d - m1[k] - xh * m2[k]);
-        al[k] += o[k];
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * pstep;
+        if (pix >= P) continue;
+        grad_of(u, da);
+        unpack8(qx[u], f);
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (f[k] - mu[k]) * rs[k];
+          const float yv = xh * gk[k] + bk[k];
+          const float d = da[k] * (yv > 0.f ? 1.f : kLReLU) * gk[k];
+          o[k] = rs[k] * (d - m1[k] - xh * m2[k]);
+          al[k] += o[k];
+        }
+        dx4[(size_t)pix * c4 + cu] = pack8(o);
       }
-      dx4[(size_t)pix * c4 + cu] = pack8(o);
     }
     if (dbias) {
       __syncthreads();                 // s_dg is free again: reuse it for the conv-bias gradient
@@ -803,12 +853,34 @@ extern "C" int es_ln_affine_bwd(const void* dy_up, int Hs, int Ws, int Hu, int W
   return ES_OK;
 }
 
+namespace es {
+int gn_cluster_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C, int groups,
+                   const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream);
+int gn_cluster_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, const void* x, const float* stats,
+                   const float* gamma, const float* beta, long slot_stride, int C, int groups, const es_group* grp,
+                   int n_groups, int total_rows, void* dx, float* dgamma, float* dbeta, float* dbias, void* stream);
+// ES_GN_LEGACY=1 selects the one-CTA-per-sample kernel (kept for A/B measurements)
+static bool gn_legacy() {
+  static const bool v = [] { const char* e = getenv("ES_GN_LEGACY"); return e && e[0] == '1'; }();
+  return v;
+}
+// ES_GN_CLUSTER_BWD=1 selects the cluster kernel for the backward too (A/B measurements: it loses to the batched loads)
+static bool gn_cluster_backward() {
+  static const bool v = [] { const char* e = getenv("ES_GN_CLUSTER_BWD"); return e && e[0] == '1'; }();
+  return v;
+}
+}  // namespace es
+
 extern "C" int es_gn_lrelu_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C,
                                int groups, const es_group* grp, int n_groups, int total_rows, void* y, float* stats,
                                void* stream) {
   ES_REQUIRE(x && gamma && beta && grp && y && stats, "null pointer");
   ES_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && groups <= 64 && C % groups == 0, "bad channels/groups");
   ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups && P > 0, "bad sizes");
+  if (!gn_legacy()) {   // cluster kernel (gn_cluster.cu): the sample's slab stays in shared memory; 1 = does not fit
+    const int rc = gn_cluster_fwd(x, gamma, beta, slot_stride, P, C, groups, grp, n_groups, total_rows, y, stats, stream);
+    if (rc != 1) return rc;
+  }
   gn_lrelu_kernel<false, false><<<total_rows, 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, nullptr, P, 1, P, 1, gamma, beta, slot_stride, C, groups, grp, n_groups,
       (__nv_bfloat16*)y, stats, nullptr, nullptr, nullptr);
@@ -824,6 +896,12 @@ extern "C" int es_gn_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu
   ES_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && groups <= 64 && C % groups == 0, "bad channels/groups");
   ES_REQUIRE(Hs <= 64 && Ws <= 64 && Hu <= 64 && Wu <= 64 && Hu >= Hs && Wu >= Ws, "bad geometry");
   ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups, "bad sizes");
+  ES_REQUIRE(Hu <= 2 * Hs && Wu <= 2 * Ws, "fan-in of more than 2 per axis");
+  if (gn_cluster_backward()) {   // measured slower than the batched-load kernel below (r01 bench_gn): opt-in only
+    const int rc = gn_cluster_bwd(dy_up, Hs, Ws, Hu, Wu, x, stats, gamma, beta, slot_stride, C, groups, grp, n_groups,
+                                  total_rows, dx, dgamma, dbeta, dbias_conv, stream);
+    if (rc != 1) return rc;
+  }
   if (Hu == Hs && Wu == Ws)
     gn_lrelu_kernel<true, false><<<total_rows, 256, 0, as_stream(stream)>>>(
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, gamma, beta, slot_stride, C, groups, grp,

@@ -111,19 +111,55 @@ class FoldedConv:
             g.o_my, g.o_oy, g.o_mx, g.o_ox, g.Ho_full, g.Wo_full = 1, 0, 1, 0, Hs, Ws
             g.alg_flops_per_row = 2.0 * self.Ho * self.Wo * N * KH * KW * C
             self.g_dgrad, self.table_all = g, tab
+            self.dg_grid = (Hs, Ws)
+        # y-only folding (35 -> 56 rows = 5 -> 8): the data gradient is folded along y too.  Source row s = per_s*j + cls
+        # collects the up-rows u with floor(u*Hs/Hu) = cls of every period; up-row u meets dy rows u + pad - ky, so the
+        # (u, ky) pairs with the same dy-row offset are pre-summed (5 or 4 distinct dy rows instead of 2 x 4 or 1 x 4 —
+        # 1.39x fewer MACs) and the result lands on the [Hs, Wu] grid: y at source resolution, x still upsampled (its
+        # fan-in stays in the norm backward).  One table-conv per source-row class.
+        self.dgrad_classes = []
+        if not self.has_dgrad and fold[0] and not fold[1] and Hu != Hs:
+            from math import gcd
+            per_o, per_s = Hu // gcd(Hu, Hs), Hs // gcd(Hu, Hs)
+            for cls in range(per_s):
+                us = [u for u in range(per_o) if u * Hs // Hu == cls]
+                offs = {}
+                for u in us:
+                    for ky in range(KH):
+                        offs.setdefault(u + pad - ky, []).append(ky)
+                taps = [(o, pad - kx, sum(1 << (ky * KW + kx) for ky in kys)) for o, kys in sorted(offs.items()) for kx in range(KW)]
+                assert len(taps) <= 32 and (len(taps) * N) % 128 == 0
+                Hp = (Hs - cls + per_s - 1) // per_s
+                g, tab = L.ESTapGeom(), L.ESFoldTable()
+                g.Hs, g.Ws, g.C, g.Hu, g.Wu, g.Ho, g.Wo, g.my, g.mx = self.Ho, self.Wo, N, self.Ho, self.Wo, Hp, Wu, per_o, 1
+                for t, (dy, dx, mask) in enumerate(taps):
+                    g.tap_dy[t], g.tap_dx[t], g.tap_koff[t] = dy, dx, t * N
+                    tab.mask[t] = mask
+                g.n_taps = tab.n_taps = len(taps)
+                g.KK, g.N = len(taps) * N, C
+                g.o_my, g.o_oy, g.o_mx, g.o_ox, g.Ho_full, g.Wo_full = per_s, cls, 1, 0, Hs, Wu
+                n_up = sum(1 for j in range(Hp) for u in us if per_o * j + u < Hu)
+                g.alg_flops_per_row = 2.0 * n_up * Wu * N * KH * KW * C
+                self.dgrad_classes.append(dict(cls=cls, taps=taps, table=tab, g=g))
+            self.has_dgrad = True
+            self.dg_grid = (Hs, Wu)
 
     def alloc(self, E, dev):
         for c in self.classes:
             T = len(c["taps"])
             c["w_f"] = torch.empty(E, self.N, T * self.C, dtype=BF, device=dev)
             c["dw_f"] = torch.empty(E, self.N, T * self.C, device=dev)
-        if self.has_dgrad:
+        for c in self.dgrad_classes:
+            c["w_d"] = torch.empty(E, self.C, len(c["taps"]) * self.N, dtype=BF, device=dev)
+        if self.has_dgrad and not self.dgrad_classes:
             self.w_d = torch.empty(E, self.C, self.table_all.n_taps * self.N, dtype=BF, device=dev)
 
     def fold(self, w_addr, slot_stride, E):
         for c in self.classes:
             L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, c["table"], c["w_f"], None)
-        if self.has_dgrad:
+        for c in self.dgrad_classes:
+            L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, c["table"], None, c["w_d"])
+        if self.has_dgrad and not self.dgrad_classes:
             L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, self.table_all, None, self.w_d)
 
     def forward(self, x, bias_addr, bias_stride, y, grp, E, R):
@@ -140,8 +176,12 @@ class FoldedConv:
             L.call("es_unfold_up2_wgrad", c["dw_f"], E, self.N, self.C, self.KH, self.KW, c["table"], dw_addr, slot_stride)
 
     def dgrad(self, dy, dx, grp, E, R):
-        """dy [R, Ho*Wo, N] -> dx [R, Hs*Ws, C] on the LOW-resolution grid (the upsample's backward is folded in)."""
-        L.call("es_igemm_taps_fwd", dy, self.w_d, None, 0, dx, self.g_dgrad, grp, E, R)
+        """dy [R, Ho*Wo, N] -> dx [R, dg_grid, C]: on the LOW-resolution grid for exact x2 folding (the upsample's backward
+        is folded in), on the [Hs, Wu] grid for y-only folding."""
+        for c in self.dgrad_classes:
+            L.call("es_igemm_taps_fwd", dy, c["w_d"], None, 0, dx, c["g"], grp, E, R)
+        if not self.dgrad_classes:
+            L.call("es_igemm_taps_fwd", dy, self.w_d, None, 0, dx, self.g_dgrad, grp, E, R)
 
 
 def Up2Conv(Hs, Ws, C, KH, KW, pad, N):
@@ -258,10 +298,11 @@ class GenEngineProton:
                 u = self.up2[name]
                 u.wgrad(s[f"a{i + 2}"], dy, a.gaddr(name + ".weight"), a.n, grp, E, R)
                 if u.has_dgrad:
-                    # folded x2 upsample: the data gradient comes out on the LOW-resolution grid (no fan-in left for the norm backward)
-                    da = empty(R, Hs * Ws, C, dtype=BF)
+                    # folded upsample: the data gradient comes out on the folded grid (x2: low resolution, no fan-in left for
+                    # the norm backward; y-only: source rows x upsampled columns)
+                    da = empty(R, u.dg_grid[0] * u.dg_grid[1], C, dtype=BF)
                     u.dgrad(dy, da, grp, E, R)
-                    up = (Hs, Ws)
+                    up = u.dg_grid
                     continue
             else:
                 # weight gradient (packed fp32, unpacked below)

@@ -380,7 +380,8 @@ def nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
 
 
-@pytest.mark.parametrize("P,C,groups_n,Hs,Ws,Hu,Wu", [(665, 256, 32, 35, 19, 56, 30), (1595, 128, 32, 55, 29, 55, 29), (1595, 64, 32, 55, 29, 55, 29)])
+@pytest.mark.parametrize("P,C,groups_n,Hs,Ws,Hu,Wu", [(665, 256, 32, 35, 19, 56, 30), (665, 256, 32, 35, 19, 35, 30), (1595, 128, 32, 55, 29, 55, 29),
+                                                    (1595, 64, 32, 55, 29, 55, 29)])
 def test_gn_lrelu_fwd_bwd(P, C, groups_n, Hs, Ws, Hu, Wu):
     counts, slots = [2, 0, 3], [0, 1, 2]
     grp, R = groups(counts, slots)
@@ -833,22 +834,27 @@ def test_y_folded_conv2_fwd_wgrad():
     w = torch.randn(E, N, C, KH, KW, generator=g) / math.sqrt(KH * KW * C)
     bias = torch.randn(E, N, generator=g) * 0.1
     f = FoldedConv(Hs, Ws, C, Hu, Wu, KH, KW, pad, N, (True, False))
-    assert len(f.classes) == 8 and abs(f.executed_ratio - 0.718) < 1e-3 and not f.has_dgrad
+    assert len(f.classes) == 8 and abs(f.executed_ratio - 0.718) < 1e-3
+    assert f.has_dgrad and len(f.dgrad_classes) == 5 and f.dg_grid == (Hs, Wu)
     f.alloc(E, DEV)
     f.fold(cuda(w), N * C * KH * KW, E)
     y = torch.zeros(R, f.Ho * f.Wo, N, dtype=BF, device=DEV)
     f.forward(cuda(x, BF), cuda(bias), N, y, grp, E, R)
     dy = bf16_round(torch.randn(R, f.Ho, f.Wo, N, generator=g))
-    want_y, want_dw, off = [], torch.zeros_like(w), 0
+    want_y, want_dw, want_dx, off = [], torch.zeros_like(w), [], 0
     for c, s in zip(counts, slots):
         if c == 0:
             continue
         xi = x[off:off + c].permute(0, 3, 1, 2)
         wi = w[s].clone().requires_grad_(True)
-        yi = F.conv2d(F.interpolate(xi, size=(Hu, Wu), mode="nearest"), wi, bias[s], padding=pad)
+        # nearest upsampling is separable: x first (the grid the folded data gradient lives on), then y
+        xx = F.interpolate(xi, size=(Hs, Wu), mode="nearest").requires_grad_(True)
+        yi = F.conv2d(F.interpolate(xx, size=(Hu, Wu), mode="nearest"), wi, bias[s], padding=pad)
+        assert torch.equal(F.interpolate(xx, size=(Hu, Wu), mode="nearest"), F.interpolate(xi, size=(Hu, Wu), mode="nearest"))
         (yi * dy[off:off + c].permute(0, 3, 1, 2)).sum().backward()
         want_y.append(yi.detach().permute(0, 2, 3, 1))
         want_dw[s] = wi.grad
+        want_dx.append(xx.grad.permute(0, 2, 3, 1))
         off += c
     check("y-folded conv2 fwd", y.float().view(R, f.Ho, f.Wo, N), torch.cat(want_y), 8e-3, 4e-2)
     dw = torch.zeros(E, N, C, KH, KW, device=DEV)
@@ -856,3 +862,6 @@ def test_y_folded_conv2_fwd_wgrad():
     for s in (1, 2):
         check(f"y-folded conv2 wgrad slot {s}", dw[s], want_dw[s], 5e-3, 2e-2)
     assert float(dw[0].abs().max()) == 0.0
+    dx = torch.zeros(R, Hs * Wu, C, dtype=BF, device=DEV)
+    f.dgrad(cuda(dy, BF), dx, grp, E, R)
+    check("y-folded conv2 dgrad", dx.float().view(R, Hs, Wu, C), torch.cat(want_dx), 1e-2, 5e-2)
