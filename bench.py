@@ -225,6 +225,7 @@ def run_b200(args):
     moe.mark_weights_changed()
     if world > 1:
         moe.enable_data_parallel()
+        moe.overlap_grad_allreduce = False if args.no_overlap_allreduce else (args.overlap_mode == "eager" or "deferred")
     g_opt, d_opt, a_opt, r_opt = setup_optimizers(moe, cfg)
     moe.train()
 
@@ -408,6 +409,9 @@ def main():
     ap.add_argument("--infer-iters", type=int, default=5)
     ap.add_argument("--cpu-batch", type=int, default=128, help="batch of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap-mode", default="deferred", choices=["deferred", "eager"])
+    ap.add_argument("--no-overlap-allreduce", action="store_true",
+                    help="A/B switch: one whole-arena gradient all-reduce after backward instead of the overlapped layer buckets")
     ap.add_argument("--per-launch", action="store_true", help="print every timed GEMM launch of the last step to stderr")
     ap.add_argument("--ncu-step", type=int, default=0, help="1: cudaProfilerStart/Stop around one train step; 2: + one inference batch")
     args = ap.parse_args()

@@ -275,9 +275,19 @@ class GenEngineProton:
         s["img1"], s["img2"] = img1, img2
         return img1, img2, (s if keep else None)
 
-    def backward(self, s, dimg1, dimg2):
-        """Accumulates every generator parameter gradient into the arena's G tensor (reference layouts)."""
+    def backward(self, s, dimg1, dimg2, on_grads_ready=None):
+        """Accumulates every generator parameter gradient into the arena's G tensor (reference layouts).
+        ``on_grads_ready(lo, hi)`` is called as soon as the last kernel writing the arena columns [lo, hi) has been
+        enqueued (layer buckets from the output conv back to fc1; they tile [0, n) exactly) — the data-parallel step
+        starts their all-reduce there."""
         a, E, R, grp = self.a, self.a.E, s["R"], s["grp"]
+        hi_col = [a.n]
+
+        def ready(first_name):
+            if on_grads_ready is not None:
+                lo = a.off[first_name] if first_name else 0
+                on_grads_ready(lo, hi_col[0])
+                hi_col[0] = lo
         for t in self.dw_p.values():
             t.zero_()
         da = empty(R, 55 * 29, 64, dtype=BF)
@@ -297,6 +307,7 @@ class GenEngineProton:
             if name in self.up2:
                 u = self.up2[name]
                 u.wgrad(s[f"a{i + 2}"], dy, a.gaddr(name + ".weight"), a.n, grp, E, R)
+                ready(name + ".weight")
                 if u.has_dgrad:
                     # folded upsample: the data gradient comes out on the folded grid (x2: low resolution, no fan-in left for
                     # the norm backward; y-only: source rows x upsampled columns)
@@ -305,24 +316,27 @@ class GenEngineProton:
                     up = u.dg_grid
                     continue
             else:
-                # weight gradient (packed fp32, unpacked below)
+                # weight gradient (packed fp32), unpacked into the reference layout
                 L.call("es_igemm_wgrad", s[f"a{i + 2}"], dy, self.dw_p[name], g, grp, E, R)
+                L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
+                ready(name + ".weight")
             # data gradient on the (upsampled) input grid
             da = empty(R, Hu * Wu, C, dtype=BF)
             L.call("es_igemm_fwd", dy, self.w_dg[name], None, 0, da, conv_geom(g.Ho, g.Wo, N, g.Ho, g.Wo, KH, KW, KH - 1 - pad, C), grp, E, R)
             up = (Hu, Wu)
+        if on_grads_ready is not None:
+            on_grads_ready(None, None)      # marker: the persistent tensor-core kernels of this backward are all enqueued
         dy2 = empty(R, self.F2, dtype=BF)
         L.call("es_ln_lrelu_bwd", da, 18, 10, up[0], up[1], 512, s["y2"], s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R, dy2)
         L.call("es_ln_affine_bwd", da, 18, 10, up[0], up[1], 512, s["y2"], dy2, s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R,
                self.row_map, a.n, a.gaddr("fc2.1.weight"), a.gaddr("fc2.1.bias"), a.gaddr("fc2.0.bias"))
         L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), a.n, self.F2, 256, self.row_map, grp, E, R)
+        ready("fc2.0.weight")           # 88 % of the generator's gradient bytes
         dh1 = zeros(R, 256)
         L.call("es_dense_dgrad", dy2, self.w_fc2, dh1, self.F2, 256, grp, E, R)
         L.call("es_gen_fc1_bwd", dh1, s["x0"], s["lin1"], a.addr("fc1.1.weight"), a.addr("fc1.1.bias"), a.n, a.n, grp, E, R,
                a.gaddr("fc1.0.weight"), a.gaddr("fc1.0.bias"), a.gaddr("fc1.1.weight"), a.gaddr("fc1.1.bias"))
-        for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
-            if name not in self.up2:
-                L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
+        ready(None)
 
 
 # =====================================================================================================================
@@ -720,8 +734,16 @@ class GenEngineNeutron:
         s["img1"], s["img2"] = img1, img2
         return img1, img2, (s if keep else None)
 
-    def backward(self, s, dimg1, dimg2):
+    def backward(self, s, dimg1, dimg2, on_grads_ready=None):
+        """``on_grads_ready(lo, hi)``: see GenEngineProton.backward."""
         a, E, R, grp, ctx = self.a, self.a.E, s["R"], s["grp"], s["ctx"]
+        hi_col = [a.n]
+
+        def ready(first_name):
+            if on_grads_ready is not None:
+                lo = a.off[first_name] if first_name else 0
+                on_grads_ready(lo, hi_col[0])
+                hi_col[0] = lo
         for t in self.dw_p.values():
             t.zero_()
         da = empty(R, 45 * 45, 64, dtype=BF)
@@ -737,24 +759,28 @@ class GenEngineNeutron:
             if name in self.up2:
                 u = self.up2[name]
                 u.wgrad(s[f"a{i + 2}"], dy, a.gaddr(name + ".weight"), a.n, grp, E, R)
+                ready(name + ".weight")
                 da = empty(R, Hs * Ws, C, dtype=BF)
                 u.dgrad(dy, da, grp, E, R)
                 up = (Hs, Ws)
                 continue
             L.call("es_igemm_wgrad", s[f"a{i + 2}"], dy, self.dw_p[name], g, grp, E, R)
+            L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
+            ready(name + ".weight")
             da = empty(R, Hu * Wu, C, dtype=BF)
             L.call("es_igemm_fwd", dy, self.w_dg[name], None, 0, da, conv_geom(g.Ho, g.Wo, N, g.Ho, g.Wo, KH, KW, KH - 1 - pad, C), grp, E, R)
             up = (Hu, Wu)
+        if on_grads_ready is not None:
+            on_grads_ready(None, None)      # marker: the persistent tensor-core kernels of this backward are all enqueued
         dy2 = self._bn_bwd(da, up, s["y2"], s["bn2"], "fc2.1", self.SP, True, self.row_map, ctx)
         L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), a.n, self.F2, 256, self.row_map, grp, E, R)
+        ready("fc2.0.weight")           # 88 % of the generator's gradient bytes
         dh1 = zeros(R, 256)
         L.call("es_dense_dgrad", dy2, self.w_fc2, dh1, self.F2, 256, grp, E, R)
         dlin = self._bn_bwd(dh1.to(BF), (1, 1), s["lin1"], s["bn1"], "fc1.1", (1, 1, 256), False, None, ctx)
         L.call("es_gen_fc1_bwd", dlin.float(), s["x0"], None, None, None, a.n, a.n, grp, E, R, a.gaddr("fc1.0.weight"),
                a.gaddr("fc1.0.bias"), None, None)
-        for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
-            if name not in self.up2:
-                L.call("es_unpack_conv_wgrad", self.dw_p[name], E, N, C, KH, KW, a.gaddr(name + ".weight"), a.n)
+        ready(None)
 
 
 class AuxEngineNeutron:

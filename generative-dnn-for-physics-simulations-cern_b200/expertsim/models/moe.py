@@ -106,6 +106,8 @@ class MoEWrapper(nn.Module):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self._dp = (dist, process_group, dist.get_world_size(process_group))
+        from .._reduce import BucketedGradReducer
+        self._reducer = BucketedGradReducer(dist, process_group)      # gradient buckets ride a communicator of their own
         # identical replicas: broadcast rank 0's parameters and buffers
         for arena in self._arenas.values():
             dist.broadcast(arena.P, 0, group=process_group)
@@ -268,6 +270,7 @@ class MoEWrapper(nn.Module):
             d_img1_aux = torch.zeros(B, HW, device=dev)
             a_a.G.zero_()
             aux.backward(sv_a, d_coords, d_img1_aux, accumulate=False)
+            self._allreduce(a_a.G)          # (data parallel) rides the side stream too
             ev_ba = s2.record_event()
 
         # ---- discriminator step (moe.py:506-527)
@@ -324,10 +327,33 @@ class MoEWrapper(nn.Module):
         main.wait_event(ev_ba)
         L.call("es_axpy", 1.0, d_img1_aux, B * HW, d_img1)
         a_g.G.zero_()
-        gen.backward(sg, d_img1, d_img2)
+        if world > 1 and getattr(self, "overlap_grad_allreduce", "deferred"):
+            # layer buckets of the generator gradient are all-reduced on the communication stream as backward produces them
+            # ("deferred": the conv buckets wait until the persistent tensor-core kernels — one CTA per SM, static tile
+            # striding, so an SM lent to NCCL stretches the whole launch — are all enqueued, and then overlap the
+            # LayerNorm / fc2 / fc1 part of the backward; True: every bucket starts as soon as it is complete)
+            red = self._reducer
+            red.begin()
+            mode, pending, heavy = getattr(self, "overlap_grad_allreduce", "deferred"), [], [True]
+
+            def on_ready(lo, hi):
+                if lo is None:
+                    heavy[0] = False
+                    if pending:             # adjacent column ranges: one bucket
+                        red.reduce(a_g.G, min(b[0] for b in pending), max(b[1] for b in pending))
+                    pending.clear()
+                elif mode == "deferred" and heavy[0]:
+                    pending.append((lo, hi))
+                else:
+                    red.reduce(a_g.G, lo, hi)
+
+            gen.backward(sg, d_img1, d_img2, on_grads_ready=on_ready)
+            assert red.n_reduced == a_g.G.numel(), "gradient buckets must cover the arena exactly once"
+            red.join()
+        else:
+            gen.backward(sg, d_img1, d_img2)
+            self._allreduce(a_g.G)
         del sg, sv1, sv2, sv_a
-        self._allreduce(a_g.G)
-        self._allreduce(a_a.G)
         self._adam(a_g, self._lr(generator_optimizers, gcfg.lr_g), gh)
         self._adam(a_a, self._lr(aux_reg_optimizers, cfgm.aux_reg.lr_a), gh)
 

@@ -110,3 +110,49 @@ def _loader_case(rank, world):
 def test_sharded_loader_covers_the_dataset_once():
     out = run2(_loader_case)
     assert abs(out[0][0] - out[0][1]) < 1e-3
+
+
+def _bucket_case(rank, world):
+    """Layer buckets of a gradient arena, reduced back to front on the reducer's own group == one whole-arena all-reduce."""
+    from expertsim._reduce import BucketedGradReducer
+    red = BucketedGradReducer(dist)
+    g = torch.Generator().manual_seed(7 + rank)
+    G = torch.randn(3, 100, generator=g)
+    whole = G.clone()
+    dist.all_reduce(whole)
+    red.begin()
+    for lo, hi in ((60, 100), (20, 60), (20, 20), (0, 20)):
+        red.reduce(G, lo, hi)
+    red.join()
+    covered = red.n_reduced == G.numel() and red.buckets == [(60, 100), (20, 60), (0, 20)]
+    G2 = torch.randn(3, 100, generator=g)
+    whole2 = G2.clone()
+    dist.all_reduce(whole2)
+    red.begin()
+    red.reduce(G2, 0, 100)
+    return bool(torch.equal(G, whole)), covered, bool(torch.equal(G2, whole2))
+
+
+def test_bucketed_gradient_reducer_equals_whole_arena_allreduce():
+    out = run2(_bucket_case)
+    assert out[0] == (True, True, True) and out[1] == (True, True, True)
+
+
+def test_generator_backward_buckets_tile_the_arena():
+    """The hook points of both generator engines hand out column ranges that tile [0, n) exactly once, back to front
+    (host logic only: the ranges come from the arena's parameter offsets)."""
+    from expertsim._arena import Arena, spec_for
+    for arch, firsts in (("proton", ["conv_layers.8.weight", "conv_layers.5.weight", "conv_layers.1.weight", "fc2.0.weight", None]),
+                         ("neutron", ["conv_layers.9.weight", "conv_layers.5.weight", "conv_layers.0.weight", "fc2.0.weight", None])):
+        a = Arena(spec_for(arch, "generator"), 1, "cpu")
+        hi, got = a.n, []
+        for f in firsts:
+            lo = a.off[f] if f else 0
+            got.append((lo, hi))
+            hi = lo
+        assert got[-1][0] == 0 and all(x[0] == y[1] for x, y in zip(got, got[1:])) and sum(h - l for l, h in got) == a.n
+        # every parameter of the layers behind a bucket's first name lies inside that bucket or a later-produced one
+        order = list(a.off)
+        for (lo, hi2), f in zip(got, firsts):
+            if f:
+                assert all(a.off[n] >= lo for n in order[order.index(f):])
