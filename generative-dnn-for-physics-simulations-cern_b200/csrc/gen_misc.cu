@@ -174,6 +174,7 @@ ln_lrelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
   }
 }
 
+template <bool FAN>
 __global__ void __launch_bounds__(512)
 ln_lrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int Hu, int Wu, int C,
                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
@@ -185,51 +186,92 @@ ln_lrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int
   const int g = find_group(grp, n_groups, r);
   if (g < 0) return;
   const int slot = grp[g].slot;
-  if (threadIdx.x == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
-  __syncthreads();
+  if (FAN) {
+    if (threadIdx.x == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+    __syncthreads();
+  }
   const int F = Hs * Ws * C, n4 = F / 8, c4 = C / 8;
   const float mean = stats[2 * r], rstd = stats[2 * r + 1];
   const __nv_bfloat16* dyr = dy_up + (size_t)r * Hu * Wu * C;
+  const uint4* d4 = reinterpret_cast<const uint4*>(dyr);
   const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * F);
-  const float* ga = gamma + slot * slot_stride;
-  const float* be = beta + slot * slot_stride;
+  const float4* ga4 = reinterpret_cast<const float4*>(gamma + slot * slot_stride);
+  const float4* be4 = reinterpret_cast<const float4*>(beta + slot * slot_stride);
   float s1 = 0.f, s2 = 0.f;
-  float xv[8], da[8];
-  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-    const int pix = i / c4, c8 = (i % c4) * 8;
-    load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
-    unpack8(__ldg(x4 + i), xv);
+  // U elements of 8 features are fetched before any is consumed (one 16-byte load in flight per thread left this kernel
+  // latency-bound); with the x2 upsample folded into conv1's data gradient the fan-in path is only used by tests
+  constexpr int U = FAN ? 1 : 4;
+  uint4 qx[U], qd[U];
+  float4 qg[U][2], qb[U][2];
+  float da[8], xv[8];
+  auto fetch = [&](int i0) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xh = (xv[k] - mean) * rstd;
-      const float gk = ga[(size_t)i * 8 + k];
-      const float yv = xh * gk + be[(size_t)i * 8 + k];
-      const float d = da[k] * (yv > 0.f ? 1.f : kLReLU) * gk;
-      s1 += d;
-      s2 += d * xh;
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < n4) {
+        qx[u] = __ldg(x4 + i);
+        if (!FAN) qd[u] = __ldg(d4 + i);
+        qg[u][0] = __ldg(ga4 + 2 * i); qg[u][1] = __ldg(ga4 + 2 * i + 1);
+        qb[u][0] = __ldg(be4 + 2 * i); qb[u][1] = __ldg(be4 + 2 * i + 1);
+      }
+    }
+  };
+  auto grad_of = [&](int u, int i) {
+    if (FAN) {
+      const int pix = i / c4, c8 = (i % c4) * 8;
+      load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+    } else {
+      unpack8(qd[u], da);
+    }
+  };
+  for (int i0 = threadIdx.x; i0 < n4; i0 += U * blockDim.x) {
+    fetch(i0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i >= n4) continue;
+      grad_of(u, i);
+      unpack8(qx[u], xv);
+      const float gk8[8] = {qg[u][0].x, qg[u][0].y, qg[u][0].z, qg[u][0].w, qg[u][1].x, qg[u][1].y, qg[u][1].z, qg[u][1].w};
+      const float bk8[8] = {qb[u][0].x, qb[u][0].y, qb[u][0].z, qb[u][0].w, qb[u][1].x, qb[u][1].y, qb[u][1].z, qb[u][1].w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (xv[k] - mean) * rstd;
+        const float yv = xh * gk8[k] + bk8[k];
+        const float d = da[k] * (yv > 0.f ? 1.f : kLReLU) * gk8[k];
+        s1 += d;
+        s2 += d * xh;
+      }
     }
   }
   s1 = block_sum(s1, red) / (float)F;
   s2 = block_sum(s2, red) / (float)F;
   uint4* dx4 = reinterpret_cast<uint4*>(dx + (size_t)r * F);
-  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-    const int pix = i / c4, c8 = (i % c4) * 8;
-    load_da8(dyr, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
-    unpack8(__ldg(x4 + i), xv);
-    float o[8];
+  for (int i0 = threadIdx.x; i0 < n4; i0 += U * blockDim.x) {
+    fetch(i0);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xh = (xv[k] - mean) * rstd;
-      const float gk = ga[(size_t)i * 8 + k];
-      const float yv = xh * gk + be[(size_t)i * 8 + k];
-      const float d = da[k] * (yv > 0.f ? 1.f : kLReLU) * gk;
-      o[k] = rstd * (d - s1 - xh * s2);
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i >= n4) continue;
+      grad_of(u, i);
+      unpack8(qx[u], xv);
+      const float gk8[8] = {qg[u][0].x, qg[u][0].y, qg[u][0].z, qg[u][0].w, qg[u][1].x, qg[u][1].y, qg[u][1].z, qg[u][1].w};
+      const float bk8[8] = {qb[u][0].x, qb[u][0].y, qb[u][0].z, qb[u][0].w, qb[u][1].x, qb[u][1].y, qb[u][1].z, qb[u][1].w};
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (xv[k] - mean) * rstd;
+        const float yv = xh * gk8[k] + bk8[k];
+        const float d = da[k] * (yv > 0.f ? 1.f : kLReLU) * gk8[k];
+        o[k] = rstd * (d - s1 - xh * s2);
+      }
+      dx4[i] = pack8(o);
     }
-    dx4[i] = pack8(o);
   }
 }
 
 // column reductions for the big LayerNorm: each thread owns 8 consecutive features and walks the rows of one group
+template <bool FAN>
 __global__ void __launch_bounds__(128)
 ln_affine_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int Hu, int Wu, int C,
                      const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dx,
@@ -239,8 +281,10 @@ ln_affine_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, in
   __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
   const es_group G = grp[blockIdx.y];
   if (G.rows == 0) return;
-  if (threadIdx.x == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
-  __syncthreads();
+  if (FAN) {
+    if (threadIdx.x == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+    __syncthreads();
+  }
   const int F = Hs * Ws * C, n4 = F / 8, c4 = C / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -251,20 +295,36 @@ ln_affine_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, in
 #pragma unroll
   for (int k = 0; k < 8; ++k) { gk[k] = ga[k]; bk[k] = be[k]; ag[k] = ab[k] = al[k] = 0.f; }
   float xv[8], da[8], dv[8];
-  for (int rr = 0; rr < G.rows; ++rr) {
-    const int r = G.row_start + rr;
-    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
-    load_da8(dy_up + (size_t)r * Hu * Wu * C, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + (size_t)r * F) + i), xv);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dx + (size_t)r * F) + i), dv);
+  constexpr int U = FAN ? 1 : 4;      // rows in flight per thread (three 16-byte loads each)
+  for (int r0 = 0; r0 < G.rows; r0 += U) {
+    uint4 qx[U], qv[U], qd[U];
+    float mu[U], rs[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xh = (xv[k] - mean) * rstd;
-      const float yv = xh * gk[k] + bk[k];
-      const float d = da[k] * (yv > 0.f ? 1.f : kLReLU);
-      ag[k] += d * xh;
-      ab[k] += d;
-      al[k] += dv[k];
+    for (int u = 0; u < U; ++u) {
+      if (r0 + u < G.rows) {
+        const int r = G.row_start + r0 + u;
+        mu[u] = stats[2 * r]; rs[u] = stats[2 * r + 1];
+        qx[u] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)r * F) + i);
+        qv[u] = __ldg(reinterpret_cast<const uint4*>(dx + (size_t)r * F) + i);
+        if (!FAN) qd[u] = __ldg(reinterpret_cast<const uint4*>(dy_up + (size_t)r * F) + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (r0 + u >= G.rows) continue;
+      if (FAN) load_da8(dy_up + (size_t)(G.row_start + r0 + u) * Hu * Wu * C, Wu, C, c8, ylo, yhi, xlo, xhi, pix / Ws, pix % Ws, da);
+      else unpack8(qd[u], da);
+      unpack8(qx[u], xv);
+      unpack8(qv[u], dv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (xv[k] - mu[u]) * rs[u];
+        const float yv = xh * gk[k] + bk[k];
+        const float d = da[k] * (yv > 0.f ? 1.f : kLReLU);
+        ag[k] += d * xh;
+        ab[k] += d;
+        al[k] += dv[k];
+      }
     }
   }
 #pragma unroll
@@ -630,6 +690,23 @@ __global__ void pack_dense_kernel(const float* __restrict__ w, long slot_stride,
   }
 }
 
+// 8 consecutive k per thread: two 16-byte loads, one 16-byte store (the scalar kernel ran at 1.5 TB/s)
+__global__ void __launch_bounds__(256)
+pack_dense_vec8_kernel(const float* __restrict__ w, long slot_stride, int N, int K8, const int* __restrict__ row_map,
+                       __nv_bfloat16* __restrict__ wp) {
+  const int slot = blockIdx.y;
+  const long total8 = (long)N * K8;
+  uint4* dst = reinterpret_cast<uint4*>(wp + (size_t)slot * total8 * 8);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total8; i += (long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K8), k8 = (int)(i - (long)n * K8);
+    const int nr = row_map ? row_map[n] : n;
+    const float4* src = reinterpret_cast<const float4*>(w + slot * slot_stride + ((long)nr * K8 + k8) * 8);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    dst[i] = pack8(f);
+  }
+}
+
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, int N, int C, int KH, int KW,
                                          float* __restrict__ dw, long slot_stride) {
   const int slot = blockIdx.y;
@@ -831,9 +908,15 @@ extern "C" int es_ln_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu
   ES_REQUIRE(dy_up && x && stats && gamma && beta && grp && dx, "null pointer");
   ES_REQUIRE(C % 8 == 0 && Hs <= 64 && Ws <= 64 && Hu <= 64 && Wu <= 64 && Hu >= Hs && Wu >= Ws, "bad geometry");
   ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups, "bad sizes");
-  ln_lrelu_bwd_kernel<<<total_rows, 512, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C,
-                                                                 (const __nv_bfloat16*)x, stats, gamma, beta,
-                                                                 slot_stride, grp, n_groups, (__nv_bfloat16*)dx);
+  ES_REQUIRE(slot_stride % 4 == 0 && (((uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "gamma/beta must be 16-byte aligned");
+  if (Hu == Hs && Wu == Ws)
+    ln_lrelu_bwd_kernel<false><<<total_rows, 512, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C,
+                                                                          (const __nv_bfloat16*)x, stats, gamma, beta,
+                                                                          slot_stride, grp, n_groups, (__nv_bfloat16*)dx);
+  else
+    ln_lrelu_bwd_kernel<true><<<total_rows, 512, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C,
+                                                                         (const __nv_bfloat16*)x, stats, gamma, beta,
+                                                                         slot_stride, grp, n_groups, (__nv_bfloat16*)dx);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
@@ -846,9 +929,14 @@ extern "C" int es_ln_affine_bwd(const void* dy_up, int Hs, int Ws, int Hu, int W
   ES_REQUIRE(C % 8 == 0 && Hs <= 64 && Ws <= 64 && Hu <= 64 && Wu <= 64, "bad geometry");
   ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups, "bad sizes");
   const int n4 = Hs * Ws * C / 8;
-  ln_affine_bwd_kernel<<<dim3(ceil_div(n4, 128), n_groups), 128, 0, as_stream(stream)>>>(
-      (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dx, stats, gamma,
-      beta, slot_stride, grp, row_map, out_slot_stride, dgamma, dbeta, dbias_lin);
+  if (Hu == Hs && Wu == Ws)
+    ln_affine_bwd_kernel<false><<<dim3(ceil_div(n4, 128), n_groups), 128, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dx, stats, gamma,
+        beta, slot_stride, grp, row_map, out_slot_stride, dgamma, dbeta, dbias_lin);
+  else
+    ln_affine_bwd_kernel<true><<<dim3(ceil_div(n4, 128), n_groups), 128, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dx, stats, gamma,
+        beta, slot_stride, grp, row_map, out_slot_stride, dgamma, dbeta, dbias_lin);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
@@ -955,6 +1043,12 @@ extern "C" int es_pack_dense_weight(const float* w, long slot_stride, int slots,
                                     void* w_packed, void* stream) {
   ES_REQUIRE(w && w_packed && slots >= 1 && N > 0 && K > 0, "bad arguments");
   const long total = (long)N * K;
+  if (K % 8 == 0 && slot_stride % 4 == 0 && (((uintptr_t)w | (uintptr_t)w_packed) & 15) == 0) {
+    pack_dense_vec8_kernel<<<dim3((unsigned)min(ceil_div_l(total / 8, 256), 148L * 16), slots), 256, 0, as_stream(stream)>>>(
+        w, slot_stride, N, K / 8, row_map, (__nv_bfloat16*)w_packed);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   pack_dense_kernel<<<dim3((unsigned)min(ceil_div_l(total, 256), 4096L), slots), 256, 0, as_stream(stream)>>>(
       w, slot_stride, N, K, row_map, (__nv_bfloat16*)w_packed);
   ES_LAUNCH_CHECK();

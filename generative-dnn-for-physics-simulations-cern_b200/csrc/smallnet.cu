@@ -674,6 +674,35 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// float4 variant (n, slot_stride multiples of 4, 16-byte aligned bases — the arenas guarantee it): 7 x 16-byte accesses per
+// thread and iteration instead of 7 x 4, which is what lets this 28 B/parameter stream approach the HBM rate
+__global__ void __launch_bounds__(256)
+adam_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v, long n4,
+                 long slot_stride4, float lr, float b1, float b2, float eps, const int32_t* __restrict__ step_count,
+                 const es_group* __restrict__ grp) {
+  const int slot = blockIdx.y;
+  if (grp && grp[slot].rows == 0) return;
+  const int t = step_count[slot];
+  const double bc1 = 1.0 - pow((double)b1, (double)t);
+  const float bc2s = (float)sqrt(1.0 - pow((double)b2, (double)t));
+  const float step = (float)((double)lr / bc1);
+  const long base = slot * slot_stride4;
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 gg = __ldg(g + base + i);
+    float4 mm = m[base + i], vv = v[base + i], pp = p[base + i];
+#define ES_ADAM1(c)                                         \
+    mm.c = mm.c + (gg.c - mm.c) * c1;                       \
+    vv.c = vv.c * b2 + gg.c * gg.c * c2;                    \
+    pp.c -= step * mm.c / (sqrtf(vv.c) / bc2s + eps);
+    ES_ADAM1(x) ES_ADAM1(y) ES_ADAM1(z) ES_ADAM1(w)
+#undef ES_ADAM1
+    m[base + i] = mm;
+    v[base + i] = vv;
+    p[base + i] = pp;
+  }
+}
+
 static inline unsigned blocks_for(long n) { return (unsigned)ceil_div_l(n, 256); }
 
 }  // namespace es
@@ -948,6 +977,13 @@ extern "C" int es_adam_step(float* p, const float* g, float* m, float* v, long n
   ES_REQUIRE(p && g && m && v && step_count && n > 0 && slots >= 1 && slots <= 1024, "bad arguments");
   adam_bump_kernel<<<1, 1024, 0, as_stream(stream)>>>(step_count, grp, slots);
   ES_LAUNCH_CHECK();
+  if (n % 4 == 0 && slot_stride % 4 == 0 && (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0) {
+    const unsigned bx4 = (unsigned)min(ceil_div_l(n / 4, 256 * 2), 148L * 8);
+    adam_vec4_kernel<<<dim3(bx4 < 1 ? 1 : bx4, slots), 256, 0, as_stream(stream)>>>(
+        (float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, slot_stride / 4, lr, beta1, beta2, eps, step_count, grp);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   const unsigned bx = (unsigned)min(ceil_div_l(n, 256 * 4), 148L * 8);
   adam_kernel<<<dim3(bx < 1 ? 1 : bx, slots), 256, 0, as_stream(stream)>>>(p, g, m, v, n, slot_stride, lr, beta1, beta2, eps,
                                                                          step_count, grp);
