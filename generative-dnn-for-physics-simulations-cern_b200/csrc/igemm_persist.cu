@@ -344,6 +344,276 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// STRIP variant for convolutions WITHOUT an upsample in front whose taps form rows (same dy, consecutive dx): conv3 forward
+// (3x3, 128 -> 64) and its data gradient (3x3, 64 -> 128), the layers where the gather is the bound — an im2col row is used
+// for only N = 64/128 MACs per element, so the 64 B/clk/SM that cp.async moves through L1TEX caps the kernel at ~50 % of the
+// tensor peak however the rest is tuned (r01: 288 / 403 TFLOP/s).
+// Here the M axis enumerates output pixels with a PADDED row pitch Wp = Wo + nx - 1, so the kx-shifted windows of one tap
+// row are ONE contiguous strip of 128 + nx - 1 source pixels: the strip is gathered once per (tap row, channel block) and
+// the nx taps are nx MMAs whose A descriptors start kx rows further down the same strip.  Row shifts of an arbitrary
+// number of 16-byte units are exact in the NO-SWIZZLE K-major canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO)) when
+// SBO = 8 x 16 B (rows fully linear, 16 B apart) and LBO = strip pitch between the eight 16-byte k-chunks of a row; B
+// (weights) stays a 128B-swizzled TMA box per tap.  Gather traffic per MAC drops by nx (3x for a 3x3), the price is
+// Wp/Wo - 1 (7 % at 29 columns) of masked output columns.
+constexpr int kSRows = 136;                      // strip rows kept per stage (>= 128 + 4 - 1)
+constexpr int kSLbo = (kSRows + 1) * 16;         // 2192 B between k-chunks: 16-byte skew keeps the 8 lanes of a row on different banks
+constexpr int kSStageA = 18432;                  // 8 * kSLbo = 17536, rounded up to 1 KB
+constexpr int kSMaxB = 384 * 128;                // nx * BN <= 384 rows of 128 B
+constexpr int kSStages = 3;
+constexpr size_t kSSmem = (size_t)kSStages * (kSStageA + kSMaxB) + 1024 + 2048;
+// RESIDENT weights: with the strip gather the weight stream became the larger operand (conv3: 147 KB of weights against
+// 100 KB of strips per 128-pixel tile, 64 B/clk/SM of L2->SM reads at the tensor rate of N = 64), but 147 KB is all there is
+// per expert — so when KK * N * 2 B fits beside the strip stages the whole matrix is loaded once per expert CHANGE (tiles are
+// visited in ascending order, so at most n_groups times per CTA) and only the strips move per tile.
+constexpr int kSResidentB = kSStages * kSMaxB;   // 144 KB: the room the per-stage weight tiles would take
+
+struct StripParams {
+  int resident;                                  // 1: the expert's whole weight matrix stays in shared memory across tiles
+  int n_strips, nx, dx0, Wp, Pp;                 // Pp = Ho * Wp
+  signed char sdy[8];
+  int skoff[8];                                  // weight column of the strip's first tap; tap i at skoff + i*C
+};
+
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(kGThreads, 1)
+igemm_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ StripParams sp,
+                   const __grid_constant__ CUtensorMap tmap_w) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN;
+  const int kStageB = sp.nx * BN * 128;
+  const bool resident = sp.resident != 0;
+  const int kStage = resident ? kSStageA : kSStageA + kStageB;       // resident: stages hold strips only
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t wbase = base + kSStages * kSStageA;                  // resident weights: [k-step][tap][BN rows x 128 B]
+  const uint32_t bar_base = base + kSStages * (kSStageA + kSMaxB);
+  const uint32_t wfull_bar = bar_base + 8u * 14, wempty_bar = bar_base + 8u * 15;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (8 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (10 + b); };
+  uint8_t* gen = smem_raw + (bar_base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * 12);
+  const uint32_t tmem_slot = bar_base + 8u * 12;
+  int* s_tiles = reinterpret_cast<int*>(gen + 128);
+  es_group* s_grp = reinterpret_cast<es_group*>(gen + 384);
+
+  const uint32_t nbuf = 2;                                       // BN <= 128: two accumulators always fit
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
+
+  if (tid < p.n_groups) {
+    const es_group gq = p.grp[tid];
+    s_grp[tid] = gq;
+    s_tiles[tid] = ceil_div(gq.rows * sp.Pp, kBM);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kSStages; ++s) {
+      mbar_init(full_bar(s), resident ? kGLoaders : kGLoaders + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    mbar_init(wfull_bar, 1);
+    mbar_init(wempty_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kGW && lane == 0) tma_prefetch_desc(&tmap_w);
+  if (warp == kGW + 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  int total_tiles = 0;
+  for (int i = 0; i < p.n_groups; ++i) total_tiles += s_tiles[i];
+  total_tiles *= p.n_tiles_n;
+  const int cblks = p.C / kBK;
+  const int nkb = sp.n_strips * cblks;                           // pipeline steps per tile
+  const int srows = kBM + sp.nx - 1;
+
+  if (warp < kGW) {
+    // ============================================================================= STRIP GATHER (256 threads, cp.async)
+    constexpr int RSTEP = kGLoaders / 8;                         // 32 rows per pass
+    constexpr int RPT = (kSRows + RSTEP - 1) / RSTEP;            // 5
+    const int chunk = tid & 7, rsub = tid >> 3;
+    uint32_t it = 0, signalled = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileInfo ti;
+      decode_tile(tile, p, s_tiles, s_grp, kBM, ti);
+      int r_base[RPT], r_oyx[RPT];                               // source pixel base of the sample (-1: no such row), oy<<8 | xv
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const int r = rsub + RSTEP * j;
+        const int v = ti.m0 + r;
+        const bool valid = r < srows && v < ti.rows * sp.Pp;
+        const int sample = valid ? v / sp.Pp : 0;
+        const int rem = valid ? v - sample * sp.Pp : 0;
+        const int oy = rem / sp.Wp;
+        r_oyx[j] = (oy << 8) | (rem - oy * sp.Wp);
+        r_base[j] = valid ? (ti.row_start + sample) * p.Hs * p.Ws : -1;
+      }
+      int cb = 0, st = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kSStages;
+        if (it >= kSStages) mbar_wait(empty_bar(s), ((it / kSStages) - 1) & 1, p.err_flag, 1);
+        const uint32_t sa = base + s * kStage;
+        const int c0 = cb * kBK + chunk * 8;
+        const int dy = sp.sdy[st];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const int r = rsub + RSTEP * j;
+          if (r < srows) {
+            const int sy = (r_oyx[j] >> 8) + dy, sx = (r_oyx[j] & 255) + sp.dx0;
+            const bool inb = r_base[j] >= 0 && sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws;
+            const __nv_bfloat16* src = p.a_src + (inb ? ((long)(r_base[j] + sy * p.Ws + sx) * p.C + c0) : 0L);
+            cp_async16_ca(sa + (uint32_t)chunk * kSLbo + (uint32_t)r * 16u, src, inb);
+          }
+        }
+        cp_async_commit();
+        if (++st == sp.n_strips) { st = 0; ++cb; }
+        if (it - signalled >= (uint32_t)kFLag) {
+          cp_async_wait<kFLag>();
+          fence_proxy_async();
+          mbar_arrive(full_bar(signalled % kSStages));
+          ++signalled;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    while (signalled < it) {
+      mbar_arrive(full_bar(signalled % kSStages));
+      ++signalled;
+    }
+  } else if (warp == kGW) {
+    // ============================================================================= TMA PRODUCER (nx weight boxes per step)
+    if (lane == 0) {
+      uint32_t it = 0, nload = 0;
+      int cur_slot = -1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileInfo ti;
+        decode_tile(tile, p, s_tiles, s_grp, kBM, ti);
+        const int wrow = ti.slot * p.Nout + ti.n0;
+        int cb = 0, st = 0;
+        if (resident) {
+          if (ti.slot == cur_slot) continue;
+          if (nload > 0) mbar_wait(wempty_bar, (nload - 1) & 1, p.err_flag, 6);   // every MMA on the old weights has completed
+          cur_slot = ti.slot;
+          ++nload;
+          mbar_arrive_expect_tx(wfull_bar, (uint32_t)(nkb * kStageB));
+          for (int kb = 0; kb < nkb; ++kb) {
+            for (int i = 0; i < sp.nx; ++i)
+              tma_load_2d(wbase + (kb * sp.nx + i) * BN * 128, &tmap_w, sp.skoff[st] + i * p.C + cb * kBK, wrow, wfull_bar);
+            if (++st == sp.n_strips) { st = 0; ++cb; }
+          }
+          continue;
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kSStages;
+          if (it >= kSStages) mbar_wait(empty_bar(s), ((it / kSStages) - 1) & 1, p.err_flag, 4);
+          mbar_arrive_expect_tx(full_bar(s), (uint32_t)kStageB);
+          for (int i = 0; i < sp.nx; ++i)
+            tma_load_2d(base + s * kStage + kSStageA + i * BN * 128, &tmap_w, sp.skoff[st] + i * p.C + cb * kBK, wrow, full_bar(s));
+          if (++st == sp.n_strips) { st = 0; ++cb; }
+        }
+      }
+    }
+  } else if (warp == kGW + 1) {
+    // ============================================================================= MMA ISSUER
+    const uint32_t idesc = make_idesc(BN, false, false);
+    uint32_t it = 0, tcount = 0, nload = 0;
+    int cur_slot = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1, use = tcount >> 1;
+      if (use >= 1) mbar_wait(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
+      bool last_of_slot = false;
+      if (resident) {
+        TileInfo ti, tn;
+        decode_tile(tile, p, s_tiles, s_grp, kBM, ti);
+        if (ti.slot != cur_slot) {
+          mbar_wait(wfull_bar, nload & 1, p.err_flag, 7);
+          cur_slot = ti.slot;
+          ++nload;
+        }
+        last_of_slot = tile + (int)gridDim.x < total_tiles && decode_tile(tile + gridDim.x, p, s_tiles, s_grp, kBM, tn) &&
+                       tn.slot != cur_slot;
+      }
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kSStages;
+        mbar_wait(full_bar(s), (it / kSStages) & 1, p.err_flag, 2);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + s * kStage;
+          const uint32_t sb = resident ? wbase + (uint32_t)(kb * sp.nx) * BN * 128 : sa + kSStageA;
+          for (int i = 0; i < sp.nx; ++i) {
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16(tacc, make_desc_nosw(sa + (uint32_t)i * 16u + (uint32_t)k * 2u * kSLbo, kSLbo, 128),
+                        make_desc(sb + i * BN * 128 + k * 32, 16, 1024), idesc, (kb | i | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+          if (kb == nkb - 1) {
+            umma_commit(tfull_bar(buf));
+            if (last_of_slot) umma_commit(wempty_bar);       // the weight buffer may be overwritten once these MMAs retire
+          }
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ============================================================================= EPILOGUE (masked padded columns)
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      TileInfo ti;
+      decode_tile(tile, p, s_tiles, s_grp, kBM, ti);
+      const uint32_t buf = tcount & 1, use = tcount >> 1;
+      mbar_wait(tfull_bar(buf), use & 1, p.err_flag, 3);
+      tc_fence_after();
+      const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
+      uint32_t r[32];
+      const uint32_t t_lane = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+      const int m = ti.m0 + q * 32 + lane;
+      bool ok = m < ti.rows * sp.Pp;
+      const int smp = ok ? m / sp.Pp : 0, rem = ok ? m - smp * sp.Pp : 0;
+      const int oa = rem / sp.Wp, ob = rem - oa * sp.Wp;
+      ok = ok && ob < p.Wo;
+      const long opix = (long)(ti.row_start + smp) * p.P_full + (oa * p.o_my + p.o_oy) * p.Wo_full + ob * p.o_mx + p.o_ox;
+      __nv_bfloat16* yrow = p.out + (opix * p.Nout + ti.n0);
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(t_lane + c, r);
+        if (ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) dst[qq] = pack8(f + 8 * qq);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));
+    }
+  }
+  __syncthreads();
+  if (warp == kGW + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Weight gradient of a convolution:  dw[slot][n][kk] += sum_pix dy[pix, n] * im2col(x)[pix, kk]   (kk = (tap, channel))
 // D tile = 128 kk (M) x N (<= 256); the reduction runs over the group's pixels in blocks of 64.  Both operands are
 // MN-major (rows = pixels): A rows are gathered 128-byte channel slices of x (line-coalesced cp.async, zero-filled for
@@ -661,6 +931,48 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the activations");
+  }
+
+  // Strip variant (see igemm_strip_kernel): no upsample, taps form rows of consecutive dx with consecutive weight columns,
+  // N <= 128.  ES_IGEMM_STRIP=0 disables it (A/B measurements).
+  {
+    static const bool strip_on = [] { const char* e = getenv("ES_IGEMM_STRIP"); return !(e && e[0] == '0'); }();
+    StripParams sp{};
+    bool okk = strip_on && p.Hu == p.Hs && p.Wu == p.Ws && p.my == 1 && p.mx == 1 && p.BN <= 128 && p.n_taps >= 2;
+    if (okk) {
+      int t = 0;
+      while (okk && t < p.n_taps) {
+        int n = 1;
+        while (t + n < p.n_taps && p.tdy[t + n] == p.tdy[t] && p.tdx[t + n] == p.tdx[t] + n && p.tkoff[t + n] == p.tkoff[t] + n * p.C) ++n;
+        if (sp.n_strips == 0) { sp.nx = n; sp.dx0 = p.tdx[t]; }
+        okk = sp.n_strips < 8 && n == sp.nx && p.tdx[t] == sp.dx0;
+        if (okk) { sp.sdy[sp.n_strips] = p.tdy[t]; sp.skoff[sp.n_strips] = p.tkoff[t]; ++sp.n_strips; }
+        t += n;
+      }
+      okk = okk && sp.nx >= 2 && sp.nx <= 4 && sp.nx * p.BN <= 384;
+    }
+    if (okk) {
+      sp.Wp = p.Wo + sp.nx - 1;
+      sp.Pp = p.Ho * sp.Wp;
+      okk = sp.Wp < 256 && (long)total_rows * sp.Pp < 2147483647L;
+      static const bool res_on = [] { const char* e = getenv("ES_IGEMM_STRIP_RESIDENT"); return e && e[0] == '1'; }();   // measured slower (conv3: 2.79 vs 2.54 ms): opt-in
+      sp.resident = res_on && p.n_tiles_n == 1 && (long)sp.n_strips * (p.C / kBK) * sp.nx * p.BN * 128 <= (long)kSResidentB;
+    }
+    if (okk) {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const long max_tiles = (ceil_div_l((long)total_rows * sp.Pp, (long)kBM) + n_groups) * p.n_tiles_n;
+      const int grid = (int)(max_tiles < sms ? max_tiles : sms);
+      static bool attr_set = false;
+      if (!attr_set) {
+        ES_CUDA(cudaFuncSetAttribute(igemm_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmem));
+        attr_set = true;
+      }
+      igemm_strip_kernel<<<grid, kGThreads, kSSmem, as_stream(stream)>>>(p, sp, tmap);
+      ES_LAUNCH_CHECK();
+      return ES_OK;
+    }
   }
 
   // Variant.  Measured on B200 (r01, per-launch CUDA events, batch 1024, E = 8; TFLOP/s for MT=1/cp.async, MT=2/cp.async,
