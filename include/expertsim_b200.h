@@ -437,6 +437,20 @@ int es_channel_sums(const float* img, int H, int W, int rows, int apply_expm1, d
 /* a, b: row-major [n, n_cols] fp64, every column sorted ascending; out[c] = mean_i |a[i,c] - b[i,c]| */
 int es_w1_sorted(const double* a, const double* b, int n, int n_cols, double* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * offline preprocessing: the producers of the `positions` and `std` inputs of the training step.
+ * ---------------------------------------------------------------------------------------------- */
+/* arg-max pixel of every image as (row, col) — np.unravel_index(np.argmax(img), img.shape), first maximum in row-major
+ * order (expertsim/train/utils.py:81-82; notebooks/calculate_and_analysis_of_max_coordinates.ipynb cell 6).
+ * img [rows][H*W] fp32; out_rowcol int32 [rows][2] and/or out_rowcol_f32 [rows][2] (the float targets the loader feeds). */
+int es_argmax_coords(const float* img, int rows, int H, int W, int32_t* out_rowcol, float* out_rowcol_f32, void* stream);
+/* per-condition-group pixel standard deviation (notebooks/calculating_diversity_for_data.ipynb cells 16-23):
+ * order[seg[g] .. seg[g+1]) lists the rows of group g (rows with identical conditioning vectors), group_of_row[r] = g.
+ * group_sums[g] (fp64, scratch + result) = sum over pixels of the population std (ddof 0) over the group's rows;
+ * out_std[r] = group_sums[group_of_row[r]] / max_g group_sums[g]. */
+int es_group_pixel_std(const float* img, int rows, int HW, const int32_t* order, const int32_t* seg, int n_groups,
+                       const int32_t* group_of_row, double* group_sums, float* out_std, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

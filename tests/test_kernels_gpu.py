@@ -865,3 +865,40 @@ def test_y_folded_conv2_fwd_wgrad():
     dx = torch.zeros(R, Hs * Wu, C, dtype=BF, device=DEV)
     f.dgrad(cuda(dy, BF), dx, grp, E, R)
     check("y-folded conv2 dgrad", dx.float().view(R, Hs, Wu, C), torch.cat(want_dx), 1e-2, 5e-2)
+
+
+# ----------------------------------------------------------------------------------------------------------- preprocessing
+def test_preprocess_kernels_match_golden_and_oracle():
+    """arg-max coordinates (bit-exact) and per-condition-group pixel std (1e-5) through the host layer."""
+    import os
+
+    import numpy as np
+
+    from expertsim.utils import preprocess as pp
+    from oracle import preprocess_oracle as po
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "preprocess_small.npz"))
+    data, cond = torch.from_numpy(gold["data"]), torch.from_numpy(gold["cond"])
+    pos = pp.max_coordinates(cuda(data))
+    assert torch.equal(pos.cpu().long(), torch.from_numpy(gold["positions"]))
+    assert torch.equal(pp.max_coordinates(cuda(data), as_float=True).cpu(), torch.from_numpy(gold["positions"]).float())
+    std = pp.condition_group_std(cuda(cond), cuda(data))
+    check("condition-group std (golden)", std, torch.from_numpy(gold["std"]), 1e-5)
+    # larger seeded case, both detector shapes, ragged groups (1 .. ~40 members), ties and an all-equal image
+    for H, W, seed in ((56, 30, 1), (44, 44, 2)):
+        g = G(seed)
+        n, ng = 3000, 211
+        rows = torch.randn(ng, 9, generator=g)
+        member = torch.randint(0, ng, (n,), generator=g)
+        c = rows[member]
+        img = torch.log1p((torch.rand(n, H, W, generator=g) < 0.03).float() * torch.ceil(torch.empty(n, H, W).exponential_(generator=g) * 20))
+        img[5] = 0.0
+        img[6, 3, 3] = img[6, 40, 20] = 9.0
+        want_pos = po.max_coordinates(img.numpy())
+        got_pos = pp.max_coordinates(cuda(img))
+        assert torch.equal(got_pos.cpu().long(), torch.from_numpy(want_pos)), "arg-max coordinates must be bit-exact"
+        want = po.condition_group_std(c.numpy(), img.numpy())
+        got, gid, sums = pp.condition_group_std(cuda(c), cuda(img), return_groups=True)
+        check(f"condition-group std {H}x{W}", got, torch.from_numpy(want), 1e-5)
+        assert int(gid.max()) + 1 == len(torch.unique(member)) and float(got.max()) == 1.0
+    with pytest.raises(RuntimeError):
+        pp.max_coordinates(data)      # host tensors are refused: no CPU fallback
