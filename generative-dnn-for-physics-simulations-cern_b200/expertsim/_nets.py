@@ -446,6 +446,20 @@ class DiscEngine:
                 L.call("es_spectral_norm_bwd", dsn[name], wsn, uu, vu, sig, O * I, E, O, I, a.gaddr(name + ".weight_orig"), n, grp, empty(E))
 
 
+def _on_side_stream(stream, keep, fn, *tensors):
+    """Run ``fn()`` (kernel launches that only PRODUCE parameter gradients) on ``stream`` behind the work enqueued so far on
+    the current stream; the tensors it reads are parked in ``keep`` until the caller has joined the stream (the caching
+    allocator would otherwise hand their memory to later allocations of the current stream)."""
+    if stream is None:
+        fn()
+        return
+    ev = torch.cuda.current_stream().record_event()
+    keep.extend(tensors)
+    with torch.cuda.stream(stream):
+        stream.wait_event(ev)
+        fn()
+
+
 # =====================================================================================================================
 # auxiliary regressor (proton): fp32 NCHW, residual feature extractor + MLP head
 # =====================================================================================================================
@@ -454,6 +468,7 @@ class AuxEngineProton:
 
     def __init__(self, arena: Arena):
         self.a = arena
+        self._wstream, self._keep = None, []
         self.c1 = conv2d(1, 56, 30, 32, 5, 5, 2, 1)                     # -> [32,27,14]
         # after MaxPool(k2,s1): [32,26,13]
         self.blocks = []
@@ -486,7 +501,9 @@ class AuxEngineProton:
 
     def _conv_bwd(self, x, dy, name, g, grp, R, dx, accumulate, want_dx=True):
         a = self.a
-        L.call("es_conv2d_bwd_weight", x, dy, g, grp, a.E, R, a.gaddr(name + ".weight"), a.gaddr(name + ".bias"), a.n, a.n)
+        # the weight gradient feeds nothing downstream in this backward: it runs beside the data-gradient chain
+        _on_side_stream(self._wstream, self._keep, lambda: L.call(
+            "es_conv2d_bwd_weight", x, dy, g, grp, a.E, R, a.gaddr(name + ".weight"), a.gaddr(name + ".bias"), a.n, a.n), x, dy)
         if want_dx:
             L.call("es_conv2d_bwd_data", dy, a.addr(name + ".weight"), a.n, g, grp, a.E, R, dx, int(accumulate))
 
@@ -544,9 +561,12 @@ class AuxEngineProton:
         s.update(feat=feat, m1=m1, h1d=h1d, m2=m2, h2d=h2d)
         return coords, s
 
-    def backward(self, s, d_coords, d_img, accumulate=True):
-        """Parameter gradients -> arena G; image gradient accumulated into d_img [R,1680]."""
+    def backward(self, s, d_coords, d_img, accumulate=True, wgrad_stream=None):
+        """Parameter gradients -> arena G; image gradient accumulated into d_img [R,1680].  With ``wgrad_stream`` the
+        convolution weight gradients are enqueued on that stream (the caller joins it before using the gradient arena and
+        drops ``s["keep"]`` afterwards); the current stream then carries only the chain that ends in d_img."""
         a, E, n, R, grp, fe = self.a, self.a.E, self.a.n, s["R"], s["grp"], self.FE
+        self._wstream, self._keep = wgrad_stream, s.setdefault("keep", [])
         masks, training = s["masks"], s["training"]
 
         def lin_bwd(x, ldx, dy, name, I, O, need_dx=True):
@@ -847,8 +867,10 @@ class AuxEngineNeutron:
         s["feat"] = feat
         return coords, s
 
-    def backward(self, s, d_coords, d_img, accumulate=True):
+    def backward(self, s, d_coords, d_img, accumulate=True, wgrad_stream=None):
+        """``wgrad_stream``: see AuxEngineProton.backward."""
         a, E, n, R, grp = self.a, self.a.E, self.a.n, s["R"], s["grp"]
+        keep = s.setdefault("keep", [])
         L.call("es_linear_bwd_weight", s["feat"], 64, d_coords, 64, 2, grp, E, R, a.gaddr("dense.weight"), a.gaddr("dense.bias"), n, n)
         dfeat = zeros(R, 64)
         L.call("es_linear_bwd_data", d_coords, a.addr("dense.weight"), n, 64, 2, grp, E, R, dfeat, 64)
@@ -872,8 +894,9 @@ class AuxEngineNeutron:
             L.call("es_bn2d_bwd_apply", d, rec["y"], c.Co, P, rec["stats"], sums2, rec["n_sg"], *common, dy)
             has_bias = (name + ".bias") in a.off
             # (a conv bias in front of a BatchNorm has an identically-zero gradient; db is still accumulated: it is free)
-            L.call("es_conv2d_bwd_weight", rec["x"], dy, c, grp, E, R, a.gaddr(name + ".weight"),
-                   a.gaddr(name + ".bias") if has_bias else None, n, n)
+            _on_side_stream(wgrad_stream, keep, lambda rec=rec, dy=dy, c=c, name=name, has_bias=has_bias: L.call(
+                "es_conv2d_bwd_weight", rec["x"], dy, c, grp, E, R, a.gaddr(name + ".weight"),
+                a.gaddr(name + ".bias") if has_bias else None, n, n), rec["x"], dy)
             if li == 0:
                 L.call("es_conv2d_bwd_data", dy, a.addr(name + ".weight"), n, c, grp, E, R, d_img, int(accumulate))
             else:

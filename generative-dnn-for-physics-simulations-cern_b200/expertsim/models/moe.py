@@ -143,14 +143,14 @@ class MoEWrapper(nn.Module):
         return r
 
     def _side_streams(self, dev):
-        """two side streams per device; with ``overlap_streams = False`` everything runs on the caller's stream"""
+        """three side streams per device; with ``overlap_streams = False`` everything runs on the caller's stream"""
         if not getattr(self, "overlap_streams", True):
             cur = torch.cuda.current_stream()
-            return cur, cur
+            return cur, cur, cur
         key = (dev.index if dev.index is not None else torch.cuda.current_device())
         if getattr(self, "_streams", None) is None or self._streams[0] != key:
-            self._streams = (key, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
-        return self._streams[1], self._streams[2]
+            self._streams = (key, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        return self._streams[1], self._streams[2], self._streams[3]
 
     @staticmethod
     def _gather(x, perm, width):
@@ -237,7 +237,7 @@ class MoEWrapper(nn.Module):
         #   D'(fake2) fwd / bwd, aux regressor fwd / bwd   || D'(fake1) fwd / bwd
         # Spectral-norm power iterations keep their reference order a -> b -> c -> d through events.
         main = torch.cuda.current_stream()
-        s1, s2 = self._side_streams(dev)
+        s1, s2, s3 = self._side_streams(dev)
         ev0 = main.record_event()
         with torch.cuda.stream(s1):
             s1.wait_event(ev0)
@@ -269,9 +269,12 @@ class MoEWrapper(nn.Module):
             L.call("es_aux_loss_grad", coords, pos_s, gh, E, B, Bg, stren_a, d_coords)
             d_img1_aux = torch.zeros(B, HW, device=dev)
             a_a.G.zero_()
-            aux.backward(sv_a, d_coords, d_img1_aux, accumulate=False)
+            aux.backward(sv_a, d_coords, d_img1_aux, accumulate=False, wgrad_stream=s3 if s3 is not s2 else None)
+            ev_ba = s2.record_event()       # d_img1_aux is complete (the conv weight gradients may still run on s3)
+            if s3 is not s2:
+                s2.wait_stream(s3)
             self._allreduce(a_a.G)          # (data parallel) rides the side stream too
-            ev_ba = s2.record_event()
+            ev_aw = s2.record_event()       # the auxiliary regressor's gradient arena is complete
 
         # ---- discriminator step (moe.py:506-527)
         main.wait_event(ev_a)
@@ -355,6 +358,7 @@ class MoEWrapper(nn.Module):
             self._allreduce(a_g.G)
         del sg, sv1, sv2, sv_a
         self._adam(a_g, self._lr(generator_optimizers, gcfg.lr_g), gh)
+        main.wait_event(ev_aw)
         self._adam(a_a, self._lr(aux_reg_optimizers, cfgm.aux_reg.lr_a), gh)
 
         # ---- router loss (moe.py:213-449) and metrics
