@@ -174,6 +174,225 @@ bn_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------ NHWC bf16, BatchNorm2d fast path
+// The generic kernels above re-load the channel's statistics / affine parameters and hash one dropout decision per ELEMENT
+// (r01b launch list, neutron: 25 ms of a 58 ms step at 0.2-0.6 TB/s).  For BatchNorm2d with C <= 256 a thread owns one
+// channel octet for the whole row: the per-channel constants live in registers, U pixels are fetched before any is
+// consumed (see gn_lrelu_kernel), and the keep decisions of an octet come from two 64-bit hashes (16 bits per element)
+// instead of eight.  The hashed dropout pattern only has to agree between the forward and the two backward kernels of
+// the same step; injected masks (parity runs) keep the reference's NCHW index.
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+__device__ __forceinline__ void keep8(const float* __restrict__ mask, uint64_t seed, size_t oct, size_t nchw_base, int P,
+                                      float p, float* ks) {
+  if (p <= 0.f) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ks[k] = 1.f;
+    return;
+  }
+  const float inv = 1.f / (1.f - p);
+  if (mask) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ks[k] = mask[nchw_base + (size_t)k * P] != 0.f ? inv : 0.f;
+    return;
+  }
+  const uint64_t h1 = mix64(seed + oct * 0x9E3779B97F4A7C15ull), h2 = mix64(h1 + 0xD1B54A32D192ED03ull);
+  const uint32_t thr = (uint32_t)(p * 65536.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    ks[k] = ((uint32_t)(h1 >> (16 * k)) & 0xFFFFu) >= thr ? inv : 0.f;
+    ks[4 + k] = ((uint32_t)(h2 >> (16 * k)) & 0xFFFFu) >= thr ? inv : 0.f;
+  }
+}
+
+// U pixels of one channel octet: x (always) and the gradient (direct, or summed over the <= 2 x 2 upsample fan-out)
+template <bool BWD, bool FAN, int U>
+struct BnFetch {
+  uint4 qx[U];
+  uint4 qd[U][FAN ? 4 : 1];
+  int nq[U];
+  __device__ __forceinline__ void load(const uint4* __restrict__ x4, const uint4* __restrict__ d4, int pix0, int pstep, int P,
+                                       int c4, int cu, int Ws, int Wu, const int* ylo, const int* yhi, const int* xlo,
+                                       const int* xhi) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = pix0 + u * pstep;
+      nq[u] = 0;
+      if (pix < P) {
+        qx[u] = __ldg(x4 + (size_t)pix * c4 + cu);
+        if (BWD) {
+          if (FAN) {
+            const int sy = pix / Ws, sx = pix - sy * Ws;
+            const int y0 = ylo[sy], ny = yhi[sy] - y0, x0 = xlo[sx], nx = xhi[sx] - x0;
+            nq[u] = ny * nx;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < ny * nx) qd[u][j] = __ldg(d4 + ((size_t)(y0 + j / nx) * Wu + x0 + j % nx) * c4 + cu);
+          } else {
+            qd[u][0] = __ldg(d4 + (size_t)pix * c4 + cu);
+          }
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void grad(int u, float* da) const {
+    unpack8(qd[u][0], da);
+    if (FAN) {
+      float t[8];
+#pragma unroll
+      for (int j = 1; j < 4; ++j)
+        if (j < nq[u]) {
+          unpack8(qd[u][j], t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) da[k] += t[k];
+        }
+    }
+  }
+};
+
+template <bool BWD, bool FAN>
+__global__ void __launch_bounds__(256)
+bn2d_reduce_fast_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int Hu,
+                        int Wu, int C, int rpc, const float* __restrict__ stats, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, long slot_stride, const float* __restrict__ mask,
+                        unsigned long long seed, float p_drop, const es_group* __restrict__ grp, int E, int total_rows,
+                        int two_pass, double* __restrict__ sums) {
+  __shared__ float s_a[256], s_b[256];
+  __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
+  const int P = Hs * Ws, c4 = C / 8;
+  const int tid = threadIdx.x, cu = tid % c4, c8 = cu * 8, pstep = 256 / c4, p0 = tid / c4;
+  if (BWD && FAN && tid == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+  s_a[tid] = 0.f; s_b[tid] = 0.f;
+  __syncthreads();
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float mu[8], rs[8], ga[8], be[8];
+  int cur = -1;
+  auto flush = [&]() {      // called by ALL threads of the CTA (cur is uniform)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&s_a[c8 + k], a[k]); atomicAdd(&s_b[c8 + k], b[k]); a[k] = 0.f; b[k] = 0.f; }
+    __syncthreads();
+    if (tid < C) {
+      double* d = sums + ((size_t)cur * C + tid) * 2;
+      atomicAdd(d, (double)s_a[tid]);
+      atomicAdd(d + 1, (double)s_b[tid]);
+      s_a[tid] = 0.f; s_b[tid] = 0.f;
+    }
+    __syncthreads();
+  };
+  constexpr int U = FAN ? 2 : 4;
+  BnFetch<BWD, FAN, U> q;
+  const int r0 = blockIdx.x * rpc, r1 = min(total_rows, r0 + rpc);
+  for (int r = r0; r < r1; ++r) {
+    const SgRow sr = sg_of_row(grp, E, r, two_pass);
+    const int sg = sr.g < 0 ? -1 : sr.sg;
+    if (sg != cur) {
+      if (cur >= 0) flush();
+      cur = sg;
+      if (BWD && sg >= 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          mu[k] = stats[((size_t)sg * C + c8 + k) * 2]; rs[k] = stats[((size_t)sg * C + c8 + k) * 2 + 1];
+          ga[k] = gamma[sr.slot * slot_stride + c8 + k]; be[k] = beta[sr.slot * slot_stride + c8 + k];
+        }
+      }
+    }
+    if (sg < 0) continue;
+    const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * P * C);
+    const uint4* d4 = BWD ? reinterpret_cast<const uint4*>(dy_up + (size_t)r * Hu * Wu * C) : nullptr;
+    float f[8], da[8], ks[8];
+    for (int pix0 = p0; pix0 < P; pix0 += U * pstep) {
+      q.load(x4, d4, pix0, pstep, P, c4, cu, Ws, Wu, ylo, yhi, xlo, xhi);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * pstep;
+        if (pix >= P) continue;
+        unpack8(q.qx[u], f);
+        if (!BWD) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { a[k] += f[k]; b[k] += f[k] * f[k]; }
+        } else {
+          q.grad(u, da);
+          keep8(mask, seed, ((size_t)r * P + pix) * c4 + cu, ((size_t)r * C + c8) * P + pix, P, p_drop, ks);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float xh = (f[k] - mu[k]) * rs[k];
+            const float pre = (xh * ga[k] + be[k]) * ks[k];            // dropout, then LeakyReLU
+            const float g2 = da[k] * (pre > 0.f ? 1.f : kLReLU) * ks[k];
+            a[k] += g2;
+            b[k] += g2 * xh;
+          }
+        }
+      }
+    }
+  }
+  if (cur >= 0) flush();
+}
+
+template <bool BWD, bool FAN>
+__global__ void __launch_bounds__(256)
+bn2d_apply_fast_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int Hu,
+                       int Wu, int C, const float* __restrict__ stats, const double* __restrict__ sums2,
+                       const float* __restrict__ n_sg, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       long slot_stride, const float* __restrict__ mask, unsigned long long seed, float p_drop,
+                       const es_group* __restrict__ grp, int E, int two_pass, __nv_bfloat16* __restrict__ out) {
+  __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
+  const int r = blockIdx.x;
+  const SgRow sr = sg_of_row(grp, E, r, two_pass);
+  const int P = Hs * Ws, c4 = C / 8;
+  uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)r * P * C);
+  if (sr.g < 0) {
+    if (BWD) for (int i = threadIdx.x; i < P * c4; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);   // see gn_lrelu_kernel
+    return;
+  }
+  if (BWD && FAN) {
+    if (threadIdx.x == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+    __syncthreads();
+  }
+  const int tid = threadIdx.x, cu = tid % c4, c8 = cu * 8, pstep = 256 / c4, p0 = tid / c4;
+  float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
+  const float inv_n = BWD ? 1.f / n_sg[sr.sg] : 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const size_t si = ((size_t)sr.sg * C + c8 + k) * 2;
+    mu[k] = stats[si]; rs[k] = stats[si + 1];
+    ga[k] = gamma[sr.slot * slot_stride + c8 + k]; be[k] = beta[sr.slot * slot_stride + c8 + k];
+    m1[k] = BWD ? (float)sums2[si] * inv_n : 0.f;
+    m2[k] = BWD ? (float)sums2[si + 1] * inv_n : 0.f;
+  }
+  const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * P * C);
+  const uint4* d4 = BWD ? reinterpret_cast<const uint4*>(dy_up + (size_t)r * Hu * Wu * C) : nullptr;
+  constexpr int U = FAN ? 2 : 4;
+  BnFetch<BWD, FAN, U> q;
+  float f[8], da[8], ks[8], o[8];
+  for (int pix0 = p0; pix0 < P; pix0 += U * pstep) {
+    q.load(x4, d4, pix0, pstep, P, c4, cu, Ws, Wu, ylo, yhi, xlo, xhi);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = pix0 + u * pstep;
+      if (pix >= P) continue;
+      unpack8(q.qx[u], f);
+      if (BWD) q.grad(u, da);
+      keep8(mask, seed, ((size_t)r * P + pix) * c4 + cu, ((size_t)r * C + c8) * P + pix, P, p_drop, ks);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (f[k] - mu[k]) * rs[k];
+        const float pre = (xh * ga[k] + be[k]) * ks[k];
+        if (!BWD) {
+          o[k] = lrelu(pre);
+        } else {
+          const float g2 = da[k] * (pre > 0.f ? 1.f : kLReLU) * ks[k];
+          o[k] = ga[k] * rs[k] * (g2 - m1[k] - xh * m2[k]);
+        }
+      }
+      o4[(size_t)pix * c4 + cu] = pack8(o);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ NCHW fp32 (aux regressor)
 // order in the reference: BatchNorm -> LeakyReLU -> Dropout.   CTA = (channel, chunk of rows).
 template <bool BWD>
@@ -315,6 +534,12 @@ using namespace es;
 
 #define BN_GEOM_OK(Hs, Ws, Hu, Wu, C) ((C) > 0 && (C) % 8 == 0 && (Hs) > 0 && (Ws) > 0 && (Hs) <= 64 && (Ws) <= 64 && (Hu) <= 64 && (Wu) <= 64 && (Hu) >= (Hs) && (Wu) >= (Ws))
 
+// BatchNorm2d fast path: per-channel statistics, C/8 octets divide the 256 threads, no channel map, fan-in <= 2 per axis
+static bool bn2d_fast(int feat_stats, int C, const int32_t* chmap, int Hs, int Ws, int Hu, int Wu) {
+  static const bool on = [] { const char* e = getenv("ES_BN_LEGACY"); return !(e && e[0] == '1'); }();
+  return on && !feat_stats && !chmap && C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && Hu <= 2 * Hs && Wu <= 2 * Ws;
+}
+
 static int rows_per_cta(int total_rows, int P_it) {
   int rpc = 4096 / (P_it > 0 ? P_it : 1);
   if (rpc < 1) rpc = 1;
@@ -329,6 +554,13 @@ extern "C" int es_bn_stats_nhwc(const void* x, int Hs, int Ws, int C, int feat_s
   ES_REQUIRE(x && grp && sums && Hs > 0 && Ws > 0 && C > 0 && C % 8 == 0 && total_rows > 0 && E >= 1 && E <= kMaxGroups, "bad arguments");
   const int P_it = feat_stats ? 1 : Hs * Ws, C_it = feat_stats ? Hs * Ws * C : C;
   const int opb = pick_opb(C_it), rpc = rows_per_cta(total_rows, P_it);
+  if (bn2d_fast(feat_stats, C, nullptr, Hs, Ws, Hs, Ws)) {
+    bn2d_reduce_fast_kernel<false, false><<<ceil_div(total_rows, rpc), 256, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)x, nullptr, Hs, Ws, Hs, Ws, C, rpc, nullptr, nullptr, nullptr, 0, nullptr, 0ull, 0.f, grp, E,
+        total_rows, two_pass, sums);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   bn_reduce_nhwc_kernel<false><<<dim3(ceil_div(total_rows, rpc), C_it / 8 / opb), 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, nullptr, Hs, Ws, Hs, Ws, C, P_it, C_it, opb, rpc, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
       0ull, 0.f, grp, E, total_rows, two_pass, sums);
@@ -354,6 +586,13 @@ extern "C" int es_bn_apply_fwd_nhwc(const void* x, int Hs, int Ws, int C, int fe
                                     const float* keep_mask, unsigned long long seed, float p_drop, const es_group* grp, int E,
                                     int total_rows, int two_pass, void* y, void* stream) {
   ES_REQUIRE(x && stats && gamma && beta && grp && y && Hs > 0 && Ws > 0 && C > 0 && C % 8 == 0 && total_rows > 0, "bad arguments");
+  if (bn2d_fast(feat_stats, C, chmap, Hs, Ws, Hs, Ws)) {
+    bn2d_apply_fast_kernel<false, false><<<total_rows, 256, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)x, nullptr, Hs, Ws, Hs, Ws, C, stats, nullptr, nullptr, gamma, beta, slot_stride, keep_mask, seed,
+        p_drop, grp, E, two_pass, (__nv_bfloat16*)y);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   bn_apply_nhwc_kernel<false><<<total_rows, 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, nullptr, Hs, Ws, Hs, Ws, C, feat_stats ? Hs * Ws * C : C, stats, nullptr, nullptr, gamma, beta,
       slot_stride, chmap, keep_mask, seed, p_drop, grp, E, two_pass, (__nv_bfloat16*)y);
@@ -369,6 +608,18 @@ extern "C" int es_bn_bwd_reduce_nhwc(const void* dy_up, int Hs, int Ws, int Hu, 
   ES_REQUIRE(BN_GEOM_OK(Hs, Ws, Hu, Wu, C), "bad geometry");
   const int P_it = feat_stats ? 1 : Hs * Ws, C_it = feat_stats ? Hs * Ws * C : C;
   const int opb = pick_opb(C_it), rpc = rows_per_cta(total_rows, P_it);
+  if (bn2d_fast(feat_stats, C, chmap, Hs, Ws, Hu, Wu)) {
+    const bool fan = Hu != Hs || Wu != Ws;
+    const dim3 grid(ceil_div(total_rows, rpc));
+#define ES_BN_RED(FANV)                                                                                                \
+    bn2d_reduce_fast_kernel<true, FANV><<<grid, 256, 0, as_stream(stream)>>>(                                          \
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, rpc, stats, gamma, beta, slot_stride,  \
+        keep_mask, seed, p_drop, grp, E, total_rows, two_pass, sums2);
+    if (fan) { ES_BN_RED(true) } else { ES_BN_RED(false) }
+#undef ES_BN_RED
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   bn_reduce_nhwc_kernel<true><<<dim3(ceil_div(total_rows, rpc), C_it / 8 / opb), 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, P_it, C_it, opb, rpc, stats, gamma, beta,
       slot_stride, chmap, keep_mask, seed, p_drop, grp, E, total_rows, two_pass, sums2);
@@ -383,6 +634,17 @@ extern "C" int es_bn_bwd_apply_nhwc(const void* dy_up, int Hs, int Ws, int Hu, i
                                     int two_pass, void* dx, void* stream) {
   ES_REQUIRE(dy_up && x && stats && sums2 && n_sg && gamma && beta && grp && dx && total_rows > 0, "bad arguments");
   ES_REQUIRE(BN_GEOM_OK(Hs, Ws, Hu, Wu, C), "bad geometry");
+  if (bn2d_fast(feat_stats, C, chmap, Hs, Ws, Hu, Wu)) {
+    const bool fan = Hu != Hs || Wu != Ws;
+#define ES_BN_APP(FANV)                                                                                                \
+    bn2d_apply_fast_kernel<true, FANV><<<total_rows, 256, 0, as_stream(stream)>>>(                                     \
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, stats, sums2, n_sg, gamma, beta,       \
+        slot_stride, keep_mask, seed, p_drop, grp, E, two_pass, (__nv_bfloat16*)dx);
+    if (fan) { ES_BN_APP(true) } else { ES_BN_APP(false) }
+#undef ES_BN_APP
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   bn_apply_nhwc_kernel<true><<<total_rows, 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, feat_stats ? Hs * Ws * C : C, stats, sums2, n_sg,
       gamma, beta, slot_stride, chmap, keep_mask, seed, p_drop, grp, E, two_pass, (__nv_bfloat16*)dx);
