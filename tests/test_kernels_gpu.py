@@ -902,3 +902,80 @@ def test_preprocess_kernels_match_golden_and_oracle():
         assert int(gid.max()) + 1 == len(torch.unique(member)) and float(got.max()) == 1.0
     with pytest.raises(RuntimeError):
         pp.max_coordinates(data)      # host tensors are refused: no CPU fallback
+
+
+# ----------------------------------------------------------------------------------------------------------- BatchNorm (neutron)
+@pytest.mark.parametrize("Hs,Ws,C,Hu,Wu", [(24, 24, 256, 24, 24), (46, 46, 128, 46, 46), (45, 45, 64, 45, 45), (13, 13, 128, 20, 22)])
+def test_bn2d_nhwc_fwd_bwd(Hs, Ws, C, Hu, Wu):
+    """BatchNorm2d + Dropout(0.2) + LeakyReLU on bf16 NHWC rows (neutron generator, fast path), two-pass batch of 3 experts:
+    (1) injected keep-masks against torch autograd (per (expert, pass) batch statistics); (2) hashed dropout: the pattern
+    the forward drew is exactly the one both backward kernels re-evaluate (backward with the mask recovered from the
+    forward output == backward with the hash)."""
+    counts, slots, E, p = [3, 0, 4], [2, 0, 1], 3, 0.2
+    gg, B = groups(counts, slots, two_pass=True)
+    R, P = 2 * B, Hs * Ws
+    g = G(Hs + C)
+    x = bf16_round(torch.randn(R, C, Hs, Ws, generator=g) * 1.5 + 0.3)
+    da = bf16_round(torch.randn(R, C, Hu, Wu, generator=g))
+    gamma, beta = 1 + .2 * torch.randn(E, C, generator=g), .1 * torch.randn(E, C, generator=g)
+    keep = (torch.rand(R, C, Hs, Ws, generator=g) >= p).float()
+    n_rows = torch.zeros(2 * E)
+    lx, lg, lb = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    want_y, off = torch.zeros(R, C, Hs, Ws), 0
+    for c, s in zip(counts, slots):
+        for ps in range(2):
+            if c:
+                r0 = 2 * off + ps * c
+                n_rows[2 * s + ps] = c
+                bn = F.batch_norm(lx[r0:r0 + c], None, None, lg[s], lb[s], training=True, eps=1e-5)
+                y = F.leaky_relu(bn * keep[r0:r0 + c] / (1 - p), 0.1)
+                want_y[r0:r0 + c] = y.detach()
+                up = F.interpolate(y, size=(Hu, Wu), mode="nearest") if (Hu, Wu) != (Hs, Ws) else y
+                (up * da[r0:r0 + c]).sum().backward()
+        off += c
+    xd, dad = cuda(nhwc(x), BF), cuda(nhwc(da), BF)
+    n_sg = cuda(n_rows * P)
+    sums = torch.zeros(2 * E, C, 2, dtype=torch.float64, device=DEV)
+    L.call("es_bn_stats_nhwc", xd, Hs, Ws, C, 0, gg, len(counts), R, 1, sums)
+    stats = torch.zeros(2 * E, C, 2, device=DEV)
+    act = torch.zeros(E, 4, dtype=torch.int32)
+    for c, s in zip(counts, slots):
+        act[s] = torch.tensor([0, c, s, c])
+    L.call("es_bn_finalize", sums, n_sg, C, 2, 1, 0.1, None, None, None, 0, None, 0, cuda(act), E, stats)
+    gd, bd = cuda(gamma), cuda(beta)
+    y = torch.zeros(R, P, C, dtype=BF, device=DEV)
+    L.call("es_bn_apply_fwd_nhwc", xd, Hs, Ws, C, 0, stats, gd, bd, C, None, cuda(keep.reshape(R, -1)), 0, p, gg, len(counts), R, 1, y)
+    check(f"bn2d fwd C={C}", y.float().view(R, Hs, Ws, C), nhwc(want_y), 8e-3)
+
+    def backward(mask, seed):
+        s2 = torch.zeros(2 * E, C, 2, dtype=torch.float64, device=DEV)
+        L.call("es_bn_bwd_reduce_nhwc", dad, Hs, Ws, Hu, Wu, C, 0, xd, stats, gd, bd, C, None, mask, seed, p, gg, len(counts), R, 1, s2)
+        dx = torch.zeros(R, P, C, dtype=BF, device=DEV)
+        L.call("es_bn_bwd_apply_nhwc", dad, Hs, Ws, Hu, Wu, C, 0, xd, stats, s2, n_sg, gd, bd, C, None, mask, seed, p, gg,
+               len(counts), R, 1, dx)
+        dg, db = torch.zeros(E, C, device=DEV), torch.zeros(E, C, device=DEV)
+        L.call("es_bn_affine_grads", s2, C, 2, 1.0, None, cuda(act), E, dg, db, C)
+        return dx, dg, db
+
+    dx, dg, db = backward(cuda(keep.reshape(R, -1)), 0)
+    check(f"bn2d bwd dx C={C}", dx.float().view(R, Hs, Ws, C), nhwc(lx.grad), 1e-2)
+    check(f"bn2d bwd dgamma C={C}", dg, lg.grad, 5e-3)
+    check(f"bn2d bwd dbeta C={C}", db, lb.grad, 5e-3)
+    # hashed dropout: recover the forward's pattern from its output (a dropped element is exactly 0) and replay it as a mask
+    seed = 0x1234567 + C
+    yh = torch.zeros(R, P, C, dtype=BF, device=DEV)
+    L.call("es_bn_apply_fwd_nhwc", xd, Hs, Ws, C, 0, stats, gd, bd, C, None, None, seed, p, gg, len(counts), R, 1, yh)
+    rows_on = torch.cat([torch.arange(2 * o, 2 * o + 2 * c) for o, c in zip([0, 3, 3], counts) if c])
+    kept = (yh.float().view(R, Hs, Ws, C)[rows_on] != 0).float()
+    frac = 1 - kept.mean().item()
+    assert abs(frac - p) < 0.01, f"dropout rate {frac:.4f}"
+    mask_nchw = torch.zeros(R, C, Hs, Ws, device=DEV)
+    mask_nchw[rows_on] = kept.permute(0, 3, 1, 2)
+    dxa, dga, dba = backward(None, seed)
+    dxb, dgb, dbb = backward(mask_nchw.reshape(R, -1).contiguous(), 0)
+    # (the fp64 partial sums meet in atomics, so the two runs may differ in the last bit — a wrong keep decision would not)
+    mism = (dxa != dxb).float().mean().item()
+    assert mism < 1e-3, f"forward and backward must draw the same dropout pattern ({mism:.2e} of dx differs)"
+    check(f"bn2d hashed-vs-replayed dx C={C}", dxa.float(), dxb.float(), 1e-4)
+    check(f"bn2d hashed-vs-replayed dgamma C={C}", dga, dgb, 1e-5)
+    check(f"bn2d hashed-vs-replayed dbeta C={C}", dba, dbb, 1e-5)
