@@ -589,13 +589,67 @@ gen_out_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   }
 }
 
+// C == 64, <= 4 taps: 8 lanes share an output pixel (one channel octet each, weights in registers); the <= 4 tap loads of
+// a lane are independent 16-byte loads that coalesce to one 128-byte line per tap and pixel, and the 8 partial dot products
+// meet in three shuffles.  (The one-thread-per-pixel kernel above issued 32 dependent loads per output: 0.49 ms for a
+// 418 MB read.)
+__global__ void __launch_bounds__(256)
+gen_out_fwd64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, long sw,
+                     long sb, int Hs, int Ws, int KH, int KW, int pad, const es_group* __restrict__ grp, int E, int two_pass,
+                     float* __restrict__ img1, float* __restrict__ img2) {
+  constexpr int C = 64, c4 = 8;
+  const int r = blockIdx.x;
+  const RowMap m = map_row(grp, E, r, two_pass);
+  if (m.g < 0) return;
+  const int slot = grp[m.g].slot;
+  const int cu = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float wr[4][8];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[t][k] = t < KH * KW ? w[slot * sw + (size_t)(cu * 8 + k) * KH * KW + t] : 0.f;
+  const float bias = b[slot * sb];
+  const int Ho = Hs + 2 * pad - KH + 1, Wo = Ws + 2 * pad - KW + 1;
+  float* dst = (m.pass ? img2 : img1) + (size_t)m.j * Ho * Wo;
+  const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * Hs * Ws * C);
+  for (int p0 = 0; p0 < Ho * Wo; p0 += 32) {       // all 32 pixel lanes iterate together (shuffles below)
+    const int p = p0 + pl;
+    const int oy = p / Wo, ox = p - oy * Wo;
+    uint4 q[4];
+    bool ok[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int ky = t / KW, kx = t - ky * KW;
+      const int sy = oy + ky - pad, sx = ox + kx - pad;
+      ok[t] = p < Ho * Wo && t < KH * KW && sy >= 0 && sy < Hs && sx >= 0 && sx < Ws;
+      if (ok[t]) q[t] = __ldg(x4 + (size_t)(sy * Ws + sx) * c4 + cu);
+    }
+    float acc = 0.f, f[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (ok[t]) {
+        unpack8(q[t], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(f[k], wr[t][k], acc);
+      }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (cu == 0 && p < Ho * Wo) dst[p] = fmaxf(acc + bias, 0.f);
+  }
+}
+
 // dx[sy,sx,c] = sum_{ky,kx} dimg_masked[sy-ky+pad, sx-kx+pad] * w[c,ky,kx];  dw[c,ky,kx] += sum dimg_masked * x;  db += sum dimg_masked
+// KT > 0: KH = KW = KT known at compile time — the tap loops unroll and the weight-gradient partials accw[tap][] stay in
+// registers (with run-time bounds they were indexed dynamically, i.e. lived in local memory: 0.7 ms for this kernel)
+template <int KT>
 __global__ void __launch_bounds__(256)
 gen_out_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, long sw, int Hs, int Ws, int C,
-                   int KH, int KW, int pad, const float* __restrict__ img1, const float* __restrict__ img2,
+                   int KH_, int KW_, int pad, const float* __restrict__ img1, const float* __restrict__ img2,
                    const float* __restrict__ dimg1, const float* __restrict__ dimg2, const es_group* __restrict__ grp,
                    int E, int two_pass, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long sb) {
   extern __shared__ float sm[];
+  const int KH = KT > 0 ? KT : KH_, KW = KT > 0 ? KT : KW_;
   const int Ho = Hs + 2 * pad - KH + 1, Wo = Ws + 2 * pad - KW + 1;
   float* s_w = sm;                       // [KH*KW][C]
   float* s_dw = s_w + KH * KW * C;       // [KH*KW][C]
@@ -631,27 +685,57 @@ gen_out_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 #pragma unroll
     for (int k = 0; k < 8; ++k) accw[t][k] = 0.f;
   float f[8];
-  for (int pix = threadIdx.x / c4; pix < Hs * Ws; pix += pstep) {
-    const int sy = pix / Ws, sx = pix % Ws;
-    unpack8(__ldg(reinterpret_cast<const uint4*>(xr + (size_t)pix * C) + cu), f);
-    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int ky = 0; ky < KH; ++ky) {
-      const int oy = sy - ky + pad;
-      if (oy < 0 || oy >= Ho) continue;
-      for (int kx = 0; kx < KW; ++kx) {
-        const int ox = sx - kx + pad;
-        if (ox < 0 || ox >= Wo) continue;
-        const float d = s_d[oy * Wo + ox];
-        const int tap = ky * KW + kx;
-        const float* wt = s_w + tap * C + cu * 8;
+  constexpr int U = 4;      // pixels whose x octet is fetched before any is consumed (latency-bound otherwise)
+  for (int pix0 = threadIdx.x / c4; pix0 < Hs * Ws; pix0 += U * pstep) {
+   uint4 qx[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          o[k] = fmaf(d, wt[k], o[k]);
-          if (tap < 4) accw[tap][k] = fmaf(d, f[k], accw[tap][k]);
+   for (int u = 0; u < U; ++u)
+     if (pix0 + u * pstep < Hs * Ws) qx[u] = __ldg(reinterpret_cast<const uint4*>(xr + (size_t)(pix0 + u * pstep) * C) + cu);
+#pragma unroll
+   for (int u = 0; u < U; ++u) {
+    const int pix = pix0 + u * pstep;
+    if (pix >= Hs * Ws) continue;
+    const int sy = pix / Ws, sx = pix % Ws;
+    unpack8(qx[u], f);
+    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (KT > 0) {
+#pragma unroll
+      for (int ky = 0; ky < (KT > 0 ? KT : 1); ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < (KT > 0 ? KT : 1); ++kx) {
+          const int oy = sy - ky + pad, ox = sx - kx + pad;
+          const bool okp = oy >= 0 && oy < Ho && ox >= 0 && ox < Wo;
+          const float d = okp ? s_d[oy * Wo + ox] : 0.f;
+          constexpr int KTT = KT > 0 ? KT : 1;
+          const int tap = ky * KTT + kx;
+          const float* wt = s_w + tap * C + cu * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            o[k] = fmaf(d, wt[k], o[k]);
+            if (tap < 4) accw[tap < 4 ? tap : 0][k] = fmaf(d, f[k], accw[tap < 4 ? tap : 0][k]);
+          }
+        }
+      }
+    } else {
+      for (int ky = 0; ky < KH; ++ky) {
+        const int oy = sy - ky + pad;
+        if (oy < 0 || oy >= Ho) continue;
+        for (int kx = 0; kx < KW; ++kx) {
+          const int ox = sx - kx + pad;
+          if (ox < 0 || ox >= Wo) continue;
+          const float d = s_d[oy * Wo + ox];
+          const int tap = ky * KW + kx;
+          const float* wt = s_w + tap * C + cu * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            o[k] = fmaf(d, wt[k], o[k]);
+            if (tap < 4) accw[tap][k] = fmaf(d, f[k], accw[tap][k]);
+          }
         }
       }
     }
     reinterpret_cast<uint4*>(dxr + (size_t)pix * C)[cu] = pack8(o);
+   }
   }
   for (int tap = 0; tap < KH * KW && tap < 4; ++tap)
 #pragma unroll
@@ -1007,6 +1091,12 @@ extern "C" int es_gen_out_fwd(const void* x, const float* w, const float* b, lon
                               float* img1, float* img2, void* stream) {
   ES_REQUIRE(x && w && b && grp_gen && img1 && (img2 || !two_pass), "null pointer");
   ES_REQUIRE(C % 8 == 0 && KH * KW * C <= 8192 && total_rows > 0 && E >= 1 && E <= kMaxGroups, "bad sizes");
+  if (C == 64 && KH * KW <= 4) {
+    gen_out_fwd64_kernel<<<total_rows, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, w, b, slot_stride_w, slot_stride_b,
+                                                                    Hs, Ws, KH, KW, pad, grp_gen, E, two_pass, img1, img2);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  }
   gen_out_fwd_kernel<<<total_rows, 256, KH * KW * C * sizeof(float), as_stream(stream)>>>(
       (const __nv_bfloat16*)x, w, b, slot_stride_w, slot_stride_b, Hs, Ws, C, KH, KW, pad, grp_gen, E, two_pass, img1, img2);
   ES_LAUNCH_CHECK();
@@ -1022,7 +1112,11 @@ extern "C" int es_gen_out_bwd(const void* x, const float* w, long slot_stride_w,
   ES_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && KH * KW <= 4 && total_rows > 0 && E >= 1 && E <= kMaxGroups, "bad sizes");
   const int Ho = Hs + 2 * pad - KH + 1, Wo = Ws + 2 * pad - KW + 1;
   const size_t smem = (2 * KH * KW * C + Ho * Wo) * sizeof(float);
-  gen_out_bwd_kernel<<<total_rows, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)x, w, slot_stride_w, Hs, Ws, C,
+  if (KH == 2 && KW == 2)
+    gen_out_bwd_kernel<2><<<total_rows, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)x, w, slot_stride_w, Hs, Ws, C,
+        KH, KW, pad, img1, img2, dimg1, dimg2, grp_gen, E, two_pass, (__nv_bfloat16*)dx, dw, db, slot_stride_b);
+  else
+  gen_out_bwd_kernel<0><<<total_rows, 256, smem, as_stream(stream)>>>((const __nv_bfloat16*)x, w, slot_stride_w, Hs, Ws, C,
                                                                    KH, KW, pad, img1, img2, dimg1, dimg2, grp_gen, E,
                                                                    two_pass, (__nv_bfloat16*)dx, dw, db, slot_stride_b);
   ES_LAUNCH_CHECK();

@@ -88,13 +88,13 @@ class MoEWrapper(nn.Module):
     def arena(self, key: str) -> Arena:
         return self._arenas[key]
 
+    def _ensure_bound(self):
+        if any(not arena.owns(arena.modules[0]) for arena in self._arenas.values()):
+            self._bind()
+
     def _engines(self):
+        self._ensure_bound()
         a = self._arenas
-        for arena in a.values():
-            if not arena.owns(arena.modules[0]):
-                self._bind()
-                a = self._arenas
-                break
         return (engine_for(a["g"], self.arch, "generator"), engine_for(a["d"], self.arch, "discriminator"),
                 engine_for(a["a"], self.arch, "aux_reg"))
 
@@ -186,7 +186,9 @@ class MoEWrapper(nn.Module):
         parity harness uses it; by default the draws come from torch's CUDA generator.  Learning rates are read from the
         optimizers (``param_groups[0]['lr']``); the update itself is the fused multi-tensor Adam over the arenas.
         Returns the reference's metric dict; values are 0-dim DEVICE tensors (no host sync inside the step)."""
-        gen, disc, aux = self._engines()
+        self._ensure_bound()
+        if self._arenas["g"].device.type != "cuda":
+            raise RuntimeError("expertsim (B200) computes on CUDA only; there is no CPU fallback")
         cfgm = self.cfg.model
         rc = cfgm.router
         E, B = self.n_experts, cond.shape[0]
@@ -203,8 +205,18 @@ class MoEWrapper(nn.Module):
             -torch.empty(B, E, device=dev).exponential_().log()
         tau = self._tau(epoch)
 
-        # ---- K1: gating + stable partition (moe.py:76-77,97-103,123-126); the skip rule B_e<=1 is min_rows=2
-        r = self._route(cond, gumbel, tau, 2 if world == 1 else 1)
+        # ---- K1: gating + stable partition (moe.py:76-77,97-103,123-126); the skip rule B_e<=1 is min_rows=2.
+        # The router (4 CTAs, latency-bound) runs on a side stream under the re-packing of the generator's bf16 weight
+        # copies, which `_engines()` enqueues on the main stream after an optimizer step.
+        main = torch.cuda.current_stream()
+        s1, s2, s3 = self._side_streams(dev)
+        ev_in = main.record_event()
+        with torch.cuda.stream(s1):
+            s1.wait_event(ev_in)
+            r = self._route(cond, gumbel, tau, 2 if world == 1 else 1)
+            ev_route = s1.record_event()
+        gen, disc, aux = self._engines()
+        main.wait_event(ev_route)
         perm, gh, gg = r["perm"], r["grp_half"], r["grp_gen"]
         counts_g = r["counts"].to(torch.float32)
         if world > 1:   # skip rule and every mean use the GLOBAL per-expert count
@@ -236,8 +248,6 @@ class MoEWrapper(nn.Module):
         #   D(real) forward            || generator forward
         #   D'(fake2) fwd / bwd, aux regressor fwd / bwd   || D'(fake1) fwd / bwd
         # Spectral-norm power iterations keep their reference order a -> b -> c -> d through events.
-        main = torch.cuda.current_stream()
-        s1, s2, s3 = self._side_streams(dev)
         ev0 = main.record_event()
         with torch.cuda.stream(s1):
             s1.wait_event(ev0)
