@@ -893,6 +893,44 @@ __global__ void fold_up2_kernel(const float* __restrict__ w, long sw, int N, int
   }
 }
 
+// All fold tables of a layer in ONE pass over the weights (round 1b: 18 single-table launches re-read the fp32 weights 18
+// times with one strided 4-byte load per output: 1.05 ms per step).  A thread owns one (n, c) filter: its KH*KW taps are
+// 64 contiguous bytes, loaded once, and every table's pre-summed taps are produced from registers.  DGRAD = false: threads
+// run along c (stores [n][t][c] coalesced); DGRAD = true: along n (stores [c][t][n] coalesced).
+constexpr int kFoldMax = 13;
+struct FoldMulti {
+  int n_tables;
+  es_fold_table t[kFoldMax];
+  __nv_bfloat16* out[kFoldMax];
+};
+
+template <bool DGRAD>
+__global__ void __launch_bounds__(256)
+fold_multi_kernel(const float* __restrict__ w, long sw, int N, int C, int KHW, const __grid_constant__ FoldMulti fm) {
+  const int slot = blockIdx.y;
+  const long total = (long)N * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int n = DGRAD ? (int)(i % N) : (int)(i / C), c = DGRAD ? (int)(i / N) : (int)(i % C);
+    const float* src = w + slot * sw + ((size_t)n * C + c) * KHW;
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = k < KHW ? __ldg(src + k) : 0.f;
+    for (int j = 0; j < fm.n_tables; ++j) {
+      const int T = fm.t[j].n_taps;
+      __nv_bfloat16* o = fm.out[j] + (size_t)slot * total * T;
+      for (int tt = 0; tt < T; ++tt) {
+        const uint32_t m = fm.t[j].mask[tt];
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if ((m >> k) & 1u) acc += v[k];         // ascending tap order, like the single-table kernel
+        if (DGRAD) o[((size_t)c * T + tt) * N + n] = f2bf(acc);
+        else o[((size_t)n * T + tt) * C + c] = f2bf(acc);
+      }
+    }
+  }
+}
+
 // thread = (n, c): reads of the folded gradient are coalesced over c, each thread writes its KH*KW contiguous outputs
 __global__ void unfold_up2_kernel(const float* __restrict__ dwf, int N, int C, int KHW, es_fold_table t,
                                   float* __restrict__ dw, long sw) {
@@ -906,6 +944,39 @@ __global__ void unfold_up2_kernel(const float* __restrict__ dwf, int N, int C, i
       const float v = src[(size_t)tt * C];
       for (uint32_t m = t.mask[tt]; m; m &= m - 1) dst[__ffs(m) - 1] += v;
     }
+  }
+}
+
+// all classes' folded weight gradients -> the reference layout in one read-modify-write of dw
+struct UnfoldMulti {
+  int n_tables;
+  es_fold_table t[kFoldMax];
+  const float* in[kFoldMax];
+};
+__global__ void __launch_bounds__(256)
+unfold_multi_kernel(int N, int C, int KHW, const __grid_constant__ UnfoldMulti um, float* __restrict__ dw, long sw) {
+  const int slot = blockIdx.y;
+  const long total = (long)N * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), n = (int)(i / C);
+    float acc[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+    for (int j = 0; j < um.n_tables; ++j) {
+      const int T = um.t[j].n_taps;
+      const float* src = um.in[j] + ((size_t)slot * N + n) * T * C + c;
+      for (int tt = 0; tt < T; ++tt) {
+        const float v = __ldg(src + (size_t)tt * C);
+        const uint32_t m = um.t[j].mask[tt];
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if ((m >> k) & 1u) acc[k] += v;
+      }
+    }
+    float* dst = dw + slot * sw + (size_t)i * KHW;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k < KHW) dst[k] += acc[k];
   }
 }
 
@@ -932,10 +1003,47 @@ extern "C" int es_fold_up2_weights(const float* w, long slot_stride, int slots, 
   return ES_OK;
 }
 
+extern "C" int es_fold_weights_multi(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW,
+                                     const es_fold_table* tables, int n_tables, void* const* outs, int dgrad_layout,
+                                     void* stream) {
+  ES_REQUIRE(w && tables && outs && slots >= 1 && N > 0 && C > 0 && KH * KW <= 32, "bad arguments");
+  ES_REQUIRE(n_tables >= 1 && n_tables <= es::kFoldMax, "1..13 tables per call");
+  es::FoldMulti fm{};
+  fm.n_tables = n_tables;
+  for (int j = 0; j < n_tables; ++j) {
+    ES_REQUIRE(tables[j].n_taps >= 1 && tables[j].n_taps <= 32 && outs[j], "bad table / output");
+    fm.t[j] = tables[j];
+    fm.out[j] = (__nv_bfloat16*)outs[j];
+  }
+  const dim3 grid((unsigned)min(es::ceil_div_l((long)N * C, 256), 148L * 4), slots);
+  if (dgrad_layout) es::fold_multi_kernel<true><<<grid, 256, 0, es::as_stream(stream)>>>(w, slot_stride, N, C, KH * KW, fm);
+  else es::fold_multi_kernel<false><<<grid, 256, 0, es::as_stream(stream)>>>(w, slot_stride, N, C, KH * KW, fm);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
 extern "C" int es_unfold_up2_wgrad(const float* dw_folded, int slots, int N, int C, int KH, int KW,
                                    const es_fold_table* t, float* dw_ref, long slot_stride, void* stream) {
   ES_REQUIRE(dw_folded && t && dw_ref && slots >= 1 && t->n_taps >= 1 && t->n_taps <= 32 && KH * KW <= 32, "bad arguments");
   es::unfold_up2_kernel<<<dim3(512, slots), 256, 0, es::as_stream(stream)>>>(dw_folded, N, C, KH * KW, *t, dw_ref, slot_stride);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
+}
+
+extern "C" int es_unfold_wgrad_multi(const float* const* dw_folded, int slots, int N, int C, int KH, int KW,
+                                     const es_fold_table* tables, int n_tables, float* dw_ref, long slot_stride,
+                                     void* stream) {
+  ES_REQUIRE(dw_folded && tables && dw_ref && slots >= 1 && N > 0 && C > 0 && KH * KW <= 32, "bad arguments");
+  ES_REQUIRE(n_tables >= 1 && n_tables <= es::kFoldMax, "1..13 tables per call");
+  es::UnfoldMulti um{};
+  um.n_tables = n_tables;
+  for (int j = 0; j < n_tables; ++j) {
+    ES_REQUIRE(tables[j].n_taps >= 1 && tables[j].n_taps <= 32 && dw_folded[j], "bad table / input");
+    um.t[j] = tables[j];
+    um.in[j] = dw_folded[j];
+  }
+  const dim3 grid((unsigned)min(es::ceil_div_l((long)N * C, 256), 148L * 4), slots);
+  es::unfold_multi_kernel<<<grid, 256, 0, es::as_stream(stream)>>>(N, C, KH * KW, um, dw_ref, slot_stride);
   ES_LAUNCH_CHECK();
   return ES_OK;
 }

@@ -112,7 +112,7 @@ def _ptr(x):
         if not x.is_contiguous():
             raise RuntimeError("non-contiguous tensor passed to the C-ABI")
         return x.data_ptr()
-    if isinstance(x, ctypes.Structure):
+    if isinstance(x, (ctypes.Structure, ctypes.Array)):
         return ctypes.addressof(x)
     if isinstance(x, int):
         return x

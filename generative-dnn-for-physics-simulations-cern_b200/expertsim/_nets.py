@@ -155,12 +155,17 @@ class FoldedConv:
             self.w_d = torch.empty(E, self.C, self.table_all.n_taps * self.N, dtype=BF, device=dev)
 
     def fold(self, w_addr, slot_stride, E):
-        for c in self.classes:
-            L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, c["table"], c["w_f"], None)
-        for c in self.dgrad_classes:
-            L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, c["table"], None, c["w_d"])
-        if self.has_dgrad and not self.dgrad_classes:
-            L.call("es_fold_up2_weights", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, self.table_all, None, self.w_d)
+        """fp32 master weights -> every folded bf16 copy: one pass over the weights per output layout"""
+        import ctypes
+        jobs = [([c["table"] for c in self.classes], [c["w_f"] for c in self.classes], 0)]
+        if self.dgrad_classes:
+            jobs.append(([c["table"] for c in self.dgrad_classes], [c["w_d"] for c in self.dgrad_classes], 1))
+        elif self.has_dgrad:
+            jobs.append(([self.table_all], [self.w_d], 1))
+        for tables, outs, dg in jobs:
+            tarr = (L.ESFoldTable * len(tables))(*tables)
+            oarr = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+            L.call("es_fold_weights_multi", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, tarr, len(tables), oarr, dg)
 
     def forward(self, x, bias_addr, bias_stride, y, grp, E, R):
         for c in self.classes:
@@ -168,12 +173,16 @@ class FoldedConv:
 
     def wgrad(self, x, dy, dw_addr, slot_stride, grp, E, R):
         """dy [R, Ho*Wo, N] -> parameter gradient in the reference layout (accumulated at dw_addr)."""
+        import ctypes
         for c in self.classes:
             c["dw_f"].zero_()
             dyp = empty(R, c["Hp"] * c["Wp"], self.N, dtype=BF)
             L.call("es_pick_pixels", dy, self.Ho, self.Wo, self.N, self.oy_per, c["py"], self.ox_per, c["px"], c["Hp"], c["Wp"], R, dyp)
             L.call("es_igemm_taps_wgrad", x, dyp, c["dw_f"], c["g_wg"], grp, E, R)
-            L.call("es_unfold_up2_wgrad", c["dw_f"], E, self.N, self.C, self.KH, self.KW, c["table"], dw_addr, slot_stride)
+        # every class's folded gradient -> the reference layout, one read-modify-write of the gradient arena
+        tarr = (L.ESFoldTable * len(self.classes))(*[c["table"] for c in self.classes])
+        iarr = (ctypes.c_void_p * len(self.classes))(*[c["dw_f"].data_ptr() for c in self.classes])
+        L.call("es_unfold_wgrad_multi", iarr, E, self.N, self.C, self.KH, self.KW, tarr, len(self.classes), dw_addr, slot_stride)
 
     def dgrad(self, dy, dx, grp, E, R):
         """dy [R, Ho*Wo, N] -> dx [R, dg_grid, C]: on the LOW-resolution grid for exact x2 folding (the upsample's backward

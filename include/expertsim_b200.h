@@ -191,9 +191,18 @@ typedef struct {
 /* w fp32 [slots][N][C][KH][KW] -> w_fwd bf16 [slots][N][n_taps][C] and/or w_dgrad bf16 [slots][C][n_taps][N] (pre-summed) */
 int es_fold_up2_weights(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW,
                         const es_fold_table* t, void* w_fwd, void* w_dgrad, void* stream);
+/* the same for several tables in ONE pass over the weights: outs[j] receives table j's folded weights, all in the forward
+ * layout [slots][N][n_taps_j][C] (dgrad_layout == 0) or all in the data-gradient layout [slots][C][n_taps_j][N] (!= 0).
+ * tables / outs are HOST arrays of n_tables <= 13 entries (copied into the launch). */
+int es_fold_weights_multi(const float* w, long slot_stride, int slots, int N, int C, int KH, int KW,
+                          const es_fold_table* tables, int n_tables, void* const* outs, int dgrad_layout, void* stream);
 /* dw_ref[slot][n][c][ky][kx] += sum over the folded taps whose mask contains (ky, kx), of dw_folded[slot][n][t][c] */
 int es_unfold_up2_wgrad(const float* dw_folded, int slots, int N, int C, int KH, int KW, const es_fold_table* t,
                         float* dw_ref, long slot_stride, void* stream);
+/* all classes at once: dw_ref[slot][n][c][ky][kx] += sum_j sum over table j's folded taps ...  (dw_folded: HOST array of
+ * n_tables <= 13 device pointers, each [slots][N][n_taps_j][C]) */
+int es_unfold_wgrad_multi(const float* const* dw_folded, int slots, int N, int C, int KH, int KW,
+                          const es_fold_table* tables, int n_tables, float* dw_ref, long slot_stride, void* stream);
 /* dst[row, a*Wo + b, :] = src[row, (a*my + oy)*Wo_full + b*mx + ox, :]  (NHWC bf16; one output phase made contiguous) */
 int es_pick_pixels(const void* src, int Ho_full, int Wo_full, int C, int my, int oy, int mx, int ox, int Ho, int Wo,
                    int total_rows, void* dst, void* stream);
