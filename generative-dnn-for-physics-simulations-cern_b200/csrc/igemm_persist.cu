@@ -12,7 +12,7 @@
 //     the KH*KW shifted re-reads of a source line hit L1 instead of L2;
 //   * the CTA is persistent (one per SM, static tile striding) with a double-buffered TMEM accumulator, so the epilogue
 //     of tile i (TMEM -> registers -> +bias -> bf16 -> global) overlaps the main loop of tile i+1.
-// Warp roles: 0-3 A gather, 4 TMA producer (B), 5 MMA issuer + TMEM owner, 6-9 epilogue (TMEM lane quarter = warp % 4).
+// Warp roles: 0-7 A gather, 8 TMA producer (B), 9 MMA issuer + TMEM owner, 10-13 epilogue (TMEM lane quarter = warp % 4).
 #include <cuda.h>
 #include <stdlib.h>
 
