@@ -369,6 +369,7 @@ constexpr int kSResidentB = kSStages * kSMaxB;   // 144 KB: the room the per-sta
 
 struct StripParams {
   int resident;                                  // 1: the expert's whole weight matrix stays in shared memory across tiles
+  int stages;                                    // pipeline depth: 3, or 4 when four (strip + nx weight boxes) stages fit
   int n_strips, nx, dx0, Wp, Pp;                 // Pp = Ho * Wp
   signed char sdy[8];
   int skoff[8];                                  // weight column of the strip's first tap; tap i at skoff + i*C
@@ -390,6 +391,7 @@ igemm_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ 
   const int kStage = resident ? kSStageA : kSStageA + kStageB;       // resident: stages hold strips only
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
+  const int ns = sp.stages;                                           // 3 or 4 (the barrier area holds 4 + 4 stage barriers)
   const uint32_t wbase = base + kSStages * kSStageA;                  // resident weights: [k-step][tap][BN rows x 128 B]
   const uint32_t bar_base = base + kSStages * (kSStageA + kSMaxB);
   const uint32_t wfull_bar = bar_base + 8u * 14, wempty_bar = bar_base + 8u * 15;
@@ -413,7 +415,7 @@ igemm_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ 
     s_tiles[tid] = ceil_div(gq.rows * sp.Pp, kBM);
   }
   if (tid == 0) {
-    for (int s = 0; s < kSStages; ++s) {
+    for (int s = 0; s < ns; ++s) {
       mbar_init(full_bar(s), resident ? kGLoaders : kGLoaders + 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -462,8 +464,8 @@ igemm_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ 
       }
       int cb = 0, st = 0;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % kSStages;
-        if (it >= kSStages) mbar_wait(empty_bar(s), ((it / kSStages) - 1) & 1, p.err_flag, 1);
+        const int s = it % ns;
+        if (it >= ns) mbar_wait(empty_bar(s), ((it / ns) - 1) & 1, p.err_flag, 1);
         const uint32_t sa = base + s * kStage;
         const int c0 = cb * kBK + chunk * 8;
         const int dy = sp.sdy[st];
@@ -482,7 +484,7 @@ igemm_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ 
         if (it - signalled >= (uint32_t)kFLag) {
           cp_async_wait<kFLag>();
           fence_proxy_async();
-          mbar_arrive(full_bar(signalled % kSStages));
+          mbar_arrive(full_bar(signalled % ns));
           ++signalled;
         }
       }
@@ -490,7 +492,7 @@ igemm_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ 
     cp_async_wait<0>();
     fence_proxy_async();
     while (signalled < it) {
-      mbar_arrive(full_bar(signalled % kSStages));
+      mbar_arrive(full_bar(signalled % ns));
       ++signalled;
     }
   } else if (warp == kGW) {
@@ -517,8 +519,8 @@ igemm_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ 
           continue;
         }
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % kSStages;
-          if (it >= kSStages) mbar_wait(empty_bar(s), ((it / kSStages) - 1) & 1, p.err_flag, 4);
+          const int s = it % ns;
+          if (it >= ns) mbar_wait(empty_bar(s), ((it / ns) - 1) & 1, p.err_flag, 4);
           mbar_arrive_expect_tx(full_bar(s), (uint32_t)kStageB);
           for (int i = 0; i < sp.nx; ++i)
             tma_load_2d(base + s * kStage + kSStageA + i * BN * 128, &tmap_w, sp.skoff[st] + i * p.C + cb * kBK, wrow, full_bar(s));
@@ -549,8 +551,8 @@ igemm_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ 
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % kSStages;
-        mbar_wait(full_bar(s), (it / kSStages) & 1, p.err_flag, 2);
+        const int s = it % ns;
+        mbar_wait(full_bar(s), (it / ns) & 1, p.err_flag, 2);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = base + s * kStage;
@@ -956,6 +958,7 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
       sp.Pp = p.Ho * sp.Wp;
       okk = sp.Wp < 256 && (long)total_rows * sp.Pp < 2147483647L;
       static const bool res_on = [] { const char* e = getenv("ES_IGEMM_STRIP_RESIDENT"); return e && e[0] == '1'; }();   // measured slower (conv3: 2.79 vs 2.54 ms): opt-in
+      sp.stages = (!res_on && 4L * (kSStageA + sp.nx * p.BN * 128) <= (long)kSStages * (kSStageA + kSMaxB)) ? 4 : 3;
       sp.resident = res_on && p.n_tiles_n == 1 && (long)sp.n_strips * (p.C / kBK) * sp.nx * p.BN * 128 <= (long)kSResidentB;
     }
     if (okk) {
