@@ -621,6 +621,7 @@ class AuxEngineProton:
         L.call("es_maxpool_bwd", dx, s["i1"], 32, 27, 14, 2, 2, 1, 1, R, dn1)
         dc1 = self._gn_bwd(dn1, s["c1"], s["st1"], f"{fe}.conv1.1", 32, 27 * 14, 8, ACT_RELU, grp, R)
         self._conv_bwd(s["img"], dc1, f"{fe}.conv1.0", self.c1, grp, R, d_img, accumulate)
+        self._wstream, self._keep = None, []        # the parked tensors now live (only) in s["keep"]
 
 
 # =====================================================================================================================
