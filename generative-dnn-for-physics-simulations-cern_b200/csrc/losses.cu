@@ -201,6 +201,20 @@ __global__ void expm1_scatter_kernel(const float* __restrict__ img, const int32_
   const int r = blockIdx.x;
   const int dst = perm ? perm[r] : r;
   const float* s = img + (size_t)r * HW;
+  if ((HW & 3) == 0) {      // 16-byte accesses (rows are 16-byte aligned then): the scalar loop ran at 0.45 of the HBM rate
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    for (int i = threadIdx.x; i < HW / 4; i += blockDim.x) {
+      const float4 q = __ldg(s4 + i);
+      const float4 v = make_float4(expm1f(q.x), expm1f(q.y), expm1f(q.z), expm1f(q.w));
+      if (out64) {
+        double2* o = reinterpret_cast<double2*>(out64 + (size_t)dst * HW) + 2 * i;
+        o[0] = make_double2((double)v.x, (double)v.y);
+        o[1] = make_double2((double)v.z, (double)v.w);
+      }
+      if (out32) reinterpret_cast<float4*>(out32 + (size_t)dst * HW)[i] = v;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
     const float v = expm1f(s[i]);
     if (out64) out64[(size_t)dst * HW + i] = (double)v;
