@@ -894,6 +894,55 @@ void fill_maps_uc(int Hs, int Ws, int Hu, int Wu, unsigned char* ymap, unsigned 
 
 using namespace es;
 
+// Host-side plan of the strip variant: fills `sp` and returns true when the tap table of `p` (BN, n_tiles_n already set) is a
+// set of tap rows the strip kernel can run (see igemm_strip_kernel).  Also exported through es_igemm_fwd_plan (CPU-testable).
+static bool strip_plan(const FwdParams& p, long total_rows, StripParams& sp) {
+  static const bool strip_on = [] { const char* e = getenv("ES_IGEMM_STRIP"); return !(e && e[0] == '0'); }();
+  sp = StripParams{};
+  bool okk = strip_on && p.Hu == p.Hs && p.Wu == p.Ws && p.my == 1 && p.mx == 1 && p.BN <= 128 && p.n_taps >= 2;
+  if (okk) {
+    int t = 0;
+    while (okk && t < p.n_taps) {
+      int n = 1;
+      while (t + n < p.n_taps && p.tdy[t + n] == p.tdy[t] && p.tdx[t + n] == p.tdx[t] + n && p.tkoff[t + n] == p.tkoff[t] + n * p.C) ++n;
+      if (sp.n_strips == 0) { sp.nx = n; sp.dx0 = p.tdx[t]; }
+      okk = sp.n_strips < 8 && n == sp.nx && p.tdx[t] == sp.dx0;
+      if (okk) { sp.sdy[sp.n_strips] = p.tdy[t]; sp.skoff[sp.n_strips] = p.tkoff[t]; ++sp.n_strips; }
+      t += n;
+    }
+    okk = okk && sp.nx >= 2 && sp.nx <= 4 && sp.nx * p.BN <= 384;
+  }
+  if (okk) {
+    sp.Wp = p.Wo + sp.nx - 1;
+    sp.Pp = p.Ho * sp.Wp;
+    okk = sp.Wp < 256 && total_rows * sp.Pp < 2147483647L;
+    static const bool res_on = [] { const char* e = getenv("ES_IGEMM_STRIP_RESIDENT"); return e && e[0] == '1'; }();   // measured slower (conv3: 2.79 vs 2.54 ms): opt-in
+    sp.stages = (!res_on && 4L * (kSStageA + sp.nx * p.BN * 128) <= (long)kSStages * (kSStageA + kSMaxB)) ? 4 : 3;
+    sp.resident = res_on && p.n_tiles_n == 1 && (long)sp.n_strips * (p.C / kBK) * sp.nx * p.BN * 128 <= (long)kSResidentB;
+  }
+  return okk;
+}
+
+// widest N tile (power of two, >= 32) that divides N
+static void pick_bn(FwdParams& p) {
+  p.BN = 256;
+  while (p.BN > 32 && p.Nout % p.BN != 0) p.BN >>= 1;
+  p.n_tiles_n = p.Nout / p.BN;
+}
+
+static void conv_taps(const es_conv_geom* g, FwdParams& p) {
+  p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
+  p.n_taps = g->KH * g->KW; p.my = 1; p.mx = 1;
+  for (int ky = 0; ky < g->KH; ++ky)
+    for (int kx = 0; kx < g->KW; ++kx) {
+      const int t = ky * g->KW + kx;
+      p.tdy[t] = (signed char)(ky - g->pad); p.tdx[t] = (signed char)(kx - g->pad); p.tkoff[t] = t * g->C;
+    }
+  p.KK = g->KH * g->KW * g->C;
+  p.Nout = g->N;
+  p.o_my = 1; p.o_oy = 0; p.o_mx = 1; p.o_ox = 0; p.Wo_full = g->Wo; p.P_full = g->Ho * g->Wo;
+}
+
 static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows, int n_groups, void* stream) {
   ES_REQUIRE(p.C > 0 && p.C % 64 == 0 && p.Hu <= 64 && p.Wu <= 64 && p.Hu >= p.Hs && p.Wu >= p.Ws && p.Ho > 0 && p.Wo > 0 &&
                  p.Ho < 256 && p.Wo < 256 && p.n_taps >= 1 && p.n_taps <= 32 && p.KK % 8 == 0,
@@ -901,11 +950,9 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
   ES_REQUIRE(n_groups >= 1 && n_groups <= kFMaxGroups && total_rows > 0, "bad group count / rows");
   p.n_groups = n_groups;
   p.P = p.Ho * p.Wo;
-  p.BN = 256;                                   // widest N tile (power of two, >= 32) that divides N
-  while (p.BN > 32 && p.Nout % p.BN != 0) p.BN >>= 1;
+  pick_bn(p);
   ES_REQUIRE(p.Nout % p.BN == 0, "N must be a multiple of 32");
   ES_REQUIRE((long)total_rows * p.Hs * p.Ws < 2147483647L && (long)total_rows * p.P_full < 2147483647L, "too many pixels");
-  p.n_tiles_n = p.Nout / p.BN;
   fill_maps_uc(p.Hs, p.Ws, p.Hu, p.Wu, p.ymap, p.xmap);
   p.a_src = (const __nv_bfloat16*)x;
   p.err_flag = fwd_err_flag();
@@ -938,29 +985,8 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
   // Strip variant (see igemm_strip_kernel): no upsample, taps form rows of consecutive dx with consecutive weight columns,
   // N <= 128.  ES_IGEMM_STRIP=0 disables it (A/B measurements).
   {
-    static const bool strip_on = [] { const char* e = getenv("ES_IGEMM_STRIP"); return !(e && e[0] == '0'); }();
     StripParams sp{};
-    bool okk = strip_on && p.Hu == p.Hs && p.Wu == p.Ws && p.my == 1 && p.mx == 1 && p.BN <= 128 && p.n_taps >= 2;
-    if (okk) {
-      int t = 0;
-      while (okk && t < p.n_taps) {
-        int n = 1;
-        while (t + n < p.n_taps && p.tdy[t + n] == p.tdy[t] && p.tdx[t + n] == p.tdx[t] + n && p.tkoff[t + n] == p.tkoff[t] + n * p.C) ++n;
-        if (sp.n_strips == 0) { sp.nx = n; sp.dx0 = p.tdx[t]; }
-        okk = sp.n_strips < 8 && n == sp.nx && p.tdx[t] == sp.dx0;
-        if (okk) { sp.sdy[sp.n_strips] = p.tdy[t]; sp.skoff[sp.n_strips] = p.tkoff[t]; ++sp.n_strips; }
-        t += n;
-      }
-      okk = okk && sp.nx >= 2 && sp.nx <= 4 && sp.nx * p.BN <= 384;
-    }
-    if (okk) {
-      sp.Wp = p.Wo + sp.nx - 1;
-      sp.Pp = p.Ho * sp.Wp;
-      okk = sp.Wp < 256 && (long)total_rows * sp.Pp < 2147483647L;
-      static const bool res_on = [] { const char* e = getenv("ES_IGEMM_STRIP_RESIDENT"); return e && e[0] == '1'; }();   // measured slower (conv3: 2.79 vs 2.54 ms): opt-in
-      sp.stages = (!res_on && 4L * (kSStageA + sp.nx * p.BN * 128) <= (long)kSStages * (kSStageA + kSMaxB)) ? 4 : 3;
-      sp.resident = res_on && p.n_tiles_n == 1 && (long)sp.n_strips * (p.C / kBK) * sp.nx * p.BN * 128 <= (long)kSResidentB;
-    }
+    bool okk = strip_plan(p, total_rows, sp);
     if (okk) {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
@@ -1018,18 +1044,29 @@ extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, lon
                  g->Wo == g->Wu + 2 * g->pad - g->KW + 1, "unsupported window (stride 1, <= 32 taps)");
   FwdParams p{};
   p.grp = grp;
-  p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
-  p.n_taps = g->KH * g->KW; p.my = 1; p.mx = 1;
-  for (int ky = 0; ky < g->KH; ++ky)
-    for (int kx = 0; kx < g->KW; ++kx) {
-      const int t = ky * g->KW + kx;
-      p.tdy[t] = (signed char)(ky - g->pad); p.tdx[t] = (signed char)(kx - g->pad); p.tkoff[t] = t * g->C;
-    }
-  p.KK = g->KH * g->KW * g->C;
-  p.Nout = g->N;
-  p.o_my = 1; p.o_oy = 0; p.o_mx = 1; p.o_ox = 0; p.Wo_full = g->Wo; p.P_full = g->Ho * g->Wo;
+  conv_taps(g, p);
   p.bias = bias; p.bias_slot_stride = bias_slot_stride; p.out = (__nv_bfloat16*)y;
   return launch_fwd(p, x, w, total_rows, n_groups, stream);
+}
+
+extern "C" int es_igemm_fwd_plan(const es_conv_geom* g, int total_rows, int32_t* plan8) {
+  ES_REQUIRE(g && plan8 && total_rows > 0, "null pointer");
+  ES_REQUIRE(g->KH >= 1 && g->KW >= 1 && g->KH * g->KW <= 32 && g->Ho == g->Hu + 2 * g->pad - g->KH + 1 &&
+                 g->Wo == g->Wu + 2 * g->pad - g->KW + 1 && g->N % 32 == 0, "unsupported window (stride 1, <= 32 taps, N % 32 == 0)");
+  FwdParams p{};
+  conv_taps(g, p);
+  pick_bn(p);
+  StripParams sp{};
+  const bool strip = strip_plan(p, total_rows, sp);
+  plan8[0] = strip ? 1 : 0;
+  plan8[1] = p.BN;
+  plan8[2] = strip ? sp.n_strips : 0;
+  plan8[3] = strip ? sp.nx : 0;
+  plan8[4] = strip ? sp.Wp : p.Wo;
+  plan8[5] = strip ? sp.stages : kFStages;
+  plan8[6] = (strip ? sp.n_strips : p.n_taps) * (p.C / kBK);                    /* pipeline steps per tile */
+  plan8[7] = (int32_t)ceil_div_l((long)(strip ? sp.Pp : p.Ho * p.Wo), kBM);     /* M tiles per row (per n tile) */
+  return ES_OK;
 }
 
 extern "C" int es_igemm_taps_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,

@@ -165,6 +165,12 @@ int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot
  * sees ceil((KH+1-py)/2)-ish distinct source rows, so four phase convs with pre-summed taps (es_fold_up2_weights) do
  * 25 instead of 64 tap-MACs per 4 outputs for k4/p1 (2.56x fewer), and the data gradient is ONE table-conv over dy
  * (my = mx = 2) writing the low-resolution gradient directly. */
+/* Host-only: which kernel variant es_igemm_fwd picks for geometry g (no device work; callable without a GPU).
+ * plan8 = {strip variant (0/1), BN, tap rows, taps per row (nx), M-axis row pitch (Wo, or Wo + nx - 1 for strips),
+ *          pipeline stages, pipeline steps per tile, M tiles per row}.  The strip variant (one gathered strip per tap row,
+ * kx taps as row-shifted A descriptors) needs: no upsample, N <= 128, 2..4 taps per row, nx * BN <= 384. */
+int es_igemm_fwd_plan(const es_conv_geom* g, int total_rows, int32_t* plan8);
+
 typedef struct {
   int32_t Hs, Ws, C;
   int32_t Hu, Wu;

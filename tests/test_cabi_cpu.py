@@ -50,3 +50,31 @@ def test_binding_rejects_host_tensors():
 
 def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(L.ESGroup) == 16 and ctypes.sizeof(L.ESConvGeom) == 44 and ctypes.sizeof(L.ESConv2d) == 40
+
+
+def test_forward_gemm_variant_plan():
+    """es_igemm_fwd_plan (host-only): which convs take the strip variant (one gathered strip per tap row, kx taps as
+    row-shifted A descriptors) and with which pipeline — no upsample, N <= 128, 2..4 taps per row, nx * BN <= 384."""
+    import ctypes
+
+    from expertsim import _lib as L
+    lib = L.load()
+
+    def plan(Hs, Ws, C, Hu, Wu, K, pad, N, rows=2048):
+        g = L.ESConvGeom(Hs, Ws, C, Hu, Wu, Hu + 2 * pad - K + 1, Wu + 2 * pad - K + 1, K, K, pad, N)
+        out = (ctypes.c_int32 * 8)()
+        assert lib.es_igemm_fwd_plan(ctypes.addressof(g), rows, ctypes.addressof(out)) == 0, L.last_error()
+        return list(out)
+
+    # proton conv3 forward (3x3, 128 -> 64) and its data gradient (64 -> 128): strips of 3 taps, padded pitch 29 + 2
+    assert plan(55, 29, 128, 55, 29, 3, 1, 64) == [1, 64, 3, 3, 31, 4, 6, (55 * 31 + 127) // 128]
+    assert plan(55, 29, 64, 55, 29, 3, 1, 128) == [1, 128, 3, 3, 31, 3, 3, (55 * 31 + 127) // 128]
+    # neutron conv9 (2x2, 128 -> 64, no padding): two rows of two taps
+    assert plan(46, 46, 128, 46, 46, 2, 0, 64)[:5] == [1, 64, 2, 2, 46]
+    # an upsample in front of the conv, N = 256, or a 1x1 "conv" (fc2) keep the tiled kernel
+    assert plan(35, 19, 256, 56, 30, 4, 1, 128)[:2] == [0, 128]
+    assert plan(55, 29, 128, 55, 29, 4, 2, 256)[:2] == [0, 256]
+    assert plan(1, 1, 256, 1, 1, 1, 0, 92160)[:3] == [0, 256, 0]
+    # 4 taps per row only while nx * BN <= 384
+    assert plan(20, 20, 64, 20, 20, 4, 1, 64)[:4] == [1, 64, 4, 4]
+    assert plan(20, 20, 64, 20, 20, 4, 1, 128)[0] == 0
