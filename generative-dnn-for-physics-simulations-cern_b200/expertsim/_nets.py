@@ -729,7 +729,9 @@ class GenEngineNeutron:
                 sites[site] = (drop[site], 0) if drop is not None else (None, _seed())
             return sites[site]
 
-        return dict(grp=grp, grp_slots=grp, R=R, two_pass=two_pass, training=training, drop=dropf,
+        # grp_slots gates the per-expert STATE updates (running statistics, affine gradients from all-reduced sums): under
+        # data parallelism that is the liveness table built from the GLOBAL counts, not this rank's rows
+        return dict(grp=grp, grp_slots=(dp or {}).get("live_gen", grp), R=R, two_pass=two_pass, training=training, drop=dropf,
                     n_rows=n_rows.repeat_interleave(2).contiguous(), allreduce=(dp or {}).get("allreduce", _noop),
                     world=(dp or {}).get("world", 1))
 
@@ -842,7 +844,8 @@ class AuxEngineNeutron:
         g = grp.view(E, 4)
         n_rows = dp["rows_global"] if dp.get("rows_global") is not None else g[:, 1].to(torch.float32)
         n_rows = n_rows.repeat_interleave(2).contiguous()
-        s = {"R": R, "grp": grp, "layers": [], "allreduce": allreduce, "world": world}
+        live = dp.get("live_half", grp)      # gates running statistics / affine gradients (global liveness under DP)
+        s = {"R": R, "grp": grp, "layers": [], "allreduce": allreduce, "world": world, "live": live}
         x = img
         for name, c, bn, site, pool in self.layers:
             has_bias = (name + ".bias") in a.off
@@ -856,7 +859,7 @@ class AuxEngineNeutron:
                 allreduce(sums)
             n_sg = (n_rows * P).contiguous()
             L.call("es_bn_finalize", sums, n_sg, c.Co, 1, int(training), 0.1, None, a.baddr(bn + ".running_mean"),
-                   a.baddr(bn + ".running_var"), a.nb, a.iaddr(bn + ".num_batches_tracked"), a.ni, grp if training else None, E, stats)
+                   a.baddr(bn + ".running_var"), a.nb, a.iaddr(bn + ".num_batches_tracked"), a.ni, live if training else None, E, stats)
             p = self.P_DROP if (training and site) else 0.0
             mask, seed = (masks[site], 0) if (masks is not None and site) else (None, _seed() if p else 0)
             act = empty(R, c.Co, c.Ho, c.Wo)
@@ -899,7 +902,7 @@ class AuxEngineNeutron:
             common = (a.addr(bn + ".weight"), a.addr(bn + ".bias"), n, rec["mask"], rec["seed"], rec["p"], grp, E, R)
             L.call("es_bn2d_bwd_reduce", d, rec["y"], c.Co, P, rec["stats"], *common, sums2)
             s["allreduce"](sums2)
-            L.call("es_bn_affine_grads", sums2, c.Co, 1, 1.0 / s["world"], None, grp, E, a.gaddr(bn + ".weight"), a.gaddr(bn + ".bias"), n)
+            L.call("es_bn_affine_grads", sums2, c.Co, 1, 1.0 / s["world"], None, s["live"], E, a.gaddr(bn + ".weight"), a.gaddr(bn + ".bias"), n)
             dy = zeros(R, c.Co, c.Ho, c.Wo)
             L.call("es_bn2d_bwd_apply", d, rec["y"], c.Co, P, rec["stats"], sums2, rec["n_sg"], *common, dy)
             has_bias = (name + ".bias") in a.off

@@ -56,7 +56,7 @@ class BucketedGradReducer:
             self.dist.all_reduce(G, op=self.dist.ReduceOp.SUM, group=self.group)
             return
         rows = [G[e, lo:hi] for e in range(G.shape[0])]
-        if G.is_cuda:
+        if G.is_cuda and self.dist.get_backend(self.group) == "nccl":
             with self.dist._coalescing_manager(group=self.group, device=G.device, async_ops=False):
                 for t in rows:
                     self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)

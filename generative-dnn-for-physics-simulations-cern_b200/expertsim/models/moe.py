@@ -66,11 +66,15 @@ class MoEWrapper(nn.Module):
     def _bind(self):
         """(Re)build the shared arenas: expert e of each network kind becomes slot e of one flat [E, n] tensor."""
         dev = next(self.router.parameters()).device
-        self._arenas = {}
+        old, self._arenas = self._arenas, {}
         for key, mods in (("g", self.generators), ("d", self.discriminators), ("a", self.aux_regs), ("r", [self.router])):
             arena = Arena(mods[0]._spec, len(mods), dev)
             for e, m in enumerate(mods):
                 arena.adopt(m, e)
+            if key in old:      # a re-bind after .to()/.cuda(): the optimizer state moves with the parameters, as torch's does
+                arena.M.copy_(old[key].M)
+                arena.V.copy_(old[key].V)
+                arena.steps.copy_(old[key].steps)
             self._arenas[key] = arena
 
     def _apply(self, fn, recurse=True):
@@ -167,11 +171,22 @@ class MoEWrapper(nn.Module):
 
     @staticmethod
     def _lr(opt, default):
+        """Learning rate of one network kind, read from the optimizer handles.  ONE fused launch updates every expert
+        with torch.optim.Adam's defaults (as training_setup.py:12-41 builds them), so the handles of a kind must agree:
+        per-expert learning rates / non-default betas or eps are refused loudly instead of being ignored."""
         if opt is None:
             return default
-        if isinstance(opt, (list, tuple)):
-            opt = opt[0]
-        return float(opt.param_groups[0]["lr"])
+        opts = list(opt) if isinstance(opt, (list, tuple)) else [opt]
+        lr = float(opts[0].param_groups[0]["lr"])
+        for o in opts:
+            for g in o.param_groups:
+                if float(g["lr"]) != lr:
+                    raise NotImplementedError(f"per-expert learning rates ({g['lr']} vs {lr}) are not supported by the fused Adam")
+                if tuple(g.get("betas", (0.9, 0.999))) != (0.9, 0.999) or float(g.get("eps", 1e-8)) != 1e-8 or \
+                        g.get("weight_decay", 0) or g.get("amsgrad", False):
+                    raise NotImplementedError("the fused Adam implements torch.optim.Adam defaults only (betas=(0.9, 0.999), "
+                                              "eps=1e-8, no weight decay / amsgrad), as the reference's setup_optimizers")
+        return lr
 
     def _tau(self, epoch):
         rc = self.cfg.model.router
@@ -219,13 +234,21 @@ class MoEWrapper(nn.Module):
         main.wait_event(ev_route)
         perm, gh, gg = r["perm"], r["grp_half"], r["grp_gen"]
         counts_g = r["counts"].to(torch.float32)
+        lv_h, lv_g = gh, gg     # LIVENESS tables: gate everything that must advance identically on every replica
         if world > 1:   # skip rule and every mean use the GLOBAL per-expert count
             self._allreduce(counts_g)
-            dead = (counts_g < 2).to(torch.int32)
-            gh[:, 1] *= 1 - dead
-            gh[:, 3] *= 1 - dead
-            gg[:, 1] *= 1 - dead
-            gg[:, 3] *= 1 - dead
+            alive = (counts_g >= 2).to(torch.int32)
+            gh[:, 1] *= alive
+            gh[:, 3] *= alive
+            gg[:, 1] *= alive
+            gg[:, 3] *= alive
+            # A rank may hold NO rows of an expert that is alive globally (unbalanced routing is the normal regime of
+            # an MoE).  The row-walking kernels see the local tables (rows = 0: nothing to do); the per-expert STATE
+            # updates — fused Adam + step counters, spectral-norm power iterations, BatchNorm running statistics and
+            # the affine gradients built from all-reduced sums — are gated on the GLOBAL count instead, otherwise the
+            # replicas would diverge for good.
+            lv_h, lv_g = gh.clone(), gg.clone()
+            lv_h[:, 1], lv_h[:, 3], lv_g[:, 1], lv_g[:, 3] = alive, alive, alive, alive
 
         # ---- expert-sorted views of the batch (cond[mask], real[mask], ...; moe.py:143,150,165-168)
         cond_s = self._gather(cond, perm, 9)
@@ -242,7 +265,8 @@ class MoEWrapper(nn.Module):
         # data-parallel context of the BatchNorm layers (neutron): SyncBN over the global per-expert rows
         dp = None
         if world > 1:
-            dp = {"allreduce": self._allreduce, "world": world, "rows_global": counts_g * (counts_g >= 2).to(torch.float32)}
+            dp = {"allreduce": self._allreduce, "world": world, "rows_global": counts_g * (counts_g >= 2).to(torch.float32),
+                  "live_gen": lv_g, "live_half": lv_h}
 
         # Independent chains of small kernels run on side streams (they are latency-bound, not throughput-bound):
         #   D(real) forward            || generator forward
@@ -251,7 +275,7 @@ class MoEWrapper(nn.Module):
         ev0 = main.record_event()
         with torch.cuda.stream(s1):
             s1.wait_event(ev0)
-            sn_a = disc.spectral(gh, self.training)
+            sn_a = disc.spectral(lv_h, self.training)
             ev_a = s1.record_event()
             s_real, _, sv_real = disc.forward(real_s, cond_s, gh, B, sn_a)
             ev_real = s1.record_event()
@@ -288,7 +312,7 @@ class MoEWrapper(nn.Module):
 
         # ---- discriminator step (moe.py:506-527)
         main.wait_event(ev_a)
-        sn_b = disc.spectral(gh, self.training)
+        sn_b = disc.spectral(lv_h, self.training)
         s_fake, _, sv_fake = disc.forward(img1, cond_s, gh, B, sn_b)
         main.wait_event(ev_real)
         d_real, d_fake = torch.zeros(B, device=dev), torch.zeros(B, device=dev)
@@ -303,15 +327,15 @@ class MoEWrapper(nn.Module):
         disc.backward(sv_fake, sn_b, d_fake, None, want_w=True)
         main.wait_event(ev_br)
         self._allreduce(a_d.G)
-        self._adam(a_d, self._lr(discriminator_optimizers, cfgm.discriminator.lr_d), gh)
+        self._adam(a_d, self._lr(discriminator_optimizers, cfgm.discriminator.lr_d), lv_h)
         del sv_real, sv_fake
 
         # ---- generator step (moe.py:529-571): D carries its UPDATED weights
-        sn_c = disc.spectral(gh, self.training)
+        sn_c = disc.spectral(lv_h, self.training)
         ev_c = main.record_event()
         with torch.cuda.stream(s1):
             s1.wait_event(ev_c)
-            sn_d = disc.spectral(gh, self.training)
+            sn_d = disc.spectral(lv_h, self.training)
             _, lat2, sv2 = disc.forward(img2, cond_s, gh, B, sn_d)
             ev_f2 = s1.record_event()
         score1, lat1, sv1 = disc.forward(img1, cond_s, gh, B, sn_c)
@@ -367,9 +391,11 @@ class MoEWrapper(nn.Module):
             gen.backward(sg, d_img1, d_img2)
             self._allreduce(a_g.G)
         del sg, sv1, sv2, sv_a
-        self._adam(a_g, self._lr(generator_optimizers, gcfg.lr_g), gh)
+        self._adam(a_g, self._lr(generator_optimizers, gcfg.lr_g), lv_h)
+        if ema_helper is not None and getattr(ema_helper, "enabled", False):
+            ema_helper.update(self, live=lv_h[:, 1])      # only the experts that took an optimizer step (loop.py:392-400)
         main.wait_event(ev_aw)
-        self._adam(a_a, self._lr(aux_reg_optimizers, cfgm.aux_reg.lr_a), gh)
+        self._adam(a_a, self._lr(aux_reg_optimizers, cfgm.aux_reg.lr_a), lv_h)
 
         # ---- router loss (moe.py:213-449) and metrics
         zero = torch.zeros((), device=dev)

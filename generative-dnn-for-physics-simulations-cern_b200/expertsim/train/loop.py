@@ -23,7 +23,11 @@ def train(cfg, train_loader, test_loader=None) -> List[Dict]:
         raise RuntimeError("expertsim (B200) trains on a CUDA device only; there is no CPU fallback")
     device = torch.device("cuda", torch.cuda.current_device())
     moe = setup_moe_system(cfg, device)
-    ema_helper = EMAHelper(moe, decay=0.99)
+    # The reference constructs the helper and hands it to every step but never calls .update() (moe.py:52-504 does not
+    # touch ``ema_helper``): with ``train.use_ema`` unset this build behaves the same.  With the flag set the generators'
+    # EMA is advanced inside the step (device-side, gated on the experts that took an optimizer step) and the evaluation
+    # of every epoch runs on the EMA weights.
+    ema_helper = EMAHelper(moe, decay=0.99, enabled=bool((cfg.get("train") or {}).get("use_ema", False)))
     gen_optims, disc_optims, aux_reg_optim, router_optim = setup_optimizers(moe, cfg)
     callbacks = setup_callbacks(cfg, moe)
     history = []
@@ -35,7 +39,13 @@ def train(cfg, train_loader, test_loader=None) -> List[Dict]:
                                     epoch, ema_helper)
         t_train = time.time() - t0
         if test_loader is not None:
-            epoch_metrics.update(evaluate_epoch(moe, test_loader, epoch, cfg, device))
+            if ema_helper.enabled:
+                ema_helper.apply_shadow(moe)
+            try:
+                epoch_metrics.update(evaluate_epoch(moe, test_loader, epoch, cfg, device))
+            finally:
+                if ema_helper.enabled:
+                    ema_helper.restore(moe)
         epoch_metrics["epoch_time"] = time.time() - t0
         epoch_metrics["epoch"] = epoch
         for cb in callbacks:
@@ -122,18 +132,28 @@ def setup_callbacks(cfg, moe) -> List:
 
 
 class EMAHelper:
-    """Exponential moving average of the generators (reference loop.py:380-418).  The shadow copy is one tensor per
-    generator arena, updated with a single lerp."""
+    """Exponential moving average of the generators (reference loop.py:380-418: shadow = decay * shadow + (1 - decay) *
+    param for the generators that got an optimizer step; apply_shadow / restore swap the weights for evaluation).  The
+    shadow is ONE tensor shaped like the generator arena, advanced with a single in-place lerp; ``live`` is the
+    device-side per-expert mask of the step (no host sync)."""
 
-    def __init__(self, moe, decay=0.999):
-        self.decay = decay
+    def __init__(self, moe, decay=0.999, enabled=False):
+        self.decay, self.enabled = decay, enabled
         self.shadow = moe.arena("g").P.clone()
         self.backup = None
 
-    def update(self, moe, updated_indices=None):
+    def update(self, moe, updated_indices=None, live=None):
         P = moe.arena("g").P
-        idx = list(range(P.shape[0])) if updated_indices is None else list(updated_indices)
-        self.shadow[idx] = self.decay * self.shadow[idx] + (1.0 - self.decay) * P[idx]
+        if self.shadow.device != P.device:
+            self.shadow = self.shadow.to(P.device)
+        w = torch.full((P.shape[0], 1), 1.0 - self.decay, device=P.device)
+        if live is not None:
+            w = w * (live.reshape(-1, 1) > 0).to(w.dtype)
+        elif updated_indices is not None:
+            mask = torch.zeros(P.shape[0], 1, device=P.device)
+            mask[list(updated_indices)] = 1.0
+            w = w * mask
+        self.shadow.lerp_(P, w)
 
     def apply_shadow(self, moe):
         a = moe.arena("g")

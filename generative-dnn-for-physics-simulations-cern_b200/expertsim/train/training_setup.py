@@ -19,12 +19,26 @@ def count_model_parameters(model):
     return sum(p.numel() for p in model.parameters() if p.requires_grad)
 
 
+def _torch_adam_defaults(lr):
+    """param_group defaults of torch.optim.Adam in the running torch version (so a state_dict written here loads into a
+    stock torch optimizer and vice versa)"""
+    d = dict(torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))], lr=float(lr)).defaults)
+    d["lr"] = float(lr)
+    return d
+
+
 class ArenaAdam:
-    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8) for one arena slot (one expert of one network kind)."""
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8) for one arena slot (one expert of one network kind).
+
+    ``state_dict()`` / ``load_state_dict()`` speak torch.optim.Adam's format (``{'state': {i: {'step', 'exp_avg',
+    'exp_avg_sq'}}, 'param_groups': [{..., 'params': [0..n-1]}]}``, parameters in ``module.parameters()`` order — the
+    reference's order, since the modules register the reference's names in the reference's order), so the
+    ``*_optim_*_epoch_N.pth`` files of the reference (train/training_utils.py:316-380) and of this build interchange in
+    both directions.  The moments themselves live in the arena (``M``, ``V``, ``steps``)."""
 
     def __init__(self, module, lr: float):
         self.module = module
-        self.defaults = dict(lr=float(lr), betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False)
+        self.defaults = _torch_adam_defaults(lr)
         self.param_groups = [dict(self.defaults, params=list(module.parameters()))]
 
     @property
@@ -45,17 +59,54 @@ class ArenaAdam:
                a.steps[s:s + 1], None)
         a.version += 1
 
+    def _names(self):
+        return [n for n, _ in self.module.named_parameters()]
+
     def state_dict(self):
         a, s = self._arena, self.module._slot
-        return {"step": int(a.steps[s]), "exp_avg": a.M[s].clone(), "exp_avg_sq": a.V[s].clone(),
-                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+        names = self._names()
+        step = int(a.steps[s])
+        state = {}
+        if step > 0:        # torch keeps no state for parameters that never stepped
+            for i, n in enumerate(names):
+                state[i] = {"step": torch.tensor(float(step)), "exp_avg": a.view(a.M, n, s).clone(),
+                            "exp_avg_sq": a.view(a.V, n, s).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(names)))
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
         a, s = self._arena, self.module._slot
-        a.steps[s] = int(sd["step"])
-        a.M[s].copy_(sd["exp_avg"])
-        a.V[s].copy_(sd["exp_avg_sq"])
-        self.param_groups[0].update(sd["param_groups"][0])
+        names = self._names()
+        if "state" in sd:                                   # torch.optim.Adam format (the reference's files, and ours)
+            groups = sd["param_groups"]
+            order = [i for g in groups for i in g["params"]]
+            if len(order) != len(names):
+                raise ValueError(f"optimizer state holds {len(order)} parameters, the module has {len(names)}")
+            steps = set()
+            a.M[s].zero_()
+            a.V[s].zero_()
+            for pos, key in enumerate(order):
+                st = sd["state"].get(key)
+                if st is None:
+                    continue
+                m, v = a.view(a.M, names[pos], s), a.view(a.V, names[pos], s)
+                if tuple(st["exp_avg"].shape) != tuple(m.shape):
+                    raise ValueError(f"{names[pos]}: optimizer state has shape {tuple(st['exp_avg'].shape)}, expected {tuple(m.shape)}")
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+            if len(steps) > 1:
+                raise ValueError(f"parameters of one module carry different step counts {sorted(steps)}: not representable "
+                                 "by the fused per-expert Adam")
+            a.steps[s] = steps.pop() if steps else 0
+            g0 = {k: v for k, v in groups[0].items() if k != "params"}
+        else:                                               # flat layout written by round-1 builds of this package
+            a.steps[s] = int(sd["step"])
+            a.M[s].copy_(sd["exp_avg"])
+            a.V[s].copy_(sd["exp_avg_sq"])
+            g0 = {k: v for k, v in sd["param_groups"][0].items() if k != "params"}
+        self.param_groups[0].update(g0)
 
 
 def setup_optimizers(wrapper, cfg) -> Tuple[List, List, List, ArenaAdam]:

@@ -38,6 +38,22 @@ class DeviceLoader:
         self.n = data["x"].shape[0]
         self.epoch, self.seed = 0, seed
 
+    @classmethod
+    def from_arrays(cls, x, cond, std, intensity, positions, batch_size, device="cuda", x_2=None, **kw):
+        """Loader over the arrays ``transform_data_for_training`` returns (data_transformations.py:118-258: x_train,
+        y_train, std_train, intensity_train, positions_train — numpy or torch, any float dtype), moved to ``device`` ONCE.
+        The reference wraps the same arrays in a TensorDataset of 6 tensors (data_transformations.py:269-271); batches
+        of this loader carry the same 6 positions ``(x, x_2, cond, std, intensity, positions)``."""
+        t = lambda a, w=None: _as_f32(a, w).to(device)
+        d = {"x": t(x), "cond": t(cond), "std": t(std, 1), "intensity": t(intensity, 1), "positions": t(positions)}
+        n = d["x"].shape[0]
+        for k, v in d.items():
+            if v.shape[0] != n:
+                raise ValueError(f"{k} holds {v.shape[0]} rows, x holds {n}")
+        if x_2 is not None:
+            d["x_2"] = t(x_2)
+        return cls(d, batch_size, **kw)
+
     def __len__(self):
         gb = self.bs * self.world
         return self.n // gb if self.drop_last else math.ceil(self.n / gb)
@@ -54,7 +70,78 @@ class DeviceLoader:
         for i in range(len(self)):
             ix = order[i * gb:(i + 1) * gb][self.rank::self.world]
             d = self.d
-            yield d["x"][ix], d["x"][ix], d["cond"][ix], d["std"][ix], d["intensity"][ix], d["positions"][ix]
+            x = d["x"][ix]
+            yield x, (d["x_2"][ix] if "x_2" in d else x), d["cond"][ix], d["std"][ix], d["intensity"][ix], d["positions"][ix]
+
+
+def _as_f32(a, width=None):
+    """numpy / torch / pandas values -> contiguous float32 CPU tensor; ``width`` reshapes 1-D columns to [n, width]"""
+    if hasattr(a, "to_numpy"):
+        a = a.to_numpy()
+    t = torch.as_tensor(a)
+    t = t.to(torch.float32)
+    if width is not None and t.dim() == 1:
+        t = t.reshape(-1, width)
+    return t.contiguous()
+
+
+class PinnedHostLoader:
+    """Batches from HOST arrays through pinned staging buffers: batch i+1 is copied host->device on a copy stream while
+    the step of batch i runs (two staging slots, one event per slot).  For sets that do not fit the device or must stay
+    on the host; same 6-tuple contract and rank sharding as DeviceLoader.  Replaces the reference's DataLoader with
+    ``pin_memory=True, prefetch_factor=4`` worker processes (data_transformations.py:273-279)."""
+
+    def __init__(self, x, cond, std, intensity, positions, batch_size, device="cuda", shuffle=False, rank=0, world=1, seed=0):
+        self.h = {"x": _as_f32(x), "cond": _as_f32(cond), "std": _as_f32(std, 1), "intensity": _as_f32(intensity, 1),
+                  "positions": _as_f32(positions)}
+        self.n, self.bs, self.dev = self.h["x"].shape[0], batch_size, torch.device(device)
+        self.shuffle, self.rank, self.world, self.seed, self.epoch = shuffle, rank, world, seed, 0
+        pin = self.dev.type == "cuda"
+        self.stage = [{k: torch.empty((batch_size,) + tuple(v.shape[1:]), pin_memory=pin) for k, v in self.h.items()} for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.dev) if pin else None
+
+    def __len__(self):
+        return self.n // (self.bs * self.world)
+
+    def _fill(self, slot, ix):
+        for k, v in self.h.items():
+            torch.index_select(v, 0, ix, out=self.stage[slot][k])
+
+    def __iter__(self):
+        order = torch.randperm(self.n, generator=torch.Generator().manual_seed(self.seed + self.epoch)) if self.shuffle \
+            else torch.arange(self.n)
+        self.epoch += 1
+        gb = self.bs * self.world
+        nb = len(self)
+        sel = lambda i: order[i * gb:(i + 1) * gb][self.rank::self.world]
+        if self.copy_stream is None:          # host-only use (CPU tests of the contract)
+            for i in range(nb):
+                self._fill(0, sel(i))
+                d = {k: v.clone() for k, v in self.stage[0].items()}
+                yield d["x"], d["x"], d["cond"], d["std"], d["intensity"], d["positions"]
+            return
+        free = [torch.cuda.Event(), torch.cuda.Event()]     # slot's previous device copy has been issued and finished
+        pending = None
+
+        def launch(i):
+            slot = i % 2
+            free[slot].synchronize()                         # the staging buffer is no longer being read by a copy
+            self._fill(slot, sel(i))
+            with torch.cuda.stream(self.copy_stream):
+                d = {k: v.to(self.dev, non_blocking=True) for k, v in self.stage[slot].items()}
+                free[slot].record(self.copy_stream)
+                ready = self.copy_stream.record_event()
+            return d, ready
+
+        if nb:
+            pending = launch(0)
+        for i in range(nb):
+            d, ready = pending
+            pending = launch(i + 1) if i + 1 < nb else None   # overlaps with the consumer's step of batch i
+            torch.cuda.current_stream(self.dev).wait_event(ready)
+            for v in d.values():
+                v.record_stream(torch.cuda.current_stream(self.dev))
+            yield d["x"], d["x"], d["cond"], d["std"], d["intensity"], d["positions"]
 
 
 def get_train_test_data_loaders(cfg, device="cuda", rank=0, world=1):
@@ -63,8 +150,9 @@ def get_train_test_data_loaders(cfg, device="cuda", rank=0, world=1):
     row 15) and raises."""
     n = cfg.dataset.get("synthetic_samples")
     if not n:
-        raise NotImplementedError("only dataset.synthetic_samples=N is supported: the reference's GEANT4 pickles are not "
-                                  "shipped and its pandas pipeline is outside the hot path")
+        raise NotImplementedError("dataset.synthetic_samples=N builds synthetic loaders; real data enters through "
+                                  "loaders_from_arrays(...) with the arrays of the reference's transform_data_for_training "
+                                  "(its GEANT4 pickles and pandas pipeline are not shipped: SURVEY.md §2 row 15)")
     arch = cfg.model.architecture
     data = synthetic_showers(arch, int(n), 0, device)
     n_test = int(int(n) * float(cfg.dataset.test_size))
@@ -72,3 +160,19 @@ def get_train_test_data_loaders(cfg, device="cuda", rank=0, world=1):
     te = {k: v[:n_test].cpu() for k, v in data.items()}
     return (DeviceLoader(tr, cfg.train.batch_size, True, rank, world),
             DeviceLoader(te, max(n_test, 1), False, 0, 1, drop_last=False))
+
+
+def loaders_from_arrays(cfg, x_train, x_test, y_train, y_test, std_train, std_test, intensity_train, intensity_test,
+                        positions_train, positions_test, device="cuda", rank=0, world=1, resident=True):
+    """(train_loader, test_loader) from the split arrays ``transform_data_for_training`` returns
+    (data_transformations.py:260-309 builds TensorDataset/DataLoader from exactly these).  ``resident`` keeps the training
+    set on the device (DeviceLoader); otherwise batches stream through pinned double-buffered staging (PinnedHostLoader)."""
+    bs = cfg.train.batch_size
+    if resident:
+        tr = DeviceLoader.from_arrays(x_train, y_train, std_train, intensity_train, positions_train, bs, device,
+                                      shuffle=False, rank=rank, world=world)
+    else:
+        tr = PinnedHostLoader(x_train, y_train, std_train, intensity_train, positions_train, bs, device, False, rank, world)
+    te = DeviceLoader.from_arrays(x_test, y_test, std_test, intensity_test, positions_test, bs, "cpu", shuffle=False,
+                                  drop_last=False)
+    return tr, te

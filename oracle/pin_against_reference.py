@@ -25,75 +25,8 @@ REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
-
-def install_reference():
-    for name in ("matplotlib", "matplotlib.pyplot", "seaborn", "wandb"):
-        if name not in sys.modules:
-            m = types.ModuleType(name)
-            m.rcParams = {}
-            sys.modules[name] = m
-    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    sys.path.insert(0, REF)
-    import expertsim  # noqa: F401  (the reference package)
-    pkg = types.ModuleType("expertsim.models")
-    pkg.__path__ = [REF + "/expertsim/models"]
-    sys.modules["expertsim.models"] = pkg
-
-
-class AttrDict(dict):
-    def __getattr__(self, k):
-        try:
-            return self[k]
-        except KeyError as e:
-            raise AttributeError(k) from e
-
-    def __setattr__(self, k, v):
-        self[k] = v
-
-
-def to_attr(d):
-    return AttrDict({k: to_attr(v) for k, v in d.items()}) if isinstance(d, dict) else d
-
-
-class NoiseInjector:
-    """Feeds pre-drawn noise to the reference's torch.randn / exponential_ / F.dropout call sites."""
-
-    def __init__(self):
-        self.randn_q, self.expo_q, self.drop_q = [], [], []
-        self._orig = {}
-
-    def __enter__(self):
-        self._orig = {"randn": torch.randn, "expo": torch.Tensor.exponential_, "drop": F.dropout}
-        inj = self
-
-        def randn(*size, **kw):
-            t = inj.randn_q.pop(0)
-            shape = tuple(size[0]) if len(size) == 1 and not isinstance(size[0], int) else tuple(size)
-            assert tuple(t.shape) == shape, (t.shape, shape)
-            return t.clone()
-
-        def exponential_(self_t, *a, **kw):
-            t = inj.expo_q.pop(0)
-            assert t.shape == self_t.shape, (t.shape, self_t.shape)
-            return self_t.copy_(t)
-
-        def dropout(x, p=0.5, training=True, inplace=False):
-            if not training:
-                return x
-            m, pm = inj.drop_q.pop(0)
-            assert abs(pm - p) < 1e-12 and m.numel() == x.numel(), (pm, p, m.shape, x.shape)
-            return x * m.view_as(x) / (1.0 - p)
-
-        torch.randn = randn
-        torch.Tensor.exponential_ = exponential_
-        F.dropout = dropout
-        return self
-
-    def __exit__(self, *a):
-        torch.randn = self._orig["randn"]
-        torch.Tensor.exponential_ = self._orig["expo"]
-        F.dropout = self._orig["drop"]
-        assert not self.randn_q and not self.expo_q and not self.drop_q, "unused injected noise"
+import oracle.ref_shim as shim  # noqa: E402
+from oracle.ref_shim import AttrDict, NoiseInjector, to_attr  # noqa: E402,F401
 
 
 def tensor_digest(t):
@@ -102,25 +35,8 @@ def tensor_digest(t):
 
 
 def build_reference_moe(orc, arch, E, seed, cfg):
-    from expertsim.models.moe import MoEWrapper
-    from expertsim.models.routers.router import RouterNetwork
-    if arch == "proton":
-        from expertsim.models.proton.generator import Generator as G
-        from expertsim.models.proton.discriminator import Discriminator as D
-        from expertsim.models.proton.aux_reg import AuxReg as A
-    else:
-        from expertsim.models.neutron.generator import GeneratorNeutron as G
-        from expertsim.models.neutron.discriminator import DiscriminatorNeutron as D
-        from expertsim.models.neutron.aux_reg import AuxRegNeutron as A
-    m = cfg.model
-    moe = MoEWrapper(G(m.noise_dim, m.cond_dim, m.generator.di_strength, m.generator.in_strength), D(m.cond_dim),
-                     A(m.aux_reg.strength), RouterNetwork(m.cond_dim, E), E, cfg, image_shape=orc.IMAGE_SHAPE[arch])
     st = orc.make_state(arch, E, seed, orc_cfg(orc, arch, E))
-    for e in range(E):
-        moe.generators[e].load_state_dict(st.gens[e])
-        moe.discriminators[e].load_state_dict(st.discs[e])
-        moe.aux_regs[e].load_state_dict(st.auxs[e])
-    moe.router.load_state_dict(st.router)
+    moe, _ = shim.build_reference_moe(arch, E, cfg, orc.IMAGE_SHAPE[arch], state=st)
     return moe, st
 
 
@@ -258,7 +174,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(os.path.dirname(HERE), "tests", "golden"))
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    install_reference()
+    shim.install_reference(REF)
     import oracle.expertsim_oracle as orc
     os.makedirs(args.out, exist_ok=True)
     meta = {"torch": torch.__version__, "generator": "oracle/pin_against_reference.py",

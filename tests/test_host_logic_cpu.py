@@ -14,7 +14,8 @@ from expertsim.models.moe import MoEWrapper
 
 
 def small_moe(E=2, arch="proton"):
-    cfg = load_config(None, [f"model.n_experts={E}", f"model.architecture={arch}"])
+    shape = "[56,30]" if arch == "proton" else "[44,44]"
+    cfg = load_config(None, [f"model.n_experts={E}", f"model.architecture={arch}", f"dataset.input_image_shape={shape}"])
     from expertsim.train.loop import setup_moe_system
     return setup_moe_system(cfg, torch.device("cpu")), cfg
 
@@ -101,6 +102,7 @@ def test_optimizer_handles_and_checkpoint_roundtrip(tmp_path):
     assert len(g) == len(d) == len(a) == 2 and g[0].param_groups[0]["lr"] == cfg.model.generator.lr_g
     assert d[0].param_groups[0]["lr"] == cfg.model.discriminator.lr_d and r.param_groups[0]["lr"] == cfg.model.router.lr_r
     moe.arena("g").M[1].fill_(0.5)
+    moe.arena("g").steps[1] = 4         # torch.optim.Adam keeps no state for parameters that never stepped
     save_models_and_architectures(str(tmp_path), 2, moe.aux_regs, a, moe.generators, g, moe.discriminators, d, moe.router, r, 7)
     assert os.path.exists(tmp_path / "gen_1_epoch_7.pth") and os.path.exists(tmp_path / "router_network_epoch_7.pth")
     ref = {k: v.clone() for k, v in moe.state_dict().items()}
@@ -108,10 +110,12 @@ def test_optimizer_handles_and_checkpoint_roundtrip(tmp_path):
         for p in moe.parameters():
             p.add_(1.0)
     moe.arena("g").M.zero_()
+    moe.arena("g").steps.zero_()
     load_checkpoint_weights(str(tmp_path), 7, moe, g, d, a, r)
     for k, v in moe.state_dict().items():
         assert torch.equal(v, ref[k]), k
-    assert float(moe.arena("g").M[1].min()) == 0.5
+    ag = moe.arena("g")
+    assert all(float(ag.view(ag.M, n, 1).min()) == 0.5 for n in ag.off) and ag.steps.tolist() == [0, 4]
 
 
 def test_device_loader_shards_are_disjoint_and_cover_the_global_batch():
@@ -146,3 +150,121 @@ def test_router_loss_helpers_match_the_oracle():
     assert torch.allclose(U.calculate_adaptive_load_balancing_loss(gates.sum(0), 1e-2), orc.adaptive_load_balancing_loss(gates.sum(0), 1e-2))
     assert torch.allclose(U.calculate_expert_utilization_entropy(gates, 0.3), orc.utilization_entropy(gates, 0.3))
     assert torch.allclose(U.calculate_expert_distribution_loss(gates, m), orc.expert_distribution_loss(gates, m))
+
+
+# ---------------------------------------------------------------------------------------------------- round 2 host rows
+def test_arena_adam_state_dict_interchanges_with_torch_adam():
+    """optimizer checkpoints in torch.optim.Adam's format, both directions (the reference saves
+    ``optimizer.state_dict()`` / pickled optimizers: train/training_utils.py:300-380, training_setup.py:46-49)."""
+    from expertsim.train.training_setup import setup_optimizers
+    moe, cfg = small_moe(E=2, arch="neutron")
+    g_o, d_o, a_o, r_o = setup_optimizers(moe, cfg)
+    assert g_o[0].state_dict()["state"] == {}                                   # torch: no state before the first step
+    a = moe.arena("d")
+    g = torch.Generator().manual_seed(0)
+    a.M.copy_(torch.randn(a.M.shape, generator=g))
+    a.V.copy_(torch.rand(a.V.shape, generator=g))
+    a.steps.copy_(torch.tensor([3, 5], dtype=torch.int32))
+    sd = d_o[1].state_dict()
+    # -> a stock torch optimizer over a module with the same parameter order
+    ref_opt = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in moe.discriminators[1].parameters()], lr=1e-5)
+    ref_opt.load_state_dict(copy.deepcopy(sd))
+    names = [n for n, _ in moe.discriminators[1].named_parameters()]
+    for i, (n, p) in enumerate(zip(names, ref_opt.param_groups[0]["params"])):
+        st = ref_opt.state[p]
+        assert float(st["step"]) == 5.0
+        assert torch.equal(st["exp_avg"], a.view(a.M, n, 1)) and torch.equal(st["exp_avg_sq"], a.view(a.V, n, 1))
+    for p in ref_opt.param_groups[0]["params"]:                                 # the loaded state is usable: one torch step
+        p.grad = torch.ones_like(p)
+    ref_opt.step()
+    # <- back into slot 0 of the arena (a reference checkpoint loaded into this build)
+    d_o[0].load_state_dict(ref_opt.state_dict())
+    assert int(a.steps[0]) == 6
+    for n, p in zip(names, ref_opt.param_groups[0]["params"]):
+        assert torch.equal(a.view(a.M, n, 0), ref_opt.state[p]["exp_avg"])
+    assert "params" in d_o[0].param_groups[0] and isinstance(d_o[0].param_groups[0]["params"][0], torch.nn.Parameter)
+    # the round-1 flat layout still loads
+    d_o[0].load_state_dict({"step": 2, "exp_avg": torch.zeros(a.n), "exp_avg_sq": torch.ones(a.n), "param_groups": [{"lr": 1e-5}]})
+    assert int(a.steps[0]) == 2 and float(a.M[0].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        bad = ref_opt.state_dict()
+        bad["param_groups"][0]["params"] = bad["param_groups"][0]["params"][:-1]
+        d_o[0].load_state_dict(bad)
+
+
+def test_optimizer_handles_must_agree():
+    from expertsim.train.training_setup import setup_optimizers
+    moe, cfg = small_moe(E=2)
+    g_o, _, _, _ = setup_optimizers(moe, cfg)
+    assert MoEWrapper._lr(g_o, 1.0) == cfg.model.generator.lr_g
+    g_o[1].param_groups[0]["lr"] = 5e-4
+    with pytest.raises(NotImplementedError):
+        MoEWrapper._lr(g_o, 1.0)
+    g_o[1].param_groups[0]["lr"] = cfg.model.generator.lr_g
+    g_o[0].param_groups[0]["betas"] = (0.5, 0.999)
+    with pytest.raises(NotImplementedError):
+        MoEWrapper._lr(g_o, 1.0)
+
+
+def test_optimizer_state_moves_with_the_parameters():
+    """re-binding the arenas (what .to()/.cuda() triggers) keeps Adam's moments and step counters"""
+    moe, _ = small_moe(E=2)
+    a = moe.arena("a")
+    a.M.fill_(0.25)
+    a.V.fill_(0.5)
+    a.steps.fill_(7)
+    moe._bind()
+    b = moe.arena("a")
+    assert b is not a and float(b.M.min()) == 0.25 and float(b.V.max()) == 0.5 and b.steps.tolist() == [7, 7]
+
+
+def test_ema_helper_advances_only_live_experts():
+    from expertsim.train.loop import EMAHelper
+    moe, _ = small_moe(E=2)
+    ema = EMAHelper(moe, decay=0.9, enabled=True)
+    P = moe.arena("g").P
+    before = P.clone()
+    P.add_(1.0)
+    ema.update(moe, live=torch.tensor([1, 0], dtype=torch.int32))
+    assert torch.allclose(ema.shadow[0], 0.9 * before[0] + 0.1 * P[0], atol=1e-6)
+    assert torch.equal(ema.shadow[1], before[1])
+    ema.update(moe, updated_indices=[1])
+    assert torch.allclose(ema.shadow[1], 0.9 * before[1] + 0.1 * P[1], atol=1e-6)
+    v0 = moe.arena("g").version
+    ema.apply_shadow(moe)
+    assert torch.equal(moe.generators[0].fc1[0].weight, ema.shadow[0][:moe.generators[0].fc1[0].weight.numel()].view(256, 19))
+    ema.restore(moe)
+    assert torch.equal(moe.arena("g").P, P) and moe.arena("g").version == v0 + 2
+
+
+def test_loaders_from_the_reference_arrays():
+    """the arrays ``transform_data_for_training`` returns -> 6-tuple batches
+    (data_transformations.py:269-271), resident or streamed through the pinned double buffer."""
+    from expertsim.utils.data import DeviceLoader, PinnedHostLoader, loaders_from_arrays
+    rng = np.random.default_rng(0)
+    n = 50
+    x = rng.random((n, 56, 30)).astype(np.float64)          # the reference's arrays are float64 / float32 mixed
+    cond = rng.standard_normal((n, 9)).astype(np.float32)
+    std, inten = rng.random(n), rng.random((n, 1)) * 100
+    pos = rng.integers(0, 30, (n, 2)).astype(np.float64)
+    dl = DeviceLoader.from_arrays(x, cond, std, inten, pos, batch_size=8, device="cpu", shuffle=False, drop_last=False)
+    batches = list(dl)
+    assert len(batches) == 7 and len(batches[0]) == 6
+    xb, x2, c, s, it, p = batches[0]
+    assert xb.dtype == torch.float32 and tuple(xb.shape) == (8, 56, 30) and tuple(s.shape) == (8, 1) and tuple(it.shape) == (8, 1)
+    assert torch.equal(xb, x2) and np.allclose(c.numpy(), cond[:8]) and np.allclose(p.numpy(), pos[:8])
+    assert tuple(batches[-1][0].shape) == (2, 56, 30)
+    # rank sharding: ranks 0/1 of 2 see alternating rows of every global batch
+    r0 = next(iter(DeviceLoader.from_arrays(x, cond, std, inten, pos, 4, "cpu", shuffle=False, rank=0, world=2)))
+    r1 = next(iter(DeviceLoader.from_arrays(x, cond, std, inten, pos, 4, "cpu", shuffle=False, rank=1, world=2)))
+    assert np.allclose(r0[2].numpy(), cond[0:8:2]) and np.allclose(r1[2].numpy(), cond[1:8:2])
+    with pytest.raises(ValueError):
+        DeviceLoader.from_arrays(x, cond[:-1], std, inten, pos, 8, "cpu")
+    # host-streamed variant: same batches
+    hl = PinnedHostLoader(x, cond, std, inten, pos, 8, device="cpu")
+    hb = list(hl)
+    assert len(hb) == 6 and all(torch.equal(a[2], b[2]) and torch.equal(a[0], b[0]) for a, b in zip(hb, batches))
+    cfg = load_config(None, ["train.batch_size=8"])
+    tr, te = loaders_from_arrays(cfg, x[10:], x[:10], cond[10:], cond[:10], std[10:], std[:10], inten[10:], inten[:10],
+                                 pos[10:], pos[:10], device="cpu")
+    assert len(tr) == 5 and len(list(te)) == 2
