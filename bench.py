@@ -10,11 +10,17 @@ losses, adaptive load-balancing router loss, batch 1024 per GPU, synthetic showe
 one full ``MoEWrapper.train_step`` (route, 2 G fwd, 4 D fwd, aux fwd, all backward passes, 3E+1 fused Adam updates,
 NCCL gradient all-reduce when N>1).
 
-One JSON line is printed by rank 0 (see the keys in ``main``).  ``value`` is timed with inputs resident in HBM;
-``e2e`` feeds every step from pinned HOST memory and reads the step's loss back.  ``roofline`` is the tcgen05
-implicit-GEMM family (dominant: >85% of step time), algorithmic FLOPs / CUDA-event time measured inside the timed region.
-``cpu_baseline`` is the CPU oracle (a PyTorch restatement of the reference's algorithm; the reference itself is Python
-+ PyTorch and /root/reference does not exist on the GPU box) on a bounded sample of the same workload.
+One JSON line is printed by rank 0 (see the keys in ``main``).  ``value`` is timed with inputs resident in HBM and NO
+per-launch instrumentation; ``e2e`` feeds every step from pinned HOST memory and reads the step's loss back.
+``roofline`` is the tcgen05 implicit-GEMM family (dominant: ~55% of step time), measured in a SECOND pass with CUDA
+events around every GEMM launch: algorithmic (un-folded direct-conv) FLOPs, EXECUTED FLOPs (after upsample folding),
+and the tensor-pipe utilisation of the committed ncu capture.  ``roofline_hbm`` holds the achieved GB/s of the loss-tail /
+gating / Adam kernels at a size that does not fit the L2.  ``extra`` carries the other BASELINE configs (neutron ZDC
+44x44 = configs[3] per-GPU slice, single expert = configs[1]); at N>1 ``dp_parity`` is the on-device proof that the
+sharded step equals the global-batch step (proton + neutron/SyncBN, balanced and with a rank holding no row of a live
+expert) and ``comm.exposed_ms`` the step time the collectives add.  ``cpu_baseline`` / ``--impl reference`` time the
+UNMODIFIED reference (``oracle/_ref``, a verbatim copy made by oracle/make_ref.py; the oracle port only if that copy is
+absent) on the box's host cores, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -111,9 +117,23 @@ def oracle_cfg(arch, E):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference leg
-def cpu_train_samples_per_s(arch, E, B, steps, warmup, threads):
-    """The reference's algorithm (oracle port, plain PyTorch fp32 on the host cores) on a bounded sample of the workload:
-    the same MoE step at batch ``B``; returns (samples/s, seconds per step)."""
+def reference_on_cpu(arch, E, B, steps, warmup, threads, showers=512):
+    """The UNMODIFIED reference (oracle/_ref or /root/reference) on the host cores, in a process of its own (its package is
+    also called ``expertsim``): MoEWrapper.train_step with its own torch.optim.Adam optimizers and random draws, batch
+    ``B``; get_predictions_from_generator_results for showers/s.  -> dict, or None if no reference copy is present."""
+    import oracle.ref_shim as shim
+    if shim.find_reference() is None:
+        return None
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "bench", "--arch", arch, "--experts", str(E), "--batch", str(B),
+           "--steps", str(steps), "--warmup", str(warmup), "--threads", str(threads), "--showers", str(showers)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise SystemExit(f"reference run failed:\n{r.stderr[-2000:]}")
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def port_on_cpu(arch, E, B, steps, warmup, threads):
+    """Fallback when no reference copy travelled: the oracle port (plain PyTorch fp32 restatement) on the host cores."""
     import oracle.expertsim_oracle as orc
     torch.set_num_threads(threads)
     st = orc.make_state(arch, E, 0, oracle_cfg(arch, E), identical_experts=True)
@@ -125,19 +145,20 @@ def cpu_train_samples_per_s(arch, E, B, steps, warmup, threads):
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     dt = sum(ts) / len(ts)
-    return B / dt, dt
-
-
-def cpu_showers_per_s(arch, n, threads):
-    import oracle.expertsim_oracle as orc
-    torch.set_num_threads(threads)
     sd = orc.make_weights(arch, "generator", 0)
     g = torch.Generator().manual_seed(0)
-    z, c = torch.randn(n, 10, generator=g), torch.randn(n, 9, generator=g)
+    z, c = torch.randn(512, 10, generator=g), torch.randn(512, 9, generator=g)
     orc.generate(arch, sd, z[:64], c[:64], batch_size=64)
     t0 = time.perf_counter()
     orc.generate(arch, sd, z, c, batch_size=256)
-    return n / (time.perf_counter() - t0)
+    return {"samples_per_s": B / dt, "s_per_step": dt, "showers_per_s": 512 / (time.perf_counter() - t0), "threads": threads}
+
+
+def cpu_leg(arch, E, B, steps, warmup, threads):
+    r = reference_on_cpu(arch, E, B, steps, warmup, threads)
+    if r is not None:
+        return r, "reference", "the unmodified reference (oracle/_ref: MoEWrapper.train_step, torch.optim.Adam, eager fp32 PyTorch)"
+    return port_on_cpu(arch, E, B, steps, warmup, threads), "port", "fp32 PyTorch restatement of the reference (oracle/; no reference copy present)"
 
 
 def run_reference(args):
@@ -146,16 +167,16 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     B = args.cpu_batch
-    v, dt = cpu_train_samples_per_s(args.arch, args.experts, B, args.steps, min(args.warmup, 1), threads)
-    shw = cpu_showers_per_s(args.arch, 512, threads)
+    r, kind, what = cpu_leg(args.arch, args.experts, B, args.steps, args.warmup, threads)
+    v = r["samples_per_s"]
+    sample = (f"{args.steps} timed MoE train steps (after {args.warmup} warm-up) of {what} at batch {B} — a bounded sample of the "
+              f"batch-{args.batch} workload — E={args.experts}, {args.arch}, {threads} host threads, {r['s_per_step']:.2f} s/step; "
+              f"showers/s on 512 showers")
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": round(v, 3), "unit": "samples/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 2),
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["s_per_step"] * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_cfg(args, note=f"bounded sample: the same MoE step at batch {B} on the host CPU"),
-            "showers_per_sec": round(shw, 2),
-            "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} MoE train steps at batch {B} (E={args.experts}, {args.arch}), fp32 PyTorch "
-                                       f"restatement of the reference on {threads} threads; showers/s on 512 showers"},
+            "config": workload_cfg(args), "showers_per_sec": round(r["showers_per_s"], 2),
+            "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": round(v, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -172,31 +193,68 @@ def workload_cfg(args, note=None):
 
 
 # ------------------------------------------------------------------------------------------------ B200 leg
+GEMM_CALLS = {"es_igemm_fwd", "es_igemm_wgrad", "es_igemm_taps_fwd", "es_igemm_taps_wgrad", "es_dense_dgrad", "es_dense_wgrad"}
+
+
 def igemm_flops(name, a):
-    """algorithmic FLOPs of one grouped GEMM launch from its logged scalar arguments."""
+    """(algorithmic, executed) FLOPs of one grouped GEMM launch from its logged scalar arguments.  ALGORITHMIC = the un-folded
+    direct convolution; EXECUTED = the MACs the tensor cores really perform: n_taps*C per output of a
+    folded class instead of KH*KW*C (equal for plain convolutions and the dense layers)."""
     ints = [x for x in a if isinstance(x, int)]
     if name in ("es_igemm_taps_fwd", "es_igemm_taps_wgrad"):
-        # phase-folded x2-upsample conv: ALGORITHMIC = the un-folded direct convolution (SURVEY.md §8d); executed MACs are
-        # n_taps*C per output instead of KH*KW*C
         g = next(x for x in a if hasattr(x, "n_taps"))
-        return g.alg_flops_per_row * ints[-1]
+        rows = ints[-1]
+        return g.alg_flops_per_row * rows, 2.0 * rows * g.Ho * g.Wo * g.N * g.n_taps * g.C
     if name in ("es_igemm_fwd", "es_igemm_wgrad"):
         g = next(x for x in a if hasattr(x, "Ho"))
-        rows = ints[-1]
-        return 2.0 * rows * g.Ho * g.Wo * g.N * g.KH * g.KW * g.C
+        f = 2.0 * ints[-1] * g.Ho * g.Wo * g.N * g.KH * g.KW * g.C
+        return f, f
     if name == "es_dense_dgrad":       # (N, K, n_groups, total_rows)
-        return 2.0 * ints[-1] * ints[0] * ints[1]
+        f = 2.0 * ints[-1] * ints[0] * ints[1]
+        return f, f
     if name == "es_dense_wgrad":       # (..., N, K, n_groups, total_rows) — leading ints may be raw addresses / strides
-        return 2.0 * ints[-1] * ints[-4] * ints[-3]
-    return 0.0
+        f = 2.0 * ints[-1] * ints[-4] * ints[-3]
+        return f, f
+    return 0.0, 0.0
+
+
+class System:
+    """one MoE system + optimizers + a pool of resident synthetic batches"""
+
+    def __init__(self, arch, E, B, dev, rank, world, pool_n, dp=True, overlap="deferred"):
+        from expertsim.train.loop import setup_moe_system
+        from expertsim.train.training_setup import setup_optimizers
+        from expertsim.utils.data import synthetic_showers
+        self.arch, self.E, self.B, self.dev, self.world, self.pool_n = arch, E, B, dev, world, pool_n
+        cfg = make_cfg(arch, E)
+        torch.manual_seed(0)
+        self.moe = moe = setup_moe_system(cfg, dev)
+        with torch.no_grad():   # experts differ (deepcopy would make them identical): seeded 1% perturbation per expert
+            gp = torch.Generator(device=dev).manual_seed(1)
+            for k in "gda":
+                P = moe.arena(k).P
+                P.mul_(1.0 + 1e-2 * torch.randn(P.shape, generator=gp, device=dev))
+        moe.mark_weights_changed()
+        if world > 1 and dp:
+            moe.enable_data_parallel()
+            moe.overlap_grad_allreduce = overlap
+        self.opts = setup_optimizers(moe, cfg)
+        moe.train()
+        self.data = synthetic_showers(arch, B * pool_n, seed=rank, device=dev)
+
+    def batch(self, i):
+        s, B, d = (i % self.pool_n) * self.B, self.B, self.data
+        return d["cond"][s:s + B], d["x"][s:s + B], d["positions"][s:s + B], d["std"][s:s + B], d["intensity"][s:s + B]
+
+    def step(self, i, host=None):
+        g_o, d_o, a_o, r_o = self.opts
+        c, x, pos, sd, it = host if host is not None else self.batch(i)
+        return self.moe.train_step(0, c, x, pos, sd, it, a_o, g_o, d_o, r_o, None, self.dev)
 
 
 def run_b200(args):
     import torch.distributed as dist
     from expertsim import _lib as L
-    from expertsim.train.loop import setup_moe_system
-    from expertsim.train.training_setup import setup_optimizers
-    from expertsim.utils.data import synthetic_showers
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,34 +272,8 @@ def run_b200(args):
     L.load()
     if not L.device_ok():
         raise SystemExit("libexpertsim_b200.so carries sm_100a code only; no usable device")
-
     arch, E, B = args.arch, args.experts, args.batch
-    cfg = make_cfg(arch, E)
-    torch.manual_seed(0)
-    moe = setup_moe_system(cfg, dev)
-    with torch.no_grad():   # experts differ (deepcopy would make them identical): seeded 1% perturbation per expert
-        gp = torch.Generator(device=dev).manual_seed(1)
-        for k in "gda":
-            P = moe.arena(k).P
-            P.mul_(1.0 + 1e-2 * torch.randn(P.shape, generator=gp, device=dev))
-    moe.mark_weights_changed()
-    if world > 1:
-        moe.enable_data_parallel()
-        moe.overlap_grad_allreduce = False if args.no_overlap_allreduce else (args.overlap_mode == "eager" or "deferred")
-    g_opt, d_opt, a_opt, r_opt = setup_optimizers(moe, cfg)
-    moe.train()
-
-    pool_n = args.pool
-    data = synthetic_showers(arch, B * pool_n, seed=rank, device=dev)
-
-    def batch(i):
-        s = (i % pool_n) * B
-        return (data["cond"][s:s + B], data["x"][s:s + B], data["positions"][s:s + B], data["std"][s:s + B],
-                data["intensity"][s:s + B])
-
-    def step(i):
-        c, x, pos, sd, it = batch(i)
-        return moe.train_step(0, c, x, pos, sd, it, a_opt, g_opt, d_opt, r_opt, None, dev)
+    pk = peaks()
 
     def barrier():
         if world > 1:
@@ -254,47 +286,84 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n):
+        """n calls of fn(i) between barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks"""
+        barrier()
+        e0.record()
+        out = None
+        for i in range(n):
+            out = fn(i)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), out
+
+    # ---- N>1: the sharded step equals the global-batch step, checked ON THE DEVICE before anything is timed (small batch,
+    # CPU oracle as the checker): proton and neutron (SyncBN), balanced and with a rank that holds no row of a live expert
+    dp_parity = None
+    if world > 1 and not args.no_dp_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from dp_parity import run_dp_parity
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))
+        dp_parity, bad = {}, []
+        for a_ in ("proton", "neutron"):
+            for unb in (False, True):
+                r = run_dp_parity(a_, dev, unbalanced=unb)
+                key = f"{a_}{'_unbalanced' if unb else ''}"
+                dp_parity[key] = {k: (float(f"{r[k]:.3e}") if isinstance(r[k], float) else r[k]) for k in
+                                  ("g", "d", "a", "replicas_identical", "rank_without_rows_of_a_live_expert", "ok")}
+                if not r["ok"]:
+                    bad.append((key, r["fails"][:4]))
+        dp_parity.update(g=max(v["g"] for v in dp_parity.values()), d=max(v["d"] for v in dp_parity.values()),
+                         a=max(v["a"] for v in dp_parity.values()),
+                         replicas_identical=all(v["replicas_identical"] for v in dp_parity.values()),
+                         reducer="deferred", global_batch=24 if 24 % world == 0 else 8 * world, n_experts=3,
+                         bound={"g": 0.2, "d": 2e-3, "a": 2e-3, "what": "relative L2 of the all-reduced gradients vs the CPU oracle's "
+                                "global-batch step (images injected); replicas bit-identical (P, M, V, steps, buffers)"})
+        if bad:
+            raise SystemExit(f"data-parallel parity broken: {bad}")
+        torch.cuda.empty_cache()
+
+    overlap = False if args.no_overlap_allreduce else args.overlap_mode
+    sysm = System(arch, E, B, dev, rank, world, args.pool, overlap=overlap)
+    moe = sysm.moe
     for i in range(args.warmup):
-        step(i)
+        sysm.step(i)
     if args.ncu_step:
         # profiling aid: `ncu --profile-from-start off ... bench.py --ncu-step` captures exactly one train step (and one
         # inference batch); nothing measured under the profiler is ever reported as a bench value
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step(args.warmup)
+        sysm.step(args.warmup)
         if args.ncu_step > 1:
             moe.eval()
             moe.generate(torch.randn(args.infer_batch, 9, device=dev), chunk=args.infer_batch)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    # ---- timed region: K steps, inputs resident in HBM
-    names = {"es_igemm_fwd", "es_igemm_wgrad", "es_igemm_taps_fwd", "es_igemm_taps_wgrad", "es_dense_dgrad", "es_dense_wgrad"}
-    L.profile = {"names": names, "log": []}
+
+    # ---- headline timed region: K steps, inputs resident in HBM, no instrumentation inside
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    barrier()
     n0 = L.n_calls
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        m = step(args.warmup + i)
-    e1.record()
-    barrier()
+    ms, m = timed(lambda i: sysm.step(args.warmup + i), args.steps)
     launches = L.n_calls - n0
-    ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
-    plog, L.profile = L.profile["log"], None
     loss = float(m["gen_loss"])
     if not (loss == loss):
         raise SystemExit("non-finite loss in the timed region")
     value = args.steps * B * world / (ms / 1e3)
 
-    # ---- roofline of the dominant kernel family (tcgen05 grouped implicit GEMM), per launch, inside the timed region
+    # ---- roofline pass (second pass, NOT the headline): CUDA events around every GEMM launch of n_prof steps
+    n_prof = max(1, min(args.steps, 5))
+    L.profile = {"names": GEMM_CALLS, "log": []}
+    ms_prof, _ = timed(lambda i: sysm.step(args.warmup + args.steps + i), n_prof)
+    plog, L.profile = L.profile["log"], None
     if args.per_launch and rank == 0:      # tuning aid: every timed GEMM launch of the last step, to stderr
-        per = len(plog) // args.steps
-        for name, a, s, e in plog[-per:]:
+        per = len(plog) // n_prof
+        for name, a, s_, e_ in plog[-per:]:
             g = next((x for x in a if hasattr(x, "Ho")), None)
             if g is not None and hasattr(g, "n_taps"):
                 geo = f"Hs{g.Hs} C{g.C} taps{g.n_taps} N{g.N} Ho{g.Ho} (folded)"
@@ -302,99 +371,162 @@ def run_b200(args):
                 geo = f"Hs{g.Hs} C{g.C} {g.KH}x{g.KW} N{g.N} Ho{g.Ho}"
             else:
                 geo = str([x for x in a if isinstance(x, int)][:3])
-            t = s.elapsed_time(e)
-            print(f"  {name:16s} {geo:34s} {t:8.3f} ms {igemm_flops(name, a) / t / 1e9:8.1f} TFLOP/s", file=sys.stderr)
+            t = s_.elapsed_time(e_)
+            fa, fe = igemm_flops(name, a)
+            print(f"  {name:16s} {geo:34s} {t:8.3f} ms {fa / t / 1e9:8.1f} TFLOP/s algorithmic {fe / t / 1e9:8.1f} executed", file=sys.stderr)
     fam = {}
-    for name, a, s, e in plog:
-        key = name
-        f = fam.setdefault(key, [0.0, 0.0, 0])
-        f[0] += igemm_flops(name, a)
-        f[1] += s.elapsed_time(e)
-        f[2] += 1
+    for name, a, s_, e_ in plog:
+        f = fam.setdefault(name, [0.0, 0.0, 0.0, 0])
+        fa, fe = igemm_flops(name, a)
+        f[0] += fa
+        f[1] += fe
+        f[2] += s_.elapsed_time(e_)
+        f[3] += 1
     tc = [fam[k] for k in ("es_igemm_fwd", "es_igemm_wgrad", "es_igemm_taps_fwd", "es_igemm_taps_wgrad") if k in fam]
-    tc_flops, tc_ms, tc_n = (sum(x[i] for x in tc) for i in range(3))
-    pk = peaks()
-    roof = {"bound": "tensor", "kernel": "igemm_persist (grouped bf16 tcgen05 implicit GEMM family: igemm_fwd_kernel + igemm_wgrad_kernel, incl. the x2-upsample-folded tap-table launches; algorithmic = un-folded direct-conv FLOPs)",
-            "achieved": round(tc_flops / (tc_ms * 1e-3) / 1e12, 2) if tc_ms else None, "peak": pk["tflops"], "unit": "TFLOP/s",
-            "frac": round(tc_flops / (tc_ms * 1e-3) / 1e12 / pk["tflops"], 4) if tc_ms else None,
-            "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch"), "traffic_source": (ncu_traffic() or {}).get("source"),
-            "algorithmic_flops_per_launch": round(tc_flops / max(tc_n, 1)),
-            "peak_source": f"{pk['src']} sustained bf16 (MEASURED_PEAKS.json)", "launches": tc_n,
-            "share_of_step": round(tc_ms / (e0.elapsed_time(e1)), 4),
-            "families": {k: {"tflops": round(v[0] / (v[1] * 1e-3) / 1e12, 2) if v[1] else None, "ms_per_step": round(v[1] / args.steps, 3),
-                             "launches_per_step": v[2] // args.steps} for k, v in fam.items()}}
+    tc_alg, tc_exe, tc_ms, tc_n = (sum(x[i] for x in tc) for i in range(4))
+    tr = ncu_traffic() or {}
+    tfl = lambda f, t: round(f / (t * 1e-3) / 1e12, 2) if t else None
+    roof = {"bound": "tensor",
+            "kernel": "igemm_persist (grouped bf16 tcgen05 implicit GEMM family: igemm_fwd_kernel + igemm_strip_kernel + igemm_wgrad_kernel, "
+                      "incl. the upsample-folded tap-table launches)",
+            "achieved": tfl(tc_alg, tc_ms), "peak": pk["tflops"], "unit": "TFLOP/s",
+            "frac": round(tc_alg / (tc_ms * 1e-3) / 1e12 / pk["tflops"], 4) if tc_ms else None,
+            "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),
+            "algorithmic_flops_per_launch": round(tc_alg / max(tc_n, 1)),
+            "executed_flops_per_launch": round(tc_exe / max(tc_n, 1)),
+            "executed_achieved": tfl(tc_exe, tc_ms),
+            "executed_frac": round(tc_exe / (tc_ms * 1e-3) / 1e12 / pk["tflops"], 4) if tc_ms else None,
+            "tensor_pipe_active_pct": tr.get("tensor_pipe_active_pct_time_weighted"),
+            "note": "frac = ALGORITHMIC (un-folded direct-conv) FLOPs / time / peak: upsample folding removes 2.56x (conv1) / 1.39x (conv2) "
+                    "of the MACs, so it is not tensor-pipe utilisation; executed_frac = FLOPs the tensor cores really perform / time / peak; "
+                    "tensor_pipe_active_pct = sm__pipe_tensor_cycles_active, time-weighted over the committed ncu capture",
+            "peak_source": f"{pk['src']} sustained bf16 (MEASURED_PEAKS.json)", "launches": tc_n, "timed_steps": n_prof,
+            "timing": "CUDA events around each launch on the launching stream, second pass after the headline timed region",
+            "share_of_step": round(tc_ms / ms_prof, 4) if ms_prof else None,
+            "families": {k: {"tflops": tfl(v[0], v[2]), "executed_tflops": tfl(v[1], v[2]), "ms_per_step": round(v[2] / n_prof, 3),
+                             "launches_per_step": v[3] // n_prof} for k, v in fam.items()}}
     step_tflops = value / world * TRAIN_FLOPS[arch] / 1e12
     roof["step_algorithmic_tflops_per_gpu"] = round(step_tflops, 2)
     roof["step_frac_of_peak"] = round(step_tflops / pk["tflops"], 4)
 
     # ---- e2e: the same step fed from pinned host memory, loss read back every step
-    host = [tuple(t.cpu().pin_memory() for t in batch(i)) for i in range(min(pool_n, 8))]
+    host = [tuple(t.cpu().pin_memory() for t in sysm.batch(i)) for i in range(min(args.pool, 8))]
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
     def e2e_step(i):
-        c, x, pos, sd, it = (t.to(dev, non_blocking=True) for t in host[i % len(host)])
-        mm = moe.train_step(0, c, x, pos, sd, it, a_opt, g_opt, d_opt, r_opt, None, dev)
-        return float(mm["gen_loss"])     # device -> host read of the step's loss
+        hb = tuple(t.to(dev, non_blocking=True) for t in host[i % len(host)])
+        return float(sysm.step(i, host=hb)["gen_loss"])     # device -> host read of the step's loss
 
     for i in range(2):
         e2e_step(i)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    ms_e2e, _ = timed(e2e_step, args.steps)
     e2e = {"value": round(args.steps * B * world / (ms_e2e / 1e3), 2), "unit": "samples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)}
 
+    # ---- N>1: what the collectives cost — the same steps with every data-parallel collective turned into a no-op
+    comm = None
+    if world > 1:
+        moe.set_collectives_enabled(False)
+        for i in range(2):
+            sysm.step(i)
+        ms_nc, _ = timed(lambda i: sysm.step(i), max(3, min(args.steps, 10)))
+        moe.set_collectives_enabled(True)
+        per_step, per_nc = ms / args.steps, ms_nc / max(3, min(args.steps, 10))
+        gb = sum(moe.arena(k).G.numel() for k in "gdar") * 4
+        comm = {"exposed_ms": round(per_step - per_nc, 3), "ms_per_step_without_collectives": round(per_nc, 3),
+                "allreduce_bytes_per_step": gb, "mode": str(overlap),
+                "what": "step time minus the time of the same step with all collectives as no-ops (gradient buckets, per-expert loss "
+                        "sums, counts, SyncBN statistics); the exposed part is dominated by fc2's fp32 gradient bucket, produced last"}
+
     # ---- batch inference: generated showers/s (router -> partition -> 8 expert generators -> expm1), device resident
+    inference = bench_inference(moe, args, dev, world, pk, arch, timed)
+    moe.train()
+
+    # ---- HBM-bound kernels (loss tails, gating, Adam) at a size the L2 does not hold; measured here, not taken from a file
+    roof_hbm = None
+    if not args.no_hbm_kernels:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from bench_hbm_kernels import measure
+        roof_hbm = measure(dev, peak=pk["gbs"])
+        for v in roof_hbm.values():
+            v["peak_source"] = f"{pk['src']} HBM copy rate (MEASURED_PEAKS.json)"
+        barrier()
+
+    # ---- the other BASELINE configs, per-GPU slice, short runs: neutron ZDC 44x44 (configs[3]) and one expert (configs[1])
+    extra = {}
+    if not args.no_extra:
+        del sysm, moe
+        torch.cuda.empty_cache()
+        for key, (a_, e_) in (("neutron", ("neutron", E)), ("e1", ("proton", 1))):
+            if (a_, e_) == (arch, E):
+                continue
+            extra[key] = short_bench(a_, e_, B, dev, rank, world, args, pk, timed, overlap)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        r, kind, what = cpu_leg(arch, E, args.cpu_batch, 3, 1, threads)
+        cpu = {"value": round(r["samples_per_s"], 3), "unit": "samples/s", "cores": threads, "kind": kind,
+               "showers_per_sec": round(r["showers_per_s"], 2),
+               "sample": f"3 timed MoE train steps (after 1 warm-up) of {what} at batch {args.cpu_batch} — a bounded sample of the "
+                         f"batch-{B} workload — E={E}, {arch}, {threads} host threads, {r['s_per_step']:.2f} s/step"}
+    line = {"metric": "train_samples_per_sec", "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_cfg(args),
+            "showers_per_sec": inference["showers_per_sec"], "inference": inference, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "clocks": clk, "loss_check": round(loss, 6),
+            "extra": extra}
+    if dp_parity is not None:
+        line["dp_parity"] = dp_parity
+    if comm is not None:
+        line["comm"] = comm
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_inference(moe, args, dev, world, pk, arch, timed):
     moe.eval()
     n_inf = args.infer_batch
     cond_inf = torch.randn(n_inf, 9, device=dev)
     for _ in range(2):
         moe.generate(cond_inf, chunk=n_inf)
-    barrier()
-    e0.record()
-    for _ in range(args.infer_iters):
-        out = moe.generate(cond_inf, chunk=n_inf)
-    e1.record()
-    barrier()
-    ms_inf = max_over_ranks(e0.elapsed_time(e1))
+    ms_inf, _ = timed(lambda i: moe.generate(cond_inf, chunk=n_inf), args.infer_iters)
     showers = args.infer_iters * n_inf * world / (ms_inf / 1e3)
     host_cond = cond_inf.cpu().pin_memory()
     out_host = torch.empty(n_inf, *moe.image_shape, pin_memory=True)
-    barrier()
-    e0.record()
-    for _ in range(args.infer_iters):
+
+    def e2e_gen(i):
         o = moe.generate(host_cond, chunk=n_inf)
         out_host.copy_(o, non_blocking=True)
-    e1.record()
-    barrier()
-    ms_inf2 = max_over_ranks(e0.elapsed_time(e1))
-    inference = {"showers_per_sec": round(showers, 1), "batch_per_gpu": n_inf, "iters": args.infer_iters,
-                 "e2e_showers_per_sec": round(args.infer_iters * n_inf * world / (ms_inf2 / 1e3), 1),
-                 "algorithmic_tflops_per_gpu": round(showers / world * (F_G[arch] + F_R) / 1e12, 2),
-                 "frac_of_peak": round(showers / world * (F_G[arch] + F_R) / 1e12 / pk["tflops"], 4)}
-    moe.train()
 
-    if rank != 0:
-        return
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, dt = cpu_train_samples_per_s(arch, E, args.cpu_batch, 4, 1, threads)
-        cpu = {"value": round(v, 3), "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"4 timed MoE train steps (after 1 warm-up) at batch {args.cpu_batch}, E={E}, {arch}: fp32 PyTorch "
-                         f"restatement of the reference (oracle/) on {threads} host threads, {dt:.1f} s/step"}
-    line = {"metric": "train_samples_per_sec", "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_cfg(args),
-            "showers_per_sec": inference["showers_per_sec"], "inference": inference, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "loss_check": round(loss, 6)}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ms_inf2, _ = timed(e2e_gen, args.infer_iters)
+    return {"showers_per_sec": round(showers, 1), "batch_per_gpu": n_inf, "iters": args.infer_iters,
+            "e2e_showers_per_sec": round(args.infer_iters * n_inf * world / (ms_inf2 / 1e3), 1),
+            "algorithmic_tflops_per_gpu": round(showers / world * (F_G[arch] + F_R) / 1e12, 2),
+            "frac_of_peak": round(showers / world * (F_G[arch] + F_R) / 1e12 / pk["tflops"], 4)}
+
+
+def short_bench(arch, E, B, dev, rank, world, args, pk, timed, overlap):
+    """train samples/s + showers/s of another BASELINE configuration (weak-scaling slice of batch B per GPU)"""
+    sysm = System(arch, E, B, dev, rank, world, min(args.pool, 8), overlap=overlap)
+    n = max(3, min(args.steps, 10))
+    for i in range(3):
+        sysm.step(i)
+    ms, m = timed(lambda i: sysm.step(3 + i), n)
+    v = n * B * world / (ms / 1e3)
+    inf = bench_inference(sysm.moe, args, dev, world, pk, arch, timed)
+    out = {"workload": f"{arch} ZDC MoE-GAN train step, E={E}, batch {B}/GPU (global {B * world}), dp{world}",
+           "train_samples_per_sec": round(v, 2), "ms_per_step": round(ms / n, 3), "steps": n, "warmup": 3,
+           "showers_per_sec": inf["showers_per_sec"], "loss_finite": bool(float(m["gen_loss"]) == float(m["gen_loss"])),
+           "step_frac_of_peak": round(v / world * TRAIN_FLOPS[arch] / 1e12 / pk["tflops"], 4)}
+    del sysm
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -409,8 +541,11 @@ def main():
     ap.add_argument("--pool", type=int, default=16, help="distinct resident input batches cycled through")
     ap.add_argument("--infer-batch", type=int, default=8192)
     ap.add_argument("--infer-iters", type=int, default=5)
-    ap.add_argument("--cpu-batch", type=int, default=128, help="batch of the bounded CPU-reference sample")
+    ap.add_argument("--cpu-batch", type=int, default=256, help="batch of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the neutron / single-expert lines of `extra`")
+    ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the roofline_hbm micro-measurements")
+    ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the on-device data-parallel parity check")
     ap.add_argument("--overlap-mode", default="deferred", choices=["deferred", "eager"])
     ap.add_argument("--no-overlap-allreduce", action="store_true",
                     help="A/B switch: one whole-arena gradient all-reduce after backward instead of the overlapped layer buckets")

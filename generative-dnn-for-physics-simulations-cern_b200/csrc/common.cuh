@@ -11,6 +11,7 @@
 namespace es {
 
 void set_error(const std::string& msg);
+int* pipeline_err_flag();   // per-device, host-mapped (api.cu); nullptr if it cannot be allocated
 
 #define ES_REQUIRE(cond, msg)                                               \
   do {                                                                      \

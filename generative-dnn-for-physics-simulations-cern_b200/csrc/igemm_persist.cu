@@ -867,16 +867,7 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int* fwd_err_flag() {
-  static int* flag = nullptr;
-  static bool init = false;
-  if (!init) {
-    init = true;
-    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) flag = nullptr;
-    else cudaMemset(flag, 0, sizeof(int));
-  }
-  return flag;
-}
+int* fwd_err_flag() { return pipeline_err_flag(); }
 
 }  // namespace
 

@@ -335,17 +335,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1) igemm_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static int g_err_flag_init = 0;
-static int* g_err_flag = nullptr;
-
-static int* err_flag_ptr() {
-  if (!g_err_flag_init) {
-    g_err_flag_init = 1;
-    if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) g_err_flag = nullptr;
-    else cudaMemset(g_err_flag, 0, sizeof(int));
-  }
-  return g_err_flag;
-}
+static int* err_flag_ptr() { return pipeline_err_flag(); }
 
 void fill_maps(IgemmParams& p) {
   // torch 'nearest': src = min(floor(dst * (in/out as float)), in-1)

@@ -124,8 +124,15 @@ class MoEWrapper(nn.Module):
     def world_size(self):
         return self._dp[2] if self._dp else 1
 
+    def set_collectives_enabled(self, on: bool):
+        """Measurement aid only (bench.py's ``comm.exposed_ms``): with ``on=False`` every data-parallel collective of the
+        step becomes a no-op, so the replicas diverge — never use it for training."""
+        self._comm_disabled = not on
+        if getattr(self, "_reducer", None) is not None:
+            self._reducer.disabled = not on
+
     def _allreduce(self, t):
-        if self._dp:
+        if self._dp and not getattr(self, "_comm_disabled", False):
             dist, pg, _ = self._dp
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg)
         return t
@@ -287,6 +294,7 @@ class MoEWrapper(nn.Module):
             # everything downstream of the generator can be compared at fp32 tolerance.  The networks' gradients are
             # discontinuous in the image (max-pool routing, ReLU/LeakyReLU kinks, GroupNorm over sparse maps): in pure
             # fp32 PyTorch a 1e-2 relative image perturbation already moves dL/d(image) by ~18% (tests/test_step_gpu.py).
+            generated = (img1.clone(), img2.clone())      # what the generator really produced, for the image check
             img1.copy_(noise["img1_sorted"].to(dev).reshape(B, HW))
             img2.copy_(noise["img2_sorted"].to(dev).reshape(B, HW))
 
@@ -451,6 +459,8 @@ class MoEWrapper(nn.Module):
                       f"n_choosen_experts_mean_epoch_{i}": counts_g[i]})
         self._last = {"idx": r["idx"], "counts": r["counts"], "perm": perm, "img1": img1, "img2": img2, "gates": r["gates"],
                       "logits": r["logits"]}
+        if "img1_sorted" in noise:
+            self._last["img1_generated"], self._last["img2_generated"] = generated
         return m
 
     def _dropout_masks(self, noise, r, B, dev):

@@ -271,6 +271,66 @@ def test_igemm_fwd_fc2_fullsize():
     check("es_igemm_fwd fc2 92160x256", y.float(), want, 6e-3, 3e-2)
 
 
+RAGGED8 = ([9, 0, 13, 7, 1, 11, 15, 8], [5, 1, 0, 7, 2, 6, 3, 4])      # 64 rows in 8 ragged expert groups (one empty, one of 1 row)
+
+
+@pytest.mark.parametrize("name", ["conv3_fwd", "conv3_dgrad", "conv2_dgrad", "conv2_fwd", "conv1_dgrad"])
+def test_igemm_fwd_many_tiles(name):
+    """The persistent path proper: 64 samples in 8 ragged expert groups = 280-800 output tiles on 148 CTAs, i.e. several tiles
+    per CTA (TMEM double-buffer wrap, pipeline phase wrap across tiles, expert changes inside a CTA's tile sequence), against
+    fp32 torch convolutions ON THE DEVICE (TF32 off) over the same bf16-rounded operands.  Bound: 6e-3 rel. L2."""
+    geo = GEOMS[name]
+    Hs, Ws, C, Hu, Wu, KH, KW, pad, N = geo
+    counts, slots = RAGGED8
+    grp, R = groups(counts, slots)
+    g = G(11 + sum(map(ord, name)))
+    x = bf16_round(torch.randn(R, Hs, Ws, C, generator=g))
+    w = bf16_round(torch.randn(8, N, KH, KW, C, generator=g) / math.sqrt(KH * KW * C))
+    bias = torch.randn(8, N, generator=g) * 0.1
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        want = ref_conv(x.to(DEV), w.to(DEV), bias.to(DEV), geo, counts, slots)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    tiles = sum((c * want.shape[1] * want.shape[2] + 127) // 128 for c in counts)
+    assert tiles >= 280
+    y = torch.zeros(R, want.shape[1], want.shape[2], N, dtype=BF, device=DEV)
+    L.call("es_igemm_fwd", cuda(x, BF), cuda(w, BF), cuda(bias), N, y, conv_geom(*geo), grp, len(counts), R)
+    torch.cuda.synchronize()
+    check(f"es_igemm_fwd {name} x64 rows, 8 ragged groups, {tiles} tiles", y.float(), want, 6e-3, 3e-2)
+
+
+@pytest.mark.parametrize("name", ["conv3_fwd", "conv2_fwd"])
+def test_igemm_wgrad_many_tiles(name):
+    """split-K weight gradient over 64 samples in 8 ragged groups (many K-chunks per CTA, RED epilogue), vs torch autograd on the
+    device; run twice: the fp32 atomics make the result order-dependent, the run-to-run difference is bounded at 1e-5."""
+    geo = GEOMS[name]
+    Hs, Ws, C, Hu, Wu, KH, KW, pad, N = geo
+    counts, slots = RAGGED8
+    grp, R = groups(counts, slots)
+    g = G(13 + sum(map(ord, name)))
+    Ho, Wo = Hu + 2 * pad - KH + 1, Wu + 2 * pad - KW + 1
+    x = bf16_round(torch.randn(R, Hs, Ws, C, generator=g))
+    dy = bf16_round(torch.randn(R, Ho, Wo, N, generator=g))
+    w = torch.zeros(8, N, KH, KW, C, requires_grad=True, device=DEV)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref_conv(x.to(DEV), w, None, geo, counts, slots).backward(dy.to(DEV))
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    runs = []
+    for _ in range(2):
+        dw = torch.zeros(8, N, KH, KW, C, device=DEV)
+        L.call("es_igemm_wgrad", cuda(x, BF), cuda(dy, BF), dw, conv_geom(*geo), grp, len(counts), R)
+        torch.cuda.synchronize()
+        runs.append(dw)
+    check(f"es_igemm_wgrad {name} x64 rows, 8 ragged groups", runs[0], w.grad, 2e-3, 1e-2)
+    check(f"es_igemm_wgrad {name} run-to-run (atomic order)", runs[1], runs[0], 1e-5)
+    assert float(runs[0][1].abs().max()) == 0.0          # slot 1 belongs to the empty group
+
+
 @pytest.mark.parametrize("name", ["conv1_fwd", "conv2_fwd", "conv3_fwd", "neutron_conv1"])
 @pytest.mark.parametrize("impl", ["es_igemm_wgrad", "es_igemm_wgrad_simt"])
 def test_igemm_wgrad(name, impl):

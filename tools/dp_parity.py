@@ -1,10 +1,19 @@
 #!/usr/bin/env python
-"""Data-parallel parity on N GPUs (launch: python -m torch.distributed.run --nproc-per-node N tools/dp_parity.py).
+"""Data-parallel parity: the sharded step must equal the single-device global-batch step.
 
-Every rank holds rows r::N of ONE global batch (and of the injected noise), runs MoEWrapper.train_step with data
-parallelism enabled, and the all-reduced gradients / losses are compared with the CPU oracle's step on the WHOLE batch:
-the sharded step must equal the single-device global-batch step.  Images are injected from the oracle so
-the comparison runs at fp32 / bf16-kernel tolerance (see tests/test_step_gpu.py for why)."""
+    python -m torch.distributed.run --nproc-per-node N tools/dp_parity.py [proton|neutron] [--unbalanced] [--one-gpu]
+
+Every rank holds rows r::N of ONE global batch (and of the injected noise), runs ``MoEWrapper.train_step`` with data
+parallelism enabled, and the all-reduced gradients / losses are compared with the CPU oracle's step on the WHOLE batch.
+Images are injected from the oracle so the comparison runs at fp32 / bf16-kernel tolerance (tests/test_step_gpu.py says
+why).  ``--unbalanced`` re-orders the global batch so that rank N-1 holds NO row of expert 0 although the expert is alive
+globally — the regime in which per-expert state updates must be gated on the global count.  After the step the replicas
+must be BIT-identical: parameters, Adam moments, step counters, float and integer buffers of all four arenas.
+
+``--one-gpu`` (or a box with fewer GPUs than ranks): all ranks share cuda:0 and the collectives run over gloo — the same
+host logic and kernels, no NCCL; this is how the driver's single-GPU test box exercises the N>1 path.
+``run_dp_parity`` is also called by ``bench.py --gpus N`` before its timed region (the ``dp_parity`` key of the line).
+"""
 import copy
 import os
 import re
@@ -12,25 +21,52 @@ import sys
 
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "generative-dnn-for-physics-simulations-cern_b200"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-import oracle.expertsim_oracle as orc  # noqa: E402
+import oracle.expertsim_oracle as orc  # noqa: E402   (the checker)
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+def unbalanced_order(idx, world, expert=0):
+    """permutation of the global batch that puts every sample of ``expert`` on positions p with p % world != world-1,
+    so the last rank (rows world-1::world) holds none of them"""
+    B = idx.numel()
+    mine = [int(i) for i in (idx == expert).nonzero(as_tuple=True)[0]]
+    rest = [i for i in range(B) if i not in set(mine)]
+    slots_ok = [p for p in range(B) if p % world != world - 1]
+    assert len(mine) <= len(slots_ok)
+    order = [None] * B
+    for p, i in zip(slots_ok, mine):
+        order[p] = i
+    free = [p for p in range(B) if order[p] is None]
+    for p, i in zip(free, rest):
+        order[p] = i
+    return torch.tensor(order)
+
+
+def replica_checksums(moe):
+    """two position-weighted integer checksums per arena tensor: equal on every rank iff the replicas are bit-identical"""
+    out = []
+    for k in "gdar":
+        a = moe.arena(k)
+        for t in (a.P, a.M, a.V, a.steps, a.Bf, a.Bi):
+            v = t.contiguous().view(-1)
+            bits = v.view(torch.int32) if v.dtype in (torch.float32, torch.int32) else v.to(torch.int64)
+            bits = bits.to(torch.int64)
+            w = (torch.arange(bits.numel(), device=bits.device) % 65521) + 1
+            out += [bits.sum(), (bits * w).sum()]
+    return torch.stack(out)
+
+
+def run_dp_parity(arch, dev, unbalanced=False, E=3, seed=7, group=None):
+    """-> dict(ok, worst relative-L2 gradient errors g/d/a, replicas_identical, empty_rank_expert, fails[...]).
+    Collective: every rank of ``group`` must call it."""
     from expertsim.config import Config
     from expertsim.train.loop import setup_moe_system
-    arch = sys.argv[1] if len(sys.argv) > 1 else "proton"
-    E, seed = 3, 7
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
     B = 24 if 24 % world == 0 else 8 * world
     H, W = orc.IMAGE_SHAPE[arch]
     ocfg = copy.deepcopy(orc.DEFAULT_CFG)
@@ -45,8 +81,14 @@ def main():
         moe.aux_regs[e].load_state_dict(st.auxs[e])
     moe.router.load_state_dict(st.router)
     moe.train()
-    moe.enable_data_parallel()
+    moe.enable_data_parallel(group)
     batch, noise = orc.make_batch(arch, B, seed), orc.make_noise(arch, B, E, seed)
+    if unbalanced:
+        with torch.no_grad():
+            gs, _ = orc.router_forward(st.router, batch["cond"], noise["gumbel"], orc.router_tau(ocfg["model"]["router"], 0))
+        order = unbalanced_order(gs.argmax(dim=1), world)
+        batch = {k: v[order] for k, v in batch.items()}
+        noise = {k: v[order] for k, v in noise.items()}
     collect = {}
     want, aux = orc.train_step(st, batch, noise, epoch=0, collect=collect)     # global batch, every rank (deterministic)
     mine = torch.arange(B)[rank::world]
@@ -60,11 +102,13 @@ def main():
             src = aux[key][e].reshape(-1, H * W) if e in aux[key] else torch.zeros(masks[e].numel(), H * W)
             rows.append(src[sel])
         nz[name] = torch.cat(rows).to(dev)
+    local_counts = [int(((masks[e] % world) == rank).sum()) for e in range(E)]
     b = sh(batch)
     got = moe.train_step(0, b["cond"], b["real_images"], b["true_positions"], b["std"], b["intensity"], noise=nz)
     torch.cuda.synchronize()
     fails = []
-    assert moe._last["idx"].cpu().tolist() == aux["idx"][mine].tolist(), "routing of the shard differs"
+    if moe._last["idx"].cpu().tolist() != aux["idx"][mine].tolist():
+        fails.append("routing of the shard differs")
     for k, v in want.items():
         g = float(got[k])
         if abs(g - v) > 3e-2 * abs(v) + 8e-3:
@@ -86,22 +130,53 @@ def main():
                 worst[key] = max(worst[key], r)
                 if r > tol[key]:
                     fails.append(f"grad {key}{e} {name}: relL2 {r:.3e}")
-    # replicas must stay bit-identical after the step
-    chk = torch.stack([moe.arena(k).P.double().sum() for k in "gdar"])
+    # the optimizer state advanced for every globally-live expert on EVERY rank (also where the rank held none of its rows)
+    live = [int(c) >= 2 for c in aux["counts"]]
+    for k in "gda":
+        steps = moe.arena(k).steps.cpu().tolist()
+        if steps != [1 if lv else 0 for lv in live]:
+            fails.append(f"Adam step counters of arena {k}: {steps}, live experts {live}")
+    # replicas must stay BIT-identical after the step: parameters, moments, step counters, buffers
+    chk = replica_checksums(moe)
     lo, hi = chk.clone(), chk.clone()
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    if not torch.equal(lo, hi):
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    identical = bool(torch.equal(lo, hi))
+    if not identical:
         fails.append("replicas diverged after the step")
     ok = torch.tensor([0 if fails else 1], device=dev)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    w = torch.tensor([worst["g"], worst["d"], worst["a"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(w, op=dist.ReduceOp.MAX, group=group)
+    empty = torch.tensor([1 if (unbalanced and local_counts[0] == 0 and live[0]) else 0], device=dev)
+    dist.all_reduce(empty, op=dist.ReduceOp.MAX, group=group)
+    return {"ok": int(ok) == 1, "g": float(w[0]), "d": float(w[1]), "a": float(w[2]), "replicas_identical": identical,
+            "world": world, "global_batch": B, "unbalanced": bool(unbalanced), "rank_without_rows_of_a_live_expert": bool(int(empty)),
+            "gen_loss": float(got["gen_loss"]), "oracle_gen_loss": want["gen_loss"], "fails": fails, "local_counts": local_counts}
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    flags = {a for a in sys.argv[1:] if a.startswith("--")}
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    one_gpu = "--one-gpu" in flags or torch.cuda.device_count() < world
+    dev = torch.device("cuda", 0 if one_gpu else local)
+    torch.cuda.set_device(dev)
+    if one_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
+    arch = args[0] if args else "proton"
+    res = run_dp_parity(arch, dev, unbalanced="--unbalanced" in flags)
     if rank == 0:
-        print(f"dp parity {arch} world={world} B={B}: worst relL2 g={worst['g']:.3e} d={worst['d']:.3e} a={worst['a']:.3e}; "
-              f"gen_loss {float(got['gen_loss']):.6f} vs oracle {want['gen_loss']:.6f}")
-    for f in fails:
+        print(f"dp parity {arch} world={world} B={res['global_batch']} backend={'gloo, ranks share cuda:0' if one_gpu else 'nccl'}"
+              f"{' UNBALANCED (a rank holds no row of live expert 0: ' + str(res['rank_without_rows_of_a_live_expert']) + ')' if res['unbalanced'] else ''}: "
+              f"worst relL2 g={res['g']:.3e} d={res['d']:.3e} a={res['a']:.3e}; replicas bit-identical: {res['replicas_identical']}; "
+              f"gen_loss {res['gen_loss']:.6f} vs oracle {res['oracle_gen_loss']:.6f}")
+    for f in res["fails"]:
         print(f"[rank {rank}] FAIL {f}")
     dist.destroy_process_group()
-    sys.exit(0 if int(ok) == 1 else 1)
+    sys.exit(0 if res["ok"] else 1)
 
 
 if __name__ == "__main__":
