@@ -344,6 +344,235 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// CTA-PAIR variant (cta_group::2).  Why: at 128 output pixels per CTA every CTA streams the WHOLE weight matrix of its expert
+// through L2 -> shared memory for each tile — conv1 forward moved 7.3 GB of L2 reads in 0.89 ms (32 B/clk/SM against the
+// ~42 B/clk/SM the fabric gives 148 SMs pulling at once), and the N <= 128 layers need 77 B/clk/SM at the tensor rate.  Two
+// CTAs of a cluster (the two SMs of a TPC) now share ONE 256-pixel tile: each gathers its own 128 im2col rows, each loads only
+// HALF of the weight tile (N/2 rows of B), and the leader issues tcgen05.mma.cta_group::2 with M = 256 — the tensor cores of
+// both SMs read A from their own shared memory and the B halves from both.  Weight traffic per SM and per FLOP halves (L2
+// and shared-memory operand reads alike), a stage shrinks to 16 + <= 16 KB so the pipeline is 6 deep instead of 4.
+// Protocol (all barriers that gate the MMA live in the LEADER, rank 0):
+//   full[s]   17 arrivals: 8 gather warps of each CTA (cp.async.wait_group -> fence.proxy.async -> __syncwarp -> lane 0
+//             arrives, remotely from rank 1) + the leader's arrive.expect_tx for BOTH weight halves; rank 1's TMA signals its
+//             bytes on the leader's barrier (cp.async.bulk.tensor ... .cta_group::2).
+//   empty[s]  tcgen05.commit multicast to BOTH CTAs (each CTA's producers wait on their own copy).
+//   tfull[b]  commit multicast to both; each CTA's epilogue drains ITS 128 accumulator rows from its own TMEM.
+//   tempty[b] 8 arrivals on the leader: one per epilogue warp of each CTA.
+template <int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGThreads, 1)
+igemm_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CUtensorMap tmap_wh) {
+  constexpr int kLag = 3;
+  constexpr int kStageB = 128 * 128;             // half of a BN <= 256 weight tile: <= 128 rows x 128 B
+  constexpr int kStage = kFStageA + kStageB;     // 32 KB
+  constexpr int kTileM = 2 * kBM;
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kStages * kStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+  uint8_t* gen = smem_raw + (bar_base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * 20);
+  const uint32_t tmem_slot = bar_base + 8u * 20;
+  int* s_tiles = reinterpret_cast<int*>(gen + 256);            // [64]
+  es_group* s_grp = reinterpret_cast<es_group*>(gen + 512);    // [64] x 16 B
+  unsigned char* s_ymap = gen + 512 + 1024;
+  unsigned char* s_xmap = s_ymap + 64;
+  signed char* s_tdy = reinterpret_cast<signed char*>(s_xmap + 64);
+  signed char* s_tdx = s_tdy + 32;
+  int* s_tkoff = reinterpret_cast<int*>(s_tdx + 32);
+
+  const int BN = p.BN, BH = p.BN / 2;
+  const uint32_t nbuf = 2 * BN <= 512 ? 2u : 1u;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < (int)nbuf * BN) tmem_cols <<= 1;
+
+  if (tid < p.n_groups) {
+    const es_group gq = p.grp[tid];
+    s_grp[tid] = gq;
+    s_tiles[tid] = ceil_div(gq.rows * p.P, kTileM);            // PAIR tiles (256 pixels) of the group
+  }
+  if (tid < 64) { s_ymap[tid] = p.ymap[tid]; s_xmap[tid] = p.xmap[tid]; }
+  if (tid < 32) { s_tdy[tid] = p.tdy[tid]; s_tdx[tid] = p.tdx[tid]; s_tkoff[tid] = p.tkoff[tid]; }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 2 * kGW + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kGW && lane == 0) tma_prefetch_desc(&tmap_wh);
+  if (warp == kGW + 1) tmem_alloc_pair(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // both CTAs' barriers are initialised before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  int total_tiles = 0;
+  for (int i = 0; i < p.n_groups; ++i) total_tiles += s_tiles[i];
+  total_tiles *= p.n_tiles_n;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int taps = p.n_taps;
+  const int cblks = p.C / kBK;
+  const int nkb = taps * cblks;
+
+  if (warp < kGW) {
+    // ========================================================================= A GATHER (this CTA's 128 rows of the pair tile)
+    constexpr int RPT = kBM / (kGLoaders / 8);
+    constexpr int RSTEP = kGLoaders / 8;
+    const int chunk = tid & 7, rsub = tid >> 3;
+    uint32_t it = 0, signalled = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      TileInfo ti;
+      decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+      const int m_first = ti.m0 + (int)rank * kBM;
+      int r_base[RPT], r_oyx[RPT];
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) {
+        const int m = m_first + rsub + RSTEP * j;
+        const bool valid = m < ti.rows * p.P;
+        const int sample = valid ? m / p.P : 0;
+        const int pix = valid ? m - sample * p.P : 0;
+        const int oy = pix / p.Wo;
+        r_oyx[j] = (oy << 8) | (pix - oy * p.Wo);
+        r_base[j] = valid ? (ti.row_start + sample) * p.Hs * p.Ws : -1;
+      }
+      int cb = 0, tap = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % kStages;
+        if (it >= (uint32_t)kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 1);
+        const uint32_t sa = base + s * kStage;
+        const int c0 = cb * kBK + chunk * 8;
+        const int ty = s_tdy[tap], tx = s_tdx[tap];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const int r = rsub + RSTEP * j;
+          const int uy = (r_oyx[j] >> 8) * p.my + ty, ux = (r_oyx[j] & 255) * p.mx + tx;
+          const bool inb = r_base[j] >= 0 && uy >= 0 && uy < p.Hu && ux >= 0 && ux < p.Wu;
+          const int sy = inb ? s_ymap[uy] : 0, sx = inb ? s_xmap[ux] : 0;
+          const __nv_bfloat16* src = p.a_src + (inb ? ((long)(r_base[j] + sy * p.Ws + sx) * p.C + c0) : 0L);
+          cp_async16_ca(sa + (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4), src, inb);
+        }
+        cp_async_commit();
+        if (++tap == taps) { tap = 0; ++cb; }
+        if (it - signalled >= (uint32_t)kLag) {
+          cp_async_wait<kLag>();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(full_bar(signalled % kStages), 0));
+          ++signalled;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    __syncwarp();
+    while (signalled < it) {
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(full_bar(signalled % kStages), 0));
+      ++signalled;
+    }
+  } else if (warp == kGW) {
+    // =========================================================================== TMA PRODUCER (this CTA's half of B)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        TileInfo ti;
+        decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+        const int wrow = ti.slot * p.Nout + ti.n0 + (int)rank * BH;
+        int cb = 0, tap = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= (uint32_t)kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), (uint32_t)BN * 128u);      // both halves
+          tma_load_2d_pair(base + s * kStage + kFStageA, &tmap_wh, s_tkoff[tap] + cb * kBK, wrow, mapa_shared(full_bar(s), 0));
+          if (++tap == taps) { tap = 0; ++cb; }
+        }
+      }
+    }
+  } else if (warp == kGW + 1) {
+    // =========================================================================== MMA ISSUER (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_m(BN, 2 * kBM, false, false);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
+        const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+        const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+        if (use >= 1) mbar_wait_cluster(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait_cluster(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = base + s * kStage;
+            const uint32_t sb = sa + kFStageA;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_pair(tacc, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
+            umma_commit_pair(empty_bar(s), 3);
+            if (kb == nkb - 1) umma_commit_pair(tfull_bar(buf), 3);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+    }
+  } else {
+    // =========================================================================== EPILOGUE (this CTA's 128 rows)
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
+      TileInfo ti;
+      decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+      const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+      const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+      mbar_wait(tfull_bar(buf), use & 1, p.err_flag, 3);
+      tc_fence_after();
+      const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
+      uint32_t r[32];
+      const uint32_t t_lane = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+      const int m = ti.m0 + (int)rank * kBM + q * 32 + lane;
+      const bool ok = m < ti.rows * p.P;
+      const int smp = ok ? m / p.P : 0, pix = ok ? m - smp * p.P : 0;
+      const int oa = pix / p.Wo, ob = pix - oa * p.Wo;
+      const long opix = (long)(ti.row_start + smp) * p.P_full + (oa * p.o_my + p.o_oy) * p.Wo_full + ob * p.o_mx + p.o_ox;
+      __nv_bfloat16* yrow = p.out + (opix * p.Nout + ti.n0);
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(t_lane + c, r);
+        if (ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) dst[qq] = pack8(f + 8 * qq);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // the leader's MMAs read the peer's shared memory: nobody leaves before both are done
+  if (warp == kGW + 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // STRIP variant for convolutions WITHOUT an upsample in front whose taps form rows (same dy, consecutive dx): conv3 forward
 // (3x3, 128 -> 64) and its data gradient (3x3, 64 -> 128), the layers where the gather is the bound — an im2col row is used
 // for only N = 64/128 MACs per element, so the 64 B/clk/SM that cp.async moves through L1TEX caps the kernel at ~50 % of the
@@ -973,11 +1202,42 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
     ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the activations");
   }
 
+  // CTA-pair variant (see igemm_pair_kernel).  ES_IGEMM_PAIR: 0 = off, 1 (default) = every launch the strip variant does not
+  // take, 2 = also instead of the strip variant (A/B measurements).
+  static const int pair_mode = [] { const char* e = getenv("ES_IGEMM_PAIR"); return e ? atoi(e) : 1; }();
+  auto launch_pair = [&]() -> int {
+    alignas(64) CUtensorMap tmap_h;
+    const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)p.Nout};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.KK * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(p.BN / 2)};
+    const CUresult rc = enc(&tmap_h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (half weight tile)");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long max_tiles = (ceil_div_l((long)total_rows * p.P, 2L * kBM) + n_groups) * p.n_tiles_n;
+    const int pairs = (int)(max_tiles < sms / 2 ? max_tiles : sms / 2);
+    constexpr int kPStages = 6;
+    constexpr size_t kPSmem = (size_t)kPStages * (kFStageA + 128 * 128) + 1024 + 2048;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ES_CUDA(cudaFuncSetAttribute(igemm_pair_kernel<kPStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem));
+      attr_set = true;
+    }
+    igemm_pair_kernel<kPStages><<<2 * pairs, kGThreads, kPSmem, as_stream(stream)>>>(p, tmap_h);
+    ES_LAUNCH_CHECK();
+    return ES_OK;
+  };
+  const bool pair_ok = pair_mode > 0 && p.BN >= 64;
+
   // Strip variant (see igemm_strip_kernel): no upsample, taps form rows of consecutive dx with consecutive weight columns,
   // N <= 128.  ES_IGEMM_STRIP=0 disables it (A/B measurements).
   {
     StripParams sp{};
     bool okk = strip_plan(p, total_rows, sp);
+    if (okk && pair_ok && pair_mode >= 2) return launch_pair();
     if (okk) {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
@@ -1000,6 +1260,7 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
   // 525.  The 128-row tile with double-buffered accumulators and the cp.async gather wins everywhere (the 3-stage pipeline
   // and the exposed epilogue of MT=2 cost more than the halved weight traffic saves; the TMA gather engine sustains about
   // half the row rate of cp.async), so it is the default; the other variants stay selectable for tuning.
+  if (pair_ok && !getenv("ES_IGEMM_FWD_VARIANT")) return launch_pair();
   int mt = 1, g4 = 0;
   if (const char* ov = getenv("ES_IGEMM_FWD_VARIANT")) {   // "mt,g4" — tuning aid
     int a = 0, b = 0;

@@ -125,7 +125,9 @@ gen_loss_grads_kernel(const float* __restrict__ img, int HW, const float* __rest
     const double* S = sums + e * 8;
     const double n = S[S_ROWS];
     float out[6] = {0, 0, 0, 0, 0, 0};
-    if (grp[e].rows > 0 && n > 0.0) {
+    // n is the expert's (global, under data parallelism all-reduced) row count: 0 for skipped experts.  Not gated on this
+    // rank's rows — a rank that holds none of a live expert's rows must report the same metrics as the others.
+    if (n > 0.0) {
       const double mstd = S[S_STD] / n;
       const double div_l = mstd * mstd * (S[S_INVDIV] / n) * di_strength;
       const double int_l = S[S_ABSERR] / n * in_strength;

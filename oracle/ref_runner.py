@@ -45,8 +45,21 @@ def attr_cfg(orc, cfg_d, arch):
 
 
 def strict_fp32():
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    """IEEE fp32 everywhere (no TF32 in cuDNN convolutions / cuBLAS), deterministic cuDNN algorithms as the reference's
+    cli.py:28-30 asks for — the comparison is against the reference's fp32 arithmetic, not against TF32 rounding."""
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    try:                                             # torch >= 2.9 precision API
+        torch.backends.fp32_precision = "ieee"
+        torch.backends.cuda.matmul.fp32_precision = "ieee"
+        torch.backends.cudnn.fp32_precision = "ieee"
+        torch.backends.cudnn.conv.fp32_precision = "ieee"
+        torch.backends.cudnn.rnn.fp32_precision = "ieee"
+    except Exception:                                # older torch: the legacy switches
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    return {"cudnn_conv": str(getattr(getattr(torch.backends.cudnn, "conv", None), "fp32_precision", "n/a")),
+            "matmul": str(getattr(torch.backends.cuda.matmul, "fp32_precision", "n/a"))}
 
 
 def queue_noise(orc, inj, arch, E, masks, noise):
@@ -99,7 +112,7 @@ def cmd_bench(a):
 def cmd_step(a):
     import oracle.expertsim_oracle as orc
     shim.install_reference()
-    strict_fp32()
+    prec = strict_fp32()
     dev = torch.device(a.device)
     E, arch, B = a.experts, a.arch, a.batch
     cfg_d = oracle_cfg(orc, arch, E)
@@ -121,7 +134,7 @@ def cmd_step(a):
         dt = time.perf_counter() - t0
     for h in hooks:
         h.remove()
-    out = {"metrics": metrics, "idx": idx, "counts": counts, "seconds": dt, "device": str(dev), "torch": torch.__version__,
+    out = {"metrics": metrics, "idx": idx, "counts": counts, "seconds": dt, "device": str(dev), "torch": torch.__version__, "fp32_precision": prec,
            "fake1": {e: f[0] for e, f in fakes.items() if f}, "fake2": {e: f[1] for e, f in fakes.items() if len(f) > 1}}
     # gradients left in .grad by the step: generator and aux regressor hold exactly the generator step's gradients; the
     # discriminator's hold D-step + G-step contributions (moe.py:564) and are therefore not exported

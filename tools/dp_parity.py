@@ -49,16 +49,17 @@ def unbalanced_order(idx, world, expert=0):
 
 def replica_checksums(moe):
     """two position-weighted integer checksums per arena tensor: equal on every rank iff the replicas are bit-identical"""
-    out = []
+    out, names = [], []
     for k in "gdar":
         a = moe.arena(k)
-        for t in (a.P, a.M, a.V, a.steps, a.Bf, a.Bi):
+        for tn, t in (("P", a.P), ("M", a.M), ("V", a.V), ("steps", a.steps), ("Bf", a.Bf), ("Bi", a.Bi)):
+            names += [f"{k}.{tn}", f"{k}.{tn}"]
             v = t.contiguous().view(-1)
             bits = v.view(torch.int32) if v.dtype in (torch.float32, torch.int32) else v.to(torch.int64)
             bits = bits.to(torch.int64)
             w = (torch.arange(bits.numel(), device=bits.device) % 65521) + 1
             out += [bits.sum(), (bits * w).sum()]
-    return torch.stack(out)
+    return torch.stack(out), names
 
 
 def run_dp_parity(arch, dev, unbalanced=False, E=3, seed=7, group=None):
@@ -137,13 +138,14 @@ def run_dp_parity(arch, dev, unbalanced=False, E=3, seed=7, group=None):
         if steps != [1 if lv else 0 for lv in live]:
             fails.append(f"Adam step counters of arena {k}: {steps}, live experts {live}")
     # replicas must stay BIT-identical after the step: parameters, moments, step counters, buffers
-    chk = replica_checksums(moe)
+    chk, chk_names = replica_checksums(moe)
     lo, hi = chk.clone(), chk.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
     identical = bool(torch.equal(lo, hi))
     if not identical:
-        fails.append("replicas diverged after the step")
+        which = sorted({n for n, a_, b_ in zip(chk_names, lo.tolist(), hi.tolist()) if a_ != b_})
+        fails.append(f"replicas diverged after the step: {which}")
     ok = torch.tensor([0 if fails else 1], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
     w = torch.tensor([worst["g"], worst["d"], worst["a"]], dtype=torch.float64, device=dev)
