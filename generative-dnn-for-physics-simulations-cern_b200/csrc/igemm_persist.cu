@@ -506,12 +506,14 @@ igemm_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ C
       for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
         const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
         const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
-        if (use >= 1) mbar_wait_cluster(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
+        if (use >= 1) mbar_wait(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
-          mbar_wait_cluster(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
+          // cta-scope wait: `.acquire.cluster` would add MEMBAR + CCTL.IVALL (an L1 invalidate) per k-block on the leader, and
+          // this thread reads nothing through the generic proxy — it only issues MMAs
+          mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = base + s * kStage;

@@ -481,14 +481,13 @@ spectral_norm_fwd_kernel(const float* __restrict__ w_orig, float* __restrict__ u
 }
 
 // Multi-CTA power iteration for the large matrices (fc1.0: 128 x 2313 per expert): three launches, no inter-CTA waits.
-//   phase 1: t = W^T u      (threads along i: coalesced rows of W), |t|^2 by atomics
-//   phase 2: s = W t        (one warp per row),                     |s|^2 by atomics
+//   phase 1: t = W^T u      (threads along i: coalesced rows of W)
+//   phase 2: s = W t        (one warp per row)
 //   phase 3: v = t/|t|, u = (s/|t|)/|s/|t||, sigma = u.(W v) = |s|/|t|, w_sn = W / sigma (elementwise, all CTAs)
 // scratch per slot: t[I], s[O], n2[2].
 __global__ void __launch_bounds__(256)
 sn_phase1_kernel(const float* __restrict__ w_orig, const float* __restrict__ u, long sw, long su, int O, int I,
                  const es_group* __restrict__ grp, float* __restrict__ scratch) {
-  __shared__ float red[32];
   __shared__ float s_u[512];
   const int slot = blockIdx.y;
   if (grp && grp[slot].rows == 0) return;
@@ -510,8 +509,6 @@ sn_phase1_kernel(const float* __restrict__ w_orig, const float* __restrict__ u, 
     a0 = (a0 + a1) + (a2 + a3);
     T[i] = a0;
   }
-  const float n = block_sum(i < I ? a0 * a0 : 0.f, red);
-  if (threadIdx.x == 0) atomicAdd(&T[I + O], n);
 }
 
 __global__ void __launch_bounds__(256)
@@ -526,10 +523,7 @@ sn_phase2_kernel(const float* __restrict__ w_orig, long sw, int O, int I, const 
   float a = 0.f;
   for (int i = lane; i < I; i += 32) a = fmaf(W[(size_t)o * I + i], T[i], a);
   a = warp_sum(a);
-  if (lane == 0) {
-    T[I + o] = a;
-    atomicAdd(&T[I + O + 1], a * a);
-  }
+  if (lane == 0) T[I + o] = a;
 }
 
 __global__ void __launch_bounds__(256)
@@ -539,8 +533,17 @@ sn_phase3_kernel(const float* __restrict__ w_orig, float* __restrict__ u, float*
   const int slot = blockIdx.y;
   if (grp && grp[slot].rows == 0) return;
   const float* T = scratch + (size_t)slot * (I + O + 2);
-  const float nt = fmaxf(sqrtf(T[I + O]), 1e-12f);          // |W^T u|
-  const float nsp = sqrtf(T[I + O + 1]) / nt;                // |W v|
+  // |t|^2 and |s|^2 are summed HERE, by every CTA, in one fixed order (strided per thread, then the shuffle tree of block_sum):
+  // bit-identical across CTAs, runs and data-parallel replicas.  (Cross-CTA atomics made u / v depend on the arrival
+  // order, and u / v are STATE: replicas drifted apart in the last bit — found by the bit-identity check of dp_parity.)
+  __shared__ float red[32];
+  float pt = 0.f, ps = 0.f;
+  for (int i = threadIdx.x; i < I; i += blockDim.x) pt = fmaf(T[i], T[i], pt);
+  for (int o = threadIdx.x; o < O; o += blockDim.x) ps = fmaf(T[I + o], T[I + o], ps);
+  const float nt2 = block_sum(pt, red);
+  const float ns2 = block_sum(ps, red);
+  const float nt = fmaxf(sqrtf(nt2), 1e-12f);               // |W^T u|
+  const float nsp = sqrtf(ns2) / nt;                         // |W v|
   const float inv_u = 1.f / (fmaxf(nsp, 1e-12f) * nt);       // u = s * inv_u
   const float sg = nsp * nsp / fmaxf(nsp, 1e-12f);           // sigma = u . (W v)
   const float inv = 1.f / sg;
@@ -889,7 +892,7 @@ extern "C" int es_spectral_norm_fwd(const float* w_orig, float* u, float* v, lon
   if (scratch && do_power_iter && O <= 512 && (long)O * I >= 16384) {
     cudaStream_t st = as_stream(stream);
     const size_t per = (size_t)I + O + 2;
-    ES_CUDA(cudaMemsetAsync(scratch, 0, per * slots * sizeof(float), st));
+    (void)per;      // every scratch element that is read is written first (t by phase 1, s by phase 2): no memset
     sn_phase1_kernel<<<dim3(ceil_div(I, 256), slots), 256, 0, st>>>(w_orig, u, slot_stride_w, slot_stride_u, O, I, grp, scratch);
     sn_phase2_kernel<<<dim3(ceil_div(O, 8), slots), 256, 0, st>>>(w_orig, slot_stride_w, O, I, grp, scratch);
     const int nb = min(64, ceil_div(O * I, 2048));

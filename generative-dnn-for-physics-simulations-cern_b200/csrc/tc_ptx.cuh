@@ -133,8 +133,14 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// RELAXED on purpose.  `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, which drains every
+// memory operation the thread has in flight — including the cp.async groups of the NEXT pipeline stages — and serialised the
+// gather (measured: the pair kernel ran 2.2x slower than the single-CTA one).  No release is needed for what the barrier
+// guards: the thread has already waited for its cp.async group (the bytes are in shared memory) and executed
+// fence.proxy.async, and the consumer is the tensor core of the SAME SM reading this CTA's shared memory through the async
+// proxy; the remote arrive only tells the leader's MMA thread that it may issue.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
