@@ -113,6 +113,8 @@ def cmd_step(a):
     import oracle.expertsim_oracle as orc
     shim.install_reference()
     prec = strict_fp32()
+    torch.backends.cudnn.enabled = bool(a.cudnn)
+    prec["cudnn_enabled"] = bool(a.cudnn)
     dev = torch.device(a.device)
     E, arch, B = a.experts, a.arch, a.batch
     cfg_d = oracle_cfg(orc, arch, E)
@@ -222,6 +224,7 @@ def main():
     ap.add_argument("--every", type=int, default=10)
     ap.add_argument("--ws-runs", type=int, default=3)
     ap.add_argument("--out", default="")
+    ap.add_argument("--cudnn", type=int, default=1, help="0: torch.backends.cudnn.enabled = False (native ATen convolutions)")
     a = ap.parse_args()
     {"bench": cmd_bench, "step": cmd_step, "train": cmd_train, "names": cmd_names}[a.cmd](a)
 
