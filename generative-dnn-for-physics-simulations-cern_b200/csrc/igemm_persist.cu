@@ -575,6 +575,184 @@ igemm_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// TMA-FED CTA-PAIR variant: BOTH operands arrive by TMA.  For a tap-table conv that reads the source directly — source pixel
+// (oy*my + dy_t, ox*mx + dx_t), no nearest-upsample map in between: the phase-folded x2 convs, their data gradients, every
+// plain conv's data gradient — the im2col rows of a tile are exactly what TMA's im2col mode enumerates: 128 consecutive base
+// pixels of a bounding box (lower corner = smallest tap offset, traversal stride = my/mx), shifted by the tap offset given in
+// the instruction, zero-filled outside the image, written as 128B-swizzled 64-channel rows — the K-major layout the MMA
+// reads.  One instruction per (tap, channel block) replaces 256 threads x 4 cp.async: no address arithmetic, no L1TEX
+// traffic (the gather read every line through L1 and wrote it to shared memory: two passes over the 128 B/clk SRAM that
+// the tensor core's operand reads also need — ncu: L1TEX 58-63 % at 27-46 % tensor), ragged expert tails simply run into the
+// next sample (the epilogue masks those rows).  6 warps: TMA producer, MMA issuer / TMEM owner, 4 epilogue warps.
+// Barrier protocol: as igemm_pair_kernel, except that full[s] takes ONE arrival (the leader's expect_tx for the four boxes of
+// the stage — A and the B half of both CTAs; rank 1's boxes signal the leader's barrier).
+struct TmaAParams {
+  int low_w, low_h;         // bounding-box lower corner = base-pixel coordinate of output (0, 0)
+};
+
+template <int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+igemm_tma_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ TmaAParams ta,
+                      const __grid_constant__ CUtensorMap tmap_wh, const __grid_constant__ CUtensorMap tmap_x) {
+  constexpr int kStageB = 128 * 128;
+  constexpr int kStage = kFStageA + kStageB;     // 32 KB
+  constexpr int kTileM = 2 * kBM;
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kStages * kStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+  uint8_t* gen = smem_raw + (bar_base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * 20);
+  const uint32_t tmem_slot = bar_base + 8u * 20;
+  int* s_tiles = reinterpret_cast<int*>(gen + 256);            // [64]
+  es_group* s_grp = reinterpret_cast<es_group*>(gen + 512);    // [64] x 16 B
+
+  const int BN = p.BN, BH = p.BN / 2;
+  const uint32_t nbuf = 2 * BN <= 512 ? 2u : 1u;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < (int)nbuf * BN) tmem_cols <<= 1;
+
+  if (tid < p.n_groups) {
+    const es_group gq = p.grp[tid];
+    s_grp[tid] = gq;
+    s_tiles[tid] = ceil_div(gq.rows * p.P, kTileM);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_wh); tma_prefetch_desc(&tmap_x); }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  int total_tiles = 0;
+  for (int i = 0; i < p.n_groups; ++i) total_tiles += s_tiles[i];
+  total_tiles *= p.n_tiles_n;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int taps = p.n_taps;
+  const int cblks = p.C / kBK;
+  const int nkb = taps * cblks;
+
+  if (warp == 0) {
+    // =========================================================================== TMA PRODUCER: A (im2col) + this CTA's half of B
+    if (lane == 0) {
+      const uint32_t lead_full0 = mapa_shared(full_bar(0), 0);
+      uint32_t it = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        TileInfo ti;
+        decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+        const int wrow = ti.slot * p.Nout + ti.n0 + (int)rank * BH;
+        // first im2col row of this CTA's half: output pixel (sample, oy, ox) -> base coordinate (lower corner + index * stride);
+        // rows past the group's end run into the next sample (masked by the epilogue) or off the tensor (zero-filled)
+        const int m = ti.m0 + (int)rank * kBM;
+        const int sample = m / p.P, pix = m - sample * p.P;
+        const int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+        const int cn = ti.row_start + sample, ch = ta.low_h + oy * p.my, cw = ta.low_w + ox * p.mx;
+        int cb = 0, tap = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= (uint32_t)kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)kFStageA + (uint32_t)BN * 128u);
+          const uint32_t lead_full = lead_full0 + 8u * s;
+          const uint32_t sa = base + s * kStage;
+          tma_im2col_4d_pair(sa, &tmap_x, cb * kBK, cw, ch, cn, (uint32_t)(p.tdx[tap] - ta.low_w), (uint32_t)(p.tdy[tap] - ta.low_h), lead_full);
+          tma_load_2d_pair(sa + kFStageA, &tmap_wh, p.tkoff[tap] + cb * kBK, wrow, lead_full);
+          if (++tap == taps) { tap = 0; ++cb; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================================== MMA ISSUER (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_m(BN, 2 * kBM, false, false);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
+        const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+        const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+        if (use >= 1) mbar_wait(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = base + s * kStage;
+            const uint32_t sb = sa + kFStageA;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_pair(tacc, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
+            umma_commit_pair(empty_bar(s), 3);
+            if (kb == nkb - 1) umma_commit_pair(tfull_bar(buf), 3);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+    }
+  } else {
+    // =========================================================================== EPILOGUE (warps 2-5: TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
+      TileInfo ti;
+      decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+      const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+      const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+      mbar_wait(tfull_bar(buf), use & 1, p.err_flag, 3);
+      tc_fence_after();
+      const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
+      uint32_t r[32];
+      const uint32_t t_lane = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+      const int m = ti.m0 + (int)rank * kBM + q * 32 + lane;
+      const bool ok = m < ti.rows * p.P;
+      const int smp = ok ? m / p.P : 0, pix = ok ? m - smp * p.P : 0;
+      const int oa = pix / p.Wo, ob = pix - oa * p.Wo;
+      const long opix = (long)(ti.row_start + smp) * p.P_full + (oa * p.o_my + p.o_oy) * p.Wo_full + ob * p.o_mx + p.o_ox;
+      __nv_bfloat16* yrow = p.out + (opix * p.Nout + ti.n0);
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(t_lane + c, r);
+        if (ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) dst[qq] = pack8(f + 8 * qq);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // STRIP variant for convolutions WITHOUT an upsample in front whose taps form rows (same dy, consecutive dx): conv3 forward
 // (3x3, 128 -> 64) and its data gradient (3x3, 64 -> 128), the layers where the gather is the bound — an im2col row is used
 // for only N = 64/128 MACs per element, so the 64 B/clk/SM that cp.async moves through L1TEX caps the kernel at ~50 % of the
@@ -1098,6 +1276,24 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+  }
+  return fn;
+}
+
 int* fwd_err_flag() { return pipeline_err_flag(); }
 
 }  // namespace
@@ -1204,9 +1400,11 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
     ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the activations");
   }
 
-  // CTA-pair variant (see igemm_pair_kernel).  ES_IGEMM_PAIR: 0 = off, 1 (default) = every launch the strip variant does not
-  // take, 2 = also instead of the strip variant (A/B measurements).
-  static const int pair_mode = [] { const char* e = getenv("ES_IGEMM_PAIR"); return e ? atoi(e) : 1; }();
+  // CTA-pair variant with the cp.async gather (see igemm_pair_kernel).  Measured on B200: on par with the single-CTA kernel
+  // (N = 256: 0.870 vs 0.858 ms, N = 128: 0.572 vs 0.542 ms) — the gather, not the weight stream, is the bound — so it is
+  // opt-in.  ES_IGEMM_PAIR: 0 (default) = off, 1 = every launch the strip / TMA-fed variants do not take, 2 = also instead of
+  // the strip variant (A/B measurements).
+  static const int pair_mode = [] { const char* e = getenv("ES_IGEMM_PAIR"); return e ? atoi(e) : 0; }();
   auto launch_pair = [&]() -> int {
     alignas(64) CUtensorMap tmap_h;
     const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)p.Nout};
@@ -1234,11 +1432,80 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
   };
   const bool pair_ok = pair_mode > 0 && p.BN >= 64;
 
+  // TMA-fed pair variant (see igemm_tma_pair_kernel): the conv reads the source directly (identity nearest maps).
+  // ES_IGEMM_TMA_A: 0 = off, 1 (default) = wherever eligible except launches the strip variant takes, 2 = also those.
+  static const int tma_a_mode = [] { const char* e = getenv("ES_IGEMM_TMA_A"); return e ? atoi(e) : 1; }();
+  auto launch_tma_pair = [&](bool& taken) -> int {
+    taken = false;
+    if (!(tma_a_mode > 0 && p.BN >= 64 && p.Hu == p.Hs && p.Wu == p.Ws)) return ES_OK;
+    EncodeIm2colFn enc_i = encode_im2col_fn();
+    if (!enc_i) return ES_OK;
+    int dmin_x = 127, dmin_y = 127, dmax_x = -128, dmax_y = -128;
+    for (int t = 0; t < p.n_taps; ++t) {
+      dmin_x = p.tdx[t] < dmin_x ? p.tdx[t] : dmin_x; dmax_x = p.tdx[t] > dmax_x ? p.tdx[t] : dmax_x;
+      dmin_y = p.tdy[t] < dmin_y ? p.tdy[t] : dmin_y; dmax_y = p.tdy[t] > dmax_y ? p.tdy[t] : dmax_y;
+    }
+    // base pixel of output index i along an axis: low + i*m, with low <= smallest tap offset; the box's upper corner makes
+    // the number of base pixels per row / column exactly Wo / Ho:  Q = (W + up - low - 1) / m + 1.  Both corners <= 0.
+    TmaAParams ta{};
+    int low[2], up[2];
+    const int ext[2] = {p.Ws, p.Hs}, outn[2] = {p.Wo, p.Ho}, mul[2] = {p.mx, p.my}, dmin[2] = {dmin_x, dmin_y}, dmax[2] = {dmax_x, dmax_y};
+    for (int a = 0; a < 2; ++a) {
+      int lo = dmin[a] < 0 ? dmin[a] : 0;
+      const int lim = ext[a] - 1 - (outn[a] - 1) * mul[a];      // up <= 0  <=>  low <= lim
+      if (lo > lim) lo = lim;
+      low[a] = lo;
+      up[a] = (outn[a] - 1) * mul[a] + 1 + lo - ext[a];
+      if (up[a] > 0 || lo < -128 || dmax[a] - lo > 255 || (ext[a] + up[a] - lo - 1) / mul[a] + 1 != outn[a]) return ES_OK;
+    }
+    ta.low_w = low[0]; ta.low_h = low[1];
+    alignas(64) CUtensorMap tmap_h, tmap_x;
+    {
+      const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)p.Nout};
+      const cuuint64_t strides[1] = {(cuuint64_t)p.KK * 2};
+      const cuuint32_t box[2] = {64, (cuuint32_t)(p.BN / 2)};
+      const CUresult rc = enc(&tmap_h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (half weight tile)");
+    }
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.Ws, (cuuint64_t)p.Hs, (cuuint64_t)total_rows};
+      const cuuint64_t strides[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.Ws * p.C * 2, (cuuint64_t)p.Hs * p.Ws * p.C * 2};
+      const cuuint32_t trav[4] = {1, (cuuint32_t)p.mx, (cuuint32_t)p.my, 1};
+      const CUresult rc = enc_i(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, low, up, 64, kBM, trav,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc != CUDA_SUCCESS) return ES_OK;                     // geometry the driver refuses: fall back to the gather variants
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long max_tiles = (ceil_div_l((long)total_rows * p.P, 2L * kBM) + n_groups) * p.n_tiles_n;
+    const int pairs = (int)(max_tiles < sms / 2 ? max_tiles : sms / 2);
+    constexpr int kPStages = 6;
+    constexpr size_t kPSmem = (size_t)kPStages * (kFStageA + 128 * 128) + 1024 + 2048;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ES_CUDA(cudaFuncSetAttribute(igemm_tma_pair_kernel<kPStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem));
+      attr_set = true;
+    }
+    igemm_tma_pair_kernel<kPStages><<<2 * pairs, 192, kPSmem, as_stream(stream)>>>(p, ta, tmap_h, tmap_x);
+    ES_LAUNCH_CHECK();
+    taken = true;
+    return ES_OK;
+  };
+
   // Strip variant (see igemm_strip_kernel): no upsample, taps form rows of consecutive dx with consecutive weight columns,
   // N <= 128.  ES_IGEMM_STRIP=0 disables it (A/B measurements).
   {
     StripParams sp{};
     bool okk = strip_plan(p, total_rows, sp);
+    if (okk && tma_a_mode >= 2) {
+      bool taken = false;
+      const int rc = launch_tma_pair(taken);
+      if (rc != ES_OK || taken) return rc;
+    }
     if (okk && pair_ok && pair_mode >= 2) return launch_pair();
     if (okk) {
       int dev = 0, sms = 148;
@@ -1262,6 +1529,11 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
   // 525.  The 128-row tile with double-buffered accumulators and the cp.async gather wins everywhere (the 3-stage pipeline
   // and the exposed epilogue of MT=2 cost more than the halved weight traffic saves; the TMA gather engine sustains about
   // half the row rate of cp.async), so it is the default; the other variants stay selectable for tuning.
+  if (!getenv("ES_IGEMM_FWD_VARIANT")) {
+    bool taken = false;
+    const int rc = launch_tma_pair(taken);
+    if (rc != ES_OK || taken) return rc;
+  }
   if (pair_ok && !getenv("ES_IGEMM_FWD_VARIANT")) return launch_pair();
   int mt = 1, g4 = 0;
   if (const char* ov = getenv("ES_IGEMM_FWD_VARIANT")) {   // "mt,g4" — tuning aid

@@ -201,4 +201,17 @@ __device__ __forceinline__ uint32_t make_idesc_m(int bn, int m, bool a_mn, bool 
          ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// TMA im2col load (cuTensorMapEncodeIm2col): 128B-swizzled rows of 64 channels for `pixelsPerColumn` consecutive base pixels
+// of the bounding box (w fastest, then h, then n), each shifted by the tap offsets {offw, offh}; out-of-tensor pixels are
+// zero-filled.  Semantics measured on sm_100a with tools/experiments/im2col_probe.cu.  `.cta_group::2`: the completion bytes
+// are signalled on a barrier that may live in the peer CTA of the pair.
+__device__ __forceinline__ void tma_im2col_4d_pair(uint32_t dst, const void* tmap, int c, int w, int h, int n, uint32_t offw,
+                                                    uint32_t offh, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};"
+      ::"r"(dst), "l"(tmap), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar_cluster_addr), "h"((unsigned short)offw), "h"((unsigned short)offh)
+      : "memory");
+}
+
 }  // namespace es
