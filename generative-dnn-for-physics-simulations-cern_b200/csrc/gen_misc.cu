@@ -347,7 +347,7 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
                 int Wu, const float* __restrict__ gamma, const float* __restrict__ beta, long slot_stride, int C,
                 int groups, const es_group* __restrict__ grp, int n_groups, __nv_bfloat16* __restrict__ out,
                 float* __restrict__ stats, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                float* __restrict__ dbias) {
+                float* __restrict__ dbias, int OWs = 0, int OWu = 0) {
   __shared__ float s_a[256], s_b[256];     // per-channel accumulators
   __shared__ float s_dg[256], s_db[256];   // per-channel affine-gradient accumulators (backward)
   __shared__ float s_g1[64], s_g2[64];     // per-group results
@@ -369,6 +369,7 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   const int cu = tid % c4, c8 = cu * 8, pstep = 256 / c4, p0 = tid / c4;
   const float cnt = (float)(cpg * P);
   if (BWD && FAN && tid == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+  if (!BWD && OWu > 0 && tid == 0) build_fanin(OWs, OWu, xlo, xhi);     // forward with the x-upsampled output layout
   s_a[tid] = 0.f; s_b[tid] = 0.f; s_dg[tid] = 0.f; s_db[tid] = 0.f;
   __syncthreads();
   const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * P * C);
@@ -415,12 +416,18 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
     float rs[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) rs[k] = s_g2[(c8 + k) / cpg];
-    uint4* y4 = reinterpret_cast<uint4*>(out + (size_t)r * P * C);
+    uint4* y4 = reinterpret_cast<uint4*>(out + (size_t)r * (OWu > 0 ? (P / OWs) * OWu : P) * C);
     for (int pix = p0; pix < P; pix += pstep) {
       unpack8(__ldg(x4 + (size_t)pix * c4 + cu), f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = lrelu((f[k] - mu[k]) * rs[k] * gk[k] + bk[k]);
-      y4[(size_t)pix * c4 + cu] = pack8(f);
+      if (OWu > 0) {      // nearest-upsampled along x: [P/OWs, OWu, C]
+        const int h = pix / OWs, w = pix - h * OWs;
+        const uint4 v = pack8(f);
+        for (int xu = xlo[w]; xu < xhi[w]; ++xu) y4[((size_t)h * OWu + xu) * c4 + cu] = v;
+      } else {
+        y4[(size_t)pix * c4 + cu] = pack8(f);
+      }
     }
   } else {
     float mu[8], rs[8];
@@ -1135,7 +1142,7 @@ extern "C" int es_ln_affine_bwd(const void* dy_up, int Hs, int Ws, int Hu, int W
 
 namespace es {
 int gn_cluster_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C, int groups,
-                   const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream);
+                   const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream, int OWs, int OWu);
 int gn_cluster_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, const void* x, const float* stats,
                    const float* gamma, const float* beta, long slot_stride, int C, int groups, const es_group* grp,
                    int n_groups, int total_rows, void* dx, float* dgamma, float* dbeta, float* dbias, void* stream);
@@ -1151,21 +1158,34 @@ static bool gn_cluster_backward() {
 }
 }  // namespace es
 
-extern "C" int es_gn_lrelu_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C,
-                               int groups, const es_group* grp, int n_groups, int total_rows, void* y, float* stats,
-                               void* stream) {
+static int gn_lrelu_fwd_impl(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C,
+                             int groups, const es_group* grp, int n_groups, int total_rows, void* y, float* stats,
+                             void* stream, int OWs, int OWu) {
   ES_REQUIRE(x && gamma && beta && grp && y && stats, "null pointer");
   ES_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && groups <= 64 && C % groups == 0, "bad channels/groups");
   ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups && P > 0, "bad sizes");
   if (!gn_legacy()) {   // cluster kernel (gn_cluster.cu): the sample's slab stays in shared memory; 1 = does not fit
-    const int rc = gn_cluster_fwd(x, gamma, beta, slot_stride, P, C, groups, grp, n_groups, total_rows, y, stats, stream);
+    const int rc = gn_cluster_fwd(x, gamma, beta, slot_stride, P, C, groups, grp, n_groups, total_rows, y, stats, stream, OWs, OWu);
     if (rc != 1) return rc;
   }
   gn_lrelu_kernel<false, false><<<total_rows, 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, nullptr, P, 1, P, 1, gamma, beta, slot_stride, C, groups, grp, n_groups,
-      (__nv_bfloat16*)y, stats, nullptr, nullptr, nullptr);
+      (__nv_bfloat16*)y, stats, nullptr, nullptr, nullptr, OWs, OWu);
   ES_LAUNCH_CHECK();
   return ES_OK;
+}
+
+extern "C" int es_gn_lrelu_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C,
+                               int groups, const es_group* grp, int n_groups, int total_rows, void* y, float* stats,
+                               void* stream) {
+  return gn_lrelu_fwd_impl(x, gamma, beta, slot_stride, P, C, groups, grp, n_groups, total_rows, y, stats, stream, 0, 0);
+}
+
+extern "C" int es_gn_lrelu_fwd_upx(const void* x, const float* gamma, const float* beta, long slot_stride, int Hs, int Ws,
+                                   int Wu, int C, int groups, const es_group* grp, int n_groups, int total_rows, void* y,
+                                   float* stats, void* stream) {
+  ES_REQUIRE(Hs > 0 && Ws > 0 && Ws <= 64 && Wu >= Ws && Wu <= 64 && Wu <= 2 * Ws, "bad x-upsample geometry");
+  return gn_lrelu_fwd_impl(x, gamma, beta, slot_stride, Hs * Ws, C, groups, grp, n_groups, total_rows, y, stats, stream, Ws, Wu);
 }
 
 extern "C" int es_gn_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, const void* x, const float* stats,

@@ -34,7 +34,7 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
                   int Wu, const float* __restrict__ gamma, const float* __restrict__ beta, long slot_stride, int C,
                   int groups, const es_group* __restrict__ grp, int n_groups, __nv_bfloat16* __restrict__ out,
                   float* __restrict__ stats, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                  float* __restrict__ dbias, int CL, int Pq) {
+                  float* __restrict__ dbias, int CL, int Pq, int OWs, int OWu) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ float s_c[4][256];        // per-channel accumulators of this CTA
   __shared__ float s_part[2][64];      // per-group partial sums, read by the other CTAs of the cluster
@@ -71,6 +71,7 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
     }
   }
   if (BWD && FAN && tid == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
+  if (!BWD && OWu > 0 && tid == 0) build_fanin(OWs, OWu, xlo, xhi);     // forward with the x-upsampled output layout
   s_c[0][tid] = 0.f; s_c[1][tid] = 0.f; s_c[2][tid] = 0.f; s_c[3][tid] = 0.f;
   __syncthreads();
   if (BWD && FAN) {
@@ -143,11 +144,20 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
 #pragma unroll
     for (int k = 0; k < 8; ++k) rs[k] = s_g2[(c8 + k) / cpg];
     uint4* y4 = reinterpret_cast<uint4*>(out + ((size_t)r * P + pb) * C);
+    uint4* yu4 = reinterpret_cast<uint4*>(out + (size_t)r * (OWu > 0 ? (P / OWs) * OWu : 0) * C);   // x-upsampled [P/OWs, OWu, C]
     for (int pl = pl0; pl < np; pl += pstep) {
       unpack8(s_x[(size_t)pl * c4 + cu], f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = lrelu((f[k] - mu[k]) * rs[k] * gk[k] + bk[k]);
-      y4[(size_t)pl * c4 + cu] = pack8(f);
+      if (OWu > 0) {
+        // the activation is stored nearest-upsampled along x (what the following conv's upsample would read): the conv then
+        // reads its source directly and both of its operands can come by TMA
+        const int pix = pb + pl, h = pix / OWs, w = pix - h * OWs;
+        const uint4 v = pack8(f);
+        for (int xu = xlo[w]; xu < xhi[w]; ++xu) yu4[((size_t)h * OWu + xu) * c4 + cu] = v;
+      } else {
+        y4[(size_t)pl * c4 + cu] = pack8(f);
+      }
     }
     cluster.sync();     // the other CTAs may still be reading this CTA's partial sums
   } else {
@@ -267,7 +277,7 @@ template <bool BWD, bool FAN>
 static int launch_gn_cluster(const void* x, const void* dy_up, int Hs, int Ws, int Hu, int Wu, const float* gamma,
                              const float* beta, long slot_stride, int C, int groups, const es_group* grp, int n_groups,
                              int total_rows, void* out, float* stats, float* dgamma, float* dbeta, float* dbias,
-                             void* stream) {
+                             void* stream, int OWs = 0, int OWu = 0) {
   int Pq = 0;
   const int bpp = (BWD ? (FAN ? 6 : 4) : 2) * C;
   const int CL = pick_cluster(Hs * Ws, bpp, &Pq);
@@ -288,14 +298,14 @@ static int launch_gn_cluster(const void* x, const void* dy_up, int Hs, int Ws, i
   cfg.attrs = at;
   cfg.numAttrs = 1;
   ES_CUDA(cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, gamma, beta,
-                             slot_stride, C, groups, grp, n_groups, (__nv_bfloat16*)out, stats, dgamma, dbeta, dbias, CL, Pq));
+                             slot_stride, C, groups, grp, n_groups, (__nv_bfloat16*)out, stats, dgamma, dbeta, dbias, CL, Pq, OWs, OWu));
   return ES_OK;
 }
 
 int gn_cluster_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C, int groups,
-                   const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream) {
+                   const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream, int OWs, int OWu) {
   return launch_gn_cluster<false, false>(x, nullptr, P, 1, P, 1, gamma, beta, slot_stride, C, groups, grp, n_groups,
-                                         total_rows, y, stats, nullptr, nullptr, nullptr, stream);
+                                         total_rows, y, stats, nullptr, nullptr, nullptr, stream, OWs, OWu);
 }
 
 int gn_cluster_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, const void* x, const float* stats,

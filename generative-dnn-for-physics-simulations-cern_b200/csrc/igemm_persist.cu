@@ -1040,6 +1040,8 @@ struct WgParams {
   int tcol[32];
   int dw_ld;                        // length of a dw row (all taps of all phases)
   int N, KK, tiles_m, splits;
+  int kmode;                        // 0: all pixel blocks of a group; 1: only its FULL 64-pixel blocks; 2: only the partial last one
+  int tile_m;                       // kk columns per work unit: 128 (single CTA) or 256 (CTA pair)
   unsigned char ymap[64], xmap[64];
   const __nv_bfloat16* x;
   float* dw;
@@ -1055,9 +1057,15 @@ __device__ __forceinline__ bool wg_decode(int t, const WgParams& p, const es_gro
   const int per_g = p.splits * p.tiles_m;
   const int g = t / per_g, rem = t - g * per_g;
   const int sp = rem / p.tiles_m, mt = rem - sp * p.tiles_m;
-  ti.m0 = mt * kBM;
+  ti.m0 = mt * (p.tile_m ? p.tile_m : kBM);
   ti.rows = s_grp[g].rows; ti.row_start = s_grp[g].row_start; ti.slot = s_grp[g].slot;
-  const int nkb = ceil_div(ti.rows * p.P, kBK);
+  const int nall = ceil_div(ti.rows * p.P, kBK), nfull = (ti.rows * p.P) / kBK;
+  if (p.kmode == 2) {               // the partial last block only (one unit per (group, kk tile); splits == 1)
+    ti.kb0 = nfull;
+    ti.kb1 = nall;
+    return ti.kb1 > ti.kb0;
+  }
+  const int nkb = p.kmode == 1 ? nfull : nall;
   const int per = ceil_div(nkb, p.splits);
   ti.kb0 = sp * per;
   ti.kb1 = min(nkb, ti.kb0 + per);
@@ -1258,6 +1266,169 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-FED CTA-PAIR weight gradient.  D tile = 256 kk (M, 128 per CTA) x N; both operands by TMA: A = two im2col boxes per CTA
+// and pixel block (64 pixels x 64 channels of x for the (tap, channel block) of each 64-wide kk segment — MN-major rows of 128 B,
+// exactly what the cp.async gather used to build), B = this CTA's half of dy (N/2 channels x 64 pixels).  One elected thread
+// feeds the pipeline; there are no gather warps and no L1TEX traffic.  im2col rows cannot be zero-filled past a group's end
+// (they run into the next sample), so this kernel reduces over the FULL 64-pixel blocks of a group only (kmode 1); the
+// partial last block of each group goes through the gather kernel (kmode 2, one k-block per unit), which zero-fills.
+// Barrier protocol as igemm_tma_pair_kernel.
+template <int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+igemm_wgrad_tma_pair_kernel(const __grid_constant__ WgParams p, const __grid_constant__ TmaAParams ta,
+                            const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x) {
+  constexpr int kStage = kFStageA + 128 * 128;   // A 16 KB + dy half <= 16 KB
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kStages * kStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+  uint8_t* gen = smem_raw + (bar_base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * 20);
+  const uint32_t tmem_slot = bar_base + 8u * 20;
+  es_group* s_grp = reinterpret_cast<es_group*>(gen + 512);
+
+  const int BN = p.N, nseg_h = BN >> 7;            // 64-channel dy segments per CTA (N/2 channels)
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
+
+  if (tid < p.n_groups) s_grp[tid] = p.grp[tid];
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_dy); tma_prefetch_desc(&tmap_x); }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int total_tiles = p.n_groups * p.splits * p.tiles_m;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // =========================================================================== TMA PRODUCER
+    if (lane == 0) {
+      const uint32_t lead_full0 = mapa_shared(full_bar(0), 0);
+      uint32_t it = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        WgTile ti;
+        if (!wg_decode(tile, p, s_grp, ti)) continue;
+        int c0[2], ow[2], oh[2];
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+          const int kk = ti.m0 + (int)rank * kBM + sg * 64;
+          const int tap = kk / p.C;
+          c0[sg] = kk - tap * p.C;
+          ow[sg] = p.tdx[tap] - ta.low_w;
+          oh[sg] = p.tdy[tap] - ta.low_h;
+        }
+        const int prow0 = ti.row_start * p.P;
+        // (sample, oy, ox) of the block's first pixel: a mixed-radix counter advanced by 64 pixels per block
+        int pidx = ti.kb0 * kBK;
+        int smp = pidx / p.P;
+        int pix = pidx - smp * p.P;
+        int oy = pix / p.Wo, ox = pix - oy * p.Wo;
+        const int dy64 = kBK / p.Wo, dx64 = kBK - dy64 * p.Wo;
+        for (int kb = ti.kb0; kb < ti.kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= (uint32_t)kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)kFStageA + (uint32_t)BN * 128u);
+          const uint32_t lead_full = lead_full0 + 8u * s;
+          const uint32_t sa = base + s * kStage;
+          const int cn = ti.row_start + smp, ch = ta.low_h + oy * p.my, cw = ta.low_w + ox * p.mx;
+#pragma unroll
+          for (int sg = 0; sg < 2; ++sg)
+            tma_im2col_4d_pair(sa + sg * 8192u, &tmap_x, c0[sg], cw, ch, cn, (uint32_t)ow[sg], (uint32_t)oh[sg], lead_full);
+          for (int sg = 0; sg < nseg_h; ++sg)
+            tma_load_2d_pair(sa + kFStageA + sg * 8192u, &tmap_dy, ((int)rank * nseg_h + sg) * 64, prow0 + kb * kBK, lead_full);
+          ox += dx64; oy += dy64;
+          if (ox >= p.Wo) { ox -= p.Wo; ++oy; }
+          while (oy >= p.Ho) { oy -= p.Ho; ++smp; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================================== MMA ISSUER (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_m(BN, 2 * kBM, true, true);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        WgTile ti;
+        if (!wg_decode(tile, p, s_grp, ti)) continue;
+        const uint32_t buf = tcount & 1;
+        if (tcount >= 2) mbar_wait(tempty_bar(buf), ((tcount >> 1) - 1) & 1, p.err_flag, 5);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
+        for (int kb = ti.kb0; kb < ti.kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = base + s * kStage;
+            const uint32_t sb = sa + kFStageA;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_pair(tacc, make_desc(sa + k * 2048, 8192, 1024), make_desc(sb + k * 2048, 8192, 1024), idesc,
+                             (kb > ti.kb0 || k) ? 1u : 0u);
+            umma_commit_pair(empty_bar(s), 3);
+            if (kb == ti.kb1 - 1) umma_commit_pair(tfull_bar(buf), 3);
+          }
+          __syncwarp();
+        }
+        ++tcount;
+      }
+      tc_fence_before();
+    }
+  } else {
+    // =========================================================================== EPILOGUE (warps 2-5): RED into dw
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      WgTile ti;
+      if (!wg_decode(tile, p, s_grp, ti)) continue;
+      const uint32_t buf = tcount & 1;
+      mbar_wait(tfull_bar(buf), (tcount >> 1) & 1, p.err_flag, 3);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+      const int kk = ti.m0 + (int)rank * kBM + q * 32 + lane;
+      const int tap = kk / p.C;
+      float* dw = p.dw + (long)ti.slot * p.dw_slot_stride + p.tcol[tap] + (kk - tap * p.C);
+      uint32_t r[32];
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(t_lane + c, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dw + (long)(c + j) * p.dw_ld, __uint_as_float(r[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0));
+      ++tcount;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1348,6 +1519,31 @@ static void pick_bn(FwdParams& p) {
   p.n_tiles_n = p.Nout / p.BN;
 }
 
+// Host-side plan of the TMA-fed pair variant (igemm_tma_pair_kernel): true when the tap table reads the source directly
+// (identity nearest maps), N tiles are >= 64 wide and the taps fit an im2col bounding box; fills the box corners
+// (index 0 = W, 1 = H).  Base pixel of output index i along an axis = low + i*m with low <= the smallest tap offset; the
+// upper corner makes the number of base pixels per row / column exactly Wo / Ho: Q = (W + up - low - 1) / m + 1; both
+// corners are kept <= 0.  The dense product (one tap on a 1x1 grid) is excluded: measured slower (0.440 vs 0.389 ms).
+static bool tma_pair_plan(const FwdParams& p, int low[2], int up[2]) {
+  if (!(p.BN >= 64 && p.Hu == p.Hs && p.Wu == p.Ws) || (p.n_taps == 1 && p.Hs * p.Ws == 1)) return false;
+  if (p.mx < 1 || p.mx > 8 || p.my < 1 || p.my > 8) return false;
+  int dmin_x = 127, dmin_y = 127, dmax_x = -128, dmax_y = -128;
+  for (int t = 0; t < p.n_taps; ++t) {
+    dmin_x = p.tdx[t] < dmin_x ? p.tdx[t] : dmin_x; dmax_x = p.tdx[t] > dmax_x ? p.tdx[t] : dmax_x;
+    dmin_y = p.tdy[t] < dmin_y ? p.tdy[t] : dmin_y; dmax_y = p.tdy[t] > dmax_y ? p.tdy[t] : dmax_y;
+  }
+  const int ext[2] = {p.Ws, p.Hs}, outn[2] = {p.Wo, p.Ho}, mul[2] = {p.mx, p.my}, dmin[2] = {dmin_x, dmin_y}, dmax[2] = {dmax_x, dmax_y};
+  for (int a = 0; a < 2; ++a) {
+    int lo = dmin[a] < 0 ? dmin[a] : 0;
+    const int lim = ext[a] - 1 - (outn[a] - 1) * mul[a];      // up <= 0  <=>  low <= lim
+    if (lo > lim) lo = lim;
+    low[a] = lo;
+    up[a] = (outn[a] - 1) * mul[a] + 1 + lo - ext[a];
+    if (up[a] > 0 || lo < -128 || dmax[a] - lo > 255 || (ext[a] + up[a] - lo - 1) / mul[a] + 1 != outn[a]) return false;
+  }
+  return true;
+}
+
 static void conv_taps(const es_conv_geom* g, FwdParams& p) {
   p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
   p.n_taps = g->KH * g->KW; p.my = 1; p.mx = 1;
@@ -1432,32 +1628,20 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
   };
   const bool pair_ok = pair_mode > 0 && p.BN >= 64;
 
-  // TMA-fed pair variant (see igemm_tma_pair_kernel): the conv reads the source directly (identity nearest maps).
-  // ES_IGEMM_TMA_A: 0 = off, 1 (default) = wherever eligible except launches the strip variant takes, 2 = also those.
-  static const int tma_a_mode = [] { const char* e = getenv("ES_IGEMM_TMA_A"); return e ? atoi(e) : 1; }();
+  // TMA-fed pair variant (see igemm_tma_pair_kernel): the conv reads the source directly (identity nearest maps).  Measured on
+  // B200 against the cp.async-gather kernels (ms per launch, batch 1024, E = 8): conv1 forward classes 0.858/0.656/0.683/0.401
+  // -> 0.593/0.464/0.487/0.288, conv2 data-gradient classes 0.582/0.486 -> 0.385/0.326, conv1 data gradient 2.262 -> 1.584,
+  // conv3 data gradient (strip variant 0.910) -> 0.628, conv3 forward (strip 1.147) -> 1.054.  The dense fc2 product (one tap on
+  // a 1x1 grid: pure weight streaming) is the one shape that lost (0.389 -> 0.440) and keeps the single-CTA kernel.
+  // ES_IGEMM_TMA_A: 0 = off, 1 = wherever eligible except launches the strip variant takes, 2 (default) = also those.
+  static const int tma_a_mode = [] { const char* e = getenv("ES_IGEMM_TMA_A"); return e ? atoi(e) : 2; }();
   auto launch_tma_pair = [&](bool& taken) -> int {
     taken = false;
-    if (!(tma_a_mode > 0 && p.BN >= 64 && p.Hu == p.Hs && p.Wu == p.Ws)) return ES_OK;
-    EncodeIm2colFn enc_i = encode_im2col_fn();
-    if (!enc_i) return ES_OK;
-    int dmin_x = 127, dmin_y = 127, dmax_x = -128, dmax_y = -128;
-    for (int t = 0; t < p.n_taps; ++t) {
-      dmin_x = p.tdx[t] < dmin_x ? p.tdx[t] : dmin_x; dmax_x = p.tdx[t] > dmax_x ? p.tdx[t] : dmax_x;
-      dmin_y = p.tdy[t] < dmin_y ? p.tdy[t] : dmin_y; dmax_y = p.tdy[t] > dmax_y ? p.tdy[t] : dmax_y;
-    }
-    // base pixel of output index i along an axis: low + i*m, with low <= smallest tap offset; the box's upper corner makes
-    // the number of base pixels per row / column exactly Wo / Ho:  Q = (W + up - low - 1) / m + 1.  Both corners <= 0.
     TmaAParams ta{};
     int low[2], up[2];
-    const int ext[2] = {p.Ws, p.Hs}, outn[2] = {p.Wo, p.Ho}, mul[2] = {p.mx, p.my}, dmin[2] = {dmin_x, dmin_y}, dmax[2] = {dmax_x, dmax_y};
-    for (int a = 0; a < 2; ++a) {
-      int lo = dmin[a] < 0 ? dmin[a] : 0;
-      const int lim = ext[a] - 1 - (outn[a] - 1) * mul[a];      // up <= 0  <=>  low <= lim
-      if (lo > lim) lo = lim;
-      low[a] = lo;
-      up[a] = (outn[a] - 1) * mul[a] + 1 + lo - ext[a];
-      if (up[a] > 0 || lo < -128 || dmax[a] - lo > 255 || (ext[a] + up[a] - lo - 1) / mul[a] + 1 != outn[a]) return ES_OK;
-    }
+    if (tma_a_mode <= 0 || !tma_pair_plan(p, low, up)) return ES_OK;
+    EncodeIm2colFn enc_i = encode_im2col_fn();
+    if (!enc_i) return ES_OK;
     ta.low_w = low[0]; ta.low_h = low[1];
     alignas(64) CUtensorMap tmap_h, tmap_x;
     {
@@ -1583,6 +1767,13 @@ extern "C" int es_igemm_fwd_plan(const es_conv_geom* g, int total_rows, int32_t*
   conv_taps(g, p);
   pick_bn(p);
   StripParams sp{};
+  int low[2], up[2];
+  if (tma_pair_plan(p, low, up)) {      // the default dispatch prefers the TMA-fed pair variant wherever it applies
+    plan8[0] = 2; plan8[1] = p.BN; plan8[2] = p.n_taps; plan8[3] = 0; plan8[4] = p.Wo; plan8[5] = 6;
+    plan8[6] = p.n_taps * (p.C / kBK);
+    plan8[7] = (int32_t)ceil_div_l((long)p.Ho * p.Wo, kBM);
+    return ES_OK;
+  }
   const bool strip = strip_plan(p, total_rows, sp);
   plan8[0] = strip ? 1 : 0;
   plan8[1] = p.BN;
@@ -1655,6 +1846,57 @@ static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, l
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  // TMA-fed CTA-pair variant (igemm_wgrad_tma_pair_kernel): x is read directly (identity nearest maps), dy has 128 or 256
+  // channels (a 64-channel half per CTA would need another swizzle), KK a multiple of 256.  It reduces over the full 64-pixel
+  // blocks of every group; the partial last block of each group goes through the gather kernel below (kmode 2).
+  static const int tma_a_mode = [] { const char* e = getenv("ES_IGEMM_TMA_A"); return e ? atoi(e) : 2; }();
+  {
+    FwdParams fp{};
+    fp.Hs = p.Hs; fp.Ws = p.Ws; fp.C = p.C; fp.Hu = p.Hu; fp.Wu = p.Wu; fp.Ho = p.Ho; fp.Wo = p.Wo;
+    fp.n_taps = p.n_taps; fp.my = p.my; fp.mx = p.mx; fp.BN = p.N;
+    for (int t = 0; t < p.n_taps; ++t) { fp.tdy[t] = p.tdy[t]; fp.tdx[t] = p.tdx[t]; }
+    int low[2], up[2];
+    EncodeIm2colFn enc_i = encode_im2col_fn();
+    if (tma_a_mode > 0 && enc_i && (p.N == 128 || p.N == 256) && p.KK % (2 * kBM) == 0 && tma_pair_plan(fp, low, up)) {
+      alignas(64) CUtensorMap tmap_x;
+      const cuuint64_t xdims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.Ws, (cuuint64_t)p.Hs, (cuuint64_t)total_rows};
+      const cuuint64_t xstrides[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.Ws * p.C * 2, (cuuint64_t)p.Hs * p.Ws * p.C * 2};
+      const cuuint32_t trav[4] = {1, (cuuint32_t)p.mx, (cuuint32_t)p.my, 1};
+      const CUresult rcx = enc_i(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), xdims, xstrides, low, up, 64, kBK, trav,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rcx == CUDA_SUCCESS) {
+        TmaAParams ta{};
+        ta.low_w = low[0]; ta.low_h = low[1];
+        WgParams pm = p;
+        pm.kmode = 1; pm.tile_m = 2 * kBM; pm.tiles_m = p.KK / (2 * kBM);
+        int sp2 = ceil_div(512, pm.tiles_m * n_groups);
+        const long full_blocks = ((long)total_rows * p.P) / kBK;
+        if (sp2 > full_blocks) sp2 = (int)full_blocks;
+        if (sp2 < 1) sp2 = 1;
+        if (sp2 > 64) sp2 = 64;
+        pm.splits = sp2;
+        constexpr int kPStages = 6;
+        constexpr size_t kPSmem = (size_t)kPStages * (kFStageA + 128 * 128) + 1024 + 2048;
+        static bool attr2 = false;
+        if (!attr2) {
+          ES_CUDA(cudaFuncSetAttribute(igemm_wgrad_tma_pair_kernel<kPStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem));
+          attr2 = true;
+        }
+        const int units = n_groups * pm.splits * pm.tiles_m;
+        const int pairs = units < sms / 2 ? units : sms / 2;
+        igemm_wgrad_tma_pair_kernel<kPStages><<<2 * pairs, 192, kPSmem, as_stream(stream)>>>(pm, ta, tmap, tmap_x);
+        ES_LAUNCH_CHECK();
+        WgParams pt = p;                  // partial last block of every group: gather kernel, one k-block per unit
+        pt.kmode = 2; pt.splits = 1;
+        const int tail_units = n_groups * pt.tiles_m;
+        igemm_wgrad_kernel<<<tail_units < sms ? tail_units : sms, kGThreads, kFSmem, as_stream(stream)>>>(pt, tmap);
+        ES_LAUNCH_CHECK();
+        return ES_OK;
+      }
+    }
+  }
   const int total = n_groups * p.splits * p.tiles_m;
   igemm_wgrad_kernel<<<total < sms ? total : sms, kGThreads, kFSmem, as_stream(stream)>>>(p, tmap);
   ES_LAUNCH_CHECK();

@@ -220,10 +220,19 @@ class GenEngineProton:
         self.g_fc2 = torch.empty(E, self.F2, device=dev)
         self.z_fc2 = torch.empty(E, self.F2, device=dev)
         self.w_fwd, self.w_dg, self.dw_p, self.up2 = {}, {}, {}, {}
+        self.upx = {}       # conv name -> (Hs, Ws, Wu): its input arrives x-upsampled from the previous norm kernel
+        import os
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
             if (Hu, Wu) == (2 * Hs, 2 * Ws):      # exact x2 nearest upsample in front of the conv: fold it away
                 self.up2[name] = Up2Conv(Hs, Ws, C, KH, KW, pad, N)
-            elif (Hu, Wu) != (Hs, Ws):            # 35x19 -> 56x30: rows repeat with period 8 (5 source rows): fold along y
+            elif (Hu, Wu) != (Hs, Ws) and os.environ.get("ES_CONV2_UPX", "1") != "0":
+                # 35x19 -> 56x30.  y: rows repeat with period 8 (5 source rows) -> folded.  x (19 -> 30, not a rational
+                # phase pattern worth folding): the previous GroupNorm kernel stores its activation nearest-upsampled along
+                # x (es_gn_lrelu_fwd_upx: +58 % bytes on one tensor), so the conv reads a [35, 30] source DIRECTLY — which
+                # is what makes its forward classes and its weight gradient TMA-fed (es_igemm_fwd_plan variant 2).
+                self.up2[name] = FoldedConv(Hs, Wu, C, Hu, Wu, KH, KW, pad, N, (True, False))
+                self.upx[name] = (Hs, Ws, Wu)
+            elif (Hu, Wu) != (Hs, Ws):            # A/B switch: nearest map along x inside the conv's gather
                 self.up2[name] = FoldedConv(Hs, Ws, C, Hu, Wu, KH, KW, pad, N, (True, False))
             if name in self.up2:
                 self.up2[name].alloc(E, dev)
@@ -273,8 +282,16 @@ class GenEngineProton:
                 self.up2[name].forward(act, a.addr(name + ".bias"), a.n, y, grp, E, R)
             else:
                 L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R)
-            nxt, st = empty(R, P, N, dtype=BF), empty(R, groups, 2)
-            L.call("es_gn_lrelu_fwd", y, a.addr(norm + ".weight"), a.addr(norm + ".bias"), a.n, P, N, groups, grp, E, R, nxt, st)
+            st = empty(R, groups, 2)
+            nxt_name = self.CONVS[i + 1][0] if i + 1 < len(self.CONVS) else None
+            if nxt_name in self.upx:    # the next conv wants its input upsampled along x
+                _, ws_, wu_ = self.upx[nxt_name]
+                nxt = empty(R, g.Ho * wu_, N, dtype=BF)
+                L.call("es_gn_lrelu_fwd_upx", y, a.addr(norm + ".weight"), a.addr(norm + ".bias"), a.n, g.Ho, g.Wo, wu_, N, groups,
+                       grp, E, R, nxt, st)
+            else:
+                nxt = empty(R, P, N, dtype=BF)
+                L.call("es_gn_lrelu_fwd", y, a.addr(norm + ".weight"), a.addr(norm + ".bias"), a.n, P, N, groups, grp, E, R, nxt, st)
             s[f"y{i + 3}"], s[f"st{i + 3}"], s[f"a{i + 3}"] = y, st, nxt
             act = nxt
         img1 = zeros(B, self.H * self.W)

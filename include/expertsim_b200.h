@@ -166,9 +166,12 @@ int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot
  * 25 instead of 64 tap-MACs per 4 outputs for k4/p1 (2.56x fewer), and the data gradient is ONE table-conv over dy
  * (my = mx = 2) writing the low-resolution gradient directly. */
 /* Host-only: which kernel variant es_igemm_fwd picks for geometry g (no device work; callable without a GPU).
- * plan8 = {strip variant (0/1), BN, tap rows, taps per row (nx), M-axis row pitch (Wo, or Wo + nx - 1 for strips),
- *          pipeline stages, pipeline steps per tile, M tiles per row}.  The strip variant (one gathered strip per tap row,
- * kx taps as row-shifted A descriptors) needs: no upsample, N <= 128, 2..4 taps per row, nx * BN <= 384. */
+ * plan8 = {variant, BN, tap rows (variant 2: taps), taps per row (nx), M-axis row pitch (Wo, or Wo + nx - 1 for strips),
+ *          pipeline stages, pipeline steps per tile, M tiles per row}.  variant 2 = TMA-fed CTA pair (A by TMA im2col, B halves
+ * by TMA, tcgen05.mma.cta_group::2): the conv reads its source directly (no nearest upsample in between), N tile >= 64, not
+ * the dense 1x1 product.  variant 1 = strip (one cp.async-gathered strip per tap row, kx taps as row-shifted A descriptors):
+ * no upsample, N <= 128, 2..4 taps per row, nx * BN <= 384 — taken where variant 2 does not apply (N = 32).  variant 0 =
+ * single-CTA kernel with the cp.async gather (nearest upsample inside the conv, fc2). */
 int es_igemm_fwd_plan(const es_conv_geom* g, int total_rows, int32_t* plan8);
 
 typedef struct {
@@ -255,6 +258,11 @@ int es_ln_lrelu_fwd(const void* x, const float* gamma, const float* beta, long s
 /* GroupNorm(groups) + LeakyReLU over NHWC bf16 [rows,P,C] (proton/generator.py:28-29,34-35,39-40). stats[row][groups][2]. */
 int es_gn_lrelu_fwd(const void* x, const float* gamma, const float* beta, long slot_stride, int P, int C, int groups,
                     const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream);
+/* Same, x is [rows,Hs,Ws,C] and y is stored NEAREST-UPSAMPLED ALONG x as [rows,Hs,Wu,C] (torch's nearest rule: source column
+ * min(floor(xu*Ws/Wu), Ws-1)) — the x half of the Upsample in front of proton conv2 (proton/generator.py:30-32), materialised by
+ * the producer so that the conv reads its source directly and both GEMM operands can come by TMA.  stats as above. */
+int es_gn_lrelu_fwd_upx(const void* x, const float* gamma, const float* beta, long slot_stride, int Hs, int Ws, int Wu, int C,
+                        int groups, const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream);
 /* Backward of norm+LeakyReLU.  `dy_up` is the gradient w.r.t. the (virtually upsampled) consumer input
  * [rows,Hu,Wu,C]; it is summed over the pixels that map to each source pixel [Hs,Ws] (nearest-upsample backward).
  * dx (bf16, gradient w.r.t. the pre-norm tensor), dgamma/dbeta/dbias_conv (fp32, atomically accumulated). */

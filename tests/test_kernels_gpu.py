@@ -301,7 +301,7 @@ def test_igemm_fwd_many_tiles(name):
     check(f"es_igemm_fwd {name} x64 rows, 8 ragged groups, {tiles} tiles", y.float(), want, 6e-3, 3e-2)
 
 
-@pytest.mark.parametrize("name", ["conv3_fwd", "conv2_fwd"])
+@pytest.mark.parametrize("name", ["conv3_fwd", "conv2_fwd", "conv2_dgrad", "conv3_dgrad"])
 def test_igemm_wgrad_many_tiles(name):
     """split-K weight gradient over 64 samples in 8 ragged groups (many K-chunks per CTA, RED epilogue), vs torch autograd on the
     device; run twice: the fp32 atomics make the result order-dependent, the run-to-run difference is bounded at 1e-5."""
@@ -331,7 +331,7 @@ def test_igemm_wgrad_many_tiles(name):
     assert float(runs[0][1].abs().max()) == 0.0          # slot 1 belongs to the empty group
 
 
-@pytest.mark.parametrize("name", ["conv1_fwd", "conv2_fwd", "conv3_fwd", "neutron_conv1"])
+@pytest.mark.parametrize("name", ["conv1_fwd", "conv2_fwd", "conv3_fwd", "neutron_conv1", "conv2_dgrad", "conv3_dgrad"])
 @pytest.mark.parametrize("impl", ["es_igemm_wgrad", "es_igemm_wgrad_simt"])
 def test_igemm_wgrad(name, impl):
     geo = GEOMS[name]
@@ -925,6 +925,59 @@ def test_y_folded_conv2_fwd_wgrad():
     dx = torch.zeros(R, Hs * Wu, C, dtype=BF, device=DEV)
     f.dgrad(cuda(dy, BF), dx, grp, E, R)
     check("y-folded conv2 dgrad", dx.float().view(R, Hs, Wu, C), torch.cat(want_dx), 1e-2, 5e-2)
+
+
+def test_gn_lrelu_fwd_upx_and_conv2_on_the_upsampled_source():
+    """proton conv2 with the x half of its upsample materialised by the GroupNorm kernel (es_gn_lrelu_fwd_upx) — the layout
+    the generator uses: norm+LeakyReLU output stored [35, 30] (nearest along x, bit-equal to torch's map), then the y-folded
+    conv reads its source directly (TMA-fed variant): forward, weight gradient and data gradient against fp32 torch."""
+    from expertsim._nets import FoldedConv
+    Hs, Ws, C, Hu, Wu, KH, KW, pad, N = 35, 19, 256, 56, 30, 4, 4, 1, 128
+    counts, slots, E = [2, 0, 3], [2, 0, 1], 3
+    grp, R = groups(counts, slots)
+    g = G(777)
+    pre = bf16_round(torch.randn(R, Hs * Ws, C, generator=g))
+    gamma, beta = 1 + 0.1 * torch.randn(E, C, generator=g), 0.1 * torch.randn(E, C, generator=g)
+    y0, st0 = torch.zeros(R, Hs * Ws, C, dtype=BF, device=DEV), torch.zeros(R, 32, 2, device=DEV)
+    L.call("es_gn_lrelu_fwd", cuda(pre, BF), cuda(gamma), cuda(beta), C, Hs * Ws, C, 32, grp, E, R, y0, st0)
+    yu, st1 = torch.zeros(R, Hs * Wu, C, dtype=BF, device=DEV), torch.zeros(R, 32, 2, device=DEV)
+    L.call("es_gn_lrelu_fwd_upx", cuda(pre, BF), cuda(gamma), cuda(beta), C, Hs, Ws, Wu, C, 32, grp, E, R, yu, st1)
+    torch.cuda.synchronize()
+    want_u = F.interpolate(y0.float().view(R, Hs, Ws, C).permute(0, 3, 1, 2), size=(Hs, Wu), mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(yu.float().view(R, Hs, Wu, C)[:2], want_u[:2]) and torch.equal(yu.float().view(R, Hs, Wu, C)[2:], want_u[2:])
+    assert torch.equal(st0, st1)
+    # the conv on the upsampled source
+    x = yu.float().view(R, Hs, Wu, C).cpu()                         # already bf16 values
+    w = torch.randn(E, N, C, KH, KW, generator=g) / math.sqrt(KH * KW * C)
+    bias = torch.randn(E, N, generator=g) * 0.1
+    f = FoldedConv(Hs, Wu, C, Hu, Wu, KH, KW, pad, N, (True, False))
+    assert len(f.classes) == 8 and f.has_dgrad and len(f.dgrad_classes) == 5 and f.dg_grid == (Hs, Wu)
+    assert all(c["g_fwd"].Wu == c["g_fwd"].Ws for c in f.classes)      # the conv reads its source directly
+    f.alloc(E, DEV)
+    f.fold(cuda(w), N * C * KH * KW, E)
+    y = torch.zeros(R, f.Ho * f.Wo, N, dtype=BF, device=DEV)
+    f.forward(yu, cuda(bias), N, y, grp, E, R)
+    dy = bf16_round(torch.randn(R, f.Ho, f.Wo, N, generator=g))
+    want_y, want_dw, want_dx, off = [], torch.zeros_like(w), [], 0
+    for c, s_ in zip(counts, slots):
+        if c == 0:
+            continue
+        xx = x[off:off + c].permute(0, 3, 1, 2).clone().requires_grad_(True)
+        wi = w[s_].clone().requires_grad_(True)
+        yi = F.conv2d(F.interpolate(xx, size=(Hu, Wu), mode="nearest"), wi, bias[s_], padding=pad)
+        (yi * dy[off:off + c].permute(0, 3, 1, 2)).sum().backward()
+        want_y.append(yi.detach().permute(0, 2, 3, 1))
+        want_dw[s_] = wi.grad
+        want_dx.append(xx.grad.permute(0, 2, 3, 1))
+        off += c
+    check("conv2 on the x-upsampled source: fwd", y.float().view(R, f.Ho, f.Wo, N), torch.cat(want_y), 8e-3, 4e-2)
+    dw = torch.zeros(E, N, C, KH, KW, device=DEV)
+    f.wgrad(yu, cuda(dy, BF), dw, N * C * KH * KW, grp, E, R)
+    for s_ in (1, 2):
+        check(f"conv2 on the x-upsampled source: wgrad slot {s_}", dw[s_], want_dw[s_], 5e-3, 2e-2)
+    dx = torch.zeros(R, Hs * Wu, C, dtype=BF, device=DEV)
+    f.dgrad(cuda(dy, BF), dx, grp, E, R)
+    check("conv2 on the x-upsampled source: dgrad", dx.float().view(R, Hs, Wu, C), torch.cat(want_dx), 1e-2, 5e-2)
 
 
 # ----------------------------------------------------------------------------------------------------------- preprocessing
