@@ -1267,21 +1267,22 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// TMA-FED CTA-PAIR weight gradient.  D tile = 256 kk (M, 128 per CTA) x N; both operands by TMA: A = two im2col boxes per CTA
-// and pixel block (64 pixels x 64 channels of x for the (tap, channel block) of each 64-wide kk segment — MN-major rows of 128 B,
-// exactly what the cp.async gather used to build), B = this CTA's half of dy (N/2 channels x 64 pixels).  One elected thread
-// feeds the pipeline; there are no gather warps and no L1TEX traffic.  im2col rows cannot be zero-filled past a group's end
-// (they run into the next sample), so this kernel reduces over the FULL 64-pixel blocks of a group only (kmode 1); the
-// partial last block of each group goes through the gather kernel (kmode 2, one k-block per unit), which zero-fills.
-// Barrier protocol as igemm_tma_pair_kernel.
-template <int kStages>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-igemm_wgrad_tma_pair_kernel(const __grid_constant__ WgParams p, const __grid_constant__ TmaAParams ta,
-                            const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x) {
-  constexpr int kStage = kFStageA + 128 * 128;   // A 16 KB + dy half <= 16 KB
+// TMA-FED weight gradient, as a CTA pair (kPair: D tile = 256 kk x N, 128 kk per CTA, tcgen05.mma.cta_group::2) or as a
+// single CTA (128 kk x N; used for N = 64, where half of dy per CTA would be a 64-byte row).  Both operands by TMA: A = two
+// im2col boxes per CTA and pixel block (64 pixels x 64 channels of x for the (tap, channel block) of each 64-wide kk segment —
+// MN-major rows of 128 B, exactly what the cp.async gather used to build), B = dy (this CTA's N/2 channels of it in a pair) x
+// 64 pixels.  One elected thread feeds the pipeline; there are no gather warps and no L1TEX traffic.  im2col rows cannot be
+// zero-filled past a group's end (they run into the next sample), so this kernel reduces over the FULL 64-pixel blocks of a
+// group only (kmode 1); the partial last block of each group goes through the gather kernel (kmode 2, one k-block per
+// unit), which zero-fills.  Barrier protocol as igemm_tma_pair_kernel.  Launched with a cluster dimension of 2 (kPair) or 1.
+template <int kStages, bool kPair>
+__global__ void __launch_bounds__(192, 1)
+igemm_wgrad_tma_kernel(const __grid_constant__ WgParams p, const __grid_constant__ TmaAParams ta,
+                       const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x) {
+  constexpr int kStage = kFStageA + 128 * 128;   // A 16 KB + dy (half) <= 16 KB
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t bar_base = base + kStages * kStage;
@@ -1294,7 +1295,8 @@ igemm_wgrad_tma_pair_kernel(const __grid_constant__ WgParams p, const __grid_con
   const uint32_t tmem_slot = bar_base + 8u * 20;
   es_group* s_grp = reinterpret_cast<es_group*>(gen + 512);
 
-  const int BN = p.N, nseg_h = BN >> 7;            // 64-channel dy segments per CTA (N/2 channels)
+  const int BN = p.N;
+  const int nseg_c = kPair ? (BN >> 7) : (BN >> 6);      // 64-channel dy segments this CTA loads
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * BN) tmem_cols <<= 1;
 
@@ -1306,26 +1308,26 @@ igemm_wgrad_tma_pair_kernel(const __grid_constant__ WgParams p, const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 8);
+      mbar_init(tempty_bar(b), kPair ? 8 : 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_dy); tma_prefetch_desc(&tmap_x); }
-  if (warp == 1) tmem_alloc_pair(tmem_slot, tmem_cols);
+  if (warp == 1) { if (kPair) tmem_alloc_pair(tmem_slot, tmem_cols); else tmem_alloc(tmem_slot, tmem_cols); }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  if (kPair) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int total_tiles = p.n_groups * p.splits * p.tiles_m;
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // =========================================================================== TMA PRODUCER
     if (lane == 0) {
-      const uint32_t lead_full0 = mapa_shared(full_bar(0), 0);
+      const uint32_t lead_full0 = kPair ? mapa_shared(full_bar(0), 0) : full_bar(0);
       uint32_t it = 0;
-      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      for (int tile = first; tile < total_tiles; tile += stride) {
         WgTile ti;
         if (!wg_decode(tile, p, s_grp, ti)) continue;
         int c0[2], ow[2], oh[2];
@@ -1339,23 +1341,28 @@ igemm_wgrad_tma_pair_kernel(const __grid_constant__ WgParams p, const __grid_con
         }
         const int prow0 = ti.row_start * p.P;
         // (sample, oy, ox) of the block's first pixel: a mixed-radix counter advanced by 64 pixels per block
-        int pidx = ti.kb0 * kBK;
+        const int pidx = ti.kb0 * kBK;
         int smp = pidx / p.P;
-        int pix = pidx - smp * p.P;
+        const int pix = pidx - smp * p.P;
         int oy = pix / p.Wo, ox = pix - oy * p.Wo;
         const int dy64 = kBK / p.Wo, dx64 = kBK - dy64 * p.Wo;
         for (int kb = ti.kb0; kb < ti.kb1; ++kb, ++it) {
           const int s = it % kStages;
           if (it >= (uint32_t)kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)kFStageA + (uint32_t)BN * 128u);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), (kPair ? 2u : 1u) * (uint32_t)kFStageA + (uint32_t)BN * 128u);
           const uint32_t lead_full = lead_full0 + 8u * s;
           const uint32_t sa = base + s * kStage;
           const int cn = ti.row_start + smp, ch = ta.low_h + oy * p.my, cw = ta.low_w + ox * p.mx;
 #pragma unroll
-          for (int sg = 0; sg < 2; ++sg)
-            tma_im2col_4d_pair(sa + sg * 8192u, &tmap_x, c0[sg], cw, ch, cn, (uint32_t)ow[sg], (uint32_t)oh[sg], lead_full);
-          for (int sg = 0; sg < nseg_h; ++sg)
-            tma_load_2d_pair(sa + kFStageA + sg * 8192u, &tmap_dy, ((int)rank * nseg_h + sg) * 64, prow0 + kb * kBK, lead_full);
+          for (int sg = 0; sg < 2; ++sg) {
+            if (kPair) tma_im2col_4d_pair(sa + sg * 8192u, &tmap_x, c0[sg], cw, ch, cn, (uint32_t)ow[sg], (uint32_t)oh[sg], lead_full);
+            else tma_im2col_4d(sa + sg * 8192u, &tmap_x, c0[sg], cw, ch, cn, (uint32_t)ow[sg], (uint32_t)oh[sg], lead_full);
+          }
+          for (int sg = 0; sg < nseg_c; ++sg) {
+            const int col = ((int)rank * nseg_c + sg) * 64;
+            if (kPair) tma_load_2d_pair(sa + kFStageA + sg * 8192u, &tmap_dy, col, prow0 + kb * kBK, lead_full);
+            else tma_load_2d(sa + kFStageA + sg * 8192u, &tmap_dy, col, prow0 + kb * kBK, lead_full);
+          }
           ox += dx64; oy += dy64;
           if (ox >= p.Wo) { ox -= p.Wo; ++oy; }
           while (oy >= p.Ho) { oy -= p.Ho; ++smp; }
@@ -1365,9 +1372,9 @@ igemm_wgrad_tma_pair_kernel(const __grid_constant__ WgParams p, const __grid_con
   } else if (warp == 1) {
     // =========================================================================== MMA ISSUER (leader CTA only)
     if (rank == 0) {
-      const uint32_t idesc = make_idesc_m(BN, 2 * kBM, true, true);
+      const uint32_t idesc = make_idesc_m(BN, kPair ? 2 * kBM : kBM, true, true);
       uint32_t it = 0, tcount = 0;
-      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      for (int tile = first; tile < total_tiles; tile += stride) {
         WgTile ti;
         if (!wg_decode(tile, p, s_grp, ti)) continue;
         const uint32_t buf = tcount & 1;
@@ -1382,11 +1389,18 @@ igemm_wgrad_tma_pair_kernel(const __grid_constant__ WgParams p, const __grid_con
             const uint32_t sa = base + s * kStage;
             const uint32_t sb = sa + kFStageA;
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              umma_bf16_pair(tacc, make_desc(sa + k * 2048, 8192, 1024), make_desc(sb + k * 2048, 8192, 1024), idesc,
-                             (kb > ti.kb0 || k) ? 1u : 0u);
-            umma_commit_pair(empty_bar(s), 3);
-            if (kb == ti.kb1 - 1) umma_commit_pair(tfull_bar(buf), 3);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t ad = make_desc(sa + k * 2048, 8192, 1024), bd = make_desc(sb + k * 2048, 8192, 1024);
+              const uint32_t acc = (kb > ti.kb0 || k) ? 1u : 0u;
+              if (kPair) umma_bf16_pair(tacc, ad, bd, idesc, acc); else umma_bf16(tacc, ad, bd, idesc, acc);
+            }
+            if (kPair) {
+              umma_commit_pair(empty_bar(s), 3);
+              if (kb == ti.kb1 - 1) umma_commit_pair(tfull_bar(buf), 3);
+            } else {
+              umma_commit(empty_bar(s));
+              if (kb == ti.kb1 - 1) umma_commit(tfull_bar(buf));
+            }
           }
           __syncwarp();
         }
@@ -1398,7 +1412,7 @@ igemm_wgrad_tma_pair_kernel(const __grid_constant__ WgParams p, const __grid_con
     // =========================================================================== EPILOGUE (warps 2-5): RED into dw
     const int q = warp & 3;
     uint32_t tcount = 0;
-    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+    for (int tile = first; tile < total_tiles; tile += stride) {
       WgTile ti;
       if (!wg_decode(tile, p, s_grp, ti)) continue;
       const uint32_t buf = tcount & 1;
@@ -1416,16 +1430,16 @@ igemm_wgrad_tma_pair_kernel(const __grid_constant__ WgParams p, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0));
+      if (lane == 0) { if (kPair) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0)); else mbar_arrive(tempty_bar(buf)); }
       ++tcount;
     }
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  if (kPair) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_pair(tmem_base, tmem_cols);
+    if (kPair) tmem_dealloc_pair(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -1847,9 +1861,9 @@ static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, l
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
-  // TMA-fed CTA-pair variant (igemm_wgrad_tma_pair_kernel): x is read directly (identity nearest maps), dy has 128 or 256
-  // channels (a 64-channel half per CTA would need another swizzle), KK a multiple of 256.  It reduces over the full 64-pixel
-  // blocks of every group; the partial last block of each group goes through the gather kernel below (kmode 2).
+  // TMA-fed variant (igemm_wgrad_tma_kernel): x is read directly (identity nearest maps).  As a CTA pair when dy has 128 or
+  // 256 channels and KK is a multiple of 256, as a single CTA for 64 channels.  It reduces over the full 64-pixel blocks of
+  // every group; the partial last block of each group goes through the gather kernel below (kmode 2).
   static const int tma_a_mode = [] { const char* e = getenv("ES_IGEMM_TMA_A"); return e ? atoi(e) : 2; }();
   {
     FwdParams fp{};
@@ -1858,7 +1872,8 @@ static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, l
     for (int t = 0; t < p.n_taps; ++t) { fp.tdy[t] = p.tdy[t]; fp.tdx[t] = p.tdx[t]; }
     int low[2], up[2];
     EncodeIm2colFn enc_i = encode_im2col_fn();
-    if (tma_a_mode > 0 && enc_i && (p.N == 128 || p.N == 256) && p.KK % (2 * kBM) == 0 && tma_pair_plan(fp, low, up)) {
+    const bool as_pair = (p.N == 128 || p.N == 256) && p.KK % (2 * kBM) == 0;
+    if (tma_a_mode > 0 && enc_i && (as_pair || p.N == 64) && tma_pair_plan(fp, low, up)) {
       alignas(64) CUtensorMap tmap_x;
       const cuuint64_t xdims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.Ws, (cuuint64_t)p.Hs, (cuuint64_t)total_rows};
       const cuuint64_t xstrides[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.Ws * p.C * 2, (cuuint64_t)p.Hs * p.Ws * p.C * 2};
@@ -1870,8 +1885,10 @@ static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, l
         TmaAParams ta{};
         ta.low_w = low[0]; ta.low_h = low[1];
         WgParams pm = p;
-        pm.kmode = 1; pm.tile_m = 2 * kBM; pm.tiles_m = p.KK / (2 * kBM);
-        int sp2 = ceil_div(512, pm.tiles_m * n_groups);
+        pm.kmode = 1;
+        pm.tile_m = as_pair ? 2 * kBM : kBM;
+        pm.tiles_m = p.KK / pm.tile_m;
+        int sp2 = ceil_div(as_pair ? 512 : 1024, pm.tiles_m * n_groups);
         const long full_blocks = ((long)total_rows * p.P) / kBK;
         if (sp2 > full_blocks) sp2 = (int)full_blocks;
         if (sp2 < 1) sp2 = 1;
@@ -1881,12 +1898,30 @@ static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, l
         constexpr size_t kPSmem = (size_t)kPStages * (kFStageA + 128 * 128) + 1024 + 2048;
         static bool attr2 = false;
         if (!attr2) {
-          ES_CUDA(cudaFuncSetAttribute(igemm_wgrad_tma_pair_kernel<kPStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem));
+          ES_CUDA(cudaFuncSetAttribute(igemm_wgrad_tma_kernel<kPStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem));
+          ES_CUDA(cudaFuncSetAttribute(igemm_wgrad_tma_kernel<kPStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem));
           attr2 = true;
         }
         const int units = n_groups * pm.splits * pm.tiles_m;
-        const int pairs = units < sms / 2 ? units : sms / 2;
-        igemm_wgrad_tma_pair_kernel<kPStages><<<2 * pairs, 192, kPSmem, as_stream(stream)>>>(pm, ta, tmap, tmap_x);
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = kPSmem;
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = as_pair ? 2 : 1;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (as_pair) {
+          const int pairs = units < sms / 2 ? units : sms / 2;
+          cfg.gridDim = dim3(2 * pairs);
+          ES_CUDA(cudaLaunchKernelEx(&cfg, igemm_wgrad_tma_kernel<kPStages, true>, pm, ta, tmap, tmap_x));
+        } else {
+          cfg.gridDim = dim3(units < sms ? units : sms);
+          ES_CUDA(cudaLaunchKernelEx(&cfg, igemm_wgrad_tma_kernel<kPStages, false>, pm, ta, tmap, tmap_x));
+        }
         ES_LAUNCH_CHECK();
         WgParams pt = p;                  // partial last block of every group: gather kernel, one k-block per unit
         pt.kmode = 2; pt.splits = 1;

@@ -214,4 +214,14 @@ __device__ __forceinline__ void tma_im2col_4d_pair(uint32_t dst, const void* tma
       : "memory");
 }
 
+// single-CTA form of the im2col load (barrier in this CTA)
+__device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const void* tmap, int c, int w, int h, int n, uint32_t offw,
+                                               uint32_t offh, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};"
+      ::"r"(dst), "l"(tmap), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar), "h"((unsigned short)offw), "h"((unsigned short)offh)
+      : "memory");
+}
+
 }  // namespace es
