@@ -8,6 +8,8 @@
 //   FWD       y[m, co]  = sum_k xcol[m, k]  w[co, k]              k = (ci, ky, kx)
 //   BWD_DATA  dx[m, ci] = sum_k dycol[m, k] w[co, ci, ky, kx]     k = (co, ky, kx), m = input pixel
 //   BWD_W     dw[co, k] += sum_m dy[m, co] xcol[m, k]             split over m, fp32 atomics
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace es {
@@ -18,6 +20,66 @@ int conv2d_bwd_data_ci1(const float* dy, const float* w, long slot_stride_w, con
 namespace {
 
 constexpr int kCM = 64, kCK = 16;
+constexpr int kPA = kCM + 8;          // pitch of the [reduction][64] operand tile: 72 -> mma fragment loads hit 32 distinct banks
+
+// ---- 3xTF32 on the (legacy, warp-level) tensor path.  The discriminator / aux-regressor convolutions keep an fp32 parity bar
+// (2e-3 on gradients that cancel heavily), which plain TF32 (10 mantissa bits) misses and bf16 tcgen05 misses by far.  Split
+// every fp32 operand x = big + small with big = tf32(x), small = tf32(x - big): a*b ~= big_a*big_b + big_a*small_b +
+// small_a*big_b drops only the small*small term (2^-22 relative) and accumulates in fp32 — fp32-class accuracy at one
+// third of the TF32 rate, still several times the FFMA rate of the register-tiled loop it replaces (which ran at
+// 10-12 TFLOP/s: 2 shared-memory loads per 8 FMAs).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& big, uint32_t& small) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(big) : "f"(x));
+  const float r = x - __uint_as_float(big);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(small) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// One 16-deep reduction chunk of the CTA tile D[64 x BN] += A^T B with A = As[16][kPA] (reduction-major, 64 rows of D
+// contiguous), B = Bs[16][BN + 8].  8 warps: warp w owns rows 16*(w&3).. and columns (w>>2)*(BN/2)..; c[j][4] = its BN/16 n8 tiles.
+template <int BN>
+__device__ __forceinline__ void chunk_mma_tf32x3(const float* __restrict__ As, const float* __restrict__ Bs, float (*c)[4]) {
+  constexpr int NT = BN / 16, PB = BN + 8;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = (w & 3) * 16 + g, n0 = (w >> 2) * (BN / 2) + g;
+#pragma unroll
+  for (int k8 = 0; k8 < kCK; k8 += 8) {
+    uint32_t ab[4], as[4];
+    split_tf32(As[(k8 + t) * kPA + r0], ab[0], as[0]);
+    split_tf32(As[(k8 + t) * kPA + r0 + 8], ab[1], as[1]);
+    split_tf32(As[(k8 + t + 4) * kPA + r0], ab[2], as[2]);
+    split_tf32(As[(k8 + t + 4) * kPA + r0 + 8], ab[3], as[3]);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      uint32_t bb[2], bs[2];
+      split_tf32(Bs[(k8 + t) * PB + n0 + 8 * j], bb[0], bs[0]);
+      split_tf32(Bs[(k8 + t + 4) * PB + n0 + 8 * j], bb[1], bs[1]);
+      mma_tf32(c[j], as, bb);      // small terms first: they are added to the accumulator before the large product
+      mma_tf32(c[j], ab, bs);
+      mma_tf32(c[j], ab, bb);
+    }
+  }
+}
+// accumulator fragments -> the [BN][64 + 4] staging tile the SIMT epilogue indexing reads (row of D contiguous)
+template <int BN>
+__device__ __forceinline__ void stage_mma_acc(float* __restrict__ Cs, const float (*c)[4]) {
+  constexpr int NT = BN / 16;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = (w & 3) * 16 + g, n0 = (w >> 2) * (BN / 2) + 2 * t;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    Cs[(n0 + 8 * j) * (kCM + 4) + r0] = c[j][0];
+    Cs[(n0 + 8 * j + 1) * (kCM + 4) + r0] = c[j][1];
+    Cs[(n0 + 8 * j) * (kCM + 4) + r0 + 8] = c[j][2];
+    Cs[(n0 + 8 * j + 1) * (kCM + 4) + r0 + 8] = c[j][3];
+  }
+}
 
 struct KEnt { int off; short ky, kx; };   // source offset of reduction index k relative to the window origin
 
@@ -33,7 +95,7 @@ __device__ __forceinline__ bool tile_of(const es_group* grp, int n_groups, int p
 }
 
 // MODE 0: forward.  MODE 1: data gradient (src = dy, "output" = dx over input pixels).
-template <int MODE, int BN>
+template <int MODE, int BN, bool TC>
 __global__ void __launch_bounds__(256)
 conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, const float* __restrict__ bias, long sw,
                  long sb, es_conv2d g, const es_group* __restrict__ grp, int n_groups, float* __restrict__ dst,
@@ -58,8 +120,9 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
   const int PXm = Hm * Wm, PXs = Hs * Ws, PXf = Hf * Wf;
   if (PXm <= 0) return;   // (a class without taps, e.g. 1x1 stride 2, still writes its zeros)
   KEnt* ktab = reinterpret_cast<KEnt*>(sm);                       // [K]
-  float* As = sm + 2 * ((K + 1) & ~1);                            // [kCK][kCM + 4]
-  float* Bs = As + kCK * (kCM + 4);                               // [kCK][BN + 4]
+  float* As = sm + 2 * ((K + 1) & ~1);                            // [kCK][kPA]
+  float* Bs = As + kCK * kPA;                                     // [kCK][BN + 8]
+  float* Cst = Bs + kCK * (BN + 8);                                // TC: [BN][kCM + 4] accumulator staging for the epilogue
   int gi, m0, mtot;
   if (!tile_of(grp, n_groups, PXm, kCM, blockIdx.x, gi, m0, mtot)) return;
   const int slot = grp[gi].slot, row_start = grp[gi].row_start;
@@ -86,6 +149,9 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float cfr[BN / 16][4];
+#pragma unroll
+  for (int j = 0; j < BN / 16; ++j) { cfr[j][0] = 0.f; cfr[j][1] = 0.f; cfr[j][2] = 0.f; cfr[j][3] = 0.f; }
   __syncthreads();
   for (int k0 = 0; k0 < K; k0 += kCK) {
     // ---- A tile: gathered source values
@@ -106,7 +172,7 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
           }
         }
       }
-      As[kk * (kCM + 4) + ml] = v;
+      As[kk * kPA + ml] = v;
     }
     // ---- B tile: weights  Bs[kk][n]
     for (int i = tid; i < kCK * BN; i += 256) {
@@ -119,24 +185,36 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
           v = __ldg(wslot + ((size_t)(k / KHWc) * g.Ci + n0 + n) * KHW + e.ky * g.KW + e.kx);
         }
       }
-      Bs[kk * (BN + 4) + n] = v;
+      Bs[kk * (BN + 8) + n] = v;
     }
     __syncthreads();
+    if (TC) {
+      chunk_mma_tf32x3<BN>(As, Bs, cfr);
+    } else {
 #pragma unroll
-    for (int kk = 0; kk < kCK; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(As + kk * (kCM + 4) + tm * 4);
-      float b[TN];
+      for (int kk = 0; kk < kCK; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(As + kk * kPA + tm * 4);
+        float b[TN];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[kk * (BN + 4) + tn * TN + j];
+        for (int j = 0; j < TN; ++j) b[j] = Bs[kk * (BN + 8) + tn * TN + j];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
-        acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
-        acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
-        acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+        for (int j = 0; j < TN; ++j) {
+          acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+          acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+          acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+          acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+        }
       }
     }
     __syncthreads();
+  }
+  if (TC) {     // fragments -> shared memory -> the same (4 pixels x TN channels) register tile the epilogue below stores
+    stage_mma_acc<BN>(Cst, cfr);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = Cst[(tn * TN + j) * (kCM + 4) + tm * 4 + i];
   }
   // ---- epilogue: NCHW store, lanes along pixels
 #pragma unroll
@@ -160,14 +238,15 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
 
 // weight gradient: CTA = (64-wide k tile, chunk of `mper` group pixels); D[k, co] += sum_m xcol[m, k] dy[m, co].
 // The gather walks pixels with an incremental (sample, oy, ox) counter — no integer division in the reduction loop.
-template <int BN>
+template <int BN, bool TC>
 __global__ void __launch_bounds__(256)
 conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy, es_conv2d g,
                        const es_group* __restrict__ grp, int n_groups, int mper, float* __restrict__ dw,
                        float* __restrict__ db, long sw, long sb) {
   constexpr int kWK = 64;                                  // k tile
-  __shared__ __align__(16) float As[kCK][kWK + 4];     // [m chunk][k tile]
-  __shared__ __align__(16) float Bs[kCK][BN + 4];      // [m chunk][co]
+  __shared__ __align__(16) float As[kCK][kPA];         // [m chunk][k tile]
+  __shared__ __align__(16) float Bs[kCK][BN + 8];      // [m chunk][co]
+  __shared__ float Cs[TC ? BN * (kCM + 4) : 1];        // TC: accumulator staging for the epilogue
   constexpr int TN = BN / 16;
   const int KHW = g.KH * g.KW, K = g.Ci * KHW, PXo = g.Ho * g.Wo, PXi = g.Hi * g.Wi;
   int gi, mbeg, mtot;
@@ -203,6 +282,9 @@ conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   float bsum = 0.f;
+  float cfr[BN / 16][4];
+#pragma unroll
+  for (int j = 0; j < BN / 16; ++j) { cfr[j][0] = 0.f; cfr[j][1] = 0.f; cfr[j][2] = 0.f; cfr[j][3] = 0.f; }
   for (int mc = mbeg; mc < mend; mc += kCK) {
     // A tile: xcol[m, k] for 16 consecutive m, 64 k
     {
@@ -236,21 +318,33 @@ conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy
 #pragma unroll
       for (int mm = 0; mm < kCK; ++mm) bsum += Bs[mm][tid];
     }
+    if (TC) {
+      chunk_mma_tf32x3<BN>(&As[0][0], &Bs[0][0], cfr);
+    } else {
 #pragma unroll
-    for (int mm = 0; mm < kCK; ++mm) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[mm][tm * 4]);
-      float b[TN];
+      for (int mm = 0; mm < kCK; ++mm) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[mm][tm * 4]);
+        float b[TN];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[mm][tn * TN + j];
+        for (int j = 0; j < TN; ++j) b[j] = Bs[mm][tn * TN + j];
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
-        acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
-        acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
-        acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+        for (int j = 0; j < TN; ++j) {
+          acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+          acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+          acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+          acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+        }
       }
     }
     __syncthreads();
+  }
+  if (TC) {
+    stage_mma_acc<BN>(Cs, cfr);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = Cs[(tn * TN + j) * (kCM + 4) + tm * 4 + i];
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -281,13 +375,19 @@ int launch_conv_gemm(const float* src, const float* w, const float* b, long sw, 
   const long tiles = ceil_div_l((long)total_rows * PXm, kCM) + n_groups;
   if (tiles >= 2147483647L) { set_error("conv gemm: too many tiles"); return ES_ERR_INVALID; }
   const int BN = Nn > 32 ? 64 : (Nn > 16 ? 32 : 16);
-  const size_t smem = (2 * (size_t)((K + 1) & ~1) + kCK * (kCM + 4) + kCK * (BN + 4)) * sizeof(float);
+  static const bool tc = [] { const char* e = getenv("ES_CONV_TF32X3"); return !(e && e[0] == '0'); }();
+  const size_t smem = (2 * (size_t)((K + 1) & ~1) + kCK * kPA + kCK * (BN + 8) + (tc ? BN * (kCM + 4) : 0)) * sizeof(float);
   if (smem > 200 * 1024) { set_error("conv gemm: reduction table does not fit in shared memory"); return ES_ERR_INVALID; }
   const dim3 grid((unsigned)tiles, ceil_div(Nn, BN), S * S);
 #define ES_LAUNCH_CG(BNV)                                                                                              \
   {                                                                                                                    \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(conv_gemm_kernel<MODE, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-    conv_gemm_kernel<MODE, BNV><<<grid, 256, smem, st>>>(src, w, b, sw, sb, *g, grp, n_groups, dst, accumulate);       \
+    if (tc) {                                                                                                          \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(conv_gemm_kernel<MODE, BNV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      conv_gemm_kernel<MODE, BNV, true><<<grid, 256, smem, st>>>(src, w, b, sw, sb, *g, grp, n_groups, dst, accumulate); \
+    } else {                                                                                                           \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(conv_gemm_kernel<MODE, BNV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      conv_gemm_kernel<MODE, BNV, false><<<grid, 256, smem, st>>>(src, w, b, sw, sb, *g, grp, n_groups, dst, accumulate); \
+    }                                                                                                                  \
   }
   if (BN == 64) ES_LAUNCH_CG(64) else if (BN == 32) ES_LAUNCH_CG(32) else ES_LAUNCH_CG(16)
 #undef ES_LAUNCH_CG
@@ -343,9 +443,11 @@ extern "C" int es_conv2d_bwd_weight(const float* x, const float* dy, const es_co
   ES_REQUIRE(ychunks < 65535 && mper < 2147483647L, "too many reduction chunks");
   const dim3 grid(ktiles, (unsigned)ychunks, ntiles);
   cudaStream_t st = as_stream(stream);
-  if (BN == 64) conv_wgrad_gemm_kernel<64><<<grid, 256, 0, st>>>(x, dy, *g, grp, n_groups, (int)mper, dw, db, slot_stride_w, slot_stride_b);
-  else if (BN == 32) conv_wgrad_gemm_kernel<32><<<grid, 256, 0, st>>>(x, dy, *g, grp, n_groups, (int)mper, dw, db, slot_stride_w, slot_stride_b);
-  else conv_wgrad_gemm_kernel<16><<<grid, 256, 0, st>>>(x, dy, *g, grp, n_groups, (int)mper, dw, db, slot_stride_w, slot_stride_b);
+  static const bool tc = [] { const char* e = getenv("ES_CONV_TF32X3"); return !(e && e[0] == '0'); }();
+#define ES_LAUNCH_WG(BNV, TCV) conv_wgrad_gemm_kernel<BNV, TCV><<<grid, 256, 0, st>>>(x, dy, *g, grp, n_groups, (int)mper, dw, db, slot_stride_w, slot_stride_b)
+  if (tc) { if (BN == 64) ES_LAUNCH_WG(64, true); else if (BN == 32) ES_LAUNCH_WG(32, true); else ES_LAUNCH_WG(16, true); }
+  else { if (BN == 64) ES_LAUNCH_WG(64, false); else if (BN == 32) ES_LAUNCH_WG(32, false); else ES_LAUNCH_WG(16, false); }
+#undef ES_LAUNCH_WG
   ES_LAUNCH_CHECK();
   return ES_OK;
 }
