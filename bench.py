@@ -221,7 +221,7 @@ def igemm_flops(name, a):
 class System:
     """one MoE system + optimizers + a pool of resident synthetic batches"""
 
-    def __init__(self, arch, E, B, dev, rank, world, pool_n, dp=True, overlap="deferred"):
+    def __init__(self, arch, E, B, dev, rank, world, pool_n, dp=True, overlap="deferred", graph=False):
         from expertsim.train.loop import setup_moe_system
         from expertsim.train.training_setup import setup_optimizers
         from expertsim.utils.data import synthetic_showers
@@ -239,6 +239,8 @@ class System:
             moe.enable_data_parallel()
             moe.overlap_grad_allreduce = overlap
         self.opts = setup_optimizers(moe, cfg)
+        if graph:
+            moe.enable_cuda_graph()
         moe.train()
         self.data = synthetic_showers(arch, B * pool_n, seed=rank, device=dev)
 
@@ -326,7 +328,7 @@ def run_b200(args):
         torch.cuda.empty_cache()
 
     overlap = False if args.no_overlap_allreduce else args.overlap_mode
-    sysm = System(arch, E, B, dev, rank, world, args.pool, overlap=overlap)
+    sysm = System(arch, E, B, dev, rank, world, args.pool, overlap=overlap, graph=args.cuda_graph)
     moe = sysm.moe
     for i in range(args.warmup):
         sysm.step(i)
@@ -513,7 +515,7 @@ def bench_inference(moe, args, dev, world, pk, arch, timed):
 
 def short_bench(arch, E, B, dev, rank, world, args, pk, timed, overlap):
     """train samples/s + showers/s of another BASELINE configuration (weak-scaling slice of batch B per GPU)"""
-    sysm = System(arch, E, B, dev, rank, world, min(args.pool, 8), overlap=overlap)
+    sysm = System(arch, E, B, dev, rank, world, min(args.pool, 8), overlap=overlap, graph=args.cuda_graph)
     n = max(3, min(args.steps, 10))
     for i in range(3):
         sysm.step(i)
@@ -543,6 +545,7 @@ def main():
     ap.add_argument("--infer-iters", type=int, default=5)
     ap.add_argument("--cpu-batch", type=int, default=256, help="batch of the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true", help="MoEWrapper.enable_cuda_graph(): replay the step as one CUDA graph")
     ap.add_argument("--no-extra", action="store_true", help="skip the neutron / single-expert lines of `extra`")
     ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the roofline_hbm micro-measurements")
     ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the on-device data-parallel parity check")

@@ -84,6 +84,55 @@ bn_reduce_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
     }
     __syncthreads();
   };
+  // one (row, pixel) of this thread's octet: accumulate into a[], b[]
+  auto visit = [&](int r, int pix, int sg, int slot) {
+    const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * P * Csp);
+    const __nv_bfloat16* dyr = BWD ? dy_up + (size_t)r * Hu * Wu * Csp : nullptr;
+    const int flat = pix * C_it + c8;                 // NHWC offset inside the row
+    unpack8(__ldg(x4 + flat / 8), f);
+    if (!BWD) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] += f[k]; b[k] += f[k] * f[k]; }
+    } else {
+      const int spix = flat / Csp, sc8 = flat - spix * Csp;
+      load_da8(dyr, Wu, Csp, sc8, ylo, yhi, xlo, xhi, spix / Ws, spix % Ws, da);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int sc = c8 + k;
+        const int pc = chmap ? chmap[sc] : sc;
+        const float mu = stats[((size_t)sg * C_it + sc) * 2], rs = stats[((size_t)sg * C_it + sc) * 2 + 1];
+        const float xh = (f[k] - mu) * rs;
+        const float ks = keep_scale(mask, seed, ((size_t)r * Csp + sc8 + k) * P + spix, p_drop);
+        const float pre = (xh * gamma[slot * slot_stride + pc] + beta[slot * slot_stride + pc]) * ks;   // dropout, then LeakyReLU
+        const float g2 = da[k] * (pre > 0.f ? 1.f : kLReLU) * ks;
+        a[k] += g2;
+        b[k] += g2 * xh;
+      }
+    }
+  };
+  if (P_it == 1) {
+    // BatchNorm1d over a flattened map (one "pixel" per row): the pixel lanes would idle (r01 launch list: ONE launch of
+    // 2.98 ms, 16 of 256 threads active), so the lanes walk ROWS instead.  blockIdx.x enumerates chunks of `rpc` rows that
+    // lie inside ONE statistics group (expert, pass) — decoded from the device-side group table — which keeps the flush
+    // uniform: one per CTA.
+    int xq = blockIdx.x, sg = -1, slot = 0, rlo = 0, rhi = 0;
+    for (int gi = 0; gi < E && sg < 0; ++gi) {
+      const es_group G = grp[gi];
+      if (G.rows == 0) continue;
+      for (int ps = 0; ps < (two_pass ? 2 : 1); ++ps) {
+        const int lo = G.row_start + (ps ? G.pass_rows : 0);
+        const int n = two_pass ? (ps ? G.rows - G.pass_rows : G.pass_rows) : G.rows;
+        const int nc = ceil_div(n, rpc);
+        if (xq < nc) { sg = 2 * G.slot + ps; slot = G.slot; rlo = lo + xq * rpc; rhi = min(lo + n, rlo + rpc); break; }
+        xq -= nc;
+      }
+    }
+    if (sg < 0) return;       // uniform over the CTA
+    for (int r = rlo + pl; r < rhi; r += lanes) visit(r, 0, sg, slot);
+    cur = sg;
+    flush();
+    return;
+  }
   const int r0 = blockIdx.x * rpc, r1 = min(total_rows, r0 + rpc);
   for (int r = r0; r < r1; ++r) {
     const SgRow q = sg_of_row(grp, E, r, two_pass);
@@ -93,31 +142,7 @@ bn_reduce_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
       cur = sg;
     }
     if (sg < 0) continue;
-    const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * P * Csp);
-    const __nv_bfloat16* dyr = BWD ? dy_up + (size_t)r * Hu * Wu * Csp : nullptr;
-    for (int pix = pl; pix < P_it; pix += lanes) {
-      const int flat = pix * C_it + c8;                 // NHWC offset inside the row
-      unpack8(__ldg(x4 + flat / 8), f);
-      if (!BWD) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { a[k] += f[k]; b[k] += f[k] * f[k]; }
-      } else {
-        const int spix = flat / Csp, sc8 = flat - spix * Csp;
-        load_da8(dyr, Wu, Csp, sc8, ylo, yhi, xlo, xhi, spix / Ws, spix % Ws, da);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int sc = c8 + k;
-          const int pc = chmap ? chmap[sc] : sc;
-          const float mu = stats[((size_t)sg * C_it + sc) * 2], rs = stats[((size_t)sg * C_it + sc) * 2 + 1];
-          const float xh = (f[k] - mu) * rs;
-          const float ks = keep_scale(mask, seed, ((size_t)r * Csp + sc8 + k) * P + spix, p_drop);
-          const float pre = (xh * gamma[q.slot * slot_stride + pc] + beta[q.slot * slot_stride + pc]) * ks;   // dropout, then LeakyReLU
-          const float g2 = da[k] * (pre > 0.f ? 1.f : kLReLU) * ks;
-          a[k] += g2;
-          b[k] += g2 * xh;
-        }
-      }
-    }
+    for (int pix = pl; pix < P_it; pix += lanes) visit(r, pix, sg, q.slot);
   }
   if (cur >= 0) flush();
 }
@@ -561,7 +586,7 @@ extern "C" int es_bn_stats_nhwc(const void* x, int Hs, int Ws, int C, int feat_s
     ES_LAUNCH_CHECK();
     return ES_OK;
   }
-  bn_reduce_nhwc_kernel<false><<<dim3(ceil_div(total_rows, rpc), C_it / 8 / opb), 256, 0, as_stream(stream)>>>(
+  bn_reduce_nhwc_kernel<false><<<dim3(ceil_div(total_rows, rpc) + (P_it == 1 ? 2 * E : 0), C_it / 8 / opb), 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, nullptr, Hs, Ws, Hs, Ws, C, P_it, C_it, opb, rpc, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
       0ull, 0.f, grp, E, total_rows, two_pass, sums);
   ES_LAUNCH_CHECK();
@@ -620,7 +645,7 @@ extern "C" int es_bn_bwd_reduce_nhwc(const void* dy_up, int Hs, int Ws, int Hu, 
     ES_LAUNCH_CHECK();
     return ES_OK;
   }
-  bn_reduce_nhwc_kernel<true><<<dim3(ceil_div(total_rows, rpc), C_it / 8 / opb), 256, 0, as_stream(stream)>>>(
+  bn_reduce_nhwc_kernel<true><<<dim3(ceil_div(total_rows, rpc) + (P_it == 1 ? 2 * E : 0), C_it / 8 / opb), 256, 0, as_stream(stream)>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_up, Hs, Ws, Hu, Wu, C, P_it, C_it, opb, rpc, stats, gamma, beta,
       slot_stride, chmap, keep_mask, seed, p_drop, grp, E, total_rows, two_pass, sums2);
   ES_LAUNCH_CHECK();
