@@ -123,33 +123,63 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+try:        # raw handle of the current stream without building a torch.cuda.Stream object (called once per launch)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:      # pragma: no cover
+    _raw_stream = None
+
 n_calls = 0  # kernels-launching C-ABI calls made so far (bench.py reports it as gpu_launches evidence)
 # Optional per-call device timing (bench.py's roofline leg): {"names": set of entry points, "log": []}.  When set, calls to
 # the named entry points are bracketed by CUDA events on the launching stream; log rows are (name, args, start, end).
 profile = None
+_fast = {}   # entry point -> (ctypes function, tuple of argument kinds: 0 pointer, 1 integer, 2 float)
+_Tensor = torch.Tensor
+
+
+def _plan(name):
+    lib = load()
+    ret, spec = _protos[name]
+    kinds = tuple(0 if k == "ptr" else (1 if k in ("int", "long") else 2) for k, _ in spec[:-1])
+    _fast[name] = ent = (getattr(lib, name), kinds)
+    return ent
 
 
 def call(name: str, *args):
-    """Call ``name(*args, stream)`` on the current torch CUDA stream; tensors are passed as raw device pointers."""
+    """Call ``name(*args, stream)`` on the current torch CUDA stream; tensors are passed as raw device pointers.
+    This is the launch path of every kernel (~400 calls per training step), so the per-call host work is kept small:
+    the prototype is resolved once per entry point, tensors take a fast path, the stream handle is read raw."""
     global n_calls
-    lib = load()
-    ret, spec = _protos[name]
-    if len(args) != len(spec) - 1:
-        raise TypeError(f"{name} takes {len(spec) - 1} arguments before the stream, got {len(args)}")
+    ent = _fast.get(name)
+    if ent is None:
+        ent = _plan(name)
+    fn, kinds = ent
+    if len(args) != len(kinds):
+        raise TypeError(f"{name} takes {len(kinds)} arguments before the stream, got {len(args)}")
     conv = []
-    for (kind, aname), a in zip(spec, args):
-        if kind == "ptr":
-            conv.append(_ptr(a))
-        elif kind in ("int", "long"):
-            conv.append(int(a))
+    push = conv.append
+    for kind, a in zip(kinds, args):
+        if kind == 0:
+            if type(a) is _Tensor:
+                if not a.is_cuda:
+                    raise RuntimeError("libexpertsim_b200 takes device pointers only; got a CPU tensor")
+                if not a.is_contiguous():
+                    raise RuntimeError("non-contiguous tensor passed to the C-ABI")
+                push(a.data_ptr())
+            else:
+                push(_ptr(a))
+        elif kind == 1:
+            push(int(a))
         else:
-            conv.append(float(a))
-    conv.append(stream_ptr())
+            push(float(a))
+    if _raw_stream is not None:
+        push(_raw_stream(torch.cuda.current_device()))
+    else:
+        push(stream_ptr())
     timed = profile is not None and name in profile["names"]
     if timed:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    rc = getattr(lib, name)(*conv)
+    rc = fn(*conv)
     if timed:
         ev1.record()
         profile["log"].append((name, tuple(a for a in args if not isinstance(a, torch.Tensor)), ev0, ev1))

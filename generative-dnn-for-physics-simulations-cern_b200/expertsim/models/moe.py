@@ -207,7 +207,7 @@ class MoEWrapper(nn.Module):
         (which also creates streams, attributes, tensor maps), the second captures, every later one copies the batch into
         the graph's static inputs and replays: the host issues 1 launch instead of ~400 (20.9 -> 0.02 ms of host time
         per step, 35.1 -> 34.1 ms on the device; tools/experiments/graph_probe.py).  Steps with injected noise (the parity
-        harness) always run eagerly; data-parallel steps (NCCL collectives inside the capture) only with ES_GRAPH_DP=1."""
+        harness) and data-parallel steps always run eagerly."""
         self._graphs = {} if on else None
         return self
 
@@ -223,9 +223,9 @@ class MoEWrapper(nn.Module):
         graphs = getattr(self, "_graphs", None)
         opts = (aux_reg_optimizers, generator_optimizers, discriminator_optimizers, router_optimizer)
         args = (cond, real_images, true_positions, std, intensity)
-        import os
-        dp_ok = self.world_size == 1 or os.environ.get("ES_GRAPH_DP", "0") == "1"    # NCCL collectives inside a capture: opt-in
-        if graphs is None or noise or not dp_ok:
+        # single-device steps only: capturing the step WITH its NCCL collectives (two communicators, a communication stream)
+        # was tried on 2 x B200 and hung in the first replay, so data-parallel steps stay eager
+        if graphs is None or noise or self.world_size > 1:
             return self._train_step_impl(epoch, *args, *opts, ema_helper, device, noise)
         key = self._graph_key(epoch, cond.shape[0], opts)
         ent = graphs.get(key)
