@@ -26,7 +26,57 @@ def empty(*shape, dtype=torch.float32):
     return torch.empty(shape, dtype=dtype, device=_dev())
 
 
-def zeros(*shape, dtype=torch.float32):
+_ITEMSIZE = {torch.float32: 4, torch.float64: 8, torch.int32: 4, torch.int64: 8, torch.bfloat16: 2, torch.uint8: 1, torch.float16: 2}
+
+
+class ZeroPool:
+    """Zero-initialised scratch of one training step from ONE memset.  The step needs ~90 zeroed buffers (accumulators of
+    atomics, gradient staging); as separate ``torch.zeros`` calls they were 88 fill launches per step (r01 launch list).
+    ``begin()`` clears one persistent byte buffer sized from the previous step's demand, ``take()`` carves 256-byte aligned
+    views, anything that does not fit (first step, a larger batch) falls back to ``torch.zeros``.  Two buffers alternate
+    and are never freed, so a view stays untouched until the step after the next begins — kernels on the side streams of a
+    step have all joined by then.  Tensors that ESCAPE the step (metrics, generated images) are never taken from here."""
+
+    def __init__(self):
+        self.bufs, self.flip, self.need = [None, None], 0, 0
+        self.cur, self.used, self.extra, self.active = None, 0, 0, False
+
+    def begin(self, dev):
+        self.flip ^= 1
+        self.cur = None
+        if self.need:
+            buf = self.bufs[self.flip]
+            if buf is None or buf.numel() < self.need or buf.device != dev:
+                buf = self.bufs[self.flip] = torch.empty(self.need, dtype=torch.uint8, device=dev)
+            buf[:self.need].zero_()
+            self.cur = buf
+        self.used, self.extra, self.active = 0, 0, True
+
+    def take(self, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = (n * _ITEMSIZE[dtype] + 255) & ~255
+        if self.cur is not None and self.used + nbytes <= self.cur.numel():
+            v = self.cur[self.used:self.used + nbytes]
+            self.used += nbytes
+            return v.view(dtype)[:n].view(tuple(shape))
+        self.extra += nbytes
+        return torch.zeros(tuple(shape), dtype=dtype, device=_dev())
+
+    def end(self):
+        self.need = max(self.need, self.used + self.extra)
+        self.active, self.cur = False, None
+
+
+ZP = ZeroPool()
+
+
+def zeros(*shape, dtype=torch.float32, escape=False):
+    """zero-filled device tensor; inside a training step (ZP.active) a view of the step's pre-cleared scratch unless the
+    tensor outlives the step (``escape``)"""
+    if ZP.active and not escape:
+        return ZP.take(shape, dtype)
     return torch.zeros(shape, dtype=dtype, device=_dev())
 
 
@@ -294,8 +344,8 @@ class GenEngineProton:
                 L.call("es_gn_lrelu_fwd", y, a.addr(norm + ".weight"), a.addr(norm + ".bias"), a.n, P, N, groups, grp, E, R, nxt, st)
             s[f"y{i + 3}"], s[f"st{i + 3}"], s[f"a{i + 3}"] = y, st, nxt
             act = nxt
-        img1 = zeros(B, self.H * self.W)
-        img2 = zeros(B, self.H * self.W) if two_pass else None
+        img1 = zeros(B, self.H * self.W, escape=True)
+        img2 = zeros(B, self.H * self.W, escape=True) if two_pass else None
         L.call("es_gen_out_fwd", act, a.addr("conv_layers.11.weight"), a.addr("conv_layers.11.bias"), a.n, a.n, 55, 29, 64, 2, 2, 1,
                grp, E, R, int(two_pass), img1, img2)
         s["img1"], s["img2"] = img1, img2
@@ -776,8 +826,8 @@ class GenEngineNeutron:
                 L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R)
             act, s[f"bn{i + 3}"] = self._bn_fwd(y, bn, (g.Ho, g.Wo, g.N), False, None, site, ctx)
             s[f"y{i + 3}"], s[f"a{i + 3}"] = y, act
-        img1 = zeros(B, self.H * self.W)
-        img2 = zeros(B, self.H * self.W) if two_pass else None
+        img1 = zeros(B, self.H * self.W, escape=True)
+        img2 = zeros(B, self.H * self.W, escape=True) if two_pass else None
         L.call("es_gen_out_fwd", act, a.addr("conv_layers.13.weight"), a.addr("conv_layers.13.bias"), a.n, a.n, 45, 45, 64, 2, 2, 0,
                grp, E, R, int(two_pass), img1, img2)
         s["img1"], s["img2"] = img1, img2

@@ -30,7 +30,7 @@ from torch import nn
 
 from .. import _lib as L
 from .._arena import Arena
-from .._nets import engine_for
+from .._nets import ZP, engine_for, zeros as _zeros
 
 IMAGE_SHAPE = {"proton": (56, 30), "neutron": (44, 44)}
 
@@ -220,6 +220,7 @@ class MoEWrapper(nn.Module):
                    device=None, noise: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         """Public entry (signature of the reference, moe.py:52-56): eager step, or CUDA-graph replay once
         ``enable_cuda_graph()`` was called (see there)."""
+        ZP.active = False          # (a step that raised half-way must not leave the scratch pool switched on)
         graphs = getattr(self, "_graphs", None)
         opts = (aux_reg_optimizers, generator_optimizers, discriminator_optimizers, router_optimizer)
         args = (cond, real_images, true_positions, std, intensity)
@@ -283,6 +284,7 @@ class MoEWrapper(nn.Module):
         # copies, which `_engines()` enqueues on the main stream after an optimizer step.
         main = torch.cuda.current_stream()
         s1, s2, s3 = self._side_streams(dev)
+        ZP.begin(dev)                   # ONE memset for every zero-initialised scratch buffer of the step
         ev_in = main.record_event()
         with torch.cuda.stream(s1):
             s1.wait_event(ev_in)
@@ -360,7 +362,7 @@ class MoEWrapper(nn.Module):
             ev_ax = s2.record_event()
             d_coords = torch.empty(B, 2, device=dev)
             L.call("es_aux_loss_grad", coords, pos_s, gh, E, B, Bg, stren_a, d_coords)
-            d_img1_aux = torch.zeros(B, HW, device=dev)
+            d_img1_aux = _zeros(B, HW)
             a_a.G.zero_()
             aux.backward(sv_a, d_coords, d_img1_aux, accumulate=False, wgrad_stream=s3 if s3 is not s2 else None)
             ev_ba = s2.record_event()       # d_img1_aux is complete (the conv weight gradients may still run on s3)
@@ -374,7 +376,7 @@ class MoEWrapper(nn.Module):
         sn_b = disc.spectral(lv_h, self.training)
         s_fake, _, sv_fake = disc.forward(img1, cond_s, gh, B, sn_b)
         main.wait_event(ev_real)
-        d_real, d_fake = torch.zeros(B, device=dev), torch.zeros(B, device=dev)
+        d_real, d_fake = _zeros(B), _zeros(B)
         loss_d = torch.zeros(E, device=dev)
         L.call("es_hinge_d", s_real, s_fake, gh, E, counts_g, Bg, d_real, d_fake, loss_d)
         a_d.G.zero_()
@@ -400,15 +402,15 @@ class MoEWrapper(nn.Module):
         score1, lat1, sv1 = disc.forward(img1, cond_s, gh, B, sn_c)
         main.wait_event(ev_f2)
         main.wait_event(ev_ax)
-        sums = torch.zeros(E, 8, dtype=torch.float64, device=dev)
-        s_out, div_out = torch.zeros(B, device=dev), torch.zeros(B, device=dev)
+        sums = _zeros(E, 8, dtype=torch.float64)
+        s_out, div_out = _zeros(B), _zeros(B)
         L.call("es_gen_loss_reduce", img1, HW, lat1, lat2, z1, z2, std_s, int_s, coords, pos_s, score1, gh, E, B,
                s_out, div_out, sums)
         self._allreduce(sums)
-        d_score1, d_coords2 = torch.zeros(B, device=dev), torch.zeros(B, 2, device=dev)   # d_coords2: same values as d_coords
-        d_lat1, d_lat2 = torch.zeros(B, 64, device=dev), torch.zeros(B, 64, device=dev)
-        d_img1, d_img2 = torch.zeros(B, HW, device=dev), torch.zeros(B, HW, device=dev)
-        d_score2 = torch.zeros(B, device=dev)
+        d_score1, d_coords2 = _zeros(B), _zeros(B, 2)   # d_coords2: same values as d_coords
+        d_lat1, d_lat2 = _zeros(B, 64), _zeros(B, 64)
+        d_img1, d_img2 = _zeros(B, HW), _zeros(B, HW)
+        d_score2 = _zeros(B)
         losses = torch.zeros(E, 6, device=dev)
         L.call("es_gen_loss_grads", img1, HW, lat1, lat2, z1, z2, std_s, int_s, coords, pos_s, s_out, div_out, gh, E, B,
                sums, Bg, float(gcfg.di_strength), float(gcfg.in_strength), stren_a, d_score1, d_lat1, d_lat2, d_coords2,
@@ -508,6 +510,7 @@ class MoEWrapper(nn.Module):
                       f"intensity_loss_experts_{i}": losses[i, 2], f"aux_reg_loss_experts_{i}": losses[i, 3],
                       f"std_intensities_experts_{i}": losses[i, 4], f"mean_intensities_experts_{i}": losses[i, 5],
                       f"n_choosen_experts_mean_epoch_{i}": counts_g[i]})
+        ZP.end()
         self._last = {"idx": r["idx"], "counts": r["counts"], "perm": perm, "img1": img1, "img2": img2, "gates": r["gates"],
                       "logits": r["logits"]}
         if "img1_sorted" in noise:
@@ -552,6 +555,7 @@ class MoEWrapper(nn.Module):
         """Batch inference (reference moe.py:650-653 routing + train/utils.py:179-205 generation): router with Gumbel
         noise at tau=1 -> arg-max expert -> every expert's generator in eval mode on its samples -> expm1, returned in
         the ORIGINAL sample order as [N,H,W] (float32, or float64 like the reference's numpy result)."""
+        ZP.active = False
         gen, _, _ = self._engines()
         E, N = self.n_experts, cond.shape[0]
         H, W = self.image_shape
