@@ -153,7 +153,11 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
 #pragma unroll
   for (int j = 0; j < BN / 16; ++j) { cfr[j][0] = 0.f; cfr[j][1] = 0.f; cfr[j][2] = 0.f; cfr[j][3] = 0.f; }
   __syncthreads();
-  for (int k0 = 0; k0 < K; k0 += kCK) {
+  // Software pipeline: the operands of reduction step k0 + 16 are fetched into registers while step k0 is multiplied out of
+  // shared memory, so the global-load latency of the gather overlaps the FMA loop instead of preceding it.
+  constexpr int NB = kCK * BN / 256;       // weight elements per thread and step
+  float areg[4], breg[NB];
+  auto fetch = [&](int k0) {
     // ---- A tile: gathered source values
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -172,10 +176,12 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
           }
         }
       }
-      As[kk * kPA + ml] = v;
+      areg[j] = v;
     }
-    // ---- B tile: weights  Bs[kk][n]
-    for (int i = tid; i < kCK * BN; i += 256) {
+    // ---- B tile: weights
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int i = tid + 256 * q;
       const int kk = i % kCK, n = i / kCK, k = k0 + kk;
       float v = 0.f;
       if (k < K && n0 + n < Nn) {
@@ -185,9 +191,20 @@ conv_gemm_kernel(const float* __restrict__ src, const float* __restrict__ w, con
           v = __ldg(wslot + ((size_t)(k / KHWc) * g.Ci + n0 + n) * KHW + e.ky * g.KW + e.kx);
         }
       }
-      Bs[kk * (BN + 8) + n] = v;
+      breg[q] = v;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kCK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[(kl + 4 * j) * kPA + ml] = areg[j];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int i = tid + 256 * q;
+      Bs[(i % kCK) * (BN + 8) + i / kCK] = breg[q];
     }
     __syncthreads();
+    if (k0 + kCK < K) fetch(k0 + kCK);
     if (TC) {
       chunk_mma_tf32x3<BN>(As, Bs, cfr);
     } else {
