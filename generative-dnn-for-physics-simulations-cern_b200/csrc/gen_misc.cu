@@ -184,7 +184,13 @@ ln_lrelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy_up, int Hs, int Ws, int
   __shared__ int ylo[64], yhi[64], xlo[64], xhi[64];
   const int r = blockIdx.x;
   const int g = find_group(grp, n_groups, r);
-  if (g < 0) return;
+  if (g < 0) {
+    // rows of skipped experts: fc2's weight-gradient kernel streams this tensor through TMA boxes that may straddle a
+    // group's end, where the rows meet a zero-padded operand — they must be finite (0 * NaN would poison the sum)
+    uint4* o4 = reinterpret_cast<uint4*>(dx + (size_t)r * Hs * Ws * C);
+    for (int i = threadIdx.x; i < Hs * Ws * C / 8; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
   const int slot = grp[g].slot;
   if (FAN) {
     if (threadIdx.x == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }

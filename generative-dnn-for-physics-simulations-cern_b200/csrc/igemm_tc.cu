@@ -382,11 +382,22 @@ int launch_igemm(const IgemmParams& p, dim3 grid, cudaStream_t st) {
 
 using namespace es;
 
+namespace es {
+int dense_wgrad_tma(const void* dy, const void* x, void* xpad, float* dw, long dw_slot_stride, int N, int K, const int32_t* row_map,
+                    const es_group* grp, int n_groups, int total_rows, cudaStream_t st);
+int dense_dgrad_tma(const void* dy, const void* w, float* dx, int N, int K, const es_group* grp, int n_groups, int total_rows,
+                    cudaStream_t st);
+}
+
 extern "C" int es_dense_dgrad(const void* dy, const void* w, float* dx, int N, int K, const es_group* grp,
                               int n_groups, int total_rows, void* stream) {
   ES_REQUIRE(dy && w && dx && grp, "null pointer");
   ES_REQUIRE(N % 64 == 0 && K % 64 == 0 && K <= 256, "need N % 64 == 0 and K in {64,128,192,256}");
   ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad group count / rows");
+  {   // TMA-fed kernel (dense_tma.cu) for the fc2 shape; 1 = shape not covered -> the gather kernel below
+    const int rc = dense_dgrad_tma(dy, w, dx, N, K, grp, n_groups, total_rows, as_stream(stream));
+    if (rc != 1) { if (rc != ES_OK) set_error("es_dense_dgrad: TMA kernel launch failed"); return rc; }
+  }
   IgemmParams p{};
   p.Hs = p.Ws = p.Hu = p.Wu = p.Ho = p.Wo = p.KH = p.KW = 1; p.pad = 0; p.P = 1;
   p.C = N;   // the gather walks the reduction dimension n in 64-wide blocks
@@ -404,10 +415,15 @@ extern "C" int es_dense_dgrad(const void* dy, const void* w, float* dx, int N, i
 }
 
 extern "C" int es_dense_wgrad(const void* dy, const void* x, float* dw, long dw_slot_stride, int N, int K,
-                              const int32_t* row_map, const es_group* grp, int n_groups, int total_rows, void* stream) {
+                              const int32_t* row_map, const es_group* grp, int n_groups, int total_rows, void* scratch,
+                              void* stream) {
   ES_REQUIRE(dy && x && dw && grp, "null pointer");
   ES_REQUIRE(N % kBM == 0 && K % 64 == 0 && K <= 256, "need N % 128 == 0 and K in {64,...,256}");
   ES_REQUIRE(n_groups >= 1 && n_groups <= kMaxGroups && total_rows > 0, "bad group count / rows");
+  {   // TMA-fed kernel (dense_tma.cu); needs the caller's scratch for the zero-padded per-group copy of x
+    const int rc = dense_wgrad_tma(dy, x, scratch, dw, dw_slot_stride, N, K, row_map, grp, n_groups, total_rows, as_stream(stream));
+    if (rc != 1) { if (rc != ES_OK) set_error("es_dense_wgrad: TMA kernel launch failed"); return rc; }
+  }
   IgemmParams p{};
   p.Hs = p.Ws = p.Hu = p.Wu = p.Ho = p.Wo = p.KH = p.KW = 1; p.pad = 0; p.P = 1; p.C = 64;
   fill_maps(p);

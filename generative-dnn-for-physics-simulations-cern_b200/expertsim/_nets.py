@@ -406,7 +406,8 @@ class GenEngineProton:
         L.call("es_ln_lrelu_bwd", da, 18, 10, up[0], up[1], 512, s["y2"], s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R, dy2)
         L.call("es_ln_affine_bwd", da, 18, 10, up[0], up[1], 512, s["y2"], dy2, s["st2"], self.g_fc2, self.z_fc2, self.F2, grp, E, R,
                self.row_map, a.n, a.gaddr("fc2.1.weight"), a.gaddr("fc2.1.bias"), a.gaddr("fc2.0.bias"))
-        L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), a.n, self.F2, 256, self.row_map, grp, E, R)
+        xpad = empty(E * ((R + 63) // 64) * 64, 256, dtype=BF)      # scratch of the TMA-fed kernel: zero-padded per-group h1
+        L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), a.n, self.F2, 256, self.row_map, grp, E, R, xpad)
         ready("fc2.0.weight")           # 88 % of the generator's gradient bytes
         dh1 = zeros(R, 256)
         L.call("es_dense_dgrad", dy2, self.w_fc2, dh1, self.F2, 256, grp, E, R)
@@ -872,7 +873,8 @@ class GenEngineNeutron:
         if on_grads_ready is not None:
             on_grads_ready(None, None)      # marker: the persistent tensor-core kernels of this backward are all enqueued
         dy2 = self._bn_bwd(da, up, s["y2"], s["bn2"], "fc2.1", self.SP, True, self.row_map, ctx)
-        L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), a.n, self.F2, 256, self.row_map, grp, E, R)
+        xpad = empty(E * ((R + 63) // 64) * 64, 256, dtype=BF)      # scratch of the TMA-fed kernel: zero-padded per-group h1
+        L.call("es_dense_wgrad", dy2, s["h1"], a.gaddr("fc2.0.weight"), a.n, self.F2, 256, self.row_map, grp, E, R, xpad)
         ready("fc2.0.weight")           # 88 % of the generator's gradient bytes
         dh1 = zeros(R, 256)
         L.call("es_dense_dgrad", dy2, self.w_fc2, dh1, self.F2, 256, grp, E, R)

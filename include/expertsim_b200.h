@@ -229,9 +229,11 @@ int es_igemm_wgrad(const void* x, const void* dy, float* dw, const es_conv_geom*
 int es_dense_dgrad(const void* dy, const void* w, float* dx, int N, int K,
                    const es_group* grp, int n_groups, int total_rows, void* stream);
 /* dense weight gradient: dw[slot*dw_slot_stride + row_map[n]*K + k] = sum_row dy[row,n] * x[row,k]  (fp32, direct store;
- * row_map (nullable) un-permutes the channels-last feature order back to the reference's NCHW flattening). */
+ * row_map (nullable) un-permutes the channels-last feature order back to the reference's NCHW flattening).
+ * scratch (nullable): n_groups * round_up(total_rows, 64) * K bf16 — the zero-padded per-group copy of x that lets the
+ * TMA-fed kernel (K = 256) stream dy boxes across group boundaries; without it the cp.async gather kernel runs. */
 int es_dense_wgrad(const void* dy, const void* x, float* dw, long dw_slot_stride, int N, int K, const int32_t* row_map,
-                   const es_group* grp, int n_groups, int total_rows, void* stream);
+                   const es_group* grp, int n_groups, int total_rows, void* scratch, void* stream);
 /* Test-only SIMT (CUDA-core, fp32 accumulate) versions of the two implicit GEMMs; same arguments.  They exist so the
  * tcgen05 path can be cross-checked on the device at sizes the CPU oracle cannot reach.  Never called by the product. */
 int es_igemm_fwd_simt(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_conv_geom* g,

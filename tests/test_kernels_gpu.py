@@ -365,7 +365,8 @@ def test_dense_dgrad_wgrad():
     check("es_dense_dgrad fc2", dx, want, 3e-3, 1e-2)
     row_map = torch.randperm(N, generator=g).to(torch.int32)
     dw = torch.zeros(3, N, K, device=DEV)
-    L.call("es_dense_wgrad", cuda(dy, BF), cuda(x, BF), dw, N * K, N, K, cuda(row_map), grp, 3, R)
+    xpad = torch.full((3 * ((R + 63) // 64) * 64, K), float("nan"), dtype=BF, device=DEV)      # scratch may hold anything
+    L.call("es_dense_wgrad", cuda(dy, BF), cuda(x, BF), dw, N * K, N, K, cuda(row_map), grp, 3, R, xpad)
     want_w = torch.zeros(3, N, K)
     want_w[2][row_map.long()] = dy[:140].T @ x[:140]
     want_w[0][row_map.long()] = dy[140:].T @ x[140:]
