@@ -302,7 +302,11 @@ conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy
   float cfr[BN / 16][4];
 #pragma unroll
   for (int j = 0; j < BN / 16; ++j) { cfr[j][0] = 0.f; cfr[j][1] = 0.f; cfr[j][2] = 0.f; cfr[j][3] = 0.f; }
-  for (int mc = mbeg; mc < mend; mc += kCK) {
+  // Software pipeline (see conv_gemm_kernel): the operands of chunk mc + 16 are fetched into registers while chunk mc is
+  // multiplied out of shared memory.
+  constexpr int NBW = BN / 16;
+  float areg[4], breg[NBW];
+  auto fetch = [&](int mc) {
     // A tile: xcol[m, k] for 16 consecutive m, 64 k
     {
       int s2 = a_s, oy = a_oy, ox = a_ox;
@@ -314,7 +318,7 @@ conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy
           if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi)
             v = __ldg(x + ((size_t)(row_start + s2) * g.Ci + ci) * PXi + iy * g.Wi + ix);
         }
-        As[ma + j][tid >> 2] = v;
+        areg[j] = v;
         if (++ox == g.Wo) { ox = 0; if (++oy == g.Ho) { oy = 0; ++s2; } }
       }
       // advance the base counter by one chunk (16 pixels)
@@ -323,14 +327,23 @@ conv_wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy
     }
     // B tile: dy[m, co]: lanes along m
 #pragma unroll
-    for (int nn = tid >> 4; nn < BN; nn += 16) {
+    for (int q = 0; q < NBW; ++q) {
+      const int nn = (tid >> 4) + 16 * q;
       float v = 0.f;
       if (mc + mb < mend && n0 + nn < g.Co) v = __ldg(dy + ((size_t)(row_start + b_s) * g.Co + n0 + nn) * PXo + b_p);
-      Bs[mb][nn] = v;
+      breg[q] = v;
     }
     b_p += kCK;
     while (b_p >= PXo) { b_p -= PXo; ++b_s; }
+  };
+  if (mbeg < mend) fetch(mbeg);
+  for (int mc = mbeg; mc < mend; mc += kCK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) As[ma + j][tid >> 2] = areg[j];
+#pragma unroll
+    for (int q = 0; q < NBW; ++q) Bs[mb][(tid >> 4) + 16 * q] = breg[q];
     __syncthreads();
+    if (mc + kCK < mend) fetch(mc + kCK);
     if (db && blockIdx.x == 0 && tid < BN) {
 #pragma unroll
       for (int mm = 0; mm < kCK; ++mm) bsum += Bs[mm][tid];
