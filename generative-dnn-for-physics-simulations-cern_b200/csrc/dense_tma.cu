@@ -10,7 +10,7 @@
 //   MODE 1  data gradient    dx[r][k] += sum_f dy[r][f] * w[slot][f][k]                 D tile = 128 rows x 256 k, reduction over f
 //           split across CTAs; dy tiles are K-major boxes {64 f, 128 rows}, w tiles MN-major boxes {64 k, 64 f}; rows past
 //           the group's end are computed with the wrong expert's weights and masked in the epilogue (RED into dx).
-// 10 warps: TMA producer, MMA issuer / TMEM owner, 8 epilogue warps; 4 stages of 48 KB; accumulators double-buffered in TMEM.
+// 6 warps: TMA producer, MMA issuer / TMEM owner, 4 epilogue warps; 4 stages of 48 KB; accumulators double-buffered in TMEM.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -68,7 +68,7 @@ __device__ __forceinline__ bool dense_decode(int u, const DenseParams& p, const 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(192, 1)
 dense_tma_kernel(const __grid_constant__ DenseParams p, const __grid_constant__ CUtensorMap tmap_a,
                  const __grid_constant__ CUtensorMap tmap_b) {
   extern __shared__ uint8_t smem_raw[];
@@ -94,7 +94,7 @@ dense_tma_kernel(const __grid_constant__ DenseParams p, const __grid_constant__ 
   }
   if (tid == 0) {
     for (int s = 0; s < kDStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
@@ -168,9 +168,9 @@ dense_tma_kernel(const __grid_constant__ DenseParams p, const __grid_constant__ 
     }
     tc_fence_before();
   } else {
-    // =========================================================================== EPILOGUE (warps 2-9; TMEM lane quarter = warp % 4,
-    // the two warps of a quarter split the 256 accumulator columns: the epilogue is store-issue bound — 128 KB per tile)
-    const int q = warp & 3, c_lo = ((warp - 2) >> 2) * (BN / 2), c_hi = c_lo + BN / 2;
+    // =========================================================================== EPILOGUE (warps 2-5; TMEM lane quarter = warp % 4).
+    // (Eight epilogue warps, two per quarter splitting the columns, were measured: 0.507 vs 0.441 ms — not used.)
+    const int q = warp & 3, c_lo = 0, c_hi = BN;
     uint32_t tcount = 0;
     for (int u = blockIdx.x; u < total; u += gridDim.x) {
       DTile t;
@@ -281,7 +281,7 @@ int dense_wgrad_tma(const void* dy, const void* x, void* xpad, float* dw, long d
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int units = n_groups * (N / kBM);
-  dense_tma_kernel<0><<<units < sms ? units : sms, 320, kDSmem, st>>>(p, ta, tb);
+  dense_tma_kernel<0><<<units < sms ? units : sms, 192, kDSmem, st>>>(p, ta, tb);
   return cudaGetLastError() == cudaSuccess ? ES_OK : ES_ERR_CUDA;
 }
 
@@ -308,7 +308,7 @@ int dense_dgrad_tma(const void* dy, const void* w, float* dx, int N, int K, cons
     attr = true;
   }
   const int units = mt * splits;
-  dense_tma_kernel<1><<<units < sms ? units : sms, 320, kDSmem, st>>>(p, ta, tb);
+  dense_tma_kernel<1><<<units < sms ? units : sms, 192, kDSmem, st>>>(p, ta, tb);
   return cudaGetLastError() == cudaSuccess ? ES_OK : ES_ERR_CUDA;
 }
 
