@@ -162,7 +162,7 @@ bn_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   const int P = Hs * Ws, n4 = P * Csp / 8;
   uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)r * P * Csp);
   if (q.g < 0) {
-    if (BWD) for (int i = threadIdx.x; i < n4; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);   // see gn_lrelu_kernel
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);   // finite rows for skipped experts: see gn_lrelu_kernel
     return;
   }
   if (BWD && threadIdx.x == 0) { build_fanin(Hs, Hu, ylo, yhi); build_fanin(Ws, Wu, xlo, xhi); }
@@ -370,7 +370,7 @@ bn2d_apply_fast_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   const int P = Hs * Ws, c4 = C / 8;
   uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)r * P * C);
   if (sr.g < 0) {
-    if (BWD) for (int i = threadIdx.x; i < P * c4; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);   // see gn_lrelu_kernel
+    for (int i = threadIdx.x; i < P * c4; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);   // finite rows for skipped experts: see gn_lrelu_kernel
     return;
   }
   if (BWD && FAN) {

@@ -363,10 +363,10 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   if (g < 0) {
     // rows of skipped experts: the gradient tensor is read by the weight-gradient GEMM through TMA boxes that may
     // straddle a group's end, where it is multiplied by zero-filled im2col rows — it must be finite there
-    if (BWD) {
-      uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)r * Hs * Ws * C);
-      for (int i = threadIdx.x; i < Hs * Ws * C / 8; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);
-    }
+    // (forward: the strip kernels of the following conv's weight gradient read x strips past a group's end against zero dy)
+    const int n16 = (BWD || OWu <= 0) ? Hs * Ws * C / 8 : (Hs * Ws / OWs) * OWu * C / 8;
+    uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)r * n16 * 8);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);
     return;
   }
   const int slot = grp[g].slot;
@@ -556,6 +556,79 @@ gn_lrelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
       for (int k = 0; k < 8; ++k) atomicAdd(&s_dg[c8 + k], al[k]);
       __syncthreads();
       if (tid < C) atomicAdd(&dbias[slot * slot_stride + tid], s_dg[tid]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- GroupNorm, stats from the conv
+// Forward GroupNorm + LeakyReLU as ONE streaming pass: the producing conv's epilogue already accumulated the per-(sample,
+// channel pair) sum and sum of squares of the stored values (es_igemm_*_fwd_sums), so mean / rstd are 32 tiny reductions per
+// CTA and every element crosses HBM once per direction with no dependency between CTAs — gridDim.y CTAs share a sample.
+// Variance = E[x^2] - mean^2 in fp32 (clamped at 0); the sums are over <= 51k bf16 values of O(1) magnitude.
+template <int U>                           // 16-byte loads in flight per thread
+__global__ void __launch_bounds__(256)
+gn_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ pair_sums, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, long slot_stride, int Hs, int Ws, int Wu, int C, int groups,
+                    const es_group* __restrict__ grp, int n_groups, __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
+  __shared__ float s_mu[64], s_rs[64];
+  __shared__ int xlo[64], xhi[64];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int g = find_group(grp, n_groups, r);
+  const int P = Hs * Ws, c4 = C / 8, cpg = C / groups;
+  if (g < 0) {
+    // rows of skipped experts: the strip kernels of the following conv's weight gradient read x strips that may run past a
+    // group's end, where they meet zero-filled dy columns — the activation must be finite there (0 x NaN = NaN)
+    const size_t n16 = (size_t)Hs * Wu * c4;
+    const size_t lo = n16 * blockIdx.y / gridDim.y, hi = n16 * (blockIdx.y + 1) / gridDim.y;
+    uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)r * Hs * Wu * C);
+    for (size_t i = lo + tid; i < hi; i += 256) o4[i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int slot = grp[g].slot;
+  if (tid < groups) {
+    const float* ps = pair_sums + ((size_t)r * (C / 2) + (size_t)tid * (cpg / 2)) * 2;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < cpg / 2; ++k) { s1 += ps[2 * k]; s2 += ps[2 * k + 1]; }
+    const float cnt = (float)(cpg * P), mu = s1 / cnt;
+    const float rstd = rsqrtf(fmaxf(s2 / cnt - mu * mu, 0.f) + kNormEps);
+    s_mu[tid] = mu; s_rs[tid] = rstd;
+    if (blockIdx.y == 0) {
+      stats[((size_t)r * groups + tid) * 2] = mu;
+      stats[((size_t)r * groups + tid) * 2 + 1] = rstd;
+    }
+  }
+  if (Wu != Ws && tid == 0) build_fanin(Ws, Wu, xlo, xhi);
+  __syncthreads();
+  const int cu = tid % c4, c8 = cu * 8, pstep = 256 / c4;
+  float gk[8], bk[8], mu[8], rs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    gk[k] = gamma[slot * slot_stride + c8 + k]; bk[k] = beta[slot * slot_stride + c8 + k];
+    mu[k] = s_mu[(c8 + k) / cpg]; rs[k] = s_rs[(c8 + k) / cpg];
+  }
+  const int per = ceil_div(P, (int)gridDim.y), p_lo = blockIdx.y * per, p_hi = min(P, p_lo + per);
+  const uint4* x4 = reinterpret_cast<const uint4*>(x + (size_t)r * P * C);
+  uint4* y4 = reinterpret_cast<uint4*>(out + (size_t)r * Hs * Wu * C);
+  for (int pix0 = p_lo + tid / c4; pix0 < p_hi; pix0 += U * pstep) {
+    uint4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (pix0 + u * pstep < p_hi) q[u] = __ldg(x4 + (size_t)(pix0 + u * pstep) * c4 + cu);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = pix0 + u * pstep;
+      if (pix >= p_hi) continue;
+      float f[8];
+      unpack8(q[u], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = lrelu((f[k] - mu[k]) * rs[k] * gk[k] + bk[k]);
+      const uint4 v = pack8(f);
+      if (Wu != Ws) {                          // nearest-upsampled along x: [Hs, Wu, C]
+        const int h = pix / Ws, w = pix - h * Ws;
+        for (int xu = xlo[w]; xu < xhi[w]; ++xu) y4[((size_t)h * Wu + xu) * c4 + cu] = v;
+      } else {
+        y4[(size_t)pix * c4 + cu] = v;
+      }
     }
   }
 }
@@ -1192,6 +1265,29 @@ extern "C" int es_gn_lrelu_fwd_upx(const void* x, const float* gamma, const floa
                                    float* stats, void* stream) {
   ES_REQUIRE(Hs > 0 && Ws > 0 && Ws <= 64 && Wu >= Ws && Wu <= 64 && Wu <= 2 * Ws, "bad x-upsample geometry");
   return gn_lrelu_fwd_impl(x, gamma, beta, slot_stride, Hs * Ws, C, groups, grp, n_groups, total_rows, y, stats, stream, Ws, Wu);
+}
+
+extern "C" int es_gn_lrelu_apply_fwd(const void* x, const float* pair_sums, const float* gamma, const float* beta, long slot_stride,
+                                     int Hs, int Ws, int Wu, int C, int groups, const es_group* grp, int n_groups, int total_rows,
+                                     void* y, float* stats, void* stream) {
+  ES_REQUIRE(x && pair_sums && gamma && beta && grp && y && stats, "null pointer");
+  ES_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0 && groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0,
+             "bad channels/groups (channel pairs must not straddle groups)");
+  ES_REQUIRE(total_rows > 0 && n_groups >= 1 && n_groups <= kMaxGroups && Hs > 0 && Ws > 0, "bad sizes");
+  ES_REQUIRE(Wu == Ws || (Ws <= 64 && Wu > Ws && Wu <= 64 && Wu <= 2 * Ws), "bad x-upsample geometry");
+  const long bytes = (long)Hs * Ws * C * 2;
+  static const long chunk_bytes = [] { const char* e = getenv("ES_GN_APPLY_KB"); return (long)(e ? atoi(e) : 512) * 1024; }();
+  int chunks = (int)((bytes + chunk_bytes - 1) / chunk_bytes);
+  chunks = chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+  static const int u_sel = [] { const char* e = getenv("ES_GN_APPLY_U"); return e ? atoi(e) : 8; }();
+  if (u_sel == 4)
+    gn_apply_fwd_kernel<4><<<dim3(total_rows, chunks), 256, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)x, pair_sums, gamma, beta, slot_stride, Hs, Ws, Wu, C, groups, grp, n_groups, (__nv_bfloat16*)y, stats);
+  else
+    gn_apply_fwd_kernel<8><<<dim3(total_rows, chunks), 256, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)x, pair_sums, gamma, beta, slot_stride, Hs, Ws, Wu, C, groups, grp, n_groups, (__nv_bfloat16*)y, stats);
+  ES_LAUNCH_CHECK();
+  return ES_OK;
 }
 
 extern "C" int es_gn_lrelu_bwd(const void* dy_up, int Hs, int Ws, int Hu, int Wu, const void* x, const float* stats,

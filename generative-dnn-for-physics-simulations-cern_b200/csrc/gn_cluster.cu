@@ -50,9 +50,14 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
   if (g < 0) {
     // rows of skipped experts: the gradient tensor is read by the weight-gradient GEMM through TMA boxes that may straddle
     // a group's end, where it meets zero-filled im2col rows — it must be finite there
-    if (BWD) {
+    // (forward: the strip kernels of the following conv's weight gradient read x strips past a group's end against zero dy)
+    if (BWD || OWu <= 0) {
       uint4* o4 = reinterpret_cast<uint4*>(out + ((size_t)r * P + pb) * C);
       for (int i = tid; i < np * c4; i += 256) o4[i] = make_uint4(0, 0, 0, 0);
+    } else if (rank == 0) {
+      const int n16 = (P / OWs) * OWu * c4;
+      uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)r * n16 * 8);
+      for (int i = tid; i < n16; i += 256) o4[i] = make_uint4(0, 0, 0, 0);
     }
     return;
   }
@@ -285,6 +290,8 @@ static int launch_gn_cluster(const void* x, const void* dy_up, int Hs, int Ws, i
   const size_t smem = (size_t)Pq * bpp;
   auto kern = gn_cluster_kernel<BWD, FAN>;
   ES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const int carve = [] { const char* e = getenv("ES_GN_CARVEOUT"); return e ? atoi(e) : 100; }();
+  if (carve >= 0) ES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)total_rows * CL);
   cfg.blockDim = dim3(256);

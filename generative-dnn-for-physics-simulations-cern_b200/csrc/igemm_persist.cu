@@ -56,6 +56,7 @@ struct FwdParams {
   const float* bias;
   long bias_slot_stride;
   __nv_bfloat16* out;
+  float* pair_sums;            // optional [total rows][Nout/2][2]: per-sample channel-pair (sum, sum of squares) of the stored outputs
   int* err_flag;
 };
 
@@ -586,6 +587,43 @@ igemm_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ C
 // next sample (the epilogue masks those rows).  6 warps: TMA producer, MMA issuer / TMEM owner, 4 epilogue warps.
 // Barrier protocol: as igemm_pair_kernel, except that full[s] takes ONE arrival (the leader's expect_tx for the four boxes of
 // the stage — A and the B half of both CTAs; rank 1's boxes signal the leader's barrier).
+// Norm fusion: the GroupNorm that follows a generator conv needs per-(sample, group) mean and variance of the conv's output —
+// a reduction over the whole sample that forced the norm kernel to read its input twice or to park it in shared memory.
+// The epilogue already holds every output value in registers, so it accumulates per-(sample, channel PAIR) sum and sum of
+// squares of the bf16-ROUNDED values it stores (what the norm kernel will read back) and the norm becomes one streaming pass.
+// f[32] = this lane's pixel, 32 consecutive channels.  The 16 pairs x 2 moments = 32 values per lane are transposed-reduced
+// over the warp's 32 pixels with 31 shuffles (recursive halving: lane L ends up with the total of value L), then one
+// coalesced 128-byte atomic add per warp.  Lanes of a warp almost always belong to one sample; a boundary costs a second round.
+__device__ __forceinline__ void epilogue_pair_sums(const float* f, bool ok, int row, float* __restrict__ sums, int half_n,
+                                                   int col0, int lane) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float a = __bfloat162float(__float2bfloat16_rn(f[2 * j])), b = __bfloat162float(__float2bfloat16_rn(f[2 * j + 1]));
+    v[2 * j] = a + b;
+    v[2 * j + 1] = a * a + b * b;
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, ok);
+  while (todo) {
+    const int lrow = __shfl_sync(0xffffffffu, row, __ffs(todo) - 1);
+    const bool mine = ok && row == lrow;
+    float w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = mine ? v[i] : 0.f;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool hi = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = hi ? w[i] : w[i + off], keep = hi ? w[i + off] : w[i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    atomicAdd(sums + ((long)lrow * half_n + (col0 >> 1)) * 2 + lane, w[0]);
+    todo &= ~__ballot_sync(0xffffffffu, mine);
+  }
+}
+
 struct TmaAParams {
   int low_w, low_h;         // bounding-box lower corner = base-pixel coordinate of output (0, 0)
 };
@@ -729,14 +767,209 @@ igemm_tma_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant
       __nv_bfloat16* yrow = p.out + (opix * p.Nout + ti.n0);
       for (int c = 0; c < BN; c += 32) {
         tmem_ld32(t_lane + c, r);
-        if (ok) {
-          float f[32];
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
+        if (ok) {
           uint4* dst = reinterpret_cast<uint4*>(yrow + c);
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) dst[qq] = pack8(f + 8 * qq);
         }
+        if (p.pair_sums) epilogue_pair_sums(f, ok, ti.row_start + smp, p.pair_sums, p.Nout >> 1, ti.n0 + c, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-fed pair kernel with TAP-ROW STRIPS.  igemm_tma_pair_kernel is bound by the L2->SM fill (one 16 KB im2col box per tap per
+// CTA against 128 x N x 64 MACs: ~41 B/clk/SM arrive, the MMA of an N = 64/128 k-block wants 4x/2x that).  When the taps of
+// the table form rows (same dy, nx consecutive dx, consecutive weight columns) the nx windows of a row are ONE strip of
+// 128 + nx - 1 base pixels if the M axis enumerates output pixels with the PADDED row pitch Wp = Wo + nx - 1 — which in TMA
+// im2col terms is just a bounding box nx - 1 columns wider: one im2col instruction of 128 + nx - 1 pixels per (strip, channel
+// block), and the nx taps are MMAs whose A descriptors start j rows (j * 128 B) further down the same 128B-swizzled strip
+// (the 128B swizzle is a function of the absolute shared-memory address, so a row-shifted start stays consistent with what
+// TMA wrote.  Measured on sm_100a: the descriptor's base-offset field must stay 0 for such starts — setting it to the row
+// phase j gives wrong products).  Fill per MAC drops by nx on the A side; the masked columns cost Wp / Wo - 1 of the MMA
+// work.  mt = 2 M sub-tiles per pair share every weight box (N <= 128: halves the weight fill as well).
+struct TStripParams {
+  int n_strips, nx, Wp, Pp;                      // Pp = Ho * Wp
+  int mt;                                        // 256-row M sub-tiles per pair tile (1 or 2): sub-tiles share every weight box
+  int stages, stage_bytes, a_bytes;              // a_bytes = strip bytes rounded up to 1 KB; stage = mt * a_bytes + nx * BN/2 * 128
+  int low_w, low_h;
+  signed char sdy[16], sdx[16];
+  int skoff[16];                                 // weight column of the strip's first tap; tap j at skoff + j*C
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+igemm_tma_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ TStripParams ts,
+                       const __grid_constant__ CUtensorMap tmap_wh, const __grid_constant__ CUtensorMap tmap_x) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int mt = ts.mt, kTileM = 2 * kBM * mt;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int kStages = ts.stages, kStage = ts.stage_bytes;
+  const uint32_t bar_base = base + kStages * kStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+  uint8_t* gen = smem_raw + (bar_base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * 20);
+  const uint32_t tmem_slot = bar_base + 8u * 20;
+  int* s_tiles = reinterpret_cast<int*>(gen + 256);            // [64]
+  es_group* s_grp = reinterpret_cast<es_group*>(gen + 512);    // [64] x 16 B
+
+  const int BN = p.BN, BH = p.BN / 2, nx = ts.nx;
+  const uint32_t acc_cols = (uint32_t)(mt * BN);                // accumulator columns per buffer: one N tile per M sub-tile
+  const uint32_t nbuf = 2 * acc_cols <= 512 ? 2u : 1u;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < nbuf * acc_cols) tmem_cols <<= 1;
+
+  if (tid < p.n_groups) {
+    const es_group gq = p.grp[tid];
+    s_grp[tid] = gq;
+    s_tiles[tid] = ceil_div(gq.rows * ts.Pp, kTileM);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_wh); tma_prefetch_desc(&tmap_x); }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  int total_tiles = 0;
+  for (int i = 0; i < p.n_groups; ++i) total_tiles += s_tiles[i];
+  total_tiles *= p.n_tiles_n;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int cblks = p.C / kBK;
+  const int nkb = ts.n_strips * cblks;
+  const uint32_t strip_bytes = (uint32_t)(kBM + nx - 1) * 128u;
+
+  if (warp == 0) {
+    // =========================================================================== TMA PRODUCER: strip (im2col) + nx half weight boxes
+    if (lane == 0) {
+      const uint32_t lead_full0 = mapa_shared(full_bar(0), 0);
+      uint32_t it = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        TileInfo ti;
+        decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+        const int wrow = ti.slot * p.Nout + ti.n0 + (int)rank * BH;
+        int cn[2], ch[2], cw[2];
+        for (int u = 0; u < mt; ++u) {
+          const int m = ti.m0 + u * 2 * kBM + (int)rank * kBM;
+          const int sample = m / ts.Pp, pix = m - sample * ts.Pp;
+          const int oy = pix / ts.Wp, ox = pix - oy * ts.Wp;
+          cn[u] = ti.row_start + sample; ch[u] = ts.low_h + oy * p.my; cw[u] = ts.low_w + ox;
+        }
+        int cb = 0, st = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= (uint32_t)kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)mt * strip_bytes + (uint32_t)(nx * BN) * 128u);
+          const uint32_t lead_full = lead_full0 + 8u * s;
+          const uint32_t sa = base + s * kStage;
+          for (int u = 0; u < mt; ++u)
+            tma_im2col_4d_pair(sa + u * ts.a_bytes, &tmap_x, cb * kBK, cw[u], ch[u], cn[u], (uint32_t)(ts.sdx[st] - ts.low_w),
+                               (uint32_t)(ts.sdy[st] - ts.low_h), lead_full);
+          for (int j = 0; j < nx; ++j)
+            tma_load_2d_pair(sa + mt * ts.a_bytes + j * BH * 128, &tmap_wh, ts.skoff[st] + j * p.C + cb * kBK, wrow, lead_full);
+          if (++st == ts.n_strips) { st = 0; ++cb; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================================== MMA ISSUER (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_m(BN, 2 * kBM, false, false);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
+        const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+        const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+        if (use >= 1) mbar_wait(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * acc_cols;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = base + s * kStage;
+            const uint32_t sb = sa + mt * ts.a_bytes;
+            for (int j = 0; j < nx; ++j) {
+              for (int u = 0; u < mt; ++u) {
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k)
+                  umma_bf16_pair(tacc + u * BN, make_desc(sa + u * ts.a_bytes + j * 128 + k * 32, 16, 1024),
+                                 make_desc(sb + j * BH * 128 + k * 32, 16, 1024), idesc, (kb | j | k) ? 1u : 0u);
+              }
+            }
+            umma_commit_pair(empty_bar(s), 3);
+            if (kb == nkb - 1) umma_commit_pair(tfull_bar(buf), 3);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+    }
+  } else {
+    // =========================================================================== EPILOGUE (warps 2-5: TMEM lane quarter = warp % 4)
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
+      TileInfo ti;
+      decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
+      const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+      const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+      mbar_wait(tfull_bar(buf), use & 1, p.err_flag, 3);
+      tc_fence_after();
+      const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
+      uint32_t r[32];
+      for (int u = 0; u < mt; ++u) {
+      const uint32_t t_lane = tmem_base + buf * acc_cols + (uint32_t)(u * BN) + ((uint32_t)(q * 32) << 16);
+      const int m = ti.m0 + u * 2 * kBM + (int)rank * kBM + q * 32 + lane;
+      bool ok = m < ti.rows * ts.Pp;
+      const int smp = ok ? m / ts.Pp : 0, pix = ok ? m - smp * ts.Pp : 0;
+      const int oa = pix / ts.Wp, ob = pix - oa * ts.Wp;
+      ok = ok && ob < p.Wo;                                      // the nx - 1 pad columns of the padded pitch are not outputs
+      const long opix = (long)(ti.row_start + smp) * p.P_full + (oa * p.o_my + p.o_oy) * p.Wo_full + ob * p.o_mx + p.o_ox;
+      __nv_bfloat16* yrow = p.out + (opix * p.Nout + ti.n0);
+      for (int c = 0; c < BN; c += 32) {
+        tmem_ld32(t_lane + c, r);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
+        if (ok) {
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) dst[qq] = pack8(f + 8 * qq);
+        }
+        if (p.pair_sums) epilogue_pair_sums(f, ok, ti.row_start + smp, p.pair_sums, p.Nout >> 1, ti.n0 + c, lane);
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -1040,7 +1273,9 @@ struct WgParams {
   int tcol[32];
   int dw_ld;                        // length of a dw row (all taps of all phases)
   int N, KK, tiles_m, splits;
-  int kmode;                        // 0: all pixel blocks of a group; 1: only its FULL 64-pixel blocks; 2: only the partial last one
+  int kmode;                        // 0: all pixel blocks of a group; 1: only its FULL 64-pixel blocks; 2: only the partial last one;
+                                    // 3: the pixels the strip kernel left over (see igemm_wgrad_strip_kernel): [pix_lo, rows*P)
+  int s_Wp, s_Pp;                   // kmode 3: padded row pitch / pixels per sample of the strip kernel's enumeration
   int tile_m;                       // kk columns per work unit: 128 (single CTA) or 256 (CTA pair)
   unsigned char ymap[64], xmap[64];
   const __nv_bfloat16* x;
@@ -1051,6 +1286,7 @@ struct WgParams {
 
 struct WgTile {
   int m0, rows, row_start, slot, kb0, kb1;
+  int pix_lo;                       // pixels below this index (group-relative) are not reduced (kmode 3), else 0
 };
 
 __device__ __forceinline__ bool wg_decode(int t, const WgParams& p, const es_group* s_grp, WgTile& ti) {
@@ -1060,6 +1296,16 @@ __device__ __forceinline__ bool wg_decode(int t, const WgParams& p, const es_gro
   ti.m0 = mt * (p.tile_m ? p.tile_m : kBM);
   ti.rows = s_grp[g].rows; ti.row_start = s_grp[g].row_start; ti.slot = s_grp[g].slot;
   const int nall = ceil_div(ti.rows * p.P, kBK), nfull = (ti.rows * p.P) / kBK;
+  ti.pix_lo = 0;
+  if (p.kmode == 3) {               // valid pixels at or after the last full 64-position block of the PADDED enumeration
+    const int pos = ((ti.rows * p.s_Pp) / kBK) * kBK;
+    const int smp = pos / p.s_Pp, rem = pos - smp * p.s_Pp;
+    const int oy = rem / p.s_Wp, t = rem - oy * p.s_Wp;
+    ti.pix_lo = smp * p.P + oy * p.Wo + min(t, p.Wo);
+    ti.kb0 = ti.pix_lo / kBK;
+    ti.kb1 = nall;
+    return ti.pix_lo < ti.rows * p.P;
+  }
   if (p.kmode == 2) {               // the partial last block only (one unit per (group, kk tile); splits == 1)
     ti.kb0 = nfull;
     ti.kb1 = nall;
@@ -1155,7 +1401,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgParams p, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < PR; ++i) {
           const int prow = rsub + PSTEP * i;
-          const bool v = smp[i] < ti.rows;
+          const bool v = smp[i] < ti.rows && kb * kBK + prow >= ti.pix_lo;
           const int oy = oyv[i], ox = oxv[i];
           const long sbase = src_base + (long)smp[i] * hw;
           const uint32_t doff = (uint32_t)prow * 128u + (uint32_t)((chunk ^ (prow & 7)) << 4);
@@ -1443,6 +1689,209 @@ igemm_wgrad_tma_kernel(const __grid_constant__ WgParams p, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TMA-fed weight gradient with TAP-ROW STRIPS.  igemm_wgrad_tma_kernel moves 16 KB of x + 8 KB of dy per CTA for every
+// 128 x N x 64 MACs: at N <= 128 the L2->SM fill (~41 B/clk/SM) is 2-4x what the MMA of that block takes (conv2: 0.75, conv3:
+// 0.40 PFLOP/s).  With the reduction (pixel) axis enumerated on the padded row pitch Wp = Wo + nx - 1 (see
+// igemm_tma_strip_kernel) the nx taps of a tap row read ONE strip of 64 + nx - 1 pixels — tap j's A operand is the same
+// MN-major tile started j rows (j * 128 B) further down — and share the dy tile: a work unit is (group, split, tap row, 128
+// channels per CTA) with nx accumulators [128 x N] side by side in TMEM.  dy is read on the same padded pitch by an im2col
+// box whose upper corner reaches nx - 1 columns past the image (zero-filled): the pad positions contribute nothing.
+// Only the full 64-position blocks of a group are reduced here; the remaining pixels go through the gather kernel (kmode 3).
+struct WgStripParams {
+  int n_rows, nx, Wp, Pp;           // tap rows, taps per row, padded pitch, Ho * Wp
+  int cchunks;                      // channel chunks per tap row: C / 128 (single CTA) or C / 256 (pair)
+  int stages, stage_bytes, seg_bytes;   // seg_bytes: one 64-channel strip segment, 1 KB aligned
+  int low_w, low_h;
+  signed char sdy[16], sdx[16];
+  int tap0[16];                     // index (into WgParams::tcol) of the row's first tap; tap j of the row is tap0 + j
+};
+
+template <bool kPair>
+__global__ void __launch_bounds__(192, 1)
+igemm_wgrad_strip_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgStripParams ws,
+                         const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x) {
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int kStages = ws.stages, kStage = ws.stage_bytes;
+  const uint32_t bar_base = base + kStages * kStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (16 + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (18 + b); };
+  uint8_t* gen = smem_raw + (bar_base - raw);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 8 * 20);
+  const uint32_t tmem_slot = bar_base + 8u * 20;
+  es_group* s_grp = reinterpret_cast<es_group*>(gen + 512);
+
+  const int BN = p.N, nx = ws.nx;
+  const int nseg_c = kPair ? (BN >> 7) : (BN >> 6);      // 64-channel dy segments this CTA loads
+  const uint32_t acc_cols = (uint32_t)(nx * BN);         // nx accumulators side by side
+  const uint32_t nbuf = 2 * acc_cols <= 512 ? 2u : 1u;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < nbuf * acc_cols) tmem_cols <<= 1;
+
+  if (tid < p.n_groups) s_grp[tid] = p.grp[tid];
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), kPair ? 8 : 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_dy); tma_prefetch_desc(&tmap_x); }
+  if (warp == 1) { if (kPair) tmem_alloc_pair(tmem_slot, tmem_cols); else tmem_alloc(tmem_slot, tmem_cols); }
+  tc_fence_before();
+  __syncthreads();
+  if (kPair) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int units_m = ws.n_rows * ws.cchunks;
+  const int total_tiles = p.n_groups * p.splits * units_m;
+  const int first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, stride = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t strip_bytes = (uint32_t)(kBK + nx - 1) * 128u;
+
+  // unit -> (group, split, tap row, channel chunk) and its range of full padded 64-position blocks
+  struct Unit { int rows, row_start, slot, kb0, kb1, rr, cc; };
+  auto decode = [&](int t, Unit& u) -> bool {
+    const int per_g = p.splits * units_m;
+    const int g = t / per_g, rem = t - g * per_g;
+    const int sp = rem / units_m, mu = rem - sp * units_m;
+    u.rr = mu / ws.cchunks; u.cc = mu - u.rr * ws.cchunks;
+    u.rows = s_grp[g].rows; u.row_start = s_grp[g].row_start; u.slot = s_grp[g].slot;
+    const int nkb = (u.rows * ws.Pp) / kBK;
+    const int per = ceil_div(nkb, p.splits);
+    u.kb0 = sp * per;
+    u.kb1 = min(nkb, u.kb0 + per);
+    return u.kb1 > u.kb0;
+  };
+
+  if (warp == 0) {
+    // =========================================================================== TMA PRODUCER
+    if (lane == 0) {
+      const uint32_t lead_full0 = kPair ? mapa_shared(full_bar(0), 0) : full_bar(0);
+      uint32_t it = 0;
+      for (int tile = first; tile < total_tiles; tile += stride) {
+        Unit u;
+        if (!decode(tile, u)) continue;
+        const int cbase = (u.cc * (kPair ? 2 : 1) + (int)rank) * kBM;     // this CTA's 128 channels
+        const uint32_t ow = (uint32_t)(ws.sdx[u.rr] - ws.low_w), oh = (uint32_t)(ws.sdy[u.rr] - ws.low_h);
+        const int pidx = u.kb0 * kBK;
+        int smp = pidx / ws.Pp;
+        const int pix = pidx - smp * ws.Pp;
+        int oy = pix / ws.Wp, ot = pix - oy * ws.Wp;
+        const int dy64 = kBK / ws.Wp, dx64 = kBK - dy64 * ws.Wp;
+        for (int kb = u.kb0; kb < u.kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= (uint32_t)kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), (kPair ? 2u : 1u) * 2u * strip_bytes + (uint32_t)BN * 128u);
+          const uint32_t lead_full = lead_full0 + 8u * s;
+          const uint32_t sa = base + s * kStage;
+          const uint32_t sb = sa + 2u * ws.seg_bytes;
+          const int cn = u.row_start + smp;
+#pragma unroll
+          for (int sg = 0; sg < 2; ++sg) {
+            if (kPair) tma_im2col_4d_pair(sa + sg * ws.seg_bytes, &tmap_x, cbase + sg * 64, ws.low_w + ot, ws.low_h + oy * p.my, cn, ow, oh, lead_full);
+            else tma_im2col_4d(sa + sg * ws.seg_bytes, &tmap_x, cbase + sg * 64, ws.low_w + ot, ws.low_h + oy * p.my, cn, ow, oh, lead_full);
+          }
+          for (int sg = 0; sg < nseg_c; ++sg) {
+            const int col = ((int)rank * nseg_c + sg) * 64;
+            if (kPair) tma_im2col_4d_pair(sb + sg * 8192u, &tmap_dy, col, ot, oy, cn, 0u, 0u, lead_full);
+            else tma_im2col_4d(sb + sg * 8192u, &tmap_dy, col, ot, oy, cn, 0u, 0u, lead_full);
+          }
+          ot += dx64; oy += dy64;
+          if (ot >= ws.Wp) { ot -= ws.Wp; ++oy; }
+          while (oy >= p.Ho) { oy -= p.Ho; ++smp; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================================== MMA ISSUER (leader CTA only)
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_m(BN, kPair ? 2 * kBM : kBM, true, true);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = first; tile < total_tiles; tile += stride) {
+        Unit u;
+        if (!decode(tile, u)) continue;
+        const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+        const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+        if (use >= 1) mbar_wait(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * acc_cols;
+        for (int kb = u.kb0; kb < u.kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = base + s * kStage;
+            const uint32_t sb = sa + 2u * ws.seg_bytes;
+            const uint32_t acc0 = kb > u.kb0 ? 1u : 0u;
+            for (int j = 0; j < nx; ++j) {
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t ad = make_desc(sa + j * 128 + k * 2048, (uint32_t)ws.seg_bytes, 1024), bd = make_desc(sb + k * 2048, 8192, 1024);
+                if (kPair) umma_bf16_pair(tacc + j * BN, ad, bd, idesc, acc0 | (k ? 1u : 0u));
+                else umma_bf16(tacc + j * BN, ad, bd, idesc, acc0 | (k ? 1u : 0u));
+              }
+            }
+            if (kPair) {
+              umma_commit_pair(empty_bar(s), 3);
+              if (kb == u.kb1 - 1) umma_commit_pair(tfull_bar(buf), 3);
+            } else {
+              umma_commit(empty_bar(s));
+              if (kb == u.kb1 - 1) umma_commit(tfull_bar(buf));
+            }
+          }
+          __syncwarp();
+        }
+        ++tcount;
+      }
+      tc_fence_before();
+    }
+  } else {
+    // =========================================================================== EPILOGUE (warps 2-5): RED into dw
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = first; tile < total_tiles; tile += stride) {
+      Unit u;
+      if (!decode(tile, u)) continue;
+      const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
+      const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+      mbar_wait(tfull_bar(buf), use & 1, p.err_flag, 3);
+      tc_fence_after();
+      const int ch = (u.cc * (kPair ? 2 : 1) + (int)rank) * kBM + q * 32 + lane;      // this thread's input channel
+      uint32_t r[32];
+      for (int j = 0; j < nx; ++j) {
+        const uint32_t t_lane = tmem_base + buf * acc_cols + (uint32_t)(j * BN) + ((uint32_t)(q * 32) << 16);
+        float* dw = p.dw + (long)u.slot * p.dw_slot_stride + p.tcol[ws.tap0[u.rr] + j] + ch;
+        for (int c = 0; c < BN; c += 32) {
+          tmem_ld32(t_lane + c, r);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) atomicAdd(dw + (long)(c + jj) * p.dw_ld, __uint_as_float(r[jj]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (kPair) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0)); else mbar_arrive(tempty_bar(buf)); }
+      ++tcount;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kPair) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    if (kPair) tmem_dealloc_pair(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1558,6 +2007,58 @@ static bool tma_pair_plan(const FwdParams& p, int low[2], int up[2]) {
   return true;
 }
 
+// Host-side plan of the strip form of the TMA-fed pair variant (igemm_tma_strip_kernel).  The tap table must be rows of L taps
+// (same dy, consecutive dx, weight columns C apart), all rows equally long; a row is cut into sub-strips of nx taps, nx the
+// largest divisor of L whose stage (strip + nx half weight boxes) still leaves a 3-deep pipeline.  Taken only when the fill
+// saved outweighs the masked pad columns by ES_TMA_STRIP_GAIN (default 1.15; 0 disables the variant).
+static bool tma_strip_plan(const FwdParams& p, long total_rows, TStripParams& ts, int low[2], int up[2]) {
+  static const double min_gain = [] { const char* e = getenv("ES_TMA_STRIP_GAIN"); return e ? atof(e) : 1.15; }();
+  ts = TStripParams{};
+  if (min_gain <= 0.0 || !(p.BN >= 64 && p.Hu == p.Hs && p.Wu == p.Ws && p.mx == 1 && p.my >= 1 && p.my <= 8 && p.n_taps >= 2)) return false;
+  int L = 0, n_rows = 0, row_t[32];
+  for (int t = 0; t < p.n_taps;) {
+    int n = 1;
+    while (t + n < p.n_taps && p.tdy[t + n] == p.tdy[t] && p.tdx[t + n] == p.tdx[t] + n && p.tkoff[t + n] == p.tkoff[t] + n * p.C) ++n;
+    if (n_rows == 0) L = n;
+    if (n != L) return false;
+    row_t[n_rows++] = t;
+    t += n;
+  }
+  if (L < 2) return false;
+  const int BH = p.BN / 2;
+  const int a_bytes = ((kBM + 8) * 128 + 1023) & ~1023;            // room for up to 128 + 8 strip rows, 1 KB aligned
+  const long room = 227L * 1024 - 1024 - 2048;
+  static const int mt_max = [] { const char* e = getenv("ES_TMA_STRIP_MT"); return e ? atoi(e) : 2; }();
+  static const int bn_max = [] { const char* e = getenv("ES_TMA_STRIP_BN"); return e ? atoi(e) : 128; }();
+  if (p.BN > bn_max) return false;    // N = 256 is mostly MMA-bound already; measured: strips lose there (3 stages, 10-20 % pad columns)
+  const int mt = (p.BN <= 128 && mt_max >= 2) ? 2 : 1;
+  int nx = 0;
+  for (int d = L; d >= 2; --d)
+    if (L % d == 0 && d <= 8 && 3L * (mt * a_bytes + d * BH * 128) <= room) { nx = d; break; }
+  if (nx == 0 || n_rows * (L / nx) > 16) return false;
+  const int Wp = p.Wo + nx - 1;
+  const double gain = (double)nx * (kBM * 128 + BH * 128) / ((kBM + nx - 1) * 128.0 + nx * BH * 128.0) * p.Wo / Wp;
+  if (gain < min_gain) return false;
+  ts.nx = nx; ts.Wp = Wp; ts.Pp = p.Ho * Wp;
+  if (Wp >= 256 || total_rows * ts.Pp >= 2147483647L) return false;
+  for (int r = 0; r < n_rows; ++r)
+    for (int j0 = 0; j0 < L; j0 += nx) {
+      const int t = row_t[r] + j0;
+      ts.sdy[ts.n_strips] = p.tdy[t]; ts.sdx[ts.n_strips] = p.tdx[t]; ts.skoff[ts.n_strips] = p.tkoff[t];
+      ++ts.n_strips;
+    }
+  ts.a_bytes = a_bytes;
+  ts.mt = mt;
+  ts.stage_bytes = mt * a_bytes + nx * BH * 128;
+  ts.stages = (int)(room / ts.stage_bytes);
+  if (ts.stages > 6) ts.stages = 6;
+  FwdParams q = p;                                                 // the im2col box enumerates Wp base pixels per row
+  q.Wo = Wp;
+  if (!tma_pair_plan(q, low, up)) return false;
+  ts.low_w = low[0]; ts.low_h = low[1];
+  return true;
+}
+
 static void conv_taps(const es_conv_geom* g, FwdParams& p) {
   p.Hs = g->Hs; p.Ws = g->Ws; p.C = g->C; p.Hu = g->Hu; p.Wu = g->Wu; p.Ho = g->Ho; p.Wo = g->Wo;
   p.n_taps = g->KH * g->KW; p.my = 1; p.mx = 1;
@@ -1571,7 +2072,8 @@ static void conv_taps(const es_conv_geom* g, FwdParams& p) {
   p.o_my = 1; p.o_oy = 0; p.o_mx = 1; p.o_ox = 0; p.Wo_full = g->Wo; p.P_full = g->Ho * g->Wo;
 }
 
-static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows, int n_groups, void* stream) {
+static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows, int n_groups, void* stream, int32_t* fused = nullptr) {
+  if (fused) *fused = 0;     // set when the launched variant accumulated p.pair_sums (the TMA-fed pair kernels do)
   ES_REQUIRE(p.C > 0 && p.C % 64 == 0 && p.Hu <= 64 && p.Wu <= 64 && p.Hu >= p.Hs && p.Wu >= p.Ws && p.Ho > 0 && p.Wo > 0 &&
                  p.Ho < 256 && p.Wo < 256 && p.n_taps >= 1 && p.n_taps <= 32 && p.KK % 8 == 0,
              "unsupported geometry (need C % 64 == 0, Hu,Wu <= 64, <= 32 taps)");
@@ -1649,6 +2151,7 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
   // a 1x1 grid: pure weight streaming) is the one shape that lost (0.389 -> 0.440) and keeps the single-CTA kernel.
   // ES_IGEMM_TMA_A: 0 = off, 1 = wherever eligible except launches the strip variant takes, 2 (default) = also those.
   static const int tma_a_mode = [] { const char* e = getenv("ES_IGEMM_TMA_A"); return e ? atoi(e) : 2; }();
+  static const bool trace = [] { const char* e = getenv("ES_IGEMM_TRACE"); return e && e[0] == '1'; }();   // variant per launch on stderr
   auto launch_tma_pair = [&](bool& taken) -> int {
     taken = false;
     TmaAParams ta{};
@@ -1690,9 +2193,64 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
     }
     igemm_tma_pair_kernel<kPStages><<<2 * pairs, 192, kPSmem, as_stream(stream)>>>(p, ta, tmap_h, tmap_x);
     ES_LAUNCH_CHECK();
+    if (fused) *fused = p.pair_sums != nullptr;
+    if (trace) fprintf(stderr, "[igemm] tma_pair C=%d N=%d taps=%d Ho=%d Wo=%d my=%d mx=%d rows=%d\n", p.C, p.Nout, p.n_taps, p.Ho, p.Wo,
+                       p.my, p.mx, total_rows);
     taken = true;
     return ES_OK;
   };
+
+  // Strip form of the TMA-fed pair variant (see igemm_tma_strip_kernel / tma_strip_plan): one im2col strip per tap row.
+  auto launch_tma_strip = [&](bool& taken) -> int {
+    taken = false;
+    TStripParams ts{};
+    int low[2], up[2];
+    if (tma_a_mode <= 0 || !tma_strip_plan(p, total_rows, ts, low, up)) return ES_OK;
+    EncodeIm2colFn enc_i = encode_im2col_fn();
+    if (!enc_i) return ES_OK;
+    alignas(64) CUtensorMap tmap_h, tmap_x;
+    {
+      const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)p.Nout};
+      const cuuint64_t strides[1] = {(cuuint64_t)p.KK * 2};
+      const cuuint32_t box[2] = {64, (cuuint32_t)(p.BN / 2)};
+      const CUresult rc = enc(&tmap_h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ES_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (half weight tile)");
+    }
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.Ws, (cuuint64_t)p.Hs, (cuuint64_t)total_rows};
+      const cuuint64_t strides[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.Ws * p.C * 2, (cuuint64_t)p.Hs * p.Ws * p.C * 2};
+      const cuuint32_t trav[4] = {1, 1, (cuuint32_t)p.my, 1};
+      const CUresult rc = enc_i(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, low, up, 64,
+                                (cuuint32_t)(kBM + ts.nx - 1), trav, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc != CUDA_SUCCESS) return ES_OK;                     // geometry the driver refuses: the per-tap variant takes it
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long max_tiles = (ceil_div_l((long)total_rows * ts.Pp, 2L * kBM * ts.mt) + n_groups) * p.n_tiles_n;
+    const int pairs = (int)(max_tiles < sms / 2 ? max_tiles : sms / 2);
+    const size_t smem = (size_t)ts.stages * ts.stage_bytes + 1024 + 2048;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ES_CUDA(cudaFuncSetAttribute(igemm_tma_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    igemm_tma_strip_kernel<<<2 * pairs, 192, smem, as_stream(stream)>>>(p, ts, tmap_h, tmap_x);
+    ES_LAUNCH_CHECK();
+    if (fused) *fused = p.pair_sums != nullptr;
+    if (trace) fprintf(stderr, "[igemm] tma_strip C=%d N=%d taps=%d mt=%d nx=%d strips=%d stages=%d Ho=%d Wo=%d my=%d rows=%d\n", p.C, p.Nout,
+                       p.n_taps, ts.mt, ts.nx, ts.n_strips, ts.stages, p.Ho, p.Wo, p.my, total_rows);
+    taken = true;
+    return ES_OK;
+  };
+  if (!getenv("ES_IGEMM_FWD_VARIANT") && tma_a_mode >= 2) {
+    bool taken = false;
+    const int rc = launch_tma_strip(taken);
+    if (rc != ES_OK || taken) return rc;
+  }
 
   // Strip variant (see igemm_strip_kernel): no upsample, taps form rows of consecutive dx with consecutive weight columns,
   // N <= 128.  ES_IGEMM_STRIP=0 disables it (A/B measurements).
@@ -1761,8 +2319,8 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
   return ES_OK;
 }
 
-extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
-                            const es_conv_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
+static int igemm_fwd_impl(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_conv_geom* g,
+                          const es_group* grp, int n_groups, int total_rows, float* pair_sums, int32_t* fused, void* stream) {
   ES_REQUIRE(x && w && y && grp && g, "null pointer");
   ES_REQUIRE(g->KH >= 1 && g->KW >= 1 && g->KH * g->KW <= 32 && g->Ho == g->Hu + 2 * g->pad - g->KH + 1 &&
                  g->Wo == g->Wu + 2 * g->pad - g->KW + 1, "unsupported window (stride 1, <= 32 taps)");
@@ -1770,7 +2328,20 @@ extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, lon
   p.grp = grp;
   conv_taps(g, p);
   p.bias = bias; p.bias_slot_stride = bias_slot_stride; p.out = (__nv_bfloat16*)y;
-  return launch_fwd(p, x, w, total_rows, n_groups, stream);
+  p.pair_sums = pair_sums;
+  return launch_fwd(p, x, w, total_rows, n_groups, stream, fused);
+}
+
+extern "C" int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
+                            const es_conv_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
+  return igemm_fwd_impl(x, w, bias, bias_slot_stride, y, g, grp, n_groups, total_rows, nullptr, nullptr, stream);
+}
+
+extern "C" int es_igemm_fwd_sums(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
+                                 const es_conv_geom* g, const es_group* grp, int n_groups, int total_rows, float* pair_sums,
+                                 int32_t* fused, void* stream) {
+  ES_REQUIRE(pair_sums && fused, "null pointer");
+  return igemm_fwd_impl(x, w, bias, bias_slot_stride, y, g, grp, n_groups, total_rows, pair_sums, fused, stream);
 }
 
 extern "C" int es_igemm_fwd_plan(const es_conv_geom* g, int total_rows, int32_t* plan8) {
@@ -1782,7 +2353,14 @@ extern "C" int es_igemm_fwd_plan(const es_conv_geom* g, int total_rows, int32_t*
   pick_bn(p);
   StripParams sp{};
   int low[2], up[2];
-  if (tma_pair_plan(p, low, up)) {      // the default dispatch prefers the TMA-fed pair variant wherever it applies
+  TStripParams ts{};
+  if (tma_strip_plan(p, total_rows, ts, low, up)) {   // variant 3: TMA-fed pair kernel with tap-row strips
+    plan8[0] = 3; plan8[1] = p.BN; plan8[2] = ts.n_strips; plan8[3] = ts.nx; plan8[4] = ts.Wp; plan8[5] = ts.stages;
+    plan8[6] = ts.n_strips * (p.C / kBK);
+    plan8[7] = (int32_t)ceil_div_l((long)ts.Pp, kBM);
+    return ES_OK;
+  }
+  if (tma_pair_plan(p, low, up)) {      // else the per-tap TMA-fed pair variant wherever it applies
     plan8[0] = 2; plan8[1] = p.BN; plan8[2] = p.n_taps; plan8[3] = 0; plan8[4] = p.Wo; plan8[5] = 6;
     plan8[6] = p.n_taps * (p.C / kBK);
     plan8[7] = (int32_t)ceil_div_l((long)p.Ho * p.Wo, kBM);
@@ -1800,8 +2378,8 @@ extern "C" int es_igemm_fwd_plan(const es_conv_geom* g, int total_rows, int32_t*
   return ES_OK;
 }
 
-extern "C" int es_igemm_taps_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
-                                 const es_tap_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
+static int igemm_taps_fwd_impl(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_tap_geom* g,
+                               const es_group* grp, int n_groups, int total_rows, float* pair_sums, int32_t* fused, void* stream) {
   ES_REQUIRE(x && w && y && grp && g, "null pointer");
   ES_REQUIRE(g->n_taps >= 1 && g->n_taps <= 32 && g->my >= 1 && g->mx >= 1 && g->o_my >= 1 && g->o_mx >= 1, "bad tap table");
   ES_REQUIRE((g->Ho - 1) * g->o_my + g->o_oy < g->Ho_full && (g->Wo - 1) * g->o_mx + g->o_ox < g->Wo_full, "output scatter out of range");
@@ -1817,7 +2395,63 @@ extern "C" int es_igemm_taps_fwd(const void* x, const void* w, const float* bias
   p.Nout = g->N;
   p.o_my = g->o_my; p.o_oy = g->o_oy; p.o_mx = g->o_mx; p.o_ox = g->o_ox; p.Wo_full = g->Wo_full; p.P_full = g->Ho_full * g->Wo_full;
   p.bias = bias; p.bias_slot_stride = bias_slot_stride; p.out = (__nv_bfloat16*)y;
-  return launch_fwd(p, x, w, total_rows, n_groups, stream);
+  p.pair_sums = pair_sums;
+  return launch_fwd(p, x, w, total_rows, n_groups, stream, fused);
+}
+
+extern "C" int es_igemm_taps_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
+                                 const es_tap_geom* g, const es_group* grp, int n_groups, int total_rows, void* stream) {
+  return igemm_taps_fwd_impl(x, w, bias, bias_slot_stride, y, g, grp, n_groups, total_rows, nullptr, nullptr, stream);
+}
+
+extern "C" int es_igemm_taps_fwd_sums(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y,
+                                      const es_tap_geom* g, const es_group* grp, int n_groups, int total_rows, float* pair_sums,
+                                      int32_t* fused, void* stream) {
+  ES_REQUIRE(pair_sums && fused, "null pointer");
+  return igemm_taps_fwd_impl(x, w, bias, bias_slot_stride, y, g, grp, n_groups, total_rows, pair_sums, fused, stream);
+}
+
+// Host-side plan of the strip form of the TMA-fed weight gradient (igemm_wgrad_strip_kernel): equal tap rows of consecutive dx
+// on a source read directly (mx = 1), N <= 128 (where the per-tap kernel is fill-bound), whole 128-channel chunks per CTA.
+static bool wgrad_strip_plan(const WgParams& p, long total_rows, bool as_pair, WgStripParams& ws, int low[2], int up[2]) {
+  static const int on = [] { const char* e = getenv("ES_WG_STRIP"); return e ? atoi(e) : 1; }();
+  ws = WgStripParams{};
+  if (!on || p.N > 128 || p.mx != 1 || p.my < 1 || p.my > 8 || p.Hu != p.Hs || p.Wu != p.Ws || p.n_taps < 2) return false;
+  if (p.C % (as_pair ? 2 * kBM : kBM) != 0) return false;
+  int L = 0, n_rows = 0, row_t[32];
+  for (int t = 0; t < p.n_taps;) {
+    int n = 1;
+    while (t + n < p.n_taps && p.tdy[t + n] == p.tdy[t] && p.tdx[t + n] == p.tdx[t] + n) ++n;
+    if (n_rows == 0) L = n;
+    if (n != L) return false;
+    row_t[n_rows++] = t;
+    t += n;
+  }
+  int nx = 0;
+  for (int d = L; d >= 2; --d)
+    if (L % d == 0 && d <= 8 && d * p.N <= 512) { nx = d; break; }
+  if (nx == 0 || n_rows * (L / nx) > 16) return false;
+  ws.nx = nx; ws.Wp = p.Wo + nx - 1; ws.Pp = p.Ho * ws.Wp;
+  if (ws.Wp >= 256 || total_rows * ws.Pp >= 2147483647L) return false;
+  for (int r = 0; r < n_rows; ++r)
+    for (int j0 = 0; j0 < L; j0 += nx) {
+      const int t = row_t[r] + j0;
+      ws.sdy[ws.n_rows] = p.tdy[t]; ws.sdx[ws.n_rows] = p.tdx[t]; ws.tap0[ws.n_rows] = t;
+      ++ws.n_rows;
+    }
+  ws.cchunks = p.C / (as_pair ? 2 * kBM : kBM);
+  ws.seg_bytes = ((kBK + nx - 1) * 128 + 1023) & ~1023;
+  ws.stage_bytes = 2 * ws.seg_bytes + (as_pair ? p.N / 2 : p.N) * 128;
+  ws.stages = (int)((227L * 1024 - 1024 - 2048) / ws.stage_bytes);
+  if (ws.stages > 8) ws.stages = 8;
+  if (ws.stages < 3) return false;
+  FwdParams q{};                                                   // the x box enumerates Wp base pixels per row
+  q.Hs = p.Hs; q.Ws = p.Ws; q.C = p.C; q.Hu = p.Hu; q.Wu = p.Wu; q.Ho = p.Ho; q.Wo = ws.Wp;
+  q.n_taps = p.n_taps; q.my = p.my; q.mx = 1; q.BN = 64;
+  for (int t = 0; t < p.n_taps; ++t) { q.tdy[t] = p.tdy[t]; q.tdx[t] = p.tdx[t]; }
+  if (!tma_pair_plan(q, low, up)) return false;
+  ws.low_w = low[0]; ws.low_h = low[1];
+  return true;
 }
 
 static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, long dw_slot_stride, int total_rows,
@@ -1865,6 +2499,7 @@ static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, l
   // 256 channels and KK is a multiple of 256, as a single CTA for 64 channels.  It reduces over the full 64-pixel blocks of
   // every group; the partial last block of each group goes through the gather kernel below (kmode 2).
   static const int tma_a_mode = [] { const char* e = getenv("ES_IGEMM_TMA_A"); return e ? atoi(e) : 2; }();
+  static const bool trace = [] { const char* e = getenv("ES_IGEMM_TRACE"); return e && e[0] == '1'; }();   // variant per launch on stderr
   {
     FwdParams fp{};
     fp.Hs = p.Hs; fp.Ws = p.Ws; fp.C = p.C; fp.Hu = p.Hu; fp.Wu = p.Wu; fp.Ho = p.Ho; fp.Wo = p.Wo;
@@ -1873,6 +2508,71 @@ static int launch_wgrad(WgParams& p, const void* x, const void* dy, float* dw, l
     int low[2], up[2];
     EncodeIm2colFn enc_i = encode_im2col_fn();
     const bool as_pair = (p.N == 128 || p.N == 256) && p.KK % (2 * kBM) == 0;
+    // strip form (igemm_wgrad_strip_kernel): one x strip per tap row, the taps of the row share it and the dy tile
+    WgStripParams ws{};
+    if (tma_a_mode > 0 && enc_i && (as_pair || p.N == 64) && wgrad_strip_plan(p, total_rows, as_pair, ws, low, up)) {
+      alignas(64) CUtensorMap tmap_x, tmap_dyi;
+      const cuuint64_t xdims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.Ws, (cuuint64_t)p.Hs, (cuuint64_t)total_rows};
+      const cuuint64_t xstrides[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.Ws * p.C * 2, (cuuint64_t)p.Hs * p.Ws * p.C * 2};
+      const cuuint32_t trav[4] = {1, 1, (cuuint32_t)p.my, 1};
+      CUresult rcx = enc_i(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), xdims, xstrides, low, up, 64,
+                           (cuuint32_t)(kBK + ws.nx - 1), trav, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rcx == CUDA_SUCCESS) {     // dy on the padded pitch: the box reaches nx - 1 columns past the image (zero-filled)
+        const cuuint64_t ddims[4] = {(cuuint64_t)p.N, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)total_rows};
+        const cuuint64_t dstrides[3] = {(cuuint64_t)p.N * 2, (cuuint64_t)p.Wo * p.N * 2, (cuuint64_t)p.Ho * p.Wo * p.N * 2};
+        const cuuint32_t trav1[4] = {1, 1, 1, 1};
+        const int dlow[2] = {0, 0}, dup[2] = {ws.nx - 1, 0};
+        rcx = enc_i(&tmap_dyi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), ddims, dstrides, dlow, dup, 64, kBK, trav1,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      if (rcx == CUDA_SUCCESS) {
+        WgParams pm = p;
+        const int units_m = ws.n_rows * ws.cchunks, workers = as_pair ? sms / 2 : sms;
+        int sp2 = (2 * workers + n_groups * units_m / 2) / (n_groups * units_m);
+        const long full_blocks = ((long)total_rows * ws.Pp) / kBK / n_groups;      // per group, roughly
+        if (sp2 > full_blocks) sp2 = (int)full_blocks;
+        if (sp2 < 1) sp2 = 1;
+        if (sp2 > 64) sp2 = 64;
+        pm.splits = sp2;
+        const size_t smem = (size_t)ws.stages * ws.stage_bytes + 1024 + 2048;
+        static bool attr3 = false;
+        if (!attr3) {
+          ES_CUDA(cudaFuncSetAttribute(igemm_wgrad_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          ES_CUDA(cudaFuncSetAttribute(igemm_wgrad_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          attr3 = true;
+        }
+        const int units = n_groups * pm.splits * units_m;
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = as_pair ? 2 : 1;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (as_pair) {
+          cfg.gridDim = dim3(2 * (units < workers ? units : workers));
+          ES_CUDA(cudaLaunchKernelEx(&cfg, igemm_wgrad_strip_kernel<true>, pm, ws, tmap_dyi, tmap_x));
+        } else {
+          cfg.gridDim = dim3(units < workers ? units : workers);
+          ES_CUDA(cudaLaunchKernelEx(&cfg, igemm_wgrad_strip_kernel<false>, pm, ws, tmap_dyi, tmap_x));
+        }
+        ES_LAUNCH_CHECK();
+        if (trace) fprintf(stderr, "[igemm] wgrad_strip C=%d N=%d taps=%d nx=%d rows=%d pair=%d stages=%d splits=%d Ho=%d Wo=%d my=%d\n", p.C, p.N,
+                           p.n_taps, ws.nx, ws.n_rows, (int)as_pair, ws.stages, pm.splits, p.Ho, p.Wo, p.my);
+        WgParams pt = p;                  // what the padded full blocks did not cover: gather kernel, masked below pix_lo
+        pt.kmode = 3; pt.splits = 1; pt.s_Wp = ws.Wp; pt.s_Pp = ws.Pp;
+        const int tail_units = n_groups * pt.tiles_m;
+        igemm_wgrad_kernel<<<tail_units < sms ? tail_units : sms, kGThreads, kFSmem, as_stream(stream)>>>(pt, tmap);
+        ES_LAUNCH_CHECK();
+        return ES_OK;
+      }
+    }
     if (tma_a_mode > 0 && enc_i && (as_pair || p.N == 64) && tma_pair_plan(fp, low, up)) {
       alignas(64) CUtensorMap tmap_x;
       const cuuint64_t xdims[4] = {(cuuint64_t)p.C, (cuuint64_t)p.Ws, (cuuint64_t)p.Hs, (cuuint64_t)total_rows};

@@ -9,6 +9,8 @@ torch only allocates device buffers.  Shapes follow the reference modules:
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -107,6 +109,9 @@ def _axis_classes(S, U, K, pad, O, fold):
             offs.setdefault((p_ + k - pad) * S // U, []).append(k)      # python floor division
         classes.append((p_, (O - p_ + per_o - 1) // per_o, sorted(offs.items())))
     return per_o, per_s, S, classes
+
+
+_FUSED_FLAG = (ctypes.c_int32 * 1)()     # host-side answer of the es_igemm_*_fwd_sums calls
 
 
 class FoldedConv:
@@ -217,9 +222,17 @@ class FoldedConv:
             oarr = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
             L.call("es_fold_weights_multi", w_addr, slot_stride, E, self.N, self.C, self.KH, self.KW, tarr, len(tables), oarr, dg)
 
-    def forward(self, x, bias_addr, bias_stride, y, grp, E, R):
+    def forward(self, x, bias_addr, bias_stride, y, grp, E, R, pair_sums=None):
+        """-> True when ``pair_sums`` (zeroed [R, N/2, 2]) received the GroupNorm sums of the whole map (every class fused)."""
+        if pair_sums is None:
+            for c in self.classes:
+                L.call("es_igemm_taps_fwd", x, c["w_f"], bias_addr, bias_stride, y, c["g_fwd"], grp, E, R)
+            return False
+        fused, flag = True, _FUSED_FLAG
         for c in self.classes:
-            L.call("es_igemm_taps_fwd", x, c["w_f"], bias_addr, bias_stride, y, c["g_fwd"], grp, E, R)
+            L.call("es_igemm_taps_fwd_sums", x, c["w_f"], bias_addr, bias_stride, y, c["g_fwd"], grp, E, R, pair_sums, flag)
+            fused = fused and flag[0] == 1
+        return fused
 
     def wgrad(self, x, dy, dw_addr, slot_stride, grp, E, R):
         """dy [R, Ho*Wo, N] -> parameter gradient in the reference layout (accumulated at dw_addr)."""
@@ -272,6 +285,7 @@ class GenEngineProton:
         self.w_fwd, self.w_dg, self.dw_p, self.up2 = {}, {}, {}, {}
         self.upx = {}       # conv name -> (Hs, Ws, Wu): its input arrives x-upsampled from the previous norm kernel
         import os
+        self.gn_fused = os.environ.get("ES_GN_FUSED", "1") != "0"      # A/B switch of the conv-epilogue GroupNorm statistics
         for name, (Hs, Ws, C, Hu, Wu, KH, KW, pad, N), _, _ in self.CONVS:
             if (Hu, Wu) == (2 * Hs, 2 * Ws):      # exact x2 nearest upsample in front of the conv: fold it away
                 self.up2[name] = Up2Conv(Hs, Ws, C, KH, KW, pad, N)
@@ -328,14 +342,24 @@ class GenEngineProton:
             g = conv_geom(*geo)
             P = g.Ho * g.Wo
             y = empty(R, P, N, dtype=BF)
+            # norm fusion: the conv's epilogue accumulates the GroupNorm sums, the norm is then one streaming pass
+            ps = zeros(R, N // 2, 2) if self.gn_fused else None
             if name in self.up2:
-                self.up2[name].forward(act, a.addr(name + ".bias"), a.n, y, grp, E, R)
+                fused = self.up2[name].forward(act, a.addr(name + ".bias"), a.n, y, grp, E, R, ps)
+            elif ps is not None:
+                L.call("es_igemm_fwd_sums", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R, ps, _FUSED_FLAG)
+                fused = _FUSED_FLAG[0] == 1
             else:
                 L.call("es_igemm_fwd", act, self.w_fwd[name], a.addr(name + ".bias"), a.n, y, g, grp, E, R)
+                fused = False
             st = empty(R, groups, 2)
             nxt_name = self.CONVS[i + 1][0] if i + 1 < len(self.CONVS) else None
-            if nxt_name in self.upx:    # the next conv wants its input upsampled along x
-                _, ws_, wu_ = self.upx[nxt_name]
+            wu_ = self.upx[nxt_name][2] if nxt_name in self.upx else g.Wo      # the next conv may want its input upsampled along x
+            if fused:
+                nxt = empty(R, g.Ho * wu_, N, dtype=BF)
+                L.call("es_gn_lrelu_apply_fwd", y, ps, a.addr(norm + ".weight"), a.addr(norm + ".bias"), a.n, g.Ho, g.Wo, wu_, N,
+                       groups, grp, E, R, nxt, st)
+            elif nxt_name in self.upx:
                 nxt = empty(R, g.Ho * wu_, N, dtype=BF)
                 L.call("es_gn_lrelu_fwd_upx", y, a.addr(norm + ".weight"), a.addr(norm + ".bias"), a.n, g.Ho, g.Wo, wu_, N, groups,
                        grp, E, R, nxt, st)

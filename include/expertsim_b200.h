@@ -157,6 +157,14 @@ typedef struct {
  * weights) and for fc2. */
 int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_conv_geom* g,
                  const es_group* grp, int n_groups, int total_rows, void* stream);
+/* Same, with the following GroupNorm's statistics fused into the epilogue (proton/generator.py:27-29,33-35,38-40: every conv
+ * is followed by GroupNorm(32)): pair_sums fp32 [total rows][N/2][2], ZEROED by the caller, receives per (row, channel pair)
+ * the sum and the sum of squares of the bf16-rounded outputs over the row's pixels (atomic adds; several calls writing
+ * disjoint pixels of one map accumulate).  *fused (HOST int) is set to 1 when the kernel variant chosen for this geometry
+ * did accumulate (the TMA-fed CTA-pair variants 2 and 3), to 0 when it did not — the caller then runs es_gn_lrelu_fwd, which
+ * computes its own statistics, instead of es_gn_lrelu_apply_fwd. */
+int es_igemm_fwd_sums(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_conv_geom* g,
+                      const es_group* grp, int n_groups, int total_rows, float* pair_sums, int32_t* fused, void* stream);
 /* Generalised reduction of the same kernel: a TAP TABLE instead of a dense KHxKW window.  Tap t reads the (virtually
  * nearest-upsampled [Hs,Ws]->[Hu,Wu]) source at (oy*my + tap_dy[t], ox*mx + tap_dx[t]) (outside [0,Hu)x[0,Wu) = zero) and
  * multiplies it with the C weights starting at column tap_koff[t] of the packed weight row of length KK.  (oy, ox) runs
@@ -169,7 +177,10 @@ int es_igemm_fwd(const void* x, const void* w, const float* bias, long bias_slot
  * plan8 = {variant, BN, tap rows (variant 2: taps), taps per row (nx), M-axis row pitch (Wo, or Wo + nx - 1 for strips),
  *          pipeline stages, pipeline steps per tile, M tiles per row}.  variant 2 = TMA-fed CTA pair (A by TMA im2col, B halves
  * by TMA, tcgen05.mma.cta_group::2): the conv reads its source directly (no nearest upsample in between), N tile >= 64, not
- * the dense 1x1 product.  variant 1 = strip (one cp.async-gathered strip per tap row, kx taps as row-shifted A descriptors):
+ * the dense 1x1 product.  variant 3 = the same CTA pair with TAP-ROW STRIPS: N tile <= 128, taps form equal rows of
+ * consecutive dx (mx = 1) — one im2col strip of 128 + nx - 1 pixels per tap row and channel block serves the nx taps as
+ * row-shifted A descriptors, two 256-row sub-tiles share each weight box; plan8[7] counts 128-row blocks of the padded pitch.
+ * variant 1 = strip (one cp.async-gathered strip per tap row, kx taps as row-shifted A descriptors):
  * no upsample, N <= 128, 2..4 taps per row, nx * BN <= 384 — taken where variant 2 does not apply (N = 32).  variant 0 =
  * single-CTA kernel with the cp.async gather (nearest upsample inside the conv, fc2). */
 int es_igemm_fwd_plan(const es_conv_geom* g, int total_rows, int32_t* plan8);
@@ -188,6 +199,9 @@ typedef struct {
 } es_tap_geom;
 int es_igemm_taps_fwd(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_tap_geom* g,
                       const es_group* grp, int n_groups, int total_rows, void* stream);
+/* tap-table form of es_igemm_fwd_sums (the classes of a folded conv write disjoint pixels of one map: their sums add up) */
+int es_igemm_taps_fwd_sums(const void* x, const void* w, const float* bias, long bias_slot_stride, void* y, const es_tap_geom* g,
+                           const es_group* grp, int n_groups, int total_rows, float* pair_sums, int32_t* fused, void* stream);
 
 /* folded-tap table of a conv behind a nearest upsample: folded tap t is the SUM of the original taps (ky, kx) whose bit
  * ky*KW + kx is set in mask[t] (they all read the same source pixel for the output class the tap belongs to; KH*KW <= 32).
@@ -265,6 +279,13 @@ int es_gn_lrelu_fwd(const void* x, const float* gamma, const float* beta, long s
  * the producer so that the conv reads its source directly and both GEMM operands can come by TMA.  stats as above. */
 int es_gn_lrelu_fwd_upx(const void* x, const float* gamma, const float* beta, long slot_stride, int Hs, int Ws, int Wu, int C,
                         int groups, const es_group* grp, int n_groups, int total_rows, void* y, float* stats, void* stream);
+/* GroupNorm + LeakyReLU as one streaming pass over x [rows,Hs,Ws,C] when the producing conv accumulated pair_sums
+ * (es_igemm_fwd_sums / es_igemm_taps_fwd_sums, all calls fused): mean / rstd per (row, group) come from the sums (variance =
+ * E[x^2] - mean^2), are written to stats like es_gn_lrelu_fwd does, and y is stored as [rows,Hs,Wu,C] — Wu == Ws: plain;
+ * Wu > Ws: nearest-upsampled along x as es_gn_lrelu_fwd_upx.  C/groups must be even. */
+int es_gn_lrelu_apply_fwd(const void* x, const float* pair_sums, const float* gamma, const float* beta, long slot_stride, int Hs,
+                          int Ws, int Wu, int C, int groups, const es_group* grp, int n_groups, int total_rows, void* y,
+                          float* stats, void* stream);
 /* Backward of norm+LeakyReLU.  `dy_up` is the gradient w.r.t. the (virtually upsampled) consumer input
  * [rows,Hu,Wu,C]; it is summed over the pixels that map to each source pixel [Hs,Ws] (nearest-upsample backward).
  * dx (bf16, gradient w.r.t. the pre-norm tensor), dgamma/dbeta/dbias_conv (fp32, atomically accumulated). */

@@ -53,7 +53,8 @@ def test_struct_layouts_match_the_header():
 
 
 def test_forward_gemm_variant_plan():
-    """es_igemm_fwd_plan (host-only): which kernel variant a conv takes.  2 = TMA-fed CTA pair (the conv reads its source
+    """es_igemm_fwd_plan (host-only): which kernel variant a conv takes.  3 = TMA-fed CTA pair with tap-row strips (N tile
+    <= 128, equal rows of consecutive taps), 2 = TMA-fed CTA pair, one im2col box per tap (the conv reads its source
     directly, N tile >= 64, not the dense product), 1 = strip (no upsample, N <= 128, 2..4 taps per row, nx * BN <= 384, where
     variant 2 does not apply), 0 = single-CTA kernel with the cp.async gather (upsample inside the conv, fc2)."""
     import ctypes
@@ -67,12 +68,12 @@ def test_forward_gemm_variant_plan():
         assert lib.es_igemm_fwd_plan(ctypes.addressof(g), rows, ctypes.addressof(out)) == 0, L.last_error()
         return list(out)
 
-    # proton conv3 forward (3x3, 128 -> 64) and its data gradient (64 -> 128): both operands by TMA, 6 stages, 9 taps
-    assert plan(55, 29, 128, 55, 29, 3, 1, 64) == [2, 64, 9, 0, 29, 6, 18, (55 * 29 + 127) // 128]
-    assert plan(55, 29, 64, 55, 29, 3, 1, 128) == [2, 128, 9, 0, 29, 6, 9, (55 * 29 + 127) // 128]
-    # conv2's data gradient geometry (4x4, pad 2, N = 256) and neutron conv9 (2x2, no padding)
+    # proton conv3 forward (3x3, 128 -> 64) and its data gradient (64 -> 128): 3 strips of 3 taps on the padded pitch 29 + 2
+    assert plan(55, 29, 128, 55, 29, 3, 1, 64) == [3, 64, 3, 3, 31, 4, 6, (55 * 31 + 127) // 128]
+    assert plan(55, 29, 64, 55, 29, 3, 1, 128) == [3, 128, 3, 3, 31, 3, 3, (55 * 31 + 127) // 128]
+    # conv2's data gradient geometry (4x4, pad 2, N = 256): one im2col box per tap; neutron conv9 (2x2, no padding): strips of 2
     assert plan(55, 29, 128, 55, 29, 4, 2, 256)[:3] == [2, 256, 16]
-    assert plan(46, 46, 128, 46, 46, 2, 0, 64)[:3] == [2, 64, 4]
+    assert plan(46, 46, 128, 46, 46, 2, 0, 64)[:5] == [3, 64, 2, 2, 46]
     # an upsample in front of the conv or the dense 1x1 product (fc2) keep the single-CTA gather kernel
     assert plan(35, 19, 256, 56, 30, 4, 1, 128)[:2] == [0, 128]
     assert plan(1, 1, 256, 1, 1, 1, 0, 92160)[:3] == [0, 256, 0]

@@ -988,6 +988,67 @@ def test_gn_lrelu_fwd_upx_and_conv2_on_the_upsampled_source():
     check("conv2 on the x-upsampled source: dgrad", dx.float().view(R, Hs, Wu, C), torch.cat(want_dx), 1e-2, 5e-2)
 
 
+@pytest.mark.parametrize("layer", ["conv1_folded_upx", "conv2_yfolded", "conv3_plain"])
+def test_groupnorm_statistics_fused_into_the_conv_epilogue(layer):
+    """Norm fusion (generator.py:27-40: conv -> GroupNorm(32) -> LeakyReLU): es_igemm_*_fwd_sums accumulates per-(row, channel
+    pair) sum / sum of squares of the stored bf16 outputs in the GEMM epilogue, es_gn_lrelu_apply_fwd normalises in one
+    streaming pass.  Checked against (a) the sums recomputed from the stored conv output in fp64, (b) the two-pass
+    es_gn_lrelu_fwd on the same conv output (statistics 1e-4, activations to bf16 rounding).  Ragged groups, an empty expert,
+    and sample boundaries inside a warp of the epilogue (P is not a multiple of 32)."""
+    import ctypes
+
+    from expertsim._nets import FoldedConv, Up2Conv, conv_geom
+    geo = {"conv1_folded_upx": (18, 10, 512, 36, 20, 4, 4, 1, 256), "conv2_yfolded": (35, 30, 256, 56, 30, 4, 4, 1, 128),
+           "conv3_plain": (55, 29, 128, 55, 29, 3, 3, 1, 64)}[layer]
+    Hs, Ws, C, Hu, Wu, KH, KW, pad, N = geo
+    counts, slots, E = [3, 1, 2], [2, 0, 1], 3
+    grp, R = groups(counts, slots, min_rows=2)       # the middle expert holds ONE row: skipped (moe.py:126-135), its row stays
+    live = torch.tensor([True] * 3 + [False] + [True] * 2, device=DEV)
+    g = G(4242)
+    x = cuda(bf16_round(torch.randn(R, Hs * Ws, C, generator=g)), BF)
+    w = torch.randn(E, N, C, KH, KW, generator=g) / math.sqrt(KH * KW * C)
+    bias = cuda(torch.randn(E, N, generator=g) * 0.5)            # a real mean offset: exercises E[x^2] - mean^2
+    gm = conv_geom(*geo)
+    Ho, Wo = gm.Ho, gm.Wo
+    y = torch.zeros(R, Ho * Wo, N, dtype=BF, device=DEV)
+    ps = torch.zeros(R, N // 2, 2, device=DEV)
+    flag = (ctypes.c_int32 * 1)()
+    if layer == "conv3_plain":
+        wp, wd = torch.empty(E, N, KH, KW, C, dtype=BF, device=DEV), torch.empty(E, C, KH, KW, N, dtype=BF, device=DEV)
+        L.call("es_pack_conv_weight", cuda(w), N * C * KH * KW, E, N, C, KH, KW, wp, wd)
+        L.call("es_igemm_fwd_sums", x, wp, bias, N, y, gm, grp, E, R, ps, flag)
+        fused = flag[0] == 1
+    else:
+        f = Up2Conv(Hs, Ws, C, KH, KW, pad, N) if layer == "conv1_folded_upx" else FoldedConv(Hs, Ws, C, Hu, Wu, KH, KW, pad, N, (True, False))
+        f.alloc(E, DEV)
+        f.fold(cuda(w), N * C * KH * KW, E)
+        fused = f.forward(x, bias, N, y, grp, E, R, ps)
+    torch.cuda.synchronize()
+    assert fused, "the TMA-fed pair variants take these geometries and accumulate the sums"
+    yf = y.double().view(R, Ho * Wo, N // 2, 2)
+    want = torch.stack([yf.sum(dim=(1, 3)), (yf * yf).sum(dim=(1, 3))], dim=-1)          # [R, N/2, 2]
+    check("epilogue channel-pair sums", ps[live], want[live].float(), 2e-5, 2e-4)
+    assert float(ps[~live].abs().max()) == 0.0
+    gamma, beta = cuda(1 + 0.1 * torch.randn(E, N, generator=g)), cuda(0.1 * torch.randn(E, N, generator=g))
+    a0, st0 = torch.zeros(R, Ho * Wo, N, dtype=BF, device=DEV), torch.zeros(R, 32, 2, device=DEV)
+    L.call("es_gn_lrelu_fwd", y, gamma, beta, N, Ho * Wo, N, 32, grp, E, R, a0, st0)
+    a0.fill_(float("nan"))
+    L.call("es_gn_lrelu_fwd", y, gamma, beta, N, Ho * Wo, N, 32, grp, E, R, a0, st0)
+    a1, st1 = torch.full((R, Ho * Wo, N), float("nan"), dtype=BF, device=DEV), torch.zeros(R, 32, 2, device=DEV)
+    L.call("es_gn_lrelu_apply_fwd", y, ps, gamma, beta, N, Ho, Wo, Wo, N, 32, grp, E, R, a1, st1)
+    check("fused statistics vs two-pass", st1[live], st0[live], 1e-4, 1e-4)
+    check("fused activations vs two-pass", a1.float(), a0.float(), 2e-3, 2e-2)
+    # rows of a skipped expert are stored as zeros by both kernels: the strip kernels of the next conv's weight gradient read
+    # activation strips past a group's end against zero-filled dy columns, and 0 x NaN would poison the sum
+    assert float(a0[~live].float().abs().max()) == 0.0 and float(a1[~live].float().abs().max()) == 0.0
+    if layer == "conv1_folded_upx":       # the layout proton conv2 reads: nearest-upsampled along x, 19 -> 30 columns
+        wu = 30
+        au, st2 = torch.full((R, Ho * wu, N), float("nan"), dtype=BF, device=DEV), torch.zeros(R, 32, 2, device=DEV)
+        L.call("es_gn_lrelu_apply_fwd", y, ps, gamma, beta, N, Ho, Wo, wu, N, 32, grp, E, R, au, st2)
+        src = torch.clamp((torch.arange(wu) * (Wo / wu)).floor().long(), max=Wo - 1).to(DEV)
+        assert torch.equal(au.view(R, Ho, wu, N), a1.view(R, Ho, Wo, N)[:, :, src, :])
+
+
 # ----------------------------------------------------------------------------------------------------------- preprocessing
 def test_preprocess_kernels_match_golden_and_oracle():
     """arg-max coordinates (bit-exact) and per-condition-group pixel std (1e-5) through the host layer."""
