@@ -24,7 +24,8 @@ constexpr int kDStages = 4;
 constexpr int kDStageA = 128 * 128;              // 16 KB: 128 f x 64 rows (MODE 0) or 128 rows x 64 f (MODE 1)
 constexpr int kDStageB = 256 * 128;              // 32 KB: 256 k x 64 reduction rows
 constexpr int kDStage = kDStageA + kDStageB;
-constexpr size_t kDSmem = (size_t)kDStages * kDStage + 1024 + 2048;
+constexpr int kDStagingPitch = 36;                // floats per staged row: 32 + 4 (16-byte accesses of a quarter-warp stay conflict-free)
+constexpr size_t kDSmem = (size_t)kDStages * kDStage + 1024 + 2048 + 4 * 32 * kDStagingPitch * 4;
 
 struct DenseParams {
   const es_group* grp;
@@ -184,22 +185,48 @@ dense_tma_kernel(const __grid_constant__ DenseParams p, const __grid_constant__ 
       if (MODE == 0) {
         const int orow = p.row_map ? p.row_map[m] : m;
         float* o = p.out + (long)t.slot * p.out_slot_stride + (long)orow * p.K;
+        // A lane owns a whole output row (TMEM lane = feature), so storing straight from registers makes every STG touch 32
+        // different 1 KB rows (ncu: lg_throttle 14 stall cycles per issue).  The 32 x 32 chunk is transposed through a
+        // per-warp shared-memory tile instead: 8 lanes then write one row's 128 contiguous bytes, 4 rows per instruction.
+        float* stg = reinterpret_cast<float*>(gen + 2048) + q * (32 * kDStagingPitch);
+        const unsigned long long oaddr = reinterpret_cast<unsigned long long>(o);
         for (int c = c_lo; c < c_hi; c += 32) {
           tmem_ld32(t_lane + c, r);
-          float4* o4 = reinterpret_cast<float4*>(o + c);
+          float4* w4 = reinterpret_cast<float4*>(stg + lane * kDStagingPitch);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            o4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            w4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3), piece = lane & 7;
+            const unsigned long long ra = __shfl_sync(0xffffffffu, oaddr, row);
+            const float4 v = *reinterpret_cast<const float4*>(stg + row * kDStagingPitch + piece * 4);
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ra) + c + piece * 4) = v;
+          }
+          __syncwarp();
         }
       } else {
+        // split-K partial sums: transposed through the same per-warp tile, then one 16-byte vector RED per 4 columns — 8 lanes
+        // cover a row's 128 contiguous bytes (32 scalar REDs per lane, each to its own 1 KB row, before)
         const bool ok = m < t.rows;
-        float* o = p.out + (long)(t.row_start + (ok ? m : 0)) * p.K;
+        float* stg = reinterpret_cast<float*>(gen + 2048) + q * (32 * kDStagingPitch);
+        const unsigned long long oaddr = ok ? reinterpret_cast<unsigned long long>(p.out + (long)(t.row_start + m) * p.K) : 0ull;
         for (int c = c_lo; c < c_hi; c += 32) {
           tmem_ld32(t_lane + c, r);
-          if (ok) {
+          float4* w4 = reinterpret_cast<float4*>(stg + lane * kDStagingPitch);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(o + c + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 8; ++j)
+            w4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3), piece = lane & 7;
+            const unsigned long long ra = __shfl_sync(0xffffffffu, oaddr, row);
+            const float4 v = *reinterpret_cast<const float4*>(stg + row * kDStagingPitch + piece * 4);
+            if (ra) atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(ra) + c + piece * 4), v);
           }
+          __syncwarp();
         }
       }
       tc_fence_before();

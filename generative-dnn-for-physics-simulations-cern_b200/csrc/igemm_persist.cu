@@ -36,7 +36,7 @@ constexpr int kFStageA = kBM * 128;            // 16 KB
 constexpr int kFStageB = 256 * 128;            // 32 KB (BN <= 256)
 constexpr int kFStage = kFStageA + kFStageB;
 constexpr int kFMaxGroups = 64;
-constexpr size_t kFSmem = (size_t)kFStages * kFStage + 1024 /*align*/ + 2048 /*barriers + tables*/;
+constexpr size_t kFSmem = (size_t)kFStages * kFStage + 1024 /*align*/ + 2048 /*barriers + tables*/ + 4096 /*bias rows of the epilogue warps*/ + 4 * 32 * 80 /*their store-transposition tiles*/;
 
 // The reduction is a TAP TABLE: tap t reads the (virtually upsampled) source at (oy*my + tdy[t], ox*mx + tdx[t]) and its C
 // weights start at column tkoff[t] of the packed weight row.  A plain conv is tdy = ky - pad, tdx = kx - pad, tkoff = t*C,
@@ -308,9 +308,18 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
       decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
       const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
       const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+      // The tile's bias row is fetched into a per-warp shared-memory row BEFORE waiting for the accumulator: with one N tile
+      // per bias segment (fc2: 360 tiles of 256 features per expert) every tile meets cold bias addresses, and 8 x 32 dependent
+      // L2 round trips inside the epilogue made it the longest stage of the pipeline (ncu: 17k cycles per tile, tensor 14 %).
+      const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
+      float* s_bias = reinterpret_cast<float*>(gen + 2048) + q * 256;
+      uint8_t* s_stage = gen + 2048 + 4096 + q * (32 * 80);
+      if (bias) {
+        for (int i = lane; i < BN; i += 32) s_bias[i] = __ldg(bias + i);
+        __syncwarp();
+      }
       mbar_wait(tfull_bar(buf), use & 1, p.err_flag, 3);
       tc_fence_after();
-      const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
       uint32_t r[32];
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
@@ -321,18 +330,30 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CU
         const int oa = pix / p.Wo, ob = pix - oa * p.Wo;
         const long opix = (long)(ti.row_start + smp) * p.P_full + (oa * p.o_my + p.o_oy) * p.Wo_full + ob * p.o_mx + p.o_ox;
         __nv_bfloat16* yrow = p.out + (opix * p.Nout + ti.n0);
+        const unsigned long long yaddr = ok ? reinterpret_cast<unsigned long long>(yrow) : 0ull;
         for (int c = 0; c < BN; c += 32) {
           tmem_ld32(t_lane + c, r);
-          if (ok) {
-            float f[32];
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
-            uint4* dst = reinterpret_cast<uint4*>(yrow + c);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? s_bias[c + j] : 0.f);
+          // A lane owns one output row, so storing from registers makes every STG touch 32 rows (16 bytes each).  The
+          // 32 x 64-byte chunk goes through a per-warp shared-memory tile (80-byte pitch) instead: 4 lanes then write one
+          // row's 64 contiguous bytes, 8 rows per instruction.
+          uint4* w4 = reinterpret_cast<uint4*>(s_stage + lane * 80);
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) dst[qq] = pack8(f + 8 * qq);
+          for (int qq = 0; qq < 4; ++qq) w4[qq] = pack8(f + 8 * qq);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane >> 2), piece = lane & 3;
+            const unsigned long long ra = __shfl_sync(0xffffffffu, yaddr, row);
+            const uint4 v = *reinterpret_cast<const uint4*>(s_stage + row * 80 + piece * 16);
+            if (ra) *reinterpret_cast<uint4*>(ra + (unsigned long long)(c * 2 + piece * 16)) = v;
           }
+          __syncwarp();
         }
       }
+      __syncwarp();                      // every lane is done with s_bias before the next tile overwrites it
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
     }
