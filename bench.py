@@ -193,7 +193,8 @@ def workload_cfg(args, note=None):
 
 
 # ------------------------------------------------------------------------------------------------ B200 leg
-GEMM_CALLS = {"es_igemm_fwd", "es_igemm_wgrad", "es_igemm_taps_fwd", "es_igemm_taps_wgrad", "es_dense_dgrad", "es_dense_wgrad"}
+GEMM_CALLS = {"es_igemm_fwd", "es_igemm_wgrad", "es_igemm_taps_fwd", "es_igemm_taps_wgrad", "es_dense_dgrad", "es_dense_wgrad",
+              "es_igemm_fwd_sums", "es_igemm_taps_fwd_sums"}      # *_sums: the same GEMMs with the GroupNorm sums in the epilogue
 
 
 def igemm_flops(name, a):
@@ -201,6 +202,7 @@ def igemm_flops(name, a):
     direct convolution; EXECUTED = the MACs the tensor cores really perform: n_taps*C per output of a
     folded class instead of KH*KW*C (equal for plain convolutions and the dense layers)."""
     ints = [x for x in a if isinstance(x, int)]
+    name = name.replace("_sums", "")
     if name in ("es_igemm_taps_fwd", "es_igemm_taps_wgrad"):
         g = next(x for x in a if hasattr(x, "n_taps"))
         rows = ints[-1]
@@ -378,7 +380,7 @@ def run_b200(args):
             print(f"  {name:16s} {geo:34s} {t:8.3f} ms {fa / t / 1e9:8.1f} TFLOP/s algorithmic {fe / t / 1e9:8.1f} executed", file=sys.stderr)
     fam = {}
     for name, a, s_, e_ in plog:
-        f = fam.setdefault(name, [0.0, 0.0, 0.0, 0])
+        f = fam.setdefault(name.replace("_sums", ""), [0.0, 0.0, 0.0, 0])
         fa, fe = igemm_flops(name, a)
         f[0] += fa
         f[1] += fe
@@ -389,8 +391,8 @@ def run_b200(args):
     tr = ncu_traffic() or {}
     tfl = lambda f, t: round(f / (t * 1e-3) / 1e12, 2) if t else None
     roof = {"bound": "tensor",
-            "kernel": "igemm_persist (grouped bf16 tcgen05 implicit GEMM family: igemm_fwd_kernel + igemm_strip_kernel + igemm_wgrad_kernel, "
-                      "incl. the upsample-folded tap-table launches)",
+            "kernel": "igemm_persist (grouped bf16 tcgen05 implicit GEMM family: igemm_tma_pair_kernel / igemm_tma_strip_kernel / "
+                      "igemm_fwd_kernel (fc2) + igemm_wgrad_tma_kernel / igemm_wgrad_strip_kernel, incl. the upsample-folded tap-table launches)",
             "achieved": tfl(tc_alg, tc_ms), "peak": pk["tflops"], "unit": "TFLOP/s",
             "frac": round(tc_alg / (tc_ms * 1e-3) / 1e12 / pk["tflops"], 4) if tc_ms else None,
             "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"),

@@ -823,6 +823,7 @@ igemm_tma_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant
 // TMA wrote.  Measured on sm_100a: the descriptor's base-offset field must stay 0 for such starts — setting it to the row
 // phase j gives wrong products).  Fill per MAC drops by nx on the A side; the masked columns cost Wp / Wo - 1 of the MMA
 // work.  mt = 2 M sub-tiles per pair share every weight box (N <= 128: halves the weight fill as well).
+constexpr int kTSThreads = 320;                  // producer warp, MMA warp, 2 x 4 epilogue warps
 struct TStripParams {
   int n_strips, nx, Wp, Pp;                      // Pp = Ho * Wp
   int mt;                                        // 256-row M sub-tiles per pair tile (1 or 2): sub-tiles share every weight box
@@ -832,7 +833,7 @@ struct TStripParams {
   int skoff[16];                                 // weight column of the strip's first tap; tap j at skoff + j*C
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTSThreads, 1)
 igemm_tma_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ TStripParams ts,
                        const __grid_constant__ CUtensorMap tmap_wh, const __grid_constant__ CUtensorMap tmap_x) {
   extern __shared__ uint8_t smem_raw[];
@@ -871,7 +872,7 @@ igemm_tma_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 8);
+      mbar_init(tempty_bar(b), 8 * mt);       // one arrival per active epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -958,9 +959,12 @@ igemm_tma_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constan
       tc_fence_before();
     }
   } else {
-    // =========================================================================== EPILOGUE (warps 2-5: TMEM lane quarter = warp % 4)
-    const int q = warp & 3;
+    // =========================================================================== EPILOGUE (warps 2-9: TMEM lane quarter = warp % 4;
+    // warps 2-5 drain M sub-tile 0, warps 6-9 sub-tile 1 — with the GroupNorm sums in it the epilogue of a 512-row tile is as
+    // long as its MMAs, two warp groups keep it off the critical path)
+    const int q = warp & 3, u = (warp - 2) >> 2;
     uint32_t tcount = 0;
+    if (u < mt)
     for (int tile = pair; tile < total_tiles; tile += n_pairs, ++tcount) {
       TileInfo ti;
       decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
@@ -970,7 +974,7 @@ igemm_tma_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constan
       tc_fence_after();
       const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
       uint32_t r[32];
-      for (int u = 0; u < mt; ++u) {
+      {
       const uint32_t t_lane = tmem_base + buf * acc_cols + (uint32_t)(u * BN) + ((uint32_t)(q * 32) << 16);
       const int m = ti.m0 + u * 2 * kBM + (int)rank * kBM + q * 32 + lane;
       bool ok = m < ti.rows * ts.Pp;
@@ -2259,7 +2263,7 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
       ES_CUDA(cudaFuncSetAttribute(igemm_tma_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_set = true;
     }
-    igemm_tma_strip_kernel<<<2 * pairs, 192, smem, as_stream(stream)>>>(p, ts, tmap_h, tmap_x);
+    igemm_tma_strip_kernel<<<2 * pairs, kTSThreads, smem, as_stream(stream)>>>(p, ts, tmap_h, tmap_x);
     ES_LAUNCH_CHECK();
     if (fused) *fused = p.pair_sums != nullptr;
     if (trace) fprintf(stderr, "[igemm] tma_strip C=%d N=%d taps=%d mt=%d nx=%d strips=%d stages=%d Ho=%d Wo=%d my=%d rows=%d\n", p.C, p.Nout,

@@ -77,6 +77,36 @@ def measure(dev="cuda", R=65536, E=8, peak=None):
         "es_adam_step (adam_vec4)": (lambda: L.call("es_adam_step", aP, aG, aM, aV, n_ad, n_ad, E, 1e-4, 0.9, 0.999, 1e-8, a_steps, None),
                                      28, E * n_ad),
     }
+    # generator norm layers at the train step's size (2048 generator rows, proton conv2 output 55 x 29 x 128, 836 MB per
+    # tensor): forward = 1 read + 1 write with the statistics from the conv epilogue; backward = 2 reads + 1 write algorithmic
+    # (the two-pass kernel really reads x and dy twice)
+    BF = torch.bfloat16
+    Rg, P, C = 2048, 55 * 29, 128
+    pg = Rg // E
+    ggrp = torch.tensor([[i * pg, pg, i, pg // 2] for i in range(E)], dtype=torch.int32, device=dev)
+    gx = rnd(Rg, P, C).to(BF)
+    gy, gdy, gdx = torch.empty_like(gx), rnd(Rg, P, C).to(BF), torch.empty_like(gx)
+    gps = torch.rand(Rg, C // 2, 2, device=dev) * 100
+    gps[..., 1] += 1e5
+    gst = torch.empty(Rg, 32, 2, device=dev)
+    gam, bet = torch.ones(E, C, device=dev), torch.zeros(E, C, device=dev)
+    dgm, dbt, dbi = torch.zeros(E, C, device=dev), torch.zeros(E, C, device=dev), torch.zeros(E, C, device=dev)
+    L.call("es_gn_lrelu_fwd", gx, gam, bet, C, P, C, 32, ggrp, E, Rg, gy, gst)
+    cases["es_gn_lrelu_apply_fwd (conv2 output)"] = (
+        lambda: L.call("es_gn_lrelu_apply_fwd", gx, gps, gam, bet, C, 55, 29, 29, C, 32, ggrp, E, Rg, gy, gst), P * C * 2 * 2, Rg)
+    cases["es_gn_lrelu_bwd (conv2 output)"] = (
+        lambda: L.call("es_gn_lrelu_bwd", gdy, 55, 29, 55, 29, gx, gst, gam, bet, C, C, 32, ggrp, E, Rg, gdx, dgm, dbt, dbi), P * C * 2 * 3, Rg)
+    # fc2 backward (TMA-fed dense kernels): the weight gradient reads dy2 (bf16) once and writes E x 92160 x 256 fp32; the data
+    # gradient reads dy2 and the bf16 weights once
+    F2, K2 = 92160, 256
+    dy2, h1 = rnd(Rg, F2).to(BF), rnd(Rg, K2).to(BF)
+    w2 = (rnd(E, F2, K2) * 0.05).to(BF)
+    dw2 = torch.empty(E, F2, K2, device=dev)
+    dh1 = torch.zeros(Rg, K2, device=dev)
+    xpad = torch.empty(E * ((Rg + 63) // 64) * 64, K2, dtype=BF, device=dev)
+    cases["es_dense_wgrad (fc2)"] = (lambda: L.call("es_dense_wgrad", dy2, h1, dw2, F2 * K2, F2, K2, None, ggrp, E, Rg, xpad),
+                                     Rg * F2 * 2 + E * F2 * K2 * 4, 1)
+    cases["es_dense_dgrad (fc2)"] = (lambda: L.call("es_dense_dgrad", dy2, w2, dh1, F2, K2, ggrp, E, Rg), Rg * F2 * 2 + E * F2 * K2 * 2, 1)
     out = {}
     for name, (fn, bytes_per_unit, units) in cases.items():
         t = timeit(fn)

@@ -31,7 +31,7 @@ ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control no
 ;;
 c)
 python bench.py --steps 2 --warmup 3 $B > $O/plain.log 2>&1 &&
-ncu --set full --clock-control none --profile-from-start off -k regex:igemm -c 48 -f -o /tmp/final_prof_igemm \
+ncu --set full --clock-control none --profile-from-start off -k regex:igemm -c 72 -f -o /tmp/final_prof_igemm \
     python bench.py --steps 2 --warmup 3 $B --ncu-step 1 > $O/ncu2.log 2>&1; echo "ncu igemm rc=$?"
 python tools/ncu_summary.py /tmp/final_prof_igemm.ncu-rep $O/final_ncu_igemm_summary.csv; mv $O/roofline_traffic.json $O/final_roofline_traffic.json 2>/dev/null
 ls -la /tmp/final_prof_*.ncu-rep
