@@ -657,7 +657,8 @@ igemm_tma_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant
   constexpr int kStage = kFStageA + kStageB;     // 32 KB
   constexpr int kTileM = 2 * kBM;
   extern __shared__ uint8_t smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (shuffle: the warp index becomes warp-uniform for the compiler, so the MMA issuer's descriptors live in uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -747,20 +748,18 @@ igemm_tma_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant
         const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
         if (use >= 1) mbar_wait(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
+        const uint32_t tacc = __shfl_sync(0xffffffffu, tmem_base, 0) + buf * (uint32_t)BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = base + s * kStage;
-            const uint32_t sb = sa + kFStageA;
+          const uint32_t sa = base + s * kStage;          // descriptors from warp-uniform values, outside the lane-0 branch
+          const uint64_t a0 = make_desc(sa, 16, 1024), b0 = make_desc(sa + kFStageA, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              umma_bf16_pair(tacc, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
-            umma_commit_pair(empty_bar(s), 3);
-            if (kb == nkb - 1) umma_commit_pair(tfull_bar(buf), 3);
-          }
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16_pair_elect(tacc, a0 + 2 * k, b0 + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit_pair_elect(empty_bar(s), 3);
+          if (kb == nkb - 1) umma_commit_pair_elect(tfull_bar(buf), 3);
           __syncwarp();
         }
       }
@@ -837,7 +836,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTSThreads, 1)
 igemm_tma_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ TStripParams ts,
                        const __grid_constant__ CUtensorMap tmap_wh, const __grid_constant__ CUtensorMap tmap_x) {
   extern __shared__ uint8_t smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the shuffle makes the warp index warp-UNIFORM for the compiler: role branches become uniform branches and the MMA issuer's
+  // descriptors stay in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int mt = ts.mt, kTileM = 2 * kBM * mt;
   const uint32_t raw = smem_u32(smem_raw);
@@ -934,25 +935,27 @@ igemm_tma_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constan
         const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
         if (use >= 1) mbar_wait(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * acc_cols;
+        const uint32_t tacc = __shfl_sync(0xffffffffu, tmem_base, 0) + buf * acc_cols;     // warp-uniform for the compiler
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = base + s * kStage;
-            const uint32_t sb = sa + mt * ts.a_bytes;
-            for (int j = 0; j < nx; ++j) {
-              for (int u = 0; u < mt; ++u) {
+          // Descriptors are built by the WHOLE warp from warp-uniform values (so they live in uniform registers) and only the
+          // instruction itself is predicated on lane 0: built inside a lane-0 branch, every tcgen05.mma dragged a 16-instruction
+          // R2UR / ELECT sequence along — ~120 cycles per issue, more than a 256 x N x 16 MMA takes at N <= 128.
+          const uint32_t sa = base + s * kStage;
+          const uint64_t a0 = make_desc(sa, 16, 1024), b0 = make_desc(sa + mt * ts.a_bytes, 16, 1024);
+          for (int j = 0; j < nx; ++j) {
+            const uint64_t bj = b0 + (uint64_t)((j * BH * 128) >> 4);
+            for (int u = 0; u < mt; ++u) {
+              const uint64_t aj = a0 + (uint64_t)((u * ts.a_bytes + j * 128) >> 4);
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k)
-                  umma_bf16_pair(tacc + u * BN, make_desc(sa + u * ts.a_bytes + j * 128 + k * 32, 16, 1024),
-                                 make_desc(sb + j * BH * 128 + k * 32, 16, 1024), idesc, (kb | j | k) ? 1u : 0u);
-              }
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_bf16_pair_elect(tacc + u * BN, aj + 2 * k, bj + 2 * k, idesc, (kb | j | k) ? 1u : 0u);
             }
-            umma_commit_pair(empty_bar(s), 3);
-            if (kb == nkb - 1) umma_commit_pair(tfull_bar(buf), 3);
           }
+          umma_commit_pair_elect(empty_bar(s), 3);
+          if (kb == nkb - 1) umma_commit_pair_elect(tfull_bar(buf), 3);
           __syncwarp();
         }
       }
@@ -1552,7 +1555,8 @@ igemm_wgrad_tma_kernel(const __grid_constant__ WgParams p, const __grid_constant
                        const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x) {
   constexpr int kStage = kFStageA + 128 * 128;   // A 16 KB + dy (half) <= 16 KB
   extern __shared__ uint8_t smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (shuffle: the warp index becomes warp-uniform for the compiler, so the MMA issuer's descriptors live in uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1651,27 +1655,25 @@ igemm_wgrad_tma_kernel(const __grid_constant__ WgParams p, const __grid_constant
         const uint32_t buf = tcount & 1;
         if (tcount >= 2) mbar_wait(tempty_bar(buf), ((tcount >> 1) - 1) & 1, p.err_flag, 5);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * (uint32_t)BN;
-        for (int kb = ti.kb0; kb < ti.kb1; ++kb, ++it) {
+        const uint32_t tacc = __shfl_sync(0xffffffffu, tmem_base, 0) + buf * (uint32_t)BN;
+        const int kb0 = __shfl_sync(0xffffffffu, ti.kb0, 0), kb1 = __shfl_sync(0xffffffffu, ti.kb1, 0);   // uniform loop bounds
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = base + s * kStage;
-            const uint32_t sb = sa + kFStageA;
+          const uint32_t sa = base + s * kStage;          // descriptors from warp-uniform values, outside the lane-0 branch
+          const uint64_t a0 = make_desc(sa, 8192, 1024), b0 = make_desc(sa + kFStageA, 8192, 1024);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t ad = make_desc(sa + k * 2048, 8192, 1024), bd = make_desc(sb + k * 2048, 8192, 1024);
-              const uint32_t acc = (kb > ti.kb0 || k) ? 1u : 0u;
-              if (kPair) umma_bf16_pair(tacc, ad, bd, idesc, acc); else umma_bf16(tacc, ad, bd, idesc, acc);
-            }
-            if (kPair) {
-              umma_commit_pair(empty_bar(s), 3);
-              if (kb == ti.kb1 - 1) umma_commit_pair(tfull_bar(buf), 3);
-            } else {
-              umma_commit(empty_bar(s));
-              if (kb == ti.kb1 - 1) umma_commit(tfull_bar(buf));
-            }
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint32_t acc = (kb > kb0 || k) ? 1u : 0u;
+            if (kPair) umma_bf16_pair_elect(tacc, a0 + 128 * k, b0 + 128 * k, idesc, acc); else umma_bf16_elect(tacc, a0 + 128 * k, b0 + 128 * k, idesc, acc);
+          }
+          if (kPair) {
+            umma_commit_pair_elect(empty_bar(s), 3);
+            if (kb == kb1 - 1) umma_commit_pair_elect(tfull_bar(buf), 3);
+          } else {
+            umma_commit_elect(empty_bar(s));
+            if (kb == kb1 - 1) umma_commit_elect(tfull_bar(buf));
           }
           __syncwarp();
         }
@@ -1737,7 +1739,8 @@ __global__ void __launch_bounds__(192, 1)
 igemm_wgrad_strip_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgStripParams ws,
                          const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x) {
   extern __shared__ uint8_t smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // (shuffle: the warp index becomes warp-uniform for the compiler, so the MMA issuer's descriptors live in uniform registers)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1849,30 +1852,29 @@ igemm_wgrad_strip_kernel(const __grid_constant__ WgParams p, const __grid_consta
         const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
         if (use >= 1) mbar_wait(tempty_bar(buf), (use - 1) & 1, p.err_flag, 5);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * acc_cols;
-        for (int kb = u.kb0; kb < u.kb1; ++kb, ++it) {
+        const uint32_t tacc = __shfl_sync(0xffffffffu, tmem_base, 0) + buf * acc_cols;
+        const int kb0 = __shfl_sync(0xffffffffu, u.kb0, 0), kb1 = __shfl_sync(0xffffffffu, u.kb1, 0);   // uniform loop bounds
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(full_bar(s), (it / kStages) & 1, p.err_flag, 2);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = base + s * kStage;
-            const uint32_t sb = sa + 2u * ws.seg_bytes;
-            const uint32_t acc0 = kb > u.kb0 ? 1u : 0u;
-            for (int j = 0; j < nx; ++j) {
+          const uint32_t sa = base + s * kStage;          // descriptors from warp-uniform values, outside the lane-0 branch
+          const uint64_t a0 = make_desc(sa, (uint32_t)ws.seg_bytes, 1024), b0 = make_desc(sa + 2u * ws.seg_bytes, 8192, 1024);
+          const uint32_t acc0 = kb > kb0 ? 1u : 0u;
+          for (int j = 0; j < nx; ++j) {
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                const uint64_t ad = make_desc(sa + j * 128 + k * 2048, (uint32_t)ws.seg_bytes, 1024), bd = make_desc(sb + k * 2048, 8192, 1024);
-                if (kPair) umma_bf16_pair(tacc + j * BN, ad, bd, idesc, acc0 | (k ? 1u : 0u));
-                else umma_bf16(tacc + j * BN, ad, bd, idesc, acc0 | (k ? 1u : 0u));
-              }
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t ad = a0 + (uint64_t)(8 * j + 128 * k), bd = b0 + 128 * k;
+              if (kPair) umma_bf16_pair_elect(tacc + j * BN, ad, bd, idesc, acc0 | (k ? 1u : 0u));
+              else umma_bf16_elect(tacc + j * BN, ad, bd, idesc, acc0 | (k ? 1u : 0u));
             }
-            if (kPair) {
-              umma_commit_pair(empty_bar(s), 3);
-              if (kb == u.kb1 - 1) umma_commit_pair(tfull_bar(buf), 3);
-            } else {
-              umma_commit(empty_bar(s));
-              if (kb == u.kb1 - 1) umma_commit(tfull_bar(buf));
-            }
+          }
+          if (kPair) {
+            umma_commit_pair_elect(empty_bar(s), 3);
+            if (kb == kb1 - 1) umma_commit_pair_elect(tfull_bar(buf), 3);
+          } else {
+            umma_commit_elect(empty_bar(s));
+            if (kb == kb1 - 1) umma_commit_elect(tfull_bar(buf));
           }
           __syncwarp();
         }

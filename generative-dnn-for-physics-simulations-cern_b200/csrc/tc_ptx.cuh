@@ -188,6 +188,35 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(mask) : "memory");
 }
+// Warp-collective forms: the whole (converged) warp executes the statement, one elected lane issues the MMA.  With the
+// operands computed by all lanes from warp-uniform values the compiler keeps them in uniform registers; a lane-0 branch around
+// the issue makes it sink the descriptor arithmetic into the branch and pay R2UR + vote sequences per instruction.
+__device__ __forceinline__ void umma_bf16_pair_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commits issued by the SAME elected lane as the umma_*_elect MMAs (tcgen05.commit tracks the executing thread's prior MMAs;
+// elect.sync picks the same leader for the same member mask every time)
+__device__ __forceinline__ void umma_commit_pair_elect(uint32_t bar, uint16_t mask) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+               ::"r"(bar) : "memory");
+}
 // TMA box into THIS CTA's shared memory, completion bytes signalled on a barrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar_cluster_addr) {
   asm volatile(
