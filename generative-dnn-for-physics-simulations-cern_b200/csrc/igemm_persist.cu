@@ -2443,7 +2443,8 @@ extern "C" int es_igemm_taps_fwd_sums(const void* x, const void* w, const float*
 static bool wgrad_strip_plan(const WgParams& p, long total_rows, bool as_pair, WgStripParams& ws, int low[2], int up[2]) {
   static const int on = [] { const char* e = getenv("ES_WG_STRIP"); return e ? atoi(e) : 1; }();
   ws = WgStripParams{};
-  if (!on || p.N > 128 || p.mx != 1 || p.my < 1 || p.my > 8 || p.Hu != p.Hs || p.Wu != p.Ws || p.n_taps < 2) return false;
+  static const int n_max = [] { const char* e = getenv("ES_WG_STRIP_N"); return e ? atoi(e) : 128; }();
+  if (!on || p.N > n_max || p.mx != 1 || p.my < 1 || p.my > 8 || p.Hu != p.Hs || p.Wu != p.Ws || p.n_taps < 2) return false;
   if (p.C % (as_pair ? 2 * kBM : kBM) != 0) return false;
   int L = 0, n_rows = 0, row_t[32];
   for (int t = 0; t < p.n_taps;) {

@@ -11,9 +11,18 @@ The reducer owns a process group of its own: ProcessGroupNCCL serialises the col
 internal stream, so a 94 MB gradient bucket queued on the default group would sit in front of the small latency-critical
 all-reduces the step issues on the compute path (per-expert loss sums, SyncBN statistics).
 
+OPTIONAL (``ES_DP_COMPRESS=1``): buckets at least ``compress_min_cols`` wide (8 Mi columns per expert row: only fc2's 23.6
+M-parameter weight gradient — 755 of the 868 MB a proton step all-reduces, produced LAST by backward and therefore the part
+that stays exposed) travel as bf16: the column range is cast to one contiguous bf16 buffer, summed, and cast back in place,
+all on the communication stream; every rank still receives the same bits.  Measured at N = 2 on B200: 32.35 ms/step against
+32.17 with fp32 messages — over NVLink 5 the two cast passes (1.1 GB of HBM traffic each) cost what the halved message
+saves, so fp32 stays the default.
+
 On CPU tensors (gloo; the host-logic tests) the same calls run synchronously.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -27,6 +36,9 @@ class BucketedGradReducer:
         self.n_reduced = 0                                # floats handed to all_reduce since the last join()
         self.buckets = []                                 # (lo, hi) of the last step, for tests / logging
         self.disabled = False                             # measurement aid (bench.py's comm.exposed_ms): account, do not send
+        # buckets at least this wide (columns per expert row) are all-reduced as bf16; None = never
+        self.compress_min_cols = (8 << 20) if os.environ.get("ES_DP_COMPRESS", "0") == "1" else None
+        self.bytes_sent = 0                               # payload bytes handed to all_reduce since begin()
 
     def _stream(self, device):
         if self._comm is None or self._comm.device != device:
@@ -34,7 +46,7 @@ class BucketedGradReducer:
         return self._comm
 
     def begin(self):
-        self.n_reduced, self.buckets = 0, []
+        self.n_reduced, self.buckets, self.bytes_sent = 0, [], 0
 
     def reduce(self, G: torch.Tensor, lo: int, hi: int):
         """SUM-all-reduce ``G[:, lo:hi]`` (one contiguous message per expert row)."""
@@ -55,6 +67,13 @@ class BucketedGradReducer:
 
     def _all_reduce_rows(self, G, lo, hi):
         """one message per expert row, all rows of the bucket in ONE grouped NCCL launch (ncclGroupStart/End)"""
+        if self.compress_min_cols is not None and hi - lo >= self.compress_min_cols:
+            buf = G[:, lo:hi].to(torch.bfloat16)          # contiguous [E, hi - lo] copy: one message
+            self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.group)
+            G[:, lo:hi].copy_(buf)
+            self.bytes_sent += buf.numel() * 2
+            return
+        self.bytes_sent += (hi - lo) * G.shape[0] * G.element_size()
         if lo == 0 and hi == G.shape[1]:
             self.dist.all_reduce(G, op=self.dist.ReduceOp.SUM, group=self.group)
             return

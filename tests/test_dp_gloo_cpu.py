@@ -133,6 +133,35 @@ def _bucket_case(rank, world):
     return bool(torch.equal(G, whole)), covered, bool(torch.equal(G2, whole2))
 
 
+def _compressed_bucket_case(rank, world):
+    """A bucket at least ``compress_min_cols`` wide travels as bf16: result = the bf16 sum of the bf16-rounded rows, identical
+    on every rank; narrower buckets stay fp32 and exact."""
+    from expertsim._reduce import BucketedGradReducer
+    red = BucketedGradReducer(dist)
+    red.compress_min_cols = 64
+    g = torch.Generator().manual_seed(11 + rank)
+    G = torch.randn(2, 100, generator=g)
+    mine = G.clone()
+    parts = [torch.zeros_like(G) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    red.begin()
+    red.reduce(G, 30, 100)       # 70 columns: compressed
+    red.reduce(G, 0, 30)         # 30 columns: fp32
+    red.join()
+    want_c = sum(p[:, 30:].to(torch.bfloat16).float() for p in parts).to(torch.bfloat16).float()
+    want_f = sum(p[:, :30] for p in parts)
+    allg = [torch.zeros_like(G) for _ in range(world)]
+    dist.all_gather(allg, G)
+    same = all(torch.equal(allg[0], a) for a in allg)
+    return (bool(torch.allclose(G[:, 30:], want_c, rtol=2 ** -7, atol=1e-6)), bool(torch.equal(G[:, :30], want_f)), same,
+            red.bytes_sent == 2 * 70 * 2 + 2 * 30 * 4)
+
+
+def test_large_gradient_buckets_travel_as_bf16():
+    out = run2(_compressed_bucket_case)
+    assert out[0] == (True, True, True, True) and out[1] == (True, True, True, True)
+
+
 def test_bucketed_gradient_reducer_equals_whole_arena_allreduce():
     out = run2(_bucket_case)
     assert out[0] == (True, True, True) and out[1] == (True, True, True)
