@@ -57,6 +57,7 @@ struct FwdParams {
   long bias_slot_stride;
   __nv_bfloat16* out;
   float* pair_sums;            // optional [total rows][Nout/2][2]: per-sample channel-pair (sum, sum of squares) of the stored outputs
+  int epi_staged;              // pair kernel: bias row prefetched to shared memory + stores transposed through it (the dense product)
   int* err_flag;
 };
 
@@ -774,9 +775,18 @@ igemm_tma_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant
       decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
       const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0u;
       const uint32_t use = nbuf == 2 ? (tcount >> 1) : tcount;
+      const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
+      // dense product (fc2: one N tile per bias segment, 184 KB between output rows): the bias row is fetched into a per-warp
+      // shared-memory row BEFORE the accumulator wait and the stores are transposed through shared memory (as igemm_fwd_kernel)
+      float* s_bias = reinterpret_cast<float*>(gen + 2048) + q * 256;
+      uint8_t* s_stage = gen + 2048 + 4096 + q * (32 * 80);
+      const bool staged = p.epi_staged != 0;
+      if (staged && bias) {
+        for (int i = lane; i < BN; i += 32) s_bias[i] = __ldg(bias + i);
+        __syncwarp();
+      }
       mbar_wait(tfull_bar(buf), use & 1, p.err_flag, 3);
       tc_fence_after();
-      const float* bias = p.bias ? p.bias + (long)ti.slot * p.bias_slot_stride + ti.n0 : nullptr;
       uint32_t r[32];
       const uint32_t t_lane = tmem_base + buf * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
       const int m = ti.m0 + (int)rank * kBM + q * 32 + lane;
@@ -785,9 +795,27 @@ igemm_tma_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant
       const int oa = pix / p.Wo, ob = pix - oa * p.Wo;
       const long opix = (long)(ti.row_start + smp) * p.P_full + (oa * p.o_my + p.o_oy) * p.Wo_full + ob * p.o_mx + p.o_ox;
       __nv_bfloat16* yrow = p.out + (opix * p.Nout + ti.n0);
+      const unsigned long long yaddr = ok ? reinterpret_cast<unsigned long long>(yrow) : 0ull;
       for (int c = 0; c < BN; c += 32) {
         tmem_ld32(t_lane + c, r);
         float f[32];
+        if (staged) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? s_bias[c + j] : 0.f);
+          uint4* w4 = reinterpret_cast<uint4*>(s_stage + lane * 80);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) w4[qq] = pack8(f + 8 * qq);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane >> 2), piece = lane & 3;
+            const unsigned long long ra = __shfl_sync(0xffffffffu, yaddr, row);
+            const uint4 v = *reinterpret_cast<const uint4*>(s_stage + row * 80 + piece * 16);
+            if (ra) *reinterpret_cast<uint4*>(ra + (unsigned long long)(c * 2 + piece * 16)) = v;
+          }
+          __syncwarp();
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]) + (bias ? __ldg(bias + c + j) : 0.f);
         if (ok) {
@@ -797,6 +825,7 @@ igemm_tma_pair_kernel(const __grid_constant__ FwdParams p, const __grid_constant
         }
         if (p.pair_sums) epilogue_pair_sums(f, ok, ti.row_start + smp, p.pair_sums, p.Nout >> 1, ti.n0 + c, lane);
       }
+      __syncwarp();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(buf), 0));
@@ -2015,7 +2044,11 @@ static void pick_bn(FwdParams& p) {
 // upper corner makes the number of base pixels per row / column exactly Wo / Ho: Q = (W + up - low - 1) / m + 1; both
 // corners are kept <= 0.  The dense product (one tap on a 1x1 grid) is excluded: measured slower (0.440 vs 0.389 ms).
 static bool tma_pair_plan(const FwdParams& p, int low[2], int up[2]) {
-  if (!(p.BN >= 64 && p.Hu == p.Hs && p.Wu == p.Ws) || (p.n_taps == 1 && p.Hs * p.Ws == 1)) return false;
+  // the dense 1x1 product (fc2) through this kernel: measured 0.287 vs 0.293 ms with the single-CTA kernel once both have the
+  // staged epilogue (bias row in shared memory, transposed stores) — neither the weight stream nor the gather is its bound;
+  // opt-in (ES_FC2_TMA_PAIR=1)
+  static const bool dense_ok = [] { const char* e = getenv("ES_FC2_TMA_PAIR"); return e && e[0] == '1'; }();
+  if (!(p.BN >= 64 && p.Hu == p.Hs && p.Wu == p.Ws) || (!dense_ok && p.n_taps == 1 && p.Hs * p.Ws == 1)) return false;
   if (p.mx < 1 || p.mx > 8 || p.my < 1 || p.my > 8) return false;
   int dmin_x = 127, dmin_y = 127, dmax_x = -128, dmax_y = -128;
   for (int t = 0; t < p.n_taps; ++t) {
@@ -2187,6 +2220,7 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
     EncodeIm2colFn enc_i = encode_im2col_fn();
     if (!enc_i) return ES_OK;
     ta.low_w = low[0]; ta.low_h = low[1];
+    p.epi_staged = (p.n_taps == 1 && p.Hs * p.Ws == 1 && !p.pair_sums) ? 1 : 0;      // the dense product (fc2)
     alignas(64) CUtensorMap tmap_h, tmap_x;
     {
       const cuuint64_t dims[2] = {(cuuint64_t)p.KK, (cuuint64_t)kFMaxGroups * (cuuint64_t)p.Nout};
@@ -2212,7 +2246,7 @@ static int launch_fwd(FwdParams& p, const void* x, const void* w, int total_rows
     const long max_tiles = (ceil_div_l((long)total_rows * p.P, 2L * kBM) + n_groups) * p.n_tiles_n;
     const int pairs = (int)(max_tiles < sms / 2 ? max_tiles : sms / 2);
     constexpr int kPStages = 6;
-    constexpr size_t kPSmem = (size_t)kPStages * (kFStageA + 128 * 128) + 1024 + 2048;
+    constexpr size_t kPSmem = (size_t)kPStages * (kFStageA + 128 * 128) + 1024 + 2048 + 4096 + 4 * 32 * 80;   // + staged epilogue
     static bool attr_set = false;
     if (!attr_set) {
       ES_CUDA(cudaFuncSetAttribute(igemm_tma_pair_kernel<kPStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem));

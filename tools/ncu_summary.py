@@ -34,7 +34,7 @@ def main():
     tens = [float(r[col["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]].replace(",", "")) for r in data]
     j = {"dram_bytes_per_launch": round(tot / len(data)), "launches": len(data),
          "tensor_pipe_active_pct_time_weighted": round(sum(d * t for d, t in zip(dur, tens)) / sum(dur), 2),
-         "source": f"{os.path.basename(out)} (ncu --set full, mean over {len(data)} captured launches of igemm_fwd_kernel / igemm_wgrad_kernel)"}
+         "source": f"{os.path.basename(out)} (ncu --set full --clock-control none of one train step: mean over the {len(data)} captured launches)"}
     json.dump(j, open(os.path.join(os.path.dirname(out), "roofline_traffic.json"), "w"), indent=1)
     print(j)
 
