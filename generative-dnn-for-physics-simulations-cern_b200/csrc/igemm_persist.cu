@@ -924,32 +924,39 @@ igemm_tma_strip_kernel(const __grid_constant__ FwdParams p, const __grid_constan
 
   if (warp == 0) {
     // =========================================================================== TMA PRODUCER: strip (im2col) + nx half weight boxes
-    if (lane == 0) {
-      const uint32_t lead_full0 = mapa_shared(full_bar(0), 0);
+    // The whole warp runs the loop on warp-uniform values (tile fields broadcast by shuffle) and every instruction is issued by
+    // the elected lane inside the asm statement, so coordinates and addresses stay in uniform registers (see the MMA issuer).
+    {
+      const uint32_t lead_full0 = __shfl_sync(0xffffffffu, mapa_shared(full_bar(0), 0), 0);
       uint32_t it = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         TileInfo ti;
         decode_tile(tile, p, s_tiles, s_grp, kTileM, ti);
-        const int wrow = ti.slot * p.Nout + ti.n0 + (int)rank * BH;
-        int cn[2], ch[2], cw[2];
-        for (int u = 0; u < mt; ++u) {
-          const int m = ti.m0 + u * 2 * kBM + (int)rank * kBM;
-          const int sample = m / ts.Pp, pix = m - sample * ts.Pp;
-          const int oy = pix / ts.Wp, ox = pix - oy * ts.Wp;
-          cn[u] = ti.row_start + sample; ch[u] = ts.low_h + oy * p.my; cw[u] = ts.low_w + ox;
-        }
+        const int t_slot = uniform_i32(ti.slot), t_n0 = uniform_i32(ti.n0), t_m0 = uniform_i32(ti.m0), t_row0 = uniform_i32(ti.row_start);
+        const int wrow = t_slot * p.Nout + t_n0 + (int)rank * BH;
+        // base coordinates of the two M sub-tiles (scalars, not arrays: a runtime-indexed array would live in local memory)
+        const int m_a = t_m0 + (int)rank * kBM, m_b = m_a + 2 * kBM;
+        const int smp_a = m_a / ts.Pp, pix_a = m_a - smp_a * ts.Pp, oy_a = pix_a / ts.Wp, ox_a = pix_a - oy_a * ts.Wp;
+        const int smp_b = m_b / ts.Pp, pix_b = m_b - smp_b * ts.Pp, oy_b = pix_b / ts.Wp, ox_b = pix_b - oy_b * ts.Wp;
+        const int cn_a = t_row0 + smp_a, ch_a = ts.low_h + oy_a * p.my, cw_a = ts.low_w + ox_a;
+        const int cn_b = t_row0 + smp_b, ch_b = ts.low_h + oy_b * p.my, cw_b = ts.low_w + ox_b;
         int cb = 0, st = 0;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kStages;
-          if (it >= (uint32_t)kStages) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), 2u * (uint32_t)mt * strip_bytes + (uint32_t)(nx * BN) * 128u);
+          if (it >= (uint32_t)kStages) {        // ONE lane polls: the producer runs ahead and spins here most of the time, and 32
+                                                // lanes spinning on try_wait slowed the whole CTA (conv3 fwd 0.85 vs 0.47 ms)
+            if (lane == 0) mbar_wait(empty_bar(s), ((it / kStages) - 1) & 1, p.err_flag, 4);
+            __syncwarp();
+          }
+          if (rank == 0) mbar_arrive_expect_tx_elect(full_bar(s), 2u * (uint32_t)mt * strip_bytes + (uint32_t)(nx * BN) * 128u);
           const uint32_t lead_full = lead_full0 + 8u * s;
           const uint32_t sa = base + s * kStage;
-          for (int u = 0; u < mt; ++u)
-            tma_im2col_4d_pair(sa + u * ts.a_bytes, &tmap_x, cb * kBK, cw[u], ch[u], cn[u], (uint32_t)(ts.sdx[st] - ts.low_w),
-                               (uint32_t)(ts.sdy[st] - ts.low_h), lead_full);
+          const uint32_t offw = (uint32_t)(ts.sdx[st] - ts.low_w), offh = (uint32_t)(ts.sdy[st] - ts.low_h);
+          tma_im2col_4d_pair_elect(sa, &tmap_x, cb * kBK, cw_a, ch_a, cn_a, offw, offh, lead_full);
+          if (mt == 2) tma_im2col_4d_pair_elect(sa + ts.a_bytes, &tmap_x, cb * kBK, cw_b, ch_b, cn_b, offw, offh, lead_full);
+#pragma unroll 1
           for (int j = 0; j < nx; ++j)
-            tma_load_2d_pair(sa + mt * ts.a_bytes + j * BH * 128, &tmap_wh, ts.skoff[st] + j * p.C + cb * kBK, wrow, lead_full);
+            tma_load_2d_pair_elect(sa + mt * ts.a_bytes + j * BH * 128, &tmap_wh, ts.skoff[st] + j * p.C + cb * kBK, wrow, lead_full);
           if (++st == ts.n_strips) { st = 0; ++cb; }
         }
       }
@@ -1832,6 +1839,8 @@ igemm_wgrad_strip_kernel(const __grid_constant__ WgParams p, const __grid_consta
 
   if (warp == 0) {
     // =========================================================================== TMA PRODUCER
+    // (one lane runs the whole loop.  The warp-uniform / elected-lane form that helps igemm_tma_strip_kernel was measured here
+    // too: conv3 weight gradient 0.562 -> 0.616 ms, conv2 0.249 -> 0.263 — not used)
     if (lane == 0) {
       const uint32_t lead_full0 = kPair ? mapa_shared(full_bar(0), 0) : full_bar(0);
       uint32_t it = 0;

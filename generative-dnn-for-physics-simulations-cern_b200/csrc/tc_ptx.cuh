@@ -253,4 +253,38 @@ __device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const void* tmap, in
       : "memory");
 }
 
+
+
+// ---- warp-collective (elected-lane) forms of the producer's instructions: see umma_bf16_pair_elect
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred e;\n\t.reg .b64 st;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_elect(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+      : "memory");
+}
+__device__ __forceinline__ void tma_im2col_4d_pair_elect(uint32_t dst, const void* tmap, int c, int w, int h, int n, uint32_t offw,
+                                                          uint32_t offh, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};\n\t}"
+      ::"r"(dst), "l"(tmap), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar_cluster_addr), "h"((unsigned short)offw), "h"((unsigned short)offh)
+      : "memory");
+}
+__device__ __forceinline__ void tma_im2col_4d_elect(uint32_t dst, const void* tmap, int c, int w, int h, int n, uint32_t offw,
+                                                     uint32_t offh, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5}], [%6], {%7, %8};\n\t}"
+      ::"r"(dst), "l"(tmap), "r"(c), "r"(w), "r"(h), "r"(n), "r"(bar), "h"((unsigned short)offw), "h"((unsigned short)offh)
+      : "memory");
+}
+__device__ __forceinline__ int uniform_i32(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 }  // namespace es
