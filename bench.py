@@ -309,6 +309,9 @@ def run_b200(args):
 
     # ---- N>1: the sharded step equals the global-batch step, checked ON THE DEVICE before anything is timed (small batch,
     # CPU oracle as the checker): proton and neutron (SyncBN), balanced and with a rank that holds no row of a live expert
+    if args.pipeline_adam is not None:
+        from expertsim.models.moe import MoEWrapper
+        MoEWrapper.pipeline_adam = bool(args.pipeline_adam)
     dp_parity = None
     if world > 1 and not args.no_dp_parity:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -320,7 +323,7 @@ def run_b200(args):
                 r = run_dp_parity(a_, dev, unbalanced=unb)
                 key = f"{a_}{'_unbalanced' if unb else ''}"
                 dp_parity[key] = {k: (float(f"{r[k]:.3e}") if isinstance(r[k], float) else r[k]) for k in
-                                  ("g", "d", "a", "replicas_identical", "rank_without_rows_of_a_live_expert", "ok")}
+                                  ("g", "d", "a", "replicas_identical", "rank_without_rows_of_a_live_expert", "pipelined_rects", "ok")}
                 if not r["ok"]:
                     bad.append((key, r["fails"][:4]))
         dp_parity.update(g=max(v["g"] for v in dp_parity.values()), d=max(v["d"] for v in dp_parity.values()),
@@ -446,9 +449,11 @@ def run_b200(args):
         comm = {"exposed_ms": round(per_step - per_nc, 3), "ms_per_step_without_collectives": round(per_nc, 3),
                 "allreduce_bytes_per_step": sent, "gradient_bytes_per_step_fp32": gb, "mode": str(overlap),
                 "fc2_bucket_dtype": "bf16" if red is not None and red.compress_min_cols is not None else "fp32",
+                "adam_pipelined_rects": int(getattr(moe, "n_pipelined_rects", 0)),
                 "what": "step time minus the time of the same step with all collectives as no-ops (gradient buckets, per-expert loss "
                         "sums, counts, SyncBN statistics); the exposed part is dominated by fc2's gradient bucket (88 % of the "
-                        "generator's gradient bytes, sent as bf16), produced last"}
+                        "generator's gradient bytes), produced last; adam_pipelined_rects > 0: the optimizer pass over that bucket "
+                        "runs rectangle by rectangle behind its chunked all-reduce"}
 
     # ---- batch inference: generated showers/s (router -> partition -> 8 expert generators -> expm1), device resident
     inference = bench_inference(moe, args, dev, world, pk, arch, timed)
@@ -560,6 +565,8 @@ def main():
     ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the roofline_hbm micro-measurements")
     ap.add_argument("--no-dp-parity", action="store_true", help="N>1: skip the on-device data-parallel parity check")
     ap.add_argument("--overlap-mode", default="deferred", choices=["deferred", "eager"])
+    ap.add_argument("--pipeline-adam", type=int, default=None, choices=[0, 1],
+                    help="A/B switch (N>1): optimizer pass over fc2's gradient bucket pipelined behind its chunked all-reduce")
     ap.add_argument("--no-overlap-allreduce", action="store_true",
                     help="A/B switch: one whole-arena gradient all-reduce after backward instead of the overlapped layer buckets")
     ap.add_argument("--per-launch", action="store_true", help="print every timed GEMM launch of the last step to stderr")

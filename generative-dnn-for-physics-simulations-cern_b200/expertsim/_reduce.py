@@ -65,6 +65,52 @@ class BucketedGradReducer:
             comm.wait_event(ev)
             self._all_reduce_rows(G, lo, hi)
 
+    def reduce_chunked(self, G: torch.Tensor, lo: int, hi: int, n_chunks: int = 4):
+        """``reduce(G, lo, hi)`` as ``n_chunks`` consecutive collectives over row blocks ``[e0, e1)`` (or, when the arena
+        has fewer rows than chunks, over column blocks of every row).  Returns ``[(e0, e1, c0, c1, event)]`` in issue order:
+        ``event`` (None on CPU tensors / when disabled) fires on the communication stream when that rectangle of G holds
+        the sum, so the caller can run the optimizer over rectangle k while rectangle k + 1 is still on the wire
+        (MoEWrapper._adam_pipelined).  Never compressed: every rectangle is summed in place."""
+        if hi <= lo:
+            return []
+        E = G.shape[0]
+        n_chunks = max(1, int(n_chunks))
+        if E >= n_chunks:
+            per = -(-E // n_chunks)
+            rects = [(e0, min(e0 + per, E), lo, hi) for e0 in range(0, E, per)]
+        else:
+            per = -(-(hi - lo) // (n_chunks // E or 1))
+            per = -(-per // 1024) * 1024                  # column blocks stay 4 KB aligned (vectorised Adam, NCCL)
+            rects = [(e, e + 1, c0, min(c0 + per, hi)) for e in range(E) for c0 in range(lo, hi, per)]
+        self.buckets.append((lo, hi))
+        self.n_reduced += (hi - lo) * E
+        if self.disabled:
+            return [r + (None,) for r in rects]
+        if not G.is_cuda:
+            for e0, e1, c0, c1 in rects:
+                self._all_reduce_rect(G, e0, e1, c0, c1)
+            return [r + (None,) for r in rects]
+        ev = torch.cuda.current_stream(G.device).record_event()
+        comm = self._stream(G.device)
+        out = []
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev)
+            for e0, e1, c0, c1 in rects:
+                self._all_reduce_rect(G, e0, e1, c0, c1)
+                out.append((e0, e1, c0, c1, comm.record_event()))
+        return out
+
+    def _all_reduce_rect(self, G, e0, e1, c0, c1):
+        self.bytes_sent += (c1 - c0) * (e1 - e0) * G.element_size()
+        rows = [G[e, c0:c1] for e in range(e0, e1)]
+        if len(rows) > 1 and G.is_cuda and self.dist.get_backend(self.group) == "nccl":
+            with self.dist._coalescing_manager(group=self.group, device=G.device, async_ops=False):
+                for t in rows:
+                    self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        else:
+            for t in rows:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
     def _all_reduce_rows(self, G, lo, hi):
         """one message per expert row, all rows of the bucket in ONE grouped NCCL launch (ncclGroupStart/End)"""
         if self.compress_min_cols is not None and hi - lo >= self.compress_min_cols:

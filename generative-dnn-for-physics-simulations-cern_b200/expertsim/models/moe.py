@@ -22,6 +22,7 @@ the gradient arenas over NCCL before each fused Adam, which reproduces the singl
 from __future__ import annotations
 
 import copy
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -40,6 +41,12 @@ def _f(v, default=0.0):
 
 
 class MoEWrapper(nn.Module):
+    # data-parallel steps: the optimizer pass over the widest gradient bucket is pipelined behind its chunked all-reduce
+    # (_adam_pipelined); ES_DP_PIPELINE_ADAM=0 falls back to join-then-one-launch
+    pipeline_adam = os.environ.get("ES_DP_PIPELINE_ADAM", "0") == "1"
+    PIPELINE_CHUNKS = int(os.environ.get("ES_DP_PIPELINE_CHUNKS", "4"))
+    PIPELINE_MIN_FLOATS = 8 << 20           # below 32 MB the bucket is not worth the extra launches
+
     def __init__(self, generator, discriminator, aux_reg, router, n_experts, cfg, image_shape):
         super().__init__()
         self.cfg = cfg
@@ -174,6 +181,40 @@ class MoEWrapper(nn.Module):
     def _adam(arena: Arena, lr, grp):
         L.call("es_adam_step", arena.P, arena.G, arena.M, arena.V, arena.n, arena.n, arena.E, float(lr), 0.9, 0.999, 1e-8,
                arena.steps, grp)
+        arena.version += 1
+
+    def _adam_pipelined(self, arena: Arena, lr, grp, rects, red):
+        """The fused Adam of a data-parallel step, run rectangle by rectangle behind the chunked all-reduce of the widest
+        gradient bucket (fc2's weight: 88 % of the generator's bytes, produced LAST by backward, so its collective cannot
+        hide behind backward kernels): the optimizer pass over rectangle k — HBM-bound, 28 B per parameter — runs while
+        rectangle k + 1 is still being summed over NVLink.  ``rects`` = BucketedGradReducer.reduce_chunked's list; the
+        columns outside the bucket follow (right of it as soon as the first event has fired — their buckets were queued
+        earlier on the same communication stream — left of it after join()).  Elementwise identical to ONE es_adam_step
+        over the arena: every call advances its own copy of the pre-step counters; the real ones take the maximum."""
+        n, E = arena.n, arena.E
+        lo, hi = min(r[2] for r in rects), max(r[3] for r in rects)
+        regions = [(0, E, hi, n, rects[0][4])] if hi < n else []
+        regions += list(rects)
+        regions += [(0, E, 0, lo, "join")] if lo > 0 else [(0, 0, 0, 0, "join")]
+        live = [r for r in regions if r[1] > r[0] and r[3] > r[2]]
+        tmp = arena.steps.unsqueeze(0).repeat(len(live), 1)        # pre-step counters, one private copy per call
+        main, k = (torch.cuda.current_stream(arena.P.device) if arena.P.is_cuda else None), 0
+        gp = grp.data_ptr() if grp is not None else None
+        for e0, e1, c0, c1, ev in regions:
+            if ev == "join":
+                red.join()
+            elif ev is not None and main is not None:
+                main.wait_event(ev)
+            if e1 <= e0 or c1 <= c0:
+                continue
+            k += 1
+            steps = tmp[k - 1]
+            off = 4 * (e0 * n + c0)
+            L.call("es_adam_step", arena.P.data_ptr() + off, arena.G.data_ptr() + off, arena.M.data_ptr() + off,
+                   arena.V.data_ptr() + off, c1 - c0, n, e1 - e0, float(lr), 0.9, 0.999, 1e-8, steps.data_ptr() + 4 * e0,
+                   None if gp is None else gp + 16 * e0)
+        # the regions tile the arena, so every slot was advanced in at least one copy (live experts: t + 1, skipped: t)
+        arena.steps.copy_(tmp.amax(0))
         arena.version += 1
 
     @staticmethod
@@ -433,6 +474,7 @@ class MoEWrapper(nn.Module):
             red = self._reducer
             red.begin()
             mode, pending, heavy = getattr(self, "overlap_grad_allreduce", "deferred"), [], [True]
+            pipe = self.pipeline_adam and red.compress_min_cols is None
 
             def on_ready(lo, hi):
                 if lo is None:
@@ -442,19 +484,35 @@ class MoEWrapper(nn.Module):
                     pending.clear()
                 elif mode == "deferred" and heavy[0]:
                     pending.append((lo, hi))
+                elif pipe and not rects and lo == a_g.off["fc2.0.weight"] and (hi - lo) * E >= self.PIPELINE_MIN_FLOATS:
+                    rects.extend(red.reduce_chunked(a_g.G, lo, hi, self.PIPELINE_CHUNKS))
                 else:
                     red.reduce(a_g.G, lo, hi)
 
+            rects = []
             gen.backward(sg, d_img1, d_img2, on_grads_ready=on_ready)
             assert red.n_reduced == a_g.G.numel(), "gradient buckets must cover the arena exactly once"
-            red.join()
+            if not rects:
+                red.join()
         else:
+            rects = []
             gen.backward(sg, d_img1, d_img2)
             self._allreduce(a_g.G)
         del sg, sv1, sv2, sv_a
-        self._adam(a_g, self._lr(generator_optimizers, gcfg.lr_g), lv_h)
-        if ema_helper is not None and getattr(ema_helper, "enabled", False):
-            ema_helper.update(self, live=lv_h[:, 1])      # only the experts that took an optimizer step (loop.py:392-400)
+
+        def finish_generator():
+            if rects:
+                self._adam_pipelined(a_g, self._lr(generator_optimizers, gcfg.lr_g), lv_h, rects, red)
+            else:
+                self._adam(a_g, self._lr(generator_optimizers, gcfg.lr_g), lv_h)
+            if ema_helper is not None and getattr(ema_helper, "enabled", False):
+                ema_helper.update(self, live=lv_h[:, 1])      # only the experts that took an optimizer step (loop.py:392-400)
+
+        self.n_pipelined_rects = len(rects)
+        if not rects:
+            finish_generator()
+        # (pipelined: the widest bucket is still on the wire — the auxiliary regressor's optimizer and the router block
+        # below do not depend on it and run first; the generator's optimizer follows them)
         main.wait_event(ev_aw)
         self._adam(a_a, self._lr(aux_reg_optimizers, cfgm.aux_reg.lr_a), lv_h)
 
@@ -501,6 +559,8 @@ class MoEWrapper(nn.Module):
         else:
             gan = router_loss = ed = diff = ent = alb = zero
 
+        if rects:
+            finish_generator()
         m = {"gen_loss": gen_losses.mean(), "disc_loss": loss_d.mean(), "div_loss": losses[:, 1].sum() / E,
              "intensity_loss": losses[:, 2].sum() / E, "aux_reg_loss": losses[:, 3].sum() / E, "router_loss": router_loss,
              "expert_distribution_loss": ed, "differentiation_loss": diff, "expert_entropy_loss": ent,

@@ -133,6 +133,36 @@ def _bucket_case(rank, world):
     return bool(torch.equal(G, whole)), covered, bool(torch.equal(G2, whole2))
 
 
+def _chunked_case(rank, world):
+    """reduce_chunked == the plain all-reduce of the same column range, for row blocks (E >= chunks) and column blocks
+    (E < chunks); the rectangles tile the bucket exactly once, in issue order"""
+    from expertsim._reduce import BucketedGradReducer
+    red = BucketedGradReducer(dist)
+    ok = []
+    for E, cols, lo, hi, chunks in ((8, 5000, 1000, 4600, 4), (3, 9000, 500, 8200, 4), (1, 9000, 0, 9000, 4), (5, 300, 10, 290, 2)):
+        g = torch.Generator().manual_seed(3 + rank)
+        G = torch.randn(E, cols, generator=g)
+        want = G.clone()
+        part = G[:, lo:hi].clone()
+        dist.all_reduce(part)
+        want[:, lo:hi] = part
+        red.begin()
+        rects = red.reduce_chunked(G, lo, hi, chunks)
+        cover = torch.zeros(E, cols, dtype=torch.int32)
+        for e0, e1, c0, c1, ev in rects:
+            cover[e0:e1, c0:c1] += 1
+            assert ev is None
+        tiled = bool((cover[:, lo:hi] == 1).all()) and int(cover.sum()) == E * (hi - lo)
+        ok.append(bool(torch.equal(G, want)) and tiled and red.n_reduced == E * (hi - lo) and red.buckets == [(lo, hi)]
+                  and red.bytes_sent == 4 * E * (hi - lo) and len(rects) >= min(chunks, E))
+    return ok
+
+
+def test_chunked_bucket_equals_plain_allreduce():
+    out = run2(_chunked_case)
+    assert out[0] == [True] * 4 and out[1] == [True] * 4
+
+
 def _compressed_bucket_case(rank, world):
     """A bucket at least ``compress_min_cols`` wide travels as bf16: result = the bf16 sum of the bf16-rounded rows, identical
     on every rank; narrower buckets stay fp32 and exact."""

@@ -298,3 +298,67 @@ def test_zero_pool_alternates_and_clears(monkeypatch):
     zp.end()
     assert zp.need >= 256 + 4096 and float(big.sum()) == 0.0
     assert not zp.active and N.zeros(2).sum() == 0
+
+
+def test_pipelined_adam_decomposition_equals_one_launch(monkeypatch):
+    """MoEWrapper._adam_pipelined (data-parallel steps) runs the fused Adam rectangle by rectangle behind the chunked
+    all-reduce.  Host logic pinned here with es_adam_step emulated over HOST pointers (same argument meaning as the C-ABI
+    entry: p/g/m/v + n + slot_stride + slots, per-slot counters advanced for live groups only): every parameter is updated
+    exactly once with the bias correction of step t + 1, the counters advance once, skipped experts stay untouched —
+    bit-identical to one launch over the arena."""
+    import ctypes
+    from types import SimpleNamespace
+    import numpy as np
+    from expertsim.models import moe as moe_mod
+
+    def view(addr, count, dt):
+        return np.ctypeslib.as_array((dt * count).from_address(addr))
+
+    calls = []
+
+    def fake_call(name, p, g, m, v, n, stride, slots, lr, b1, b2, eps, steps, grp):
+        assert name == "es_adam_step"
+        calls.append((n, slots))
+        st = view(steps if isinstance(steps, int) else steps.data_ptr(), slots, ctypes.c_int32)
+        gr = None if grp is None else view(grp if isinstance(grp, int) else grp.data_ptr(), slots * 4, ctypes.c_int32).reshape(slots, 4)
+        ptr = lambda a: a if isinstance(a, int) else a.data_ptr()
+        for s_ in range(slots):
+            if gr is not None and gr[s_, 1] == 0:
+                continue
+            st[s_] += 1
+            t = int(st[s_])
+            P, G_, M, V = (view(ptr(a) + 4 * s_ * stride, n, ctypes.c_float) for a in (p, g, m, v))
+            M[:] = M + (G_ - M) * np.float32(1 - b1)
+            V[:] = V * np.float32(b2) + G_ * G_ * np.float32(1 - b2)
+            step = np.float32(lr / (1 - b1 ** t))
+            P[:] = P - step * M / (np.sqrt(V) / np.float32(np.sqrt(1 - b2 ** t)) + np.float32(eps))
+
+    monkeypatch.setattr(moe_mod.L, "call", fake_call)
+    E, n = 5, 4096
+    g = torch.Generator().manual_seed(1)
+
+    def arena():
+        g.manual_seed(1)
+        return SimpleNamespace(P=torch.randn(E, n, generator=g), G=torch.randn(E, n, generator=g), M=torch.randn(E, n, generator=g) * .1,
+                               V=torch.rand(E, n, generator=g) * .1, steps=torch.tensor([3, 0, 7, 7, 1], dtype=torch.int32), n=n, E=E,
+                               version=0)
+
+    grp = torch.tensor([[0, 4, 0, 4], [4, 0, 1, 0], [4, 2, 2, 2], [6, 0, 3, 0], [6, 9, 4, 9]], dtype=torch.int32)
+    one = arena()
+    moe_mod.MoEWrapper._adam(one, 1e-3, grp)
+    joins = []
+    red = SimpleNamespace(join=lambda: joins.append(len(calls)))
+    for rects in ([(0, 2, 1024, 3072, None), (2, 4, 1024, 3072, None), (4, 5, 1024, 3072, None)],        # row blocks, both remainders
+                  [(e, e + 1, c, c + 2048, None) for e in range(E) for c in (0, 2048)],                  # column blocks, whole arena
+                  [(0, 5, 0, 3072, None)]):                                                              # no left remainder
+        calls.clear(), joins.clear()
+        pip = arena()
+        moe_mod.MoEWrapper._adam_pipelined(SimpleNamespace(), pip, 1e-3, grp, rects, red)
+        for k in ("P", "M", "V", "steps"):
+            assert torch.equal(getattr(pip, k), getattr(one, k)), k
+        assert pip.version == 1 and len(joins) == 1
+        hi = max(r[3] for r in rects)
+        lo = min(r[2] for r in rects)
+        assert len(calls) == len(rects) + (hi < n) + (lo > 0)
+        assert joins[0] == len(calls) - (lo > 0)          # only the columns left of the bucket wait for join()
+    assert one.steps.tolist() == [4, 0, 8, 7, 2]

@@ -825,6 +825,32 @@ def test_elementwise_and_adam():
     assert torch.equal(dp[1].cpu(), p[1])
 
 
+def test_adam_pipelined_rectangles_equal_one_launch():
+    """MoEWrapper._adam_pipelined through the real es_adam_step: row blocks + both column remainders, and column blocks of
+    single rows, against ONE launch over the arena — bit-identical parameters, moments and counters (skipped slot untouched)"""
+    from types import SimpleNamespace
+    from expertsim.models.moe import MoEWrapper
+    g = G(31)
+    E, n = 5, 1 << 16
+    P0, G0 = torch.randn(E, n, generator=g), torch.randn(E, n, generator=g)
+    M0, V0 = torch.randn(E, n, generator=g) * .1, torch.rand(E, n, generator=g) * .1
+    grp, _ = groups([4, 0, 2, 0, 9])
+
+    def arena():
+        return SimpleNamespace(P=cuda(P0.clone()), G=cuda(G0.clone()), M=cuda(M0.clone()), V=cuda(V0.clone()),
+                               steps=torch.tensor([3, 0, 7, 7, 1], dtype=torch.int32, device=DEV), n=n, E=E, version=0)
+    one = arena()
+    MoEWrapper._adam(one, 1e-3, grp)
+    red = SimpleNamespace(join=lambda: None)
+    for rects in ([(0, 2, 4096, 60000, None), (2, 4, 4096, 60000, None), (4, 5, 4096, 60000, None)],
+                  [(e, e + 1, c, min(c + 24576, n), None) for e in range(E) for c in range(0, n, 24576)]):
+        pip = arena()
+        MoEWrapper._adam_pipelined(SimpleNamespace(), pip, 1e-3, grp, rects, red)
+        for k in ("P", "M", "V", "steps"):
+            assert torch.equal(getattr(pip, k), getattr(one, k)), k
+    assert one.steps.cpu().tolist() == [4, 0, 8, 7, 2] and torch.equal(one.P[1].cpu(), P0[1])
+
+
 def test_expm1_scatter():
     g = G(5)
     R, HW = 9, 1680

@@ -137,6 +137,15 @@ def run_dp_parity(arch, dev, unbalanced=False, E=3, seed=7, group=None):
         steps = moe.arena(k).steps.cpu().tolist()
         if steps != [1 if lv else 0 for lv in live]:
             fails.append(f"Adam step counters of arena {k}: {steps}, live experts {live}")
+    # the generator's Adam touched every element of every live expert exactly once (first step from zero moments:
+    # exp_avg == (1 - beta1) * gradient; twice would give 0.19 g, a missed rectangle 0) — the pipelined form included
+    ag = moe.arena("g")
+    c1 = torch.tensor(1.0) - torch.tensor(0.9)
+    for e in range(E):
+        m_want = ag.G[e] * float(c1) if live[e] else torch.zeros_like(ag.G[e])
+        if not torch.allclose(ag.M[e], m_want, rtol=1e-5, atol=1e-30):
+            bad = int((~torch.isclose(ag.M[e], m_want, rtol=1e-5, atol=1e-30)).sum())
+            fails.append(f"generator exp_avg of expert {e} is not one Adam step of the reduced gradient ({bad} elements)")
     # replicas must stay BIT-identical after the step: parameters, moments, step counters, buffers
     chk, chk_names = replica_checksums(moe)
     lo, hi = chk.clone(), chk.clone()
@@ -154,7 +163,8 @@ def run_dp_parity(arch, dev, unbalanced=False, E=3, seed=7, group=None):
     dist.all_reduce(empty, op=dist.ReduceOp.MAX, group=group)
     return {"ok": int(ok) == 1, "g": float(w[0]), "d": float(w[1]), "a": float(w[2]), "replicas_identical": identical,
             "world": world, "global_batch": B, "unbalanced": bool(unbalanced), "rank_without_rows_of_a_live_expert": bool(int(empty)),
-            "gen_loss": float(got["gen_loss"]), "oracle_gen_loss": want["gen_loss"], "fails": fails, "local_counts": local_counts}
+            "gen_loss": float(got["gen_loss"]), "oracle_gen_loss": want["gen_loss"], "fails": fails, "local_counts": local_counts,
+            "pipelined_rects": int(getattr(moe, "n_pipelined_rects", 0))}
 
 
 def main():
@@ -174,7 +184,7 @@ def main():
         print(f"dp parity {arch} world={world} B={res['global_batch']} backend={'gloo, ranks share cuda:0' if one_gpu else 'nccl'}"
               f"{' UNBALANCED (a rank holds no row of live expert 0: ' + str(res['rank_without_rows_of_a_live_expert']) + ')' if res['unbalanced'] else ''}: "
               f"worst relL2 g={res['g']:.3e} d={res['d']:.3e} a={res['a']:.3e}; replicas bit-identical: {res['replicas_identical']}; "
-              f"gen_loss {res['gen_loss']:.6f} vs oracle {res['oracle_gen_loss']:.6f}")
+              f"gen_loss {res['gen_loss']:.6f} vs oracle {res['oracle_gen_loss']:.6f}; pipelined Adam rectangles: {res['pipelined_rects']}")
     for f in res["fails"]:
         print(f"[rank {rank}] FAIL {f}")
     dist.destroy_process_group()
