@@ -272,10 +272,13 @@ def run_b200(args):
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
-        # the gradient buckets run when the SMs are otherwise idle (after backward): give NCCL more channels and larger
-        # staging buffers than its defaults (measured at N = 2: exposed communication 1.93 -> 1.71 ms per step)
-        os.environ.setdefault("NCCL_MIN_NCHANNELS", "64")
-        os.environ.setdefault("NCCL_BUFFSIZE", str(16 << 20))
+        # the gradient buckets run when the SMs are otherwise idle (after backward): two GPUs talk over point-to-point
+        # NVLink rings, which need more channels and larger staging buffers than NCCL's defaults to fill the 18 links
+        # (measured at N = 2: exposed communication 1.93 -> 1.71 ms per step).  N > 2 keeps NCCL's own choice (NVLS /
+        # tree over the NVSwitch) as in the round-1 4- and 8-GPU runs: the setting was never measured there.
+        if world == 2:
+            os.environ.setdefault("NCCL_MIN_NCHANNELS", "64")
+            os.environ.setdefault("NCCL_BUFFSIZE", str(16 << 20))
         dist.init_process_group("nccl", device_id=dev)
     L.load()
     if not L.device_ok():
