@@ -480,7 +480,10 @@ def run_b200(args):
         for key, (a_, e_) in (("neutron", ("neutron", E)), ("e1", ("proton", 1))):
             if (a_, e_) == (arch, E):
                 continue
-            extra[key] = short_bench(a_, e_, B, dev, rank, world, args, pk, timed, overlap)
+            try:
+                extra[key] = short_bench(a_, e_, B, dev, rank, world, args, pk, timed, overlap)
+            except Exception as ex:      # a side line must never cost the headline line (the error is reported in its place)
+                extra[key] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
     if rank != 0:
         if world > 1:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Data-parallel parity: the sharded step must equal the single-device global-batch step.
 
-    python -m torch.distributed.run --nproc-per-node N tools/dp_parity.py [proton|neutron] [--unbalanced] [--one-gpu]
+    python -m torch.distributed.run --nproc-per-node N tools/dp_parity.py [proton|neutron] [--unbalanced] [--one-gpu] [--experts=E]
 
 Every rank holds rows r::N of ONE global batch (and of the injected noise), runs ``MoEWrapper.train_step`` with data
 parallelism enabled, and the all-reduced gradients / losses are compared with the CPU oracle's step on the WHOLE batch.
@@ -179,7 +179,8 @@ def main():
     else:
         dist.init_process_group("nccl", device_id=dev)
     arch = args[0] if args else "proton"
-    res = run_dp_parity(arch, dev, unbalanced="--unbalanced" in flags)
+    n_exp = next((int(f.split("=", 1)[1]) for f in flags if f.startswith("--experts=")), 3)
+    res = run_dp_parity(arch, dev, unbalanced="--unbalanced" in flags, E=n_exp)
     if rank == 0:
         print(f"dp parity {arch} world={world} B={res['global_batch']} backend={'gloo, ranks share cuda:0' if one_gpu else 'nccl'}"
               f"{' UNBALANCED (a rank holds no row of live expert 0: ' + str(res['rank_without_rows_of_a_live_expert']) + ')' if res['unbalanced'] else ''}: "
