@@ -362,3 +362,27 @@ def test_pipelined_adam_decomposition_equals_one_launch(monkeypatch):
         assert len(calls) == len(rects) + (hi < n) + (lo > 0)
         assert joins[0] == len(calls) - (lo > 0)          # only the columns left of the bucket wait for join()
     assert one.steps.tolist() == [4, 0, 8, 7, 2]
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The measured lines under profiles/ (written by bench.py on the B200) carry every key the bench contract names —
+    both arms — so a change of bench.py that drops one shows up here before it reaches the GPU box."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.loads(open(os.path.join(root, "profiles", "r02_bench_n1.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in line, k
+    assert line["config"]["workload"] and "model" not in line["config"]
+    assert line["gpu_launches"] > 0 and line["warmup"] >= 3 and line["higher_is_better"] is True
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"]) and line["e2e"]["h2d_bytes_per_step"] > 0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "executed_frac", "tensor_pipe_active_pct"} <= set(line["roofline"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"]) and line["cpu_baseline"]["kind"] == "reference"
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
+    ref = json.loads(open(os.path.join(root, "profiles", "r02_bench_reference.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["config"] == line["config"] and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "reference"
+    two = json.loads(open(os.path.join(root, "profiles", "r02_bench_n2_adam_pipelined.json")).read().strip().splitlines()[-1])
+    assert two["n_gpus"] == 2 and two["dp_parity"]["replicas_identical"] is True and two["comm"]["adam_pipelined_rects"] == 4
